@@ -1,0 +1,110 @@
+"""Seeded input generators for the golden/parity cases (shared by make_golden.py, the oracle tests
+and the GPU parity tests).  numpy RandomState streams are stable across numpy versions."""
+import numpy as np
+
+
+def _gaussian_probe(size, mag_sigma, phase_max, phase_sigma):
+    py = np.arange(size[0]) - (size[0] - 1.) / 2
+    px = np.arange(size[1]) - (size[1] - 1.) / 2
+    pxx, pyy = np.meshgrid(px, py)
+    mag = np.exp(-(pxx ** 2 + pyy ** 2) / (2 * mag_sigma ** 2))
+    ph = phase_max * np.exp(-(pxx ** 2 + pyy ** 2) / (2 * phase_sigma ** 2))
+    return mag * np.cos(ph), mag * np.sin(ph)
+
+
+def _smooth_noise(rs, shape, scale):
+    """Band-limited positive random field (sum of a few random cosines) * scale."""
+    grids = np.meshgrid(*[np.arange(s) for s in shape], indexing='ij')
+    f = np.zeros(shape)
+    for _ in range(6):
+        k = rs.uniform(-0.35, 0.35, size=len(shape))
+        ph = rs.uniform(0, 2 * np.pi)
+        f += np.cos(sum(2 * np.pi * ki * g for ki, g in zip(k, grids)) + ph)
+    f = (f - f.min()) / (f.max() - f.min() + 1e-12)
+    f = f + 0.15 * rs.uniform(size=shape)
+    return (f * scale).astype('float32')
+
+
+CASES = {
+    # 3-D ptychotomography, the shape of BASELINE config D scaled down: P=72, overhanging probes.
+    'ptycho3d_p72': dict(kind='ptycho', obj_size=(80, 80, 80), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                         theta=0.7, n_theta=7, i_theta=3,
+                         pos=[(-36, -36), (4, 5), (-10, 30), (8, -20)], n_modes=1, free_prop_cm='inf',
+                         unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=11,
+                         loss='lsq', raw_data_type='magnitude'),
+    # same geometry, Poisson loss on intensity data, sign_convention -1, normalize_fft
+    'ptycho3d_p72_poisson': dict(kind='ptycho', obj_size=(80, 80, 80), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                                 theta=-1.9, n_theta=7, i_theta=5,
+                                 pos=[(0, 0), (8, 8), (-5, 3)], n_modes=1, free_prop_cm='inf',
+                                 unknown_type='delta_beta', delta_scale=5e-4, beta_scale=5e-5, seed=12,
+                                 loss='poisson', raw_data_type='intensity', sign_convention=-1, normalize_fft=True,
+                                 poisson_multiplier=3.0),
+    # 2-D ptychography with probe modes + probe and position refinement (BASELINE config B shape, small)
+    'ptycho2d_modes': dict(kind='ptycho', obj_size=(128, 128, 1), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                           theta=0.0, n_theta=1, i_theta=0,
+                           pos=[(-10, -10), (20, 31), (56, 56), (60, -12), (0, 40), (33, 7)], n_modes=3,
+                           free_prop_cm='inf', unknown_type='delta_beta', delta_scale=3e-2, beta_scale=3e-3, seed=13,
+                           loss='lsq', raw_data_type='magnitude', optimize_probe=True, optimize_all_probe_pos=True),
+    # 2-D ptychography, real_imag unknown, P=64, intensity data (BASELINE config C shape, small)
+    'ptycho2d_realimag_p64': dict(kind='ptycho', obj_size=(100, 90, 1), probe_size=(64, 64), energy_ev=8801.12,
+                                  psize_cm=1.3279e-6, theta=0.0, n_theta=1, i_theta=0,
+                                  pos=[(-8, -8), (10, 12), (36, 26), (40, -5), (3, 30)], n_modes=2,
+                                  free_prop_cm='inf', unknown_type='real_imag', delta_scale=0.3, beta_scale=0.3, seed=14,
+                                  loss='lsq', raw_data_type='intensity', optimize_probe=True,
+                                  optimize_all_probe_pos=True),
+    # full-field multislice tomography, the reference CI config's shape (BASELINE config A)
+    'fullfield64': dict(kind='fullfield', obj_size=(64, 64, 64), probe_size=(64, 64), energy_ev=800., psize_cm=0.67e-7,
+                        theta=2.3, n_theta=5, i_theta=2, pos=[(0, 0)], n_modes=1, free_prop_cm=0,
+                        unknown_type='delta_beta', delta_scale=2e-3, beta_scale=3e-4, seed=15,
+                        loss='lsq', raw_data_type='magnitude', alpha_d=1e-9 * 64 ** 3, alpha_b=1e-10 * 64 ** 3,
+                        gamma=1e-6),
+}
+
+
+def make_inputs(name):
+    c = dict(CASES[name])
+    rs = np.random.RandomState(c['seed'])
+    Y, X, Z = c['obj_size']
+    P = c['probe_size']
+    M = c['n_modes']
+    if c['unknown_type'] == 'delta_beta':
+        d = _smooth_noise(rs, (Y, X, Z), c['delta_scale'])
+        b = _smooth_noise(rs, (Y, X, Z), c['beta_scale'])
+        obj = np.stack([d, b], -1).astype('float32')
+    else:
+        mag = 1.0 - _smooth_noise(rs, (Y, X, Z), c['delta_scale'])
+        ph = _smooth_noise(rs, (Y, X, Z), c['beta_scale'] * 3)
+        obj = np.stack([mag * np.cos(ph), mag * np.sin(ph)], -1).astype('float32')
+    if c['kind'] == 'fullfield':
+        pr = np.ones((1,) + tuple(P), 'float32')
+        pi = np.zeros((1,) + tuple(P), 'float32')
+    else:
+        r0, i0 = _gaussian_probe(P, 6.0, 0.5, 6.0)
+        pr = np.stack([r0 * (1 + 0.3 * m) + 0.05 * rs.normal(size=P) * np.abs(r0) for m in range(M)]).astype('float32')
+        pi = np.stack([i0 * (1 - 0.2 * m) + 0.05 * rs.normal(size=P) * np.abs(r0) for m in range(M)]).astype('float32')
+    pos = np.array(c['pos'], dtype='int64')
+    B = len(pos)
+    # synthetic "measured" data: positive, smooth-ish, same order of magnitude as a plausible prediction
+    amp = float(np.sqrt((pr ** 2 + pi ** 2).sum()))
+    if c['free_prop_cm'] == 'inf' and not c.get('normalize_fft', False) and c.get('sign_convention', 1) == 1:
+        scale = amp * 2.0
+    else:
+        scale = amp / np.sqrt(P[0] * P[1]) * 2.0
+    prj = (scale * rs.uniform(0.2, 1.0, size=(B,) + tuple(P))).astype('float32')
+    if c['loss'] == 'poisson':
+        # Poisson loss has a 1/a term: keep the case well conditioned by giving the measured data the
+        # far-field envelope of the probe behind a random phase screen (instead of white noise).
+        screen = np.exp(1j * _smooth_noise(rs, tuple(P), 2.0))
+        ff = np.fft.fftshift(np.fft.ifft2((pr[0] + 1j * pi[0]) * screen, norm='ortho'
+                                          if c.get('normalize_fft', False) else None))
+        env = np.abs(ff) + 1e-3 * np.abs(ff).max()
+        prj = (env[None] * rs.uniform(0.7, 1.3, size=(B,) + tuple(P))).astype('float32')
+    if c['raw_data_type'] == 'intensity':
+        prj = (prj ** 2).astype('float32')
+    n_theta = c['n_theta']
+    ppc = None
+    if c.get('optimize_all_probe_pos', False):
+        ppc = rs.uniform(-0.6, 0.6, size=(n_theta, 16, 2)).astype('float32')
+    ind = np.arange(B) + 2 if ppc is not None else np.arange(B)
+    return dict(cfg=c, obj=obj, probe_real=pr, probe_imag=pi, pos=pos, prj=prj, probe_pos_correction=ppc,
+                this_ind_batch=ind)

@@ -1,0 +1,60 @@
+"""Helpers shared by the oracle tests and the GPU parity tests (test infrastructure)."""
+import numpy as np
+import torch
+from cases import make_inputs
+from oracle import multislice_oracle as orc
+
+
+def compact_grad(g, seed=0):
+    g = np.asarray(g, dtype='float64')
+    rs = np.random.RandomState(seed)
+    flat = g.reshape(-1)
+    idx = rs.randint(0, flat.size, size=4096)
+    out = {'norm': np.sqrt((flat ** 2).sum()), 'sample_idx': idx.astype('int64'), 'sample': flat[idx].astype('float32')}
+    for ax in range(3):
+        out['proj%d' % ax] = g.sum(axis=ax).astype('float32')
+    return out
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype='float64')
+    b = np.asarray(b, dtype='float64')
+    return float(np.sqrt(((a - b) ** 2).sum()) / (np.sqrt((b ** 2).sum()) + 1e-300))
+
+
+def case_cfg(name):
+    inp = make_inputs(name)
+    c = inp['cfg']
+    Y, X, Z = c['obj_size']
+    sign = c.get('sign_convention', 1)
+    voxel_nm = np.array([c['psize_cm']] * 3) * 1e7
+    lmbda_nm = 1240. / c['energy_ev']
+    h = orc.get_kernel(voxel_nm[-1], lmbda_nm, voxel_nm, c['probe_size'], fresnel_approx=True, sign_convention=sign)
+    cfg = dict(this_obj_size=[Y, X, Z], probe_size=list(c['probe_size']), energy_ev=c['energy_ev'], psize_cm=c['psize_cm'],
+               h=h, free_prop_cm=c['free_prop_cm'], unknown_type=c['unknown_type'], binning=1,
+               normalize_fft=c.get('normalize_fft', False), sign_convention=sign, scale_ri_by_k=True,
+               fresnel_approx=True, optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), two_d_mode=(Z == 1),
+               loss_function_type=c['loss'], raw_data_type=c['raw_data_type'],
+               poisson_multiplier=c.get('poisson_multiplier', 1.))
+    coord = None if Z == 1 else orc.rotation_coords([Y, X, Z], np.float32(c['theta']))
+    reg = None
+    if c.get('alpha_d') or c.get('gamma'):
+        reg = dict(alpha_d=c.get('alpha_d'), alpha_b=c.get('alpha_b'), gamma=c.get('gamma'))
+    return inp, cfg, coord, reg
+
+
+def run_oracle_case(name, dtype=torch.float32):
+    inp, cfg, coord, reg = case_cfg(name)
+    c = inp['cfg']
+    want = ['obj']
+    if c.get('optimize_probe', False):
+        want += ['probe_real', 'probe_imag']
+    ppc = None
+    if inp['probe_pos_correction'] is not None:
+        ppc = torch.tensor(inp['probe_pos_correction']).to(dtype)
+        want += ['probe_pos_correction']
+    loss, data_loss, pred, grads = orc.ptycho_loss_and_grads(
+        torch.tensor(inp['obj']).to(dtype), torch.tensor(inp['probe_real']).to(dtype),
+        torch.tensor(inp['probe_imag']).to(dtype), inp['pos'], torch.tensor(inp['prj']).to(dtype), coord, cfg, reg=reg,
+        probe_pos_correction=ppc, this_i_theta=c['i_theta'], this_ind_batch=inp['this_ind_batch'], want=tuple(want))
+    return inp, float(loss), pred.numpy(), {k: v.numpy() for k, v in grads.items()}

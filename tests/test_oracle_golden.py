@@ -1,0 +1,43 @@
+"""CPU: the oracle restatement (oracle/multislice_oracle.py) against golden vectors produced by the
+UNMODIFIED reference (tests/golden/make_golden.py).  Tolerances: fp32 restatement vs fp32 reference,
+1e-4 relative (north_star); in practice agreement is ~1e-6."""
+import os
+import numpy as np
+import pytest
+import torch
+from cases import CASES
+from oracle_util import run_oracle_case, compact_grad, rel_err
+from oracle import multislice_oracle as orc
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+TOL = 1e-4
+
+
+@pytest.mark.parametrize('name', sorted(CASES.keys()))
+def test_oracle_matches_reference_golden(name):
+    gold = np.load(os.path.join(GOLD, name + '.npz'))
+    inp, loss, pred, grads = run_oracle_case(name, torch.float32)
+    assert abs(loss - float(gold['loss'])) <= TOL * abs(float(gold['loss']))
+    assert rel_err(pred, gold['pred']) < TOL
+    cg = compact_grad(grads['obj'])
+    assert abs(cg['norm'] - float(gold['gobj_norm'])) <= TOL * float(gold['gobj_norm'])
+    for k in ('proj0', 'proj1', 'proj2', 'sample'):
+        assert rel_err(cg[k], gold['gobj_' + k]) < TOL, k
+    for k in ('probe_real', 'probe_imag', 'probe_pos_correction'):
+        if 'g_' + k in gold.files:
+            assert rel_err(grads[k], gold['g_' + k]) < TOL, k
+
+
+def test_oracle_adam_matches_reference_golden():
+    """adam_step vs AdamOptimizer.apply_gradient (optimizers.py:275-337): three calls, repeated step index."""
+    from make_golden import adam_inputs
+    gold = np.load(os.path.join(GOLD, 'adam.npz'))
+    x, g_ls, steps = adam_inputs()
+    xt = torch.tensor(x)
+    m = torch.zeros_like(xt)
+    v = torch.zeros_like(xt)
+    for i, (g, st) in enumerate(zip(g_ls, steps)):
+        xt, m, v = orc.adam_step(xt, torch.tensor(g), m, v, st, step_size=1e-5)
+        np.testing.assert_allclose(xt.numpy(), gold['x%d' % i], rtol=1e-6, atol=1e-12)
+        np.testing.assert_allclose(m.numpy(), gold['m%d' % i], rtol=1e-6, atol=1e-30)
+        np.testing.assert_allclose(v.numpy(), gold['v%d' % i], rtol=1e-6, atol=1e-30)
