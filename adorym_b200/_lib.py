@@ -1,0 +1,100 @@
+"""ctypes binding of the C ABI declared in include/adorym_b200.h (the hand-written sm_100a kernels).
+
+There is NO CPU fallback: if the in-tree CUDA library is missing and cannot be built, or a tensor is not a
+contiguous CUDA tensor, these functions raise.
+"""
+import ctypes
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, 'libadorym_b200.so')
+
+c_int, c_float, c_void_p, c_longlong = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
+
+
+class MultisliceCfg(ctypes.Structure):
+    """struct adm_multislice_cfg (include/adorym_b200.h)."""
+    _fields_ = [('P', c_int), ('n_slices', c_int), ('B', c_int), ('M', c_int), ('Y', c_int), ('X', c_int),
+                ('k1', c_float), ('sign_convention', c_int), ('unknown_type', c_int), ('free_prop', c_int),
+                ('normalize_fft', c_int), ('probe_per_pattern', c_int)]
+
+
+P_CFG = ctypes.POINTER(MultisliceCfg)
+
+# name -> argtypes; every entry point returns int (0 = ok).  Must list every symbol of include/adorym_b200.h.
+SIGNATURES = {
+    'adm_abi_version': [],
+    'adm_prepare_transfer_function': [c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
+    'adm_multislice_fwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_multislice_bwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p],
+    'adm_detector_loss': [c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p, c_void_p, c_void_p],
+    'adm_rotate_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_rotate_adj': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_adam_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float, c_int,
+                      c_int, c_void_p, c_void_p],
+    'adm_regularizer_l1tv': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
+                             c_void_p],
+    'adm_probe_shift_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_probe_shift_bwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+}
+
+ERRORS = {1: 'bad argument', 2: 'unsupported configuration', 3: 'CUDA launch error'}
+
+
+def bind(cdll):
+    """Attach argtypes/restype for every ABI symbol; raises AttributeError if one is missing."""
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(cdll, name)
+        fn.argtypes = argtypes
+        fn.restype = c_int
+    return cdll
+
+
+_lib = None
+launch_count = 0          # number of kernel-launching ABI calls made by this process (bench.py reports it)
+
+
+def get_lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            from . import build as _build   # nvcc is part of the image; this is a build step, not a fallback
+            _build.build()
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError('adorym_b200: CUDA library %s is missing; run `python -m adorym_b200.build`' % LIB_PATH)
+        _lib = bind(ctypes.CDLL(LIB_PATH))
+        if _lib.adm_abi_version() != 1:
+            raise RuntimeError('adorym_b200: ABI version mismatch')
+    return _lib
+
+
+def check(rc, name):
+    if rc != 0:
+        if rc == 2:
+            raise NotImplementedError('adorym_b200.%s: %s' % (name, ERRORS[2]))
+        raise RuntimeError('adorym_b200.%s failed: %s' % (name, ERRORS.get(rc, rc)))
+
+
+def call(name, *args):
+    global launch_count
+    rc = getattr(get_lib(), name)(*args)
+    launch_count += 1
+    check(rc, name)
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError('adorym_b200: expected a CUDA tensor (there is no CPU path)')
+    if not t.is_contiguous():
+        raise RuntimeError('adorym_b200: expected a contiguous tensor')
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,134 @@
+/*
+ * adorym_b200 -- C ABI of the B200-native multislice forward-model + gradient + update hot path.
+ *
+ * Drop-in boundary for mdw771/adorym's hot path.  The reference is pure Python; the
+ * "FFI" it would bind is a ctypes/pybind stub called from a torch.autograd.Function that replaces
+ *   - adorym/propagate.py:131-288   multislice_propagate_batch  (+ wrappers.py:699-779 fft2/ifft2/convolve,
+ *                                    wrappers.py:600-608 exp_complex, forward_model.py:313-331 patch gather,
+ *                                    util.py:1327-1351 pad_object)            -> adm_multislice_fwd / _bwd
+ *   - adorym/forward_model.py:88-103, 353, 371-375 (norm + mismatch loss)     -> adm_detector_loss
+ *   - adorym/util.py:536-552 apply_rotation / wrappers.py:1105-1147 grid_sample and its autograd transpose
+ *                                                                              -> adm_rotate_fwd / adm_rotate_adj
+ *   - adorym/optimizers.py:275-337  AdamOptimizer.apply_gradient              -> adm_adam_step
+ *   - adorym/regularizers.py:30-110 + util.py:1427-1440 (L1 / reweighted L1 / TV value and gradient)
+ *                                                                              -> adm_regularizer_l1tv
+ *   - adorym/util.py:380-397 realign_image_fourier on the probe (+ transpose)  -> adm_probe_shift_fwd / _bwd
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer to contiguous fp32 (or int32) memory owned by the caller
+ *     (PyTorch allocations); kernels never allocate, workspaces are passed in;
+ *   - complex arrays are interleaved (re, im) pairs; the object is [..., 2] = (delta, beta) or (re, im);
+ *   - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); all work is enqueued
+ *     asynchronously on it; no host synchronisation inside;
+ *   - return value: 0 = ok, 1 = bad argument, 2 = unsupported configuration, 3 = CUDA launch error
+ *     (cudaGetLastError); there is NO CPU fallback.
+ */
+#ifndef ADORYM_B200_H
+#define ADORYM_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ADM_ABI_VERSION 1
+
+/* unknown_type */
+#define ADM_DELTA_BETA 0
+#define ADM_REAL_IMAG 1
+/* free_prop */
+#define ADM_PROP_NONE 0  /* free_prop_cm in (0, None): detector sees the exit wave (propagate.py:263)        */
+#define ADM_PROP_FAR 1   /* free_prop_cm == 'inf': fftshift(fft2) or fftshift(ifft2) (propagate.py:264-270)  */
+#define ADM_PROP_NEAR 2  /* finite distance: one more Fresnel convolution (propagate.py:271-280, :537-553)   */
+/* loss_type / raw_data_type (forward_model.py:88-103) */
+#define ADM_LOSS_LSQ 0
+#define ADM_LOSS_POISSON 1
+#define ADM_RAW_MAGNITUDE 0
+#define ADM_RAW_INTENSITY 1
+
+typedef struct adm_multislice_cfg {
+    int P;                 /* patch / probe edge (square); supported: 64, 72                                  */
+    int n_slices;          /* Nz, number of object slices traversed (binning == 1)                            */
+    int B;                 /* diffraction patterns (probe positions) in this minibatch                        */
+    int M;                 /* incoherent probe modes                                                          */
+    int Y, X;              /* in-plane extent of the (rotated) object volume, layout [Nz][Y][X][2]            */
+    float k1;              /* 2*pi*dz/lambda if scale_ri_by_k else 1 (propagate.py:215)                       */
+    int sign_convention;   /* +1 or -1 (propagate.py:236-241)                                                 */
+    int unknown_type;      /* ADM_DELTA_BETA / ADM_REAL_IMAG                                                  */
+    int free_prop;         /* ADM_PROP_*                                                                      */
+    int normalize_fft;     /* far field with norm='ortho' (wrappers.py:725-756)                               */
+    int probe_per_pattern; /* 0: probe is [M][P][P][2]; 1: probe is [B][M][P][P][2] (per-position shifted)    */
+} adm_multislice_cfg;
+
+/* ABI / build identification. */
+int adm_abi_version(void);
+
+/* Permute + transpose + scale a [P][P] complex transfer function H (natural fftfreq order, as built by
+ * adorym/propagate.py:62-81 get_kernel) into the layout the in-shared-memory mixed-radix FFT passes read.
+ * out[px][py] = scale * (conj ? conj(H) : H)[perm(py)][perm(px)].  Use scale = 1/P^2 for a propagation step. */
+int adm_prepare_transfer_function(int P, const float* H, int conj, float scale, float* out, void* stream);
+
+/* Forward multislice for B*M wavefields (replaces propagate.py:131-288 + the gather of forward_model.py:313-331).
+ *   rot_obj  [Nz][Y][X][2]      rotated object, slice-major
+ *   probe    [M][P][P][2] or [B][M][P][P][2]
+ *   pos      [B][2] int32 (y, x) top-left corner of each patch in object pixels; may be negative / overhang:
+ *            out-of-object voxels read as vacuum ((0,0) delta_beta, (1,0) real_imag; util.py:1335-1350)
+ *   Hprep    prepared in-object transfer function (adm_prepare_transfer_function, conj=0, scale=1/P^2)
+ *   Hfree    prepared free-space transfer function for ADM_PROP_NEAR, else NULL
+ *   psi_ckpt [B][M][Nz][P][P][2] out: wavefield entering every slice (consumed by adm_multislice_bwd)
+ *   det      [B][M][P][P][2]     out: complex wavefield on the detector (far field is fftshift-ed)        */
+int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* rot_obj, const float* probe, const int* pos,
+                       const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* stream);
+
+/* Analytic adjoint of adm_multislice_fwd (replaces torch.autograd.grad over the taped slice loop,
+ * wrappers.py:300-331).
+ *   g_det     [B][M][P][P][2]   dL/d(det) as (dL/dRe, dL/dIm)
+ *   HprepC    prepared conj in-object transfer function (conj=1, scale=1/P^2); HfreeC likewise or NULL
+ *   g_rot_obj [Nz][Y][X][2]     ACCUMULATED (+=) gradient w.r.t. the rotated object (scatter-add of patches)
+ *   g_probe   [M][P][P][2] ACCUMULATED over patterns, or [B][M][P][P][2] WRITTEN if probe_per_pattern; may be
+ *             NULL when the probe gradient is not needed                                                     */
+int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* rot_obj, const int* pos, const float* HprepC,
+                       const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_rot_obj,
+                       float* g_probe, void* stream);
+
+/* Detector magnitude, mismatch loss and residual (forward_model.py:88-103,353,371-375).
+ *   det [B][M][P][P][2]; meas [B][P][P] = |prj| as stored (magnitude or intensity, see raw_data_type);
+ *   mask [P][P] (1 = valid pixel) or NULL (beamstop, forward_model.py:128-136)
+ *   pred [B][P][P] out: sqrt(sum_m |det_m|^2);  g_det [B][M][P][P][2] out (may be NULL): dL/d(det);
+ *   loss_per_pattern [B] out: sum over valid pixels of the per-pixel loss term (NOT divided);
+ *   inv_n: 1 / (B * n_valid_pixels) -- the mean's divisor, applied to g_det only.                           */
+int adm_detector_loss(int B, int M, int P, int loss_type, int raw_data_type, float poisson_multiplier, float inv_n,
+                      const float* det, const float* meas, const float* mask, float* pred, float* g_det,
+                      float* loss_per_pattern, void* stream);
+
+/* Tomographic rotation about y (util.py:536-552 -> grid_sample bilinear / border / align_corners=False).
+ *   obj  [Y][X][Z][2] (reference layout);  grid [X*Z][2] fp32 NORMALISED coordinates (gz, gx) exactly as
+ *   wrappers.py:1137 builds them from the fp16 lookup table;  rot [Z][Y][X][2] (slice-major) out.          */
+int adm_rotate_fwd(int Y, int X, int Z, const float* obj, const float* grid, float* rot, void* stream);
+/* Exact transpose: g_obj [Y][X][Z][2] += R^T g_rot  (g_rot [Z][Y][X][2]).                                   */
+int adm_rotate_adj(int Y, int X, int Z, const float* g_rot, const float* grid, float* g_obj, void* stream);
+
+/* Fused Adam (optimizers.py:309-318) with optional epilogue.  In place on x, m, v (n floats each).
+ *   step = i_batch of the reference (bias correction uses step+1)
+ *   flags: bit0 clip x to >= 0 (ptychography.py:1138-1139); bit1 zero channel 0 (absorption_only);
+ *          bit2 zero channel 1 (phase_only) (ptychography.py:1140-1142); n must be even if bit1|bit2
+ *   mask: per-voxel [n/2] multiplier applied to both channels (array_ops.py:239-244) or NULL               */
+int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, float step_size, float b1, float b2,
+                  float eps, int step, int flags, const float* mask, void* stream);
+
+/* L1 / reweighted-L1 / TV regulariser on obj [Y][X][Z][2], delta_beta type (regularizers.py:30-110).
+ *   value[0] += alpha_d*mean(w0|d|) + alpha_b*mean(w1|b|) + gamma*(TV3d(d) + TV3d(b));  g_obj += gradient.
+ *   weight_l1 [Y][X][Z][2] or NULL; value / g_obj may be NULL.                                             */
+int adm_regularizer_l1tv(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d, float alpha_b,
+                         float gamma, float* value, float* g_obj, void* stream);
+
+/* Sub-pixel Fourier shift of the probe per pattern (util.py:380-397 as used at forward_model.py:296-303).
+ *   probe [M][P][P][2]; shift [B][2] (y, x); out [B][M][P][P][2].                                          */
+int adm_probe_shift_fwd(int B, int M, int P, const float* probe, const float* shift, float* out, void* stream);
+/* Transpose: g_probe [M][P][P][2] += sum_b S_b^H g_out[b];  g_shift [B][2] += dL/d(shift) (accumulated over modes; zero it first).        */
+int adm_probe_shift_bwd(int B, int M, int P, const float* probe, const float* shift, const float* g_out,
+                        float* g_probe, float* g_shift, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ADORYM_B200_H */

@@ -1,0 +1,106 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes handle on the host-emulated kernels (tests/emu/libadm_emu.so) and a numpy
+orchestration of one loss+gradient evaluation, mirroring what adorym_b200.ops does on the GPU."""
+import ctypes
+import os
+import sys
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+from build_emu import build  # noqa: E402
+from adorym_b200._lib import SIGNATURES, MultisliceCfg, bind  # signature table only  # noqa: E402
+
+_emu = None
+PI = 3.14159265359
+
+
+def emu():
+    global _emu
+    if _emu is None:
+        _emu = bind(ctypes.CDLL(build()))
+    return _emu
+
+
+def P(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+def ck(rc):
+    assert rc == 0, 'emu call failed rc=%d' % rc
+
+
+def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *, unknown_type='delta_beta',
+                       free_prop='inf', sign_convention=1, normalize_fft=False, loss='lsq', raw_data_type='magnitude',
+                       poisson_multiplier=1.0, shift=None, reg=None, Hfree=None):
+    L = emu()
+    Y, X, Z, _ = obj.shape
+    M, Pp, _ = probe_real.shape
+    B = len(pos)
+    obj = np.ascontiguousarray(obj, dtype='float32')
+    if grid is not None:
+        rot = np.zeros((Z, Y, X, 2), 'float32')
+        ck(L.adm_rotate_fwd(Y, X, Z, P(obj), P(grid), P(rot), None))
+    else:
+        rot = np.ascontiguousarray(obj.transpose(2, 0, 1, 3))
+    probe = np.ascontiguousarray(np.stack([probe_real, probe_imag], -1), dtype='float32')
+    ppp = 0
+    if shift is not None:
+        shift = np.ascontiguousarray(shift, dtype='float32')
+        pb = np.zeros((B, M, Pp, Pp, 2), 'float32')
+        ck(L.adm_probe_shift_fwd(B, M, Pp, P(probe), P(shift), P(pb), None))
+        probe_in, ppp = pb, 1
+    else:
+        probe_in = probe
+    Hn = np.ascontiguousarray(np.stack([H.real, H.imag], -1), dtype='float32')
+    Hp = np.zeros_like(Hn)
+    Hc = np.zeros_like(Hn)
+    ck(L.adm_prepare_transfer_function(Pp, P(Hn), 0, 1.0 / (Pp * Pp), P(Hp), None))
+    ck(L.adm_prepare_transfer_function(Pp, P(Hn), 1, 1.0 / (Pp * Pp), P(Hc), None))
+    Hfp = Hfc = None
+    fp = {'none': 0, 'inf': 1, 'near': 2}[free_prop]
+    if fp == 2:
+        Hf = np.ascontiguousarray(np.stack([Hfree.real, Hfree.imag], -1), dtype='float32')
+        Hfp, Hfc = np.zeros_like(Hf), np.zeros_like(Hf)
+        ck(L.adm_prepare_transfer_function(Pp, P(Hf), 0, 1.0 / (Pp * Pp), P(Hfp), None))
+        ck(L.adm_prepare_transfer_function(Pp, P(Hf), 1, 1.0 / (Pp * Pp), P(Hfc), None))
+    cfg = MultisliceCfg(P=Pp, n_slices=Z, B=B, M=M, Y=Y, X=X, k1=float(np.float32(k1)), sign_convention=sign_convention,
+                        unknown_type=0 if unknown_type == 'delta_beta' else 1, free_prop=fp,
+                        normalize_fft=int(normalize_fft), probe_per_pattern=ppp)
+    posi = np.ascontiguousarray(pos, dtype='int32')
+    ckpt = np.zeros((B, M, Z, Pp, Pp, 2), 'float32')
+    det = np.zeros((B, M, Pp, Pp, 2), 'float32')
+    ck(L.adm_multislice_fwd(ctypes.byref(cfg), P(rot), P(probe_in), P(posi), P(Hp), P(Hfp), P(ckpt), P(det), None))
+    pred = np.zeros((B, Pp, Pp), 'float32')
+    gdet = np.zeros_like(det)
+    lpp = np.zeros((B,), 'float32')
+    meas = np.ascontiguousarray(prj_abs, dtype='float32')
+    inv_n = 1.0 / (B * Pp * Pp)
+    ck(L.adm_detector_loss(B, M, Pp, 0 if loss == 'lsq' else 1, 0 if raw_data_type == 'magnitude' else 1,
+                           poisson_multiplier, inv_n, P(det), P(meas), None, P(pred), P(gdet), P(lpp), None))
+    loss_val = float(lpp.astype('float64').sum() * inv_n)
+    g_rot = np.zeros_like(rot)
+    g_probe_in = np.zeros_like(probe_in)
+    ck(L.adm_multislice_bwd(ctypes.byref(cfg), P(rot), P(posi), P(Hc), P(Hfc), P(ckpt), P(gdet), P(g_rot),
+                            P(g_probe_in), None))
+    out = {'loss': loss_val, 'pred': pred, 'det': det}
+    if shift is not None:
+        g_probe = np.zeros_like(probe)
+        g_shift = np.zeros((B, 2), 'float32')
+        ck(L.adm_probe_shift_bwd(B, M, Pp, P(probe), P(shift), P(g_probe_in), P(g_probe), P(g_shift), None))
+        out['g_shift'] = g_shift
+    else:
+        g_probe = g_probe_in
+    out['g_probe_real'] = g_probe[..., 0]
+    out['g_probe_imag'] = g_probe[..., 1]
+    if grid is not None:
+        g_obj = np.zeros_like(obj)
+        ck(L.adm_rotate_adj(Y, X, Z, P(g_rot), P(grid), P(g_obj), None))
+    else:
+        g_obj = np.ascontiguousarray(g_rot.transpose(1, 2, 0, 3))
+    if reg:
+        val = np.zeros((1,), 'float32')
+        ck(L.adm_regularizer_l1tv(Y, X, Z, P(obj), None, float(reg.get('alpha_d') or 0.), float(reg.get('alpha_b') or 0.),
+                                  float(reg.get('gamma') or 0.), P(val), P(g_obj), None))
+        out['loss'] += float(val[0])
+    out['g_obj'] = g_obj
+    return out

@@ -1,0 +1,73 @@
+// TEST INFRASTRUCTURE ONLY: a minimal "CUDA on the CPU" execution layer so that the kernel sources in
+// adorym_b200/csrc can be compiled as C++ (-DADM_HOST_EMU) and their LOGIC unit-tested in the GPU-less
+// build container.  One OS thread per CUDA thread, CTAs run one after another.  The product never
+// loads the library built from this header (adorym_b200/_lib.py only opens the nvcc-built .so).
+#pragma once
+#include <atomic>
+#include <condition_variable>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+struct emu_dim3 { unsigned x, y, z; emu_dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
+typedef emu_dim3 dim3;
+typedef void* cudaStream_t;
+
+struct EmuBarrier {
+    std::mutex m; std::condition_variable cv; unsigned n, count = 0, gen = 0;
+    explicit EmuBarrier(unsigned n_) : n(n_) {}
+    void wait() {
+        std::unique_lock<std::mutex> lk(m);
+        unsigned g = gen;
+        if (++count == n) { count = 0; ++gen; cv.notify_all(); }
+        else cv.wait(lk, [&] { return gen != g; });
+    }
+};
+
+static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
+static thread_local EmuBarrier* emu_bar = nullptr;
+static thread_local char* emu_smem = nullptr;
+
+#define __syncthreads() emu_bar->wait()
+#define __global__ static
+#define __device__
+#define __host__
+#define __forceinline__ inline
+#define __restrict__
+#define __launch_bounds__(...)
+
+static inline float emu_atomic_add(float* p, float v) {
+    std::atomic_ref<float> r(*p);
+    float old = r.load();
+    while (!r.compare_exchange_weak(old, old + v)) {}
+    return old;
+}
+#define atomicAdd(p, v) emu_atomic_add((p), (v))
+
+template <class F>
+static void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
+    unsigned nthreads = block.x * block.y * block.z;
+    std::vector<char> smem(smem_bytes + 64);
+    for (unsigned bz = 0; bz < grid.z; ++bz)
+    for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+        EmuBarrier bar(nthreads);
+        std::memset(smem.data(), 0xCD, smem.size());   // poison: uninitialised smem reads show up as garbage
+        std::vector<std::thread> th;
+        th.reserve(nthreads);
+        for (unsigned t = 0; t < nthreads; ++t) {
+            th.emplace_back([&, t] {
+                threadIdx = emu_dim3(t % block.x, (t / block.x) % block.y, t / (block.x * block.y));
+                blockIdx = emu_dim3(bx, by, bz);
+                blockDim = block; gridDim = grid;
+                emu_bar = &bar;
+                emu_smem = smem.data();
+                body();
+            });
+        }
+        for (auto& x : th) x.join();
+    }
+}

@@ -1,0 +1,60 @@
+"""CPU: the kernel SOURCES (adorym_b200/csrc/*.cu) compiled as C++ under a host emulation of the CUDA execution
+model (tests/emu/) and checked against the oracle / the reference goldens.  This validates index permutations,
+butterflies, adjoints and the C ABI in the GPU-less container; the real parity tests are tests/test_gpu_parity.py."""
+import os
+import sys
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), 'emu'))
+from oracle_util import case_cfg, run_oracle_case, rel_err, compact_grad  # noqa: E402
+from oracle import multislice_oracle as orc  # noqa: E402
+import emu_lib  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def run_emu_case(name):
+    inp, cfg, coord, reg = case_cfg(name)
+    c = inp['cfg']
+    Y, X, Z = c['obj_size']
+    grid = None
+    if coord is not None:
+        grid = np.ascontiguousarray(orc.grid_normalise(coord, X, Z).numpy(), dtype='float32')
+    voxel_nm = c['psize_cm'] * 1e7
+    k1 = 2. * orc.PI * voxel_nm / (1240. / c['energy_ev'])
+    shift = None
+    if inp['probe_pos_correction'] is not None:
+        shift = inp['probe_pos_correction'][c['i_theta'], inp['this_ind_batch']]
+    fp = 'inf' if c['free_prop_cm'] == 'inf' else ('none' if c['free_prop_cm'] in (0, None) else 'near')
+    return inp, emu_lib.loss_and_grads_emu(
+        inp['obj'], inp['probe_real'], inp['probe_imag'], inp['pos'], inp['prj'], grid, cfg['h'], k1,
+        unknown_type=c['unknown_type'], free_prop=fp, sign_convention=c.get('sign_convention', 1),
+        normalize_fft=c.get('normalize_fft', False), loss=c['loss'], raw_data_type=c['raw_data_type'],
+        poisson_multiplier=c.get('poisson_multiplier', 1.), shift=shift, reg=reg)
+
+
+@pytest.mark.parametrize('name', ['ptycho2d_modes', 'ptycho2d_realimag_p64', 'fullfield64', 'ptycho3d_p72',
+                                  'ptycho3d_p72_poisson'])
+def test_emulated_kernels_match_oracle_and_golden(name):
+    inp, out = run_emu_case(name)
+    _, loss, pred, grads = run_oracle_case(name, torch.float64)
+    gold = np.load(os.path.join(GOLD, name + '.npz'))
+    gtol = 1e-3 if 'poisson' in name else 1e-4
+    assert abs(out['loss'] - loss) <= 1e-4 * abs(loss)
+    assert abs(out['loss'] - float(gold['loss'])) <= 1e-4 * abs(float(gold['loss']))
+    assert rel_err(out['pred'], pred) < 1e-4
+    assert rel_err(out['pred'], gold['pred']) < 1e-4
+    assert rel_err(out['g_obj'], grads['obj']) < gtol
+    cg = compact_grad(out['g_obj'])
+    for k in ('proj0', 'proj1', 'proj2', 'sample'):
+        assert rel_err(cg[k], gold['gobj_' + k]) < gtol, k
+    if 'probe_real' in grads:
+        assert rel_err(out['g_probe_real'], grads['probe_real']) < 1e-4
+        assert rel_err(out['g_probe_imag'], grads['probe_imag']) < 1e-4
+        assert rel_err(out['g_probe_real'], gold['g_probe_real']) < 1e-4
+    if 'probe_pos_correction' in grads:
+        c = inp['cfg']
+        g_ref = grads['probe_pos_correction'][c['i_theta'], inp['this_ind_batch']]
+        assert rel_err(out['g_shift'], g_ref) < 1e-4
