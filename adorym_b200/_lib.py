@@ -77,9 +77,39 @@ def check(rc, name):
         raise RuntimeError('adorym_b200.%s failed: %s' % (name, ERRORS.get(rc, rc)))
 
 
+_timing = None           # None, or a list of (name, start_event, end_event) filled while timing is enabled
+
+
+def enable_timing(on=True):
+    """Record a CUDA-event pair around every ABI call on the current stream (bench.py's per-kernel roofline)."""
+    global _timing
+    _timing = [] if on else None
+
+
+def timing_summary():
+    """-> {name: (n_calls, total_ms)}; synchronises."""
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, e0, e1 in (_timing or []):
+        n, t = out.get(name, (0, 0.0))
+        out[name] = (n + 1, t + e0.elapsed_time(e1))
+    return out
+
+
 def call(name, *args):
     global launch_count
-    rc = getattr(get_lib(), name)(*args)
+    fn = getattr(get_lib(), name)
+    if _timing is not None:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        _timing.append((name, e0, e1))
+    else:
+        rc = fn(*args)
     launch_count += 1
     check(rc, name)
 

@@ -1,0 +1,120 @@
+"""One-process-per-GPU communicator with the (tiny) mpi4py surface the reference's hot loop uses
+(adorym/pseudo.py:107-139 is the interface spec): Get_rank, Get_size, Barrier, bcast, allreduce(SUM).
+
+Replaces the pickled, host-staged mpi4py collectives (adorym/ptychography.py:1113-1114, optimizers.py:1025-1079)
+by torch.distributed: NCCL over NVLink 5 / NVSwitch for CUDA tensors, gloo for the CPU tests."""
+import os
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+class Comm(object):
+    def __init__(self):
+        self._on = dist.is_available() and dist.is_initialized()
+
+    def Get_rank(self):
+        return dist.get_rank() if self._on else 0
+
+    def Get_size(self):
+        return dist.get_world_size() if self._on else 1
+
+    def Barrier(self):
+        if self._on:
+            dist.barrier()
+
+    def bcast(self, obj, root=0):
+        if not self._on:
+            return obj
+        box = [obj]
+        dist.broadcast_object_list(box, src=root)
+        return box[0]
+
+    def Bcast(self, arr, root=0):
+        if self._on:
+            t = torch.from_numpy(arr)
+            if dist.get_backend() == 'nccl':
+                tc = t.cuda()
+                dist.broadcast(tc, src=root)
+                t.copy_(tc.cpu())
+            else:
+                dist.broadcast(t, src=root)
+        return arr
+
+    def allreduce(self, x):
+        """SUM all-reduce (no division: quirk 3).  CUDA tensors are reduced in place over NCCL."""
+        if not self._on:
+            return x
+        if torch.is_tensor(x):
+            dist.all_reduce(x, op=dist.ReduceOp.SUM)
+            return x
+        a = np.asarray(x)
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if dist.get_backend() == 'nccl':
+            tc = t.cuda()
+            dist.all_reduce(tc, op=dist.ReduceOp.SUM)
+            return tc.cpu().numpy()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t.numpy()
+
+
+def init_from_env(backend=None):
+    """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).
+    Returns (rank, world_size, local_rank).  A no-op for single-process runs."""
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    if world > 1 and not dist.is_initialized():
+        if backend is None:
+            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+        os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
+        os.environ.setdefault('MASTER_PORT', '29500')
+        if backend == 'nccl':
+            torch.cuda.set_device(local)
+            dist.init_process_group(backend=backend, rank=rank, world_size=world,
+                                    device_id=torch.device('cuda', local))
+        else:
+            dist.init_process_group(backend=backend, rank=rank, world_size=world)
+    return rank, world, local
+
+
+def rank_minibatch(ind_list_rand, i_batch, rank, minibatch_size, n_ranks):
+    """This rank's (i_theta, sorted spot indices) of global chunk i_batch (adorym/ptychography.py:901-909);
+    a short last chunk is topped up from chunk 0 (quirk 7)."""
+    n_tot = minibatch_size * n_ranks
+    c = ind_list_rand[i_batch]
+    if len(c) < n_tot:
+        c = np.concatenate([c, ind_list_rand[0][:n_tot - len(c)]])
+        ind_list_rand[i_batch] = c
+    this_i_theta = int(c[rank * minibatch_size, 0])
+    this_ind_batch = np.sort(c[rank * minibatch_size:(rank + 1) * minibatch_size, 1])
+    return this_i_theta, this_ind_batch
+
+
+def epoch_task_list(i_epoch, n_theta, n_pos, minibatch_size, n_ranks, two_d_mode=False, theta_ls=None,
+                    randomize_probe_pos=False, update_scheme='immediate'):
+    """Shuffled (angle, spot) list of one epoch split into global chunks of minibatch_size * n_ranks
+    (adorym/ptychography.py:786-847).  Deterministic in i_epoch, identical on every rank."""
+    n_tot = minibatch_size * n_ranks
+    rs = np.random.RandomState(i_epoch)
+    if not two_d_mode:
+        theta_ind_ls = np.arange(n_theta)
+        rs.shuffle(theta_ind_ls)
+    else:
+        i0 = 0
+        if theta_ls is not None:
+            i0 = int(np.nonzero(np.abs(np.asarray(theta_ls) - theta_ls[0]) < 1e-5)[0][0])
+        theta_ind_ls = np.array([i0])
+    blocks = []
+    for i_theta in theta_ind_ls:
+        spots = np.arange(n_pos)
+        if randomize_probe_pos:
+            spots = rs.choice(spots, len(spots), replace=False)
+        if update_scheme == 'immediate' and n_pos % minibatch_size != 0:
+            spots = np.append(spots, rs.choice(spots[:-n_pos % minibatch_size], minibatch_size - (n_pos % minibatch_size),
+                                               replace=False))
+        elif update_scheme == 'per angle' and n_pos % n_tot != 0:
+            spots = np.append(spots, rs.choice(spots[:-n_pos % n_tot], n_tot - (n_pos % n_tot), replace=False))
+        blocks.append(np.stack([np.full(len(spots), i_theta), spots], axis=1))
+    ind = np.concatenate(blocks, axis=0).astype('int32')
+    return [ind[i:i + n_tot] for i in range(0, len(ind), n_tot)]

@@ -1,0 +1,391 @@
+"""ForwardModel classes with the reference's signatures (adorym/forward_model.py), backed by the fused kernels.
+
+`predict` keeps the explicit positional argument list the driver builds by name from `argument_ls`
+(adorym/ptychography.py:1017-1028, forward_model.py:173-175); `get_loss_function()` returns a function with that
+same argument list whose result is a scalar torch tensor carrying a grad_fn, so `Differentiator.get_gradients`
+(torch.autograd.grad over [obj, probe_real, probe_imag, ...]) works unchanged -- the graph consists of the
+autograd.Functions of adorym_b200.ops instead of a taped slice loop.
+"""
+import inspect
+import numpy as np
+import torch
+
+from . import ops
+from .propagate import get_kernel, _free_prop_mode
+from .util import RotationTable
+
+
+def _np_int_positions(this_pos_batch):
+    return np.round(np.asarray(this_pos_batch)).astype(int)
+
+
+class ForwardModel(object):
+    """Parent forward model (adorym/forward_model.py:28-161)."""
+
+    def __init__(self, loss_function_type='lsq', distribution_mode=None, device=None, common_vars_dict=None,
+                 raw_data_type='magnitude', simulation_mode=False):
+        if distribution_mode is not None:
+            raise NotImplementedError('adorym_b200: distribution_mode=%r is out of scope (data parallelism over NCCL '
+                                      'replaces the MPI distribution modes)' % (distribution_mode,))
+        self.loss_function_type = loss_function_type
+        self.argument_ls = []
+        self.regularizer_dict = {}
+        self.distribution_mode = distribution_mode
+        self.device = device
+        self.simulation_mode = simulation_mode
+        self._current_loss = 0
+        self.raw_data_type = raw_data_type
+        self.i_call = 0
+        self.common_vars = common_vars_dict
+        if common_vars_dict is not None:
+            cv = common_vars_dict
+            self.unknown_type = cv['unknown_type']
+            self.normalize_fft = cv['normalize_fft']
+            self.sign_convention = cv['sign_convention']
+            self.rotate_out_of_loop = cv['rotate_out_of_loop']
+            self.scale_ri_by_k = cv['scale_ri_by_k']
+            self.is_minus_logged = cv['is_minus_logged']
+            self.forward_algorithm = cv['forward_algorithm']
+            self.stdout_options = cv.get('stdout_options', {})
+            self.poisson_multiplier = cv['poisson_multiplier']
+            self.common_probe_pos = cv['common_probe_pos']
+            self.binning = cv['binning']
+            self.prj = cv['prj']
+        self.loss_args = {}
+        self.reg_list = []
+        self._plans = {}
+        self._rot_table = None
+        self.last_reg_value = None
+
+    # -- the reference exposes current_loss as a float; reading it synchronises (forward_model.py:140-146) --
+    @property
+    def current_loss(self):
+        v = self._current_loss
+        return float(v.item()) if torch.is_tensor(v) else float(v)
+
+    @current_loss.setter
+    def current_loss(self, v):
+        self._current_loss = v
+
+    def update_loss_args(self, kwargs):
+        self.loss_args = kwargs
+
+    def add_regularizers(self, reg_list):
+        self.reg_list = reg_list
+
+    def get_regularization_value(self, obj, device=None):
+        reg = None
+        for r in self.reg_list:
+            v = r.get_value(obj, distribution_mode=self.distribution_mode, device=device)
+            reg = v if reg is None else reg + v
+        self.last_reg_value = reg
+        return reg
+
+    def get_argument_index(self, arg):
+        for i, a in enumerate(self.argument_ls):
+            if a == arg:
+                return i
+        raise ValueError('{} is not in the argument list.'.format(arg))
+
+    # ------------------------------------------------------------------------------------------------
+    def _device(self, obj):
+        if not obj.is_cuda:
+            raise RuntimeError('adorym_b200 has no CPU path: the object must live on a CUDA device')
+        return obj.device
+
+    def _check_unsupported(self, names):
+        cv = self.common_vars
+        for n in names:
+            if cv.get(n, False):
+                raise NotImplementedError('adorym_b200: option %s is not on the accelerated path yet' % n)
+        if cv.get('initial_tilt', None) is not None:
+            raise NotImplementedError('adorym_b200: initial_tilt is not on the accelerated path yet')
+        if cv.get('pure_projection', False):
+            raise NotImplementedError('adorym_b200: pure_projection is not on the accelerated path')
+        if self.binning != 1:
+            raise NotImplementedError('adorym_b200: binning > 1 is not on the accelerated path')
+        if self.forward_algorithm != 'fresnel':
+            raise NotImplementedError('adorym_b200: forward_algorithm=%r' % (self.forward_algorithm,))
+
+    def _rotation_grid(self, this_i_theta, device):
+        cv = self.common_vars
+        if self._rot_table is None:
+            n_theta = cv['n_theta']
+            folder = 'arrsize_{}_{}_{}_ntheta_{}'.format(*cv['this_obj_size'], n_theta)
+            self._rot_table = RotationTable(cv['this_obj_size'], cv['theta_ls'], device,
+                                            src_folder=folder if cv.get('precalculate_rotation_coords', True) else None)
+        return self._rot_table.grid(this_i_theta)
+
+    def _rotated_object(self, obj, this_i_theta):
+        """-> slice-major [Nz, Y, X, 2] view/copy of the object at angle this_i_theta."""
+        cv = self.common_vars
+        dev = self._device(obj)
+        if cv['two_d_mode']:
+            Y, X, Z = obj.shape[:3]
+            return obj.reshape(Y, X, 2).unsqueeze(0) if Z == 1 else obj.permute(2, 0, 1, 3).contiguous()
+        if self.rotate_out_of_loop:
+            raise NotImplementedError('adorym_b200: rotate_out_of_loop is not on the accelerated path yet')
+        return ops.RotateFn.apply(obj, self._rotation_grid(this_i_theta, dev))
+
+    def _plan(self, dev, P, Nz, Y, X, free_prop_cm):
+        cv = self.common_vars
+        mode = _free_prop_mode(free_prop_cm)
+        key = (P, Nz, Y, X, mode, float(free_prop_cm) if mode == 'near' else 0., str(dev))
+        plan = self._plans.get(key)
+        if plan is None:
+            ds_level = cv.get('ds_level', 1)
+            psize_cm = cv['psize_cm'] * ds_level
+            h_free = None
+            if mode == 'near':
+                voxel_nm = np.array([psize_cm] * 3) * 1.e7
+                h_free = get_kernel(float(free_prop_cm) * 1e7, 1240. / cv['energy_ev'], voxel_nm, [P, P],
+                                    sign_convention=self.sign_convention)   # quirk 10: always paraxial
+            plan = ops.MultislicePlan(P, Nz, Y, X, ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k),
+                                      cv['h'] if Nz > 1 else None, dev, sign_convention=self.sign_convention,
+                                      unknown_type=self.unknown_type, free_prop=mode,
+                                      normalize_fft=self.normalize_fft, h_free=h_free)
+            self._plans[key] = plan
+        return plan
+
+    # ------------------------------------------------------------------------------------------------
+    def get_data(self, this_i_theta, this_ind_batch, theta_downsample=None, ds_level=1):
+        """adorym/forward_model.py:113-119.  `prj` may be an HDF5-like dataset / ndarray (host; |.| and H2D copy per
+        minibatch as in the reference) or a CUDA tensor of magnitudes already resident on the device."""
+        if theta_downsample is None:
+            theta_downsample = 1
+        prj = self.prj
+        dev = self.device
+        ind = np.asarray(this_ind_batch)
+        it = int(this_i_theta) * theta_downsample
+        if torch.is_tensor(prj) and prj.is_cuda:
+            frames = prj[it]
+            if not (len(ind) == frames.shape[0] and np.array_equal(ind, np.arange(len(ind)))):
+                frames = frames.index_select(0, torch.as_tensor(ind, device=prj.device, dtype=torch.long))
+            batch = (frames.abs() if frames.is_complex() else frames).to(dev, dtype=torch.float32)
+        elif torch.is_tensor(prj):
+            # host tensor (ideally pinned): gather into a pinned staging buffer, asynchronous H2D copy
+            frames = prj[it]
+            if not (len(ind) == frames.shape[0] and np.array_equal(ind, np.arange(len(ind)))):
+                shp = (len(ind),) + tuple(frames.shape[1:])
+                if getattr(self, '_stage', None) is None or self._stage.shape != shp or self._stage.dtype != frames.dtype:
+                    self._stage = torch.empty(shp, dtype=frames.dtype).pin_memory()
+                torch.index_select(frames, 0, torch.as_tensor(ind, dtype=torch.long), out=self._stage)
+                frames = self._stage
+            batch = frames.to(dev, non_blocking=True)
+            batch = (batch.abs() if batch.is_complex() else batch).to(torch.float32)
+        else:
+            a = np.abs(np.asarray(prj[it, ind]))
+            batch = torch.from_numpy(np.ascontiguousarray(a, dtype='float32')).to(dev)
+        if ds_level > 1:
+            batch = batch[:, ::ds_level, ::ds_level]
+        return batch
+
+    def _beamstop_mask(self, dev):
+        bs = self.common_vars.get('beamstop', None)
+        if bs is None:
+            return None
+        m = torch.as_tensor(bs, dtype=torch.float32, device=dev)
+        return (m >= 1e-5).float().contiguous()
+
+    def loss(self, this_pred_batch, this_prj_batch, obj):
+        """Last-layer loss from predicted magnitudes (adorym/forward_model.py:121-147) -- API-compatible path built
+        from library ops; `get_loss_function()` uses the fused kernel (`_fused_loss`) instead."""
+        from .regularizers import mismatch_loss_from_magnitude
+        mask = self._beamstop_mask(this_pred_batch.device)
+        loss = mismatch_loss_from_magnitude(this_pred_batch, this_prj_batch, self.loss_function_type, self.raw_data_type,
+                                            self.poisson_multiplier, mask)
+        if len(self.reg_list) > 0:
+            loss = loss + self.get_regularization_value(obj, device=self.device)
+        self._current_loss = loss.detach()
+        return loss
+
+    def _fused_loss(self, det, this_prj_batch, obj):
+        """detector magnitude + mismatch + residual in one kernel, then the regularisers."""
+        mask = self._beamstop_mask(det.device)
+        loss, pred, lpp = ops.DetectorLossFn.apply(det, this_prj_batch, mask, self.loss_function_type,
+                                                   self.raw_data_type, self.poisson_multiplier)
+        self.last_pred = pred
+        self.last_loss_per_pattern = lpp
+        if len(self.reg_list) > 0:
+            loss = loss + self.get_regularization_value(obj, device=self.device)
+        self._current_loss = loss.detach()
+        return loss
+
+    def predict(self, *args, **kwargs):
+        pass
+
+    def get_loss_function(self):
+        def calculate_loss(obj, this_i_theta, this_ind_batch, *args, **kwargs):
+            theta_downsample = self.common_vars['theta_downsample']
+            ds_level = self.common_vars['ds_level']
+            this_pred_batch = self.predict(*args, **kwargs)
+            this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
+            return self.loss(this_pred_batch, this_prj_batch, obj)
+        return calculate_loss
+
+
+class PtychographyModel(ForwardModel):
+    """adorym/forward_model.py:164-401."""
+
+    def __init__(self, loss_function_type='lsq', distribution_mode=None, device=None, common_vars_dict=None,
+                 raw_data_type='magnitude', simulation_mode=False, run_bfloat16=False, run_float64=False):
+        super(PtychographyModel, self).__init__(loss_function_type, distribution_mode, device, common_vars_dict,
+                                                raw_data_type, simulation_mode=simulation_mode)
+        if run_bfloat16 or run_float64:
+            raise NotImplementedError('adorym_b200: the accelerated path computes in fp32 only')
+        args = inspect.getfullargspec(self.predict).args
+        args.pop(0)
+        self.argument_ls = args
+        self.run_bfloat16 = run_bfloat16
+        self.run_float64 = run_float64
+
+    def _detector_field(self, obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
+                        this_ind_batch):
+        """rotate -> (shift probe) -> fused gather + multislice -> complex detector field [B, M, P, P, 2]."""
+        cv = self.common_vars
+        self._check_unsupported(['optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
+                                 'optimize_tilt'])
+        dev = self._device(obj)
+        probe_size = cv['probe_size']
+        if probe_size[0] != probe_size[1]:
+            raise NotImplementedError('adorym_b200: only square probes are supported')
+        this_obj_size = cv['this_obj_size']
+        pos = _np_int_positions(this_pos_batch)
+        rot = self._rotated_object(obj, this_i_theta)
+        probe = torch.stack([probe_real, probe_imag], dim=-1)
+        if probe.dim() == 3:
+            probe = probe.unsqueeze(0)
+        # per-position probe shift: quirk 8, positive corrections only trigger it (forward_model.py:297,304)
+        if cv['optimize_all_probe_pos'] or bool((probe_pos_correction > 1e-3).any()):
+            idx = torch.as_tensor(np.asarray(this_ind_batch), device=dev, dtype=torch.long)
+            shift = probe_pos_correction[int(this_i_theta)].index_select(0, idx).to(torch.float32)
+            probe = ops.ProbeShiftFn.apply(probe, shift)
+        plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
+        pos_t = torch.from_numpy(np.ascontiguousarray(pos, dtype='int32')).to(dev)
+        return ops.MultisliceFn.apply(rot, probe, pos_t, plan)
+
+    def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,
+                probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
+        """Detected magnitudes [minibatch_size, len_probe_y, len_probe_x] (adorym/forward_model.py:179-387)."""
+        det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
+                                   this_ind_batch)
+        self.i_call += 1
+        return ops.DetectorMagnitudeFn.apply(det)
+
+    def get_loss_function(self):
+        def calculate_loss(obj, probe_real, probe_imag, probe_defocus_mm,
+                           probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                           probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
+            theta_downsample = self.common_vars['theta_downsample']
+            ds_level = self.common_vars['ds_level']
+            det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
+                                       this_ind_batch)
+            self.i_call += 1
+            this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
+            return self._fused_loss(det, this_prj_batch, obj)
+        return calculate_loss
+
+
+class SingleBatchFullfieldModel(PtychographyModel):
+    """adorym/forward_model.py:404-490: one full-field projection per step (probe covers the whole object)."""
+
+    def __init__(self, loss_function_type='lsq', distribution_mode=None, device=None, common_vars_dict=None,
+                 raw_data_type='magnitude', simulation_mode=False, *args, **kwargs):
+        super(SingleBatchFullfieldModel, self).__init__(loss_function_type, distribution_mode, device, common_vars_dict,
+                                                        raw_data_type, simulation_mode=simulation_mode, *args, **kwargs)
+
+    def _detector_field(self, obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
+                        this_ind_batch):
+        cv = self.common_vars
+        self._check_unsupported(['optimize_prj_pos_offset'])
+        dev = self._device(obj)
+        probe_size = cv['probe_size']
+        this_obj_size = cv['this_obj_size']
+        if list(probe_size) != list(this_obj_size[:2]):
+            raise ValueError('SingleBatchFullfieldModel needs probe_size == obj_size[:2]')
+        rot = self._rotated_object(obj, this_i_theta)
+        probe = torch.stack([probe_real, probe_imag], dim=-1)
+        if probe.dim() == 3:
+            probe = probe.unsqueeze(0)
+        plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
+        pos_t = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        return ops.MultisliceFn.apply(rot, probe, pos_t, plan)
+
+    def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,
+                probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
+        det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
+                                   this_ind_batch)
+        self.i_call += 1
+        if self.simulation_mode:
+            return det[:, 0, :, :, 0], det[:, 0, :, :, 1]      # (real, imag), forward_model.py:487-488
+        return ops.DetectorMagnitudeFn.apply(det)
+
+
+class MultiDistModel(ForwardModel):
+    """adorym/forward_model.py:809-1092: one thin object, several near-field propagation distances.
+
+    Accelerated for the single-block case (n_blocks == 1, safe_zone_width == 0, forward_algorithm == 'fresnel')
+    with frame sizes the shared-memory FFT supports; everything else raises NotImplementedError."""
+
+    def __init__(self, loss_function_type='lsq', distribution_mode=None, device=None, common_vars_dict=None,
+                 raw_data_type='magnitude', simulation_mode=False, *args, **kwargs):
+        super(MultiDistModel, self).__init__(loss_function_type, distribution_mode, device, common_vars_dict,
+                                             raw_data_type, simulation_mode=simulation_mode)
+        a = inspect.getfullargspec(self.predict).args
+        a.pop(0)
+        self.argument_ls = a
+
+    def _detector_fields(self, obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj):
+        cv = self.common_vars
+        self._check_unsupported(['optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
+                                 'optimize_all_probe_pos', 'optimize_free_prop', 'optimize_prj_affine',
+                                 'optimize_ctf_lg_kappa'])
+        if safe_zone_width not in (0, None):
+            raise NotImplementedError('adorym_b200: MultiDistModel with safe_zone_width > 0 is not accelerated yet')
+        dists = [float(d) for d in np.asarray(free_prop_cm.detach().cpu() if torch.is_tensor(free_prop_cm) else free_prop_cm)]
+        n_dists = len(dists)
+        if prj.shape[1] // n_dists != 1:
+            raise NotImplementedError('adorym_b200: MultiDistModel with sub-divided frames (n_blocks > 1)')
+        dev = self._device(obj)
+        this_obj_size = cv['this_obj_size']
+        P = this_obj_size[0]
+        if this_obj_size[0] != this_obj_size[1]:
+            raise NotImplementedError('adorym_b200: only square frames are supported')
+        rot = self._rotated_object(obj, 0)
+        probe = torch.stack([probe_real, probe_imag], dim=-1)
+        if probe.dim() == 3:
+            probe = probe.unsqueeze(0)
+        pos_t = torch.zeros((1, 2), dtype=torch.int32, device=dev)
+        dets = []
+        for d in dists:
+            plan = self._plan(dev, P, this_obj_size[2], this_obj_size[0], this_obj_size[1], d)
+            dets.append(ops.MultisliceFn.apply(rot, probe, pos_t, plan))
+        return torch.cat(dets, 0)      # [n_dists, M, P, P, 2]
+
+    def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,
+                probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                probe_pos_correction, this_ind_batch, free_prop_cm, safe_zone_width, prj_affine_ls, ctf_lg_kappa,
+                prj_pos_offset):
+        det = self._detector_fields(obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj)
+        self.i_call += 1
+        return ops.DetectorMagnitudeFn.apply(det)
+
+    def get_loss_function(self):
+        def calculate_loss(obj, probe_real, probe_imag, probe_defocus_mm,
+                           probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                           probe_pos_correction, this_ind_batch, free_prop_cm, safe_zone_width,
+                           prj_affine_ls, ctf_lg_kappa, prj_pos_offset):
+            theta_downsample = self.common_vars['theta_downsample']
+            if theta_downsample is None:
+                theta_downsample = 1
+            det = self._detector_fields(obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj)
+            self.i_call += 1
+            n_dists = det.shape[0]
+            n_blocks = prj.shape[1] // n_dists
+            ind = np.asarray(this_ind_batch)
+            full = np.concatenate([ind + i * n_blocks for i in range(n_dists)])       # forward_model.py:1058-1061
+            this_prj_batch = self.get_data(this_i_theta, full, theta_downsample=theta_downsample, ds_level=1)
+            return self._fused_loss(det, this_prj_batch, obj)
+        return calculate_loss

@@ -1,0 +1,283 @@
+"""torch.autograd.Function wrappers over the C ABI (include/adorym_b200.h).
+
+These replace, on the hot path, the reference's `wrappers.py` fft2/ifft2/exp_complex/grid_sample calls and the
+autograd-traced slice loop of `propagate.py:208-258` by hand-written sm_100a kernels with analytic adjoints.
+All tensors are contiguous fp32 CUDA tensors; complex fields are [..., 2] (re, im).  No CPU path exists.
+"""
+import ctypes
+import math
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import MultisliceCfg, call, ptr, stream_ptr
+
+PI = 3.14159265359          # adorym/constants.py
+UNKNOWN_TYPES = {'delta_beta': 0, 'real_imag': 1}
+LOSS_TYPES = {'lsq': 0, 'poisson': 1}
+RAW_TYPES = {'magnitude': 0, 'intensity': 1}
+SUPPORTED_P = (64, 72)
+
+
+def _f32c(t):
+    if t.dtype != torch.float32:
+        t = t.float()
+    return t if t.is_contiguous() else t.contiguous()
+
+
+# ------------------------------------------------------------------------------------------------------
+# transfer functions
+# ------------------------------------------------------------------------------------------------------
+def prepare_transfer_function(h, device, conj=False):
+    """h: complex ndarray [P, P] in natural fftfreq order (adorym/propagate.py:62-81 get_kernel, float64).
+    Returns the permuted / transposed / (1/P^2)-scaled fp32 device copy the FFT passes read."""
+    h = np.asarray(h)
+    P = h.shape[0]
+    if h.shape != (P, P) or P not in SUPPORTED_P:
+        raise NotImplementedError('adorym_b200: transfer function of shape %s (supported P: %s)' % (h.shape, SUPPORTED_P))
+    hn = torch.from_numpy(np.stack([h.real, h.imag], -1).astype('float32')).to(device)   # f64 -> f32 as propagate.py:202-204
+    out = torch.empty_like(hn)
+    call('adm_prepare_transfer_function', P, ptr(hn), int(bool(conj)), 1.0 / (P * P), ptr(out), stream_ptr())
+    return out
+
+
+class MultislicePlan(object):
+    """Static description of one multislice configuration + prepared transfer functions (cached per model)."""
+
+    def __init__(self, P, n_slices, Y, X, k1, h, device, sign_convention=1, unknown_type='delta_beta', free_prop='none',
+                 normalize_fft=False, h_free=None):
+        if P not in SUPPORTED_P:
+            raise NotImplementedError('adorym_b200: probe size %d is not supported yet (supported: %s)' % (P, SUPPORTED_P))
+        self.P, self.n_slices, self.Y, self.X = int(P), int(n_slices), int(Y), int(X)
+        self.k1 = float(k1)
+        self.sign_convention = int(sign_convention)
+        self.unknown_type = UNKNOWN_TYPES[unknown_type]
+        self.free_prop = {'none': 0, 'inf': 1, 'near': 2}[free_prop]
+        self.normalize_fft = int(bool(normalize_fft))
+        self.device = device
+        self.Hp = self.Hc = self.Hfp = self.Hfc = None
+        if h is not None:
+            self.Hp = prepare_transfer_function(h, device, conj=False)
+            self.Hc = prepare_transfer_function(h, device, conj=True)
+        elif self.n_slices > 1:
+            raise ValueError('a transfer function is required when n_slices > 1')
+        if self.free_prop == 2:
+            self.set_free_kernel(h_free)
+
+    def set_free_kernel(self, h_free):
+        self.Hfp = prepare_transfer_function(h_free, self.device, conj=False)
+        self.Hfc = prepare_transfer_function(h_free, self.device, conj=True)
+
+    def cfg(self, B, M, probe_per_pattern):
+        return MultisliceCfg(P=self.P, n_slices=self.n_slices, B=int(B), M=int(M), Y=self.Y, X=self.X, k1=self.k1,
+                             sign_convention=self.sign_convention, unknown_type=self.unknown_type,
+                             free_prop=self.free_prop, normalize_fft=self.normalize_fft,
+                             probe_per_pattern=int(bool(probe_per_pattern)))
+
+
+# ------------------------------------------------------------------------------------------------------
+# multislice
+# ------------------------------------------------------------------------------------------------------
+class MultisliceFn(torch.autograd.Function):
+    """det[B,M,P,P,2] = multislice(rot_obj[Nz,Y,X,2], probe[M,P,P,2] | [B,M,P,P,2], pos[B,2] int32)."""
+
+    @staticmethod
+    def forward(ctx, rot_obj, probe, pos, plan):
+        rot_obj = _f32c(rot_obj)
+        probe = _f32c(probe)
+        if pos.dtype != torch.int32 or not pos.is_cuda:
+            raise RuntimeError('pos must be an int32 CUDA tensor [B, 2]')
+        pos = pos.contiguous()
+        P, Nz = plan.P, plan.n_slices
+        if tuple(rot_obj.shape) != (Nz, plan.Y, plan.X, 2):
+            raise RuntimeError('rot_obj must be [Nz, Y, X, 2] = %s, got %s' % ((Nz, plan.Y, plan.X, 2), tuple(rot_obj.shape)))
+        B = pos.shape[0]
+        per_pattern = probe.dim() == 5
+        M = probe.shape[1] if per_pattern else probe.shape[0]
+        if tuple(probe.shape[-3:]) != (P, P, 2) or (per_pattern and probe.shape[0] != B):
+            raise RuntimeError('probe must be [M,P,P,2] or [B,M,P,P,2]')
+        cfg = plan.cfg(B, M, per_pattern)
+        ckpt = torch.empty((B, M, Nz, P, P, 2), dtype=torch.float32, device=rot_obj.device)
+        det = torch.empty((B, M, P, P, 2), dtype=torch.float32, device=rot_obj.device)
+        call('adm_multislice_fwd', ctypes.byref(cfg), ptr(rot_obj), ptr(probe), ptr(pos), ptr(plan.Hp), ptr(plan.Hfp),
+             ptr(ckpt), ptr(det), stream_ptr())
+        ctx.plan, ctx.cfg, ctx.per_pattern = plan, cfg, per_pattern
+        ctx.probe_shape = tuple(probe.shape)
+        ctx.save_for_backward(rot_obj, pos, ckpt)
+        return det
+
+    @staticmethod
+    def backward(ctx, g_det):
+        rot_obj, pos, ckpt = ctx.saved_tensors
+        plan = ctx.plan
+        g_det = _f32c(g_det)
+        g_rot = torch.zeros_like(rot_obj)
+        g_probe = None
+        if ctx.needs_input_grad[1]:
+            g_probe = torch.zeros(ctx.probe_shape, dtype=torch.float32, device=rot_obj.device)
+        call('adm_multislice_bwd', ctypes.byref(ctx.cfg), ptr(rot_obj), ptr(pos), ptr(plan.Hc), ptr(plan.Hfc), ptr(ckpt),
+             ptr(g_det), ptr(g_rot), ptr(g_probe), stream_ptr())
+        return (g_rot if ctx.needs_input_grad[0] else None), g_probe, None, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# rotation
+# ------------------------------------------------------------------------------------------------------
+def normalized_grid(coord_old, X, Z, device):
+    """LUT (fp16 [X*Z, 2], columns x', z') -> normalised grid_sample coordinates (gz, gx) fp32 on `device`, with the
+    arithmetic of adorym/wrappers.py:1124-1141 on the CPU path (fp64 upcast at util.py:539-540, cast at :1141)."""
+    g = np.asarray(coord_old).astype('float64')[:, ::-1]
+    shp32 = np.array([X, Z], dtype='float32')                     # sic: wrappers.py:1135-1137 divides (z', x') by (X, Z)
+    inv = (np.float32(1.) / shp32).astype('float64')              # `1. / arr_shape` is an fp32 tensor op there
+    g = -1 + 2. * g / shp32.astype('float64') + inv
+    return torch.from_numpy(np.ascontiguousarray(g.astype('float32'))).to(device)
+
+
+class RotateFn(torch.autograd.Function):
+    """rot[Z,Y,X,2] (slice-major) = bilinear/border rotation of obj[Y,X,Z,2] about y given the normalised grid."""
+
+    @staticmethod
+    def forward(ctx, obj, grid):
+        obj = _f32c(obj)
+        Y, X, Z, _ = obj.shape
+        rot = torch.empty((Z, Y, X, 2), dtype=torch.float32, device=obj.device)
+        call('adm_rotate_fwd', Y, X, Z, ptr(obj), ptr(grid), ptr(rot), stream_ptr())
+        ctx.save_for_backward(grid)
+        ctx.shape = (Y, X, Z)
+        return rot
+
+    @staticmethod
+    def backward(ctx, g_rot):
+        (grid,) = ctx.saved_tensors
+        Y, X, Z = ctx.shape
+        g_obj = torch.zeros((Y, X, Z, 2), dtype=torch.float32, device=g_rot.device)
+        call('adm_rotate_adj', Y, X, Z, ptr(_f32c(g_rot)), ptr(grid), ptr(g_obj), stream_ptr())
+        return g_obj, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# detector magnitude / loss
+# ------------------------------------------------------------------------------------------------------
+def _detector_call(det, meas, mask, loss_type, raw_type, pm, inv_n, want_grad):
+    B, M, P = det.shape[0], det.shape[1], det.shape[2]
+    pred = torch.empty((B, P, P), dtype=torch.float32, device=det.device)
+    lpp = torch.empty((B,), dtype=torch.float32, device=det.device)
+    g_det = torch.empty_like(det) if want_grad else None
+    call('adm_detector_loss', B, M, P, loss_type, raw_type, float(pm), float(inv_n), ptr(det), ptr(meas), ptr(mask),
+         ptr(pred), ptr(g_det), ptr(lpp), stream_ptr())
+    return pred, lpp, g_det
+
+
+class DetectorLossFn(torch.autograd.Function):
+    """Fused |det| + mismatch loss + residual.  Returns (loss, pred[B,P,P], loss_per_pattern[B])."""
+
+    @staticmethod
+    def forward(ctx, det, meas, mask, loss_function_type, raw_data_type, poisson_multiplier):
+        det = _f32c(det)
+        meas = _f32c(meas)
+        B, M, P = det.shape[0], det.shape[1], det.shape[2]
+        n_valid = P * P if mask is None else int((mask >= 1e-5).sum().item())
+        inv_n = 1.0 / (B * n_valid)
+        pred, lpp, g_det = _detector_call(det, meas, mask, LOSS_TYPES[loss_function_type], RAW_TYPES[raw_data_type],
+                                          poisson_multiplier, inv_n, True)
+        ctx.save_for_backward(g_det)
+        loss = lpp.sum() * inv_n
+        ctx.mark_non_differentiable(pred, lpp)
+        return loss, pred, lpp
+
+    @staticmethod
+    def backward(ctx, g_loss, g_pred, g_lpp):
+        (g_det,) = ctx.saved_tensors
+        return g_det * g_loss, None, None, None, None, None
+
+
+class DetectorMagnitudeFn(torch.autograd.Function):
+    """pred[B,P,P] = sqrt(sum_m |det_m|^2) (forward_model.py:353 / :371-375), zero subgradient at 0."""
+
+    @staticmethod
+    def forward(ctx, det):
+        det = _f32c(det)
+        B, M, P = det.shape[0], det.shape[1], det.shape[2]
+        dummy = torch.zeros((B, P, P), dtype=torch.float32, device=det.device)
+        pred, _, _ = _detector_call(det, dummy, None, 0, 0, 1.0, 1.0, False)
+        ctx.save_for_backward(det, pred)
+        return pred
+
+    @staticmethod
+    def backward(ctx, g_pred):
+        det, pred = ctx.saved_tensors
+        c = torch.where(pred > 0, g_pred / pred, torch.zeros_like(pred))
+        return det * c[:, None, :, :, None]
+
+
+# ------------------------------------------------------------------------------------------------------
+# probe shift
+# ------------------------------------------------------------------------------------------------------
+class ProbeShiftFn(torch.autograd.Function):
+    """out[B,M,P,P,2] = per-pattern Fourier shift of probe[M,P,P,2] by shift[B,2] (y, x) (util.py:380-397)."""
+
+    @staticmethod
+    def forward(ctx, probe, shift):
+        probe = _f32c(probe)
+        shift = _f32c(shift)
+        M, P = probe.shape[0], probe.shape[1]
+        B = shift.shape[0]
+        out = torch.empty((B, M, P, P, 2), dtype=torch.float32, device=probe.device)
+        call('adm_probe_shift_fwd', B, M, P, ptr(probe), ptr(shift), ptr(out), stream_ptr())
+        ctx.save_for_backward(probe, shift)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        probe, shift = ctx.saved_tensors
+        M, P = probe.shape[0], probe.shape[1]
+        B = shift.shape[0]
+        g_probe = torch.zeros_like(probe)
+        g_shift = torch.zeros_like(shift)
+        call('adm_probe_shift_bwd', B, M, P, ptr(probe), ptr(shift), ptr(_f32c(g_out)), ptr(g_probe), ptr(g_shift),
+             stream_ptr())
+        return g_probe, g_shift
+
+
+# ------------------------------------------------------------------------------------------------------
+# regulariser / Adam
+# ------------------------------------------------------------------------------------------------------
+class RegL1TVFn(torch.autograd.Function):
+    """alpha_d mean(w0|d|) + alpha_b mean(w1|b|) + gamma (TV3d(d) + TV3d(b)) on obj[Y,X,Z,2] (delta_beta)."""
+
+    @staticmethod
+    def forward(ctx, obj, weight_l1, alpha_d, alpha_b, gamma):
+        obj = _f32c(obj)
+        Y, X, Z, _ = obj.shape
+        val = torch.zeros((1,), dtype=torch.float32, device=obj.device)
+        g = torch.zeros_like(obj)
+        w = _f32c(weight_l1) if weight_l1 is not None else None
+        call('adm_regularizer_l1tv', Y, X, Z, ptr(obj), ptr(w), float(alpha_d or 0.), float(alpha_b or 0.),
+             float(gamma or 0.), ptr(val), ptr(g), stream_ptr())
+        ctx.save_for_backward(g)
+        return val[0]
+
+    @staticmethod
+    def backward(ctx, g_val):
+        (g,) = ctx.saved_tensors
+        return g * g_val, None, None, None, None
+
+
+def adam_step_(x, m, v, g, step, step_size=0.001, b1=0.9, b2=0.999, eps=1e-7, clip_nonneg=False,
+               zero_channel=None, mask=None):
+    """In-place fused Adam on fp32 CUDA tensors (optimizers.py:309-318) + optional epilogue."""
+    for t in (x, m, v, g):
+        if t.dtype != torch.float32:
+            raise RuntimeError('adam_step_: fp32 tensors required')
+    flags = (1 if clip_nonneg else 0) | (2 if zero_channel == 0 else 0) | (4 if zero_channel == 1 else 0)
+    call('adm_adam_step', ptr(x), ptr(m), ptr(v), ptr(_f32c(g)), x.numel(), float(step_size), float(b1), float(b2),
+         float(eps), int(step), flags, ptr(mask), stream_ptr())
+    return x
+
+
+def k1_of(energy_ev, psize_cm, scale_ri_by_k=True, ds_level=1):
+    """k1 = 2 pi dz / lambda (propagate.py:148,215)."""
+    if not scale_ri_by_k:
+        return 1.0
+    lmbda_nm = 1240. / energy_ev
+    return 2. * PI * (psize_cm * ds_level * 1.e7) / lmbda_nm

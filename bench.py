@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""Benchmark of the multislice forward + gradient + update hot path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # our arm (sm_100a kernels)
+    python bench.py --impl reference --steps K --warmup W    # the reference algorithm's CPU path (oracle port)
+
+Workload (N = 1 and per rank for N > 1): BASELINE config D, `multislice_ptycho_256_theta` -- 256^3 delta/beta object,
+72x72 probe, 23x23 = 529 probe positions per angle (step 12, origin -36), 256 slices, far-field detector, lsq loss +
+L1 + TV regularisers, Adam (demos/multislice_ptycho_256_theta.py:52-93).  One "step" = one minibatch iteration of
+the reference driver with minibatch_size = 529 (all positions of one rotation angle on each rank): rotate the object,
+multislice forward, loss, analytic adjoint, transpose rotation, regulariser, [NCCL all-reduce SUM of the object
+gradient], fused Adam.  Angles are sharded over ranks (weak scaling: per-GPU work is fixed).  Data are synthetic
+(forward-simulated from a seeded phantom with the same kernels before the timed region).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = 'diffraction patterns/sec (fwd+grad+update) at 256^3'
+UNIT = 'patterns/s'
+
+CFG_D = dict(obj_size=(256, 256, 256), probe_size=(72, 72), energy_ev=5000., psize_cm=1.e-7,
+             alpha_d=1e-9 * 1.7e7, alpha_b=1e-10 * 1.7e7, gamma=1e-9 * 1.7e7, learning_rate=5e-5,
+             n_theta=500, probe_mag_sigma=6, probe_phase_sigma=6, probe_phase_max=0.5)
+
+
+def probe_positions():
+    return np.array([(y, x) for y in (np.arange(23) * 12) - 36 for x in (np.arange(23) * 12) - 36], dtype='int64')
+
+
+def workload_name(mb):
+    return ('multislice_ptycho_256_theta (BASELINE configs[3]): 256^3 object, 72x72 probe, 529 positions/angle, 256 slices, '
+            'far field, lsq+L1+TV, Adam; minibatch_size=%d (one rotation angle per GPU per step)' % mb)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks line")
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler(object):
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.rows = []
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, smax, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
+                'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+# CPU arm: the reference algorithm restated (oracle port), all host threads, bounded sample
+# ---------------------------------------------------------------------------------------------------------
+def cpu_reference_run(steps, warmup, sizes=(2, 8), seed=0):
+    """Times the oracle's rotate + fwd + autograd + Adam on the config-D geometry on the host cores.
+
+    A full 529-pattern step would take minutes on the CPU, so each timed step is a BOUNDED SAMPLE of n patterns of one
+    angle, for two sample sizes; the per-step time is linear in n (t = a + b n: a = rotation + regulariser + Adam on the
+    256^3 volume, b = multislice fwd + backward per pattern), and the reported value is the throughput that fit gives
+    for the benchmark's minibatch of 529 patterns, 529 / (a + 529 b).  The raw timings are returned as well."""
+    import torch
+    from oracle import multislice_oracle as orc
+    c = CFG_D
+    Y, X, Z = c['obj_size']
+    P = list(c['probe_size'])
+    rs = np.random.RandomState(seed)
+    obj = torch.tensor(np.stack([rs.normal(8.7e-7, 1e-7, (Y, X, Z)), rs.normal(5.1e-8, 1e-8, (Y, X, Z))], -1).astype('float32'))
+    pr, pi = orc.gaussian_probe(P, 1, c['probe_mag_sigma'], c['probe_phase_max'], c['probe_phase_sigma'])
+    pr = torch.tensor(pr[None].astype('float32'))
+    pi = torch.tensor(pi[None].astype('float32'))
+    pos = probe_positions()
+    voxel_nm = np.array([c['psize_cm']] * 3) * 1e7
+    h = orc.get_kernel(voxel_nm[-1], 1240. / c['energy_ev'], voxel_nm, P)
+    cfg = dict(this_obj_size=[Y, X, Z], probe_size=P, energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=h,
+               free_prop_cm='inf', unknown_type='delta_beta')
+    reg = dict(alpha_d=c['alpha_d'], alpha_b=c['alpha_b'], gamma=c['gamma'])
+    theta_ls = np.linspace(0, 2 * np.pi, c['n_theta'], dtype='float32')
+    m = torch.zeros_like(obj)
+    v = torch.zeros_like(obj)
+    t_of_n = {}
+    it = 0
+    for n in sizes:
+        prj = torch.tensor(rs.uniform(0.5, 1.5, (n, P[0], P[1])).astype('float32'))
+        ts = []
+        for k in range(warmup + steps):
+            t0 = time.perf_counter()
+            i_theta = (7 * it + 3) % c['n_theta']
+            ind = np.sort(rs.choice(len(pos), n, replace=False))
+            lut = orc.rotation_coords([Y, X, Z], theta_ls[i_theta])
+            loss, _, _, grads = orc.ptycho_loss_and_grads(obj, pr, pi, pos[ind], prj, lut, cfg, reg=reg, want=('obj',))
+            obj, m, v = orc.adam_step(obj, grads['obj'], m, v, it, step_size=c['learning_rate'])
+            it += 1
+            if k >= warmup:
+                ts.append(time.perf_counter() - t0)
+        t_of_n[n] = float(np.mean(ts))
+    n1, n2 = sizes
+    b = (t_of_n[n2] - t_of_n[n1]) / (n2 - n1)
+    a = max(t_of_n[n1] - b * n1, 0.0)
+    value = 529.0 / (a + 529.0 * b)
+    sample = ('oracle port of the reference PyTorch-CPU path, config-D geometry (256^3, P=72, 256 slices, far field, lsq+L1+TV, '
+              'Adam); timed steps of %d and %d patterns of one angle: %.2f s and %.2f s per step (= %.3f and %.3f patterns/s '
+              'raw); linear fit t = %.2f s + %.3f s/pattern scaled to the 529-pattern minibatch'
+              % (n1, n2, t_of_n[n1], t_of_n[n2], n1 / t_of_n[n1], n2 / t_of_n[n2], a, b))
+    return {'value': value, 'ms_per_step_529': 1e3 * (a + 529.0 * b), 'cores': torch.get_num_threads(), 'sample': sample}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 2))
+    warmup = max(0, min(args.warmup, 1))
+    r = cpu_reference_run(steps, warmup)
+    line = {'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': args.gpus, 'steps': steps, 'warmup': warmup,
+            'ms_per_step': r['ms_per_step_529'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic', 'impl': 'reference',
+            'config': {'workload': workload_name(args.minibatch), 'obj_size': [256, 256, 256], 'probe_size': [72, 72],
+                       'minibatch_size': args.minibatch, 'n_slices': 256},
+            'cpu_baseline': {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']},
+            'e2e': {'value': r['value'], 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+            'gpu_launches': 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------
+def make_phantom(torch, dev, shape, seed):
+    """Seeded smooth 'foam' phantom: delta ~ 0..1e-5, beta = delta / 10."""
+    g = torch.Generator(device=dev).manual_seed(seed)
+    low = torch.rand((1, 1, 24, 24, 24), device=dev, generator=g)
+    up = torch.nn.functional.interpolate(low, size=shape, mode='trilinear', align_corners=False)[0, 0]
+    d = torch.clamp(up - 0.45, min=0) * 2e-5
+    return torch.stack([d, d / 10], -1).contiguous()
+
+
+class StepRunner(object):
+    """One data-parallel rank of the reference's batch loop (ptychography.py:859-1271), through the public classes
+    (PtychographyModel.get_loss_function + Differentiator.get_gradients + AdamOptimizer.apply_gradient)."""
+
+    def __init__(self, torch, ab, dev, rank, world, n_steps_total, mb):
+        self.torch, self.ab, self.dev, self.rank, self.world = torch, ab, dev, rank, world
+        c = CFG_D
+        Y, X, Z = c['obj_size']
+        P = list(c['probe_size'])
+        self.pos = probe_positions()[:mb]
+        self.mb = mb
+        full_theta = np.linspace(0, 2 * np.pi, c['n_theta'], dtype='float32')
+        # angle schedule: the reference's shuffled order for epoch 0 dealt round-robin to the ranks
+        # (ptychography.py:791-847: consecutive chunks of minibatch_size*n_ranks entries, one angle per rank)
+        order = np.arange(c['n_theta'])
+        np.random.RandomState(0).shuffle(order)
+        my_angles = [int(order[(i * world + rank) % c['n_theta']]) for i in range(n_steps_total)]
+        self.n_theta = n_steps_total
+        self.theta_ls = full_theta[my_angles]          # the model sees exactly the angles this rank will visit
+        voxel_nm = np.array([c['psize_cm']] * 3) * 1e7
+        h = ab.get_kernel(voxel_nm[-1], 1240. / c['energy_ev'], voxel_nm, P)
+        cv = dict(unknown_type='delta_beta', normalize_fft=False, sign_convention=1, rotate_out_of_loop=False,
+                  scale_ri_by_k=True, is_minus_logged=False, forward_algorithm='fresnel', stdout_options={},
+                  poisson_multiplier=1., common_probe_pos=True, binning=1, prj=None, device_obj=dev, probe_size=P,
+                  fresnel_approx=True, two_d_mode=False, minibatch_size=mb, ds_level=1, this_obj_size=[Y, X, Z],
+                  energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=h, pure_projection=False, n_dp_batch=20,
+                  free_prop_cm='inf', optimize_probe_defocusing=False, optimize_probe_pos_offset=False,
+                  optimize_prj_pos_offset=False, optimize_all_probe_pos=False, optimize_tilt=False, initial_tilt=None,
+                  n_probe_modes=1, n_theta=self.n_theta, precalculate_rotation_coords=False, theta_ls=self.theta_ls,
+                  theta_downsample=None, beamstop=None)
+        self.fm = ab.PtychographyModel(loss_function_type='lsq', device=dev, common_vars_dict=cv, raw_data_type='magnitude')
+        mag, ph = ab.generate_gaussian_map(P, 1, c['probe_mag_sigma'], c['probe_phase_max'], c['probe_phase_sigma'])
+        self.probe_real = torch.tensor((mag * np.cos(ph))[None].astype('float32'), device=dev)
+        self.probe_imag = torch.tensor((mag * np.sin(ph))[None].astype('float32'), device=dev)
+        self.zero_ppc = torch.zeros([self.n_theta, len(self.pos), 2], device=dev)
+        self.ind = np.arange(mb)
+        # synthetic measured data (adorym/simulation.py:659-671 recipe): predict() with the true object, untimed
+        truth = make_phantom(torch, dev, (Y, X, Z), 0)
+        frames = []
+        with torch.no_grad():
+            for i in range(self.n_theta):
+                frames.append(self.fm.predict(truth, self.probe_real, self.probe_imag, None, None, i, self.pos, None,
+                                              self.zero_ppc, self.ind, None, None))
+        del truth
+        self.prj_dev = torch.stack(frames)                                   # [n_theta, mb, P, P] device resident
+        self.prj_host = self.prj_dev.cpu().pin_memory()                      # host copy for the e2e leg
+        self.frame_bytes = int(self.prj_dev[0].numel() * 4)
+        rs = np.random.RandomState(0)
+        init = np.stack([rs.normal(8.7e-7, 1e-7, (Y, X, Z)), rs.normal(5.1e-8, 1e-8, (Y, X, Z))], -1).astype('float32')
+        self.obj0 = torch.tensor(init, device=dev)
+        self.fm.add_regularizers([ab.L1Regularizer(c['alpha_d'], c['alpha_b']), ab.TVRegularizer(c['gamma'])])
+        self.diff = ab.Differentiator()
+        self.diff.create_loss_node(self.fm.get_loss_function(), [0])
+        self.reset()
+
+    def reset(self):
+        torch, ab = self.torch, self.ab
+        self.obj = self.obj0.clone().requires_grad_(True)
+        self.opt = ab.AdamOptimizer('obj', options_dict={'step_size': CFG_D['learning_rate']})
+        self.opt.create_container(list(self.obj.shape), False, self.dev)
+        self.gradient = torch.zeros_like(self.obj0)
+        self.i_step = 0
+
+    def step(self, host_data):
+        """One minibatch iteration.  host_data=True: the measured frames live in pinned host memory (H2D copy inside the
+        step, via ForwardModel.get_data) and the loss is read back to the host, as reconstruct_ptychography does."""
+        torch = self.torch
+        i_theta = self.i_step % self.n_theta
+        self.fm.prj = self.prj_host if host_data else self.prj_dev
+        args = dict(obj=self.obj, probe_real=self.probe_real, probe_imag=self.probe_imag, probe_defocus_mm=None,
+                    probe_pos_offset=None, this_i_theta=i_theta, this_pos_batch=self.pos, prj=self.fm.prj,
+                    probe_pos_correction=self.zero_ppc, this_ind_batch=self.ind, tilt_ls=None, prj_pos_offset=None)
+        grads = self.diff.get_gradients(**args)
+        self.gradient.zero_()
+        self.gradient += grads[0]
+        if self.world > 1:
+            torch.distributed.all_reduce(self.gradient, op=torch.distributed.ReduceOp.SUM)
+        with torch.no_grad():
+            new = self.opt.apply_gradient(self.obj, self.gradient, self.i_step, **self.opt.options_dict)
+        self.obj = new.requires_grad_(True)
+        self.i_step += 1
+        return self.fm.current_loss if host_data else None
+
+
+def run_gpu_arm(args):
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py: no CUDA device; the GPU arm has no CPU fallback (use --impl reference for the CPU arm)')
+    from adorym_b200 import dist as adist
+    rank, world, local = adist.init_from_env('nccl')
+    if world != args.gpus and world > 1:
+        args.gpus = world
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
+    import adorym_b200 as ab
+    from adorym_b200 import _lib
+    mb = args.minibatch
+    K, W = args.steps, max(args.warmup, 3)
+    runner = StepRunner(torch, ab, dev, rank, world, K + W, mb)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(host_data, with_kernel_timing):
+        runner.reset()
+        for _ in range(W):
+            runner.step(host_data)
+        barrier()
+        if with_kernel_timing:
+            _lib.enable_timing(True)
+        l0 = _lib.launch_count
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(K):
+            runner.step(host_data)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = _lib.launch_count - l0
+        ksum = _lib.timing_summary() if with_kernel_timing else {}
+        _lib.enable_timing(False)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches, ksum
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, launches, ksum = timed(False, True)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_e2e, _, _ = timed(True, False)
+
+    if rank != 0:
+        return
+    value = world * mb * K / (ms_dev * 1e-3)
+    e2e = world * mb * K / (ms_e2e * 1e-3)
+    # ---- roofline of the dominant kernel (algorithmic bytes) ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json hbm_gbs)' if 'hbm_gbs' in peaks else 'fallback 6650 GB/s (B200_PROFILING.md)'
+    P, Nz = 72, 256
+    p8 = P * P * Nz * 8
+    d8 = P * P * 8
+    alg = {'adm_multislice_bwd': mb * (3 * p8 + d8),      # read (delta,beta), read psi checkpoint, accumulate gradient
+           'adm_multislice_fwd': mb * (2 * p8 + d8)}      # read (delta,beta), write psi checkpoint, write detector field
+    dom = max(alg.keys(), key=lambda k: ksum.get(k, (0, 0.0))[1])
+    n_dom, t_dom = ksum.get(dom, (1, float('nan')))
+    achieved = alg[dom] / (t_dom / max(n_dom, 1) * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, 'profiles', 'traffic.json'))).get(dom)
+    except Exception:
+        pass
+    roofline = {'bound': 'hbm', 'kernel': dom, 'achieved': achieved, 'peak': peak, 'unit': 'GB/s', 'frac': achieved / peak,
+                'traffic': traffic, 'peak_source': peak_src, 'algorithmic_bytes_per_launch': alg[dom],
+                'avg_launch_ms': t_dom / max(n_dom, 1),
+                'kernel_ms_per_step': {k: v[1] / K for k, v in sorted(ksum.items())}}
+    # whole-step algorithmic bytes: B (5 p8 + d4) + 4 V8 (rotation fwd + adj) + 7 V8 (Adam) + 2 V8 (regulariser)
+    V8 = 256 ** 3 * 8
+    step_bytes = mb * (5 * p8 + P * P * 4) + 4 * V8 + 7 * V8 + 2 * V8
+    roofline['step_frac'] = (step_bytes / (ms_dev / K * 1e-3) / 1e9) / peak
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        r = cpu_reference_run(1, 1)
+        cpu = {'value': r['value'], 'unit': UNIT, 'cores': r['cores'], 'kind': 'port', 'sample': r['sample']}
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W,
+            'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic',
+            'config': {'workload': workload_name(mb), 'obj_size': [256, 256, 256], 'probe_size': [72, 72],
+                       'minibatch_size': mb, 'n_slices': 256, 'parallelism': 'dp%d (angles sharded, NCCL all-reduce SUM of '
+                       'the object gradient)' % world,
+                       'l2_policy': 'inputs larger than L2: 134 MB volumes, %.1f GB psi checkpoints per step vs 126 MB L2'
+                                    % (mb * p8 / 1e9)},
+            'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
+            'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': runner.frame_bytes + mb * 8,
+                    'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K},
+            'gpu_launches': launches}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--minibatch', type=int, default=529)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    if args.impl == 'reference':
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+    try:
+        import torch.distributed as d
+        if d.is_available() and d.is_initialized():
+            d.destroy_process_group()
+    except Exception:
+        pass
+
+
+if __name__ == '__main__':
+    main()
