@@ -10,6 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, 'libadorym_b200.so')
 
 c_int, c_float, c_void_p, c_longlong = ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_longlong
+c_double = ctypes.c_double
 
 
 class MultisliceCfg(ctypes.Structure):
@@ -32,7 +33,7 @@ SIGNATURES = {
                           c_void_p, c_void_p, c_void_p],
     'adm_rotate_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_rotate_adj': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
-    'adm_adam_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_float, c_float, c_float, c_float, c_int,
+    'adm_adam_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double, c_double, c_int,
                       c_int, c_void_p, c_void_p],
     'adm_regularizer_l1tv': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
                              c_void_p],

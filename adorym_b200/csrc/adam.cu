@@ -6,66 +6,103 @@
 #include "../../include/adorym_b200.h"
 
 struct AdamArgs {
-    float step_size, b1, b2, omb1, omb2, inv_q1, inv_q2, eps;
+    float step_size, b1, b2, omb1, omb2, q1, q2, eps;
     int flags;
 };
 
-__global__ void __launch_bounds__(256) k_adam(float* x, float* m, float* v, const float* g, long long n2, AdamArgs a,
+// One Adam element update with the reference's exact fp32 operation sequence (optimizers.py:309-318 evaluated by
+// torch on fp32 tensors: every product, sum, quotient and sqrt individually rounded to nearest, no FMA
+// contraction, true divisions), so the result is bit-identical to the reference's CPU path.
+ADM_DEV void adam_update(float& x, float& m, float& v, float g, const AdamArgs& a) {
+#ifndef ADM_HOST_EMU
+    float mm = __fadd_rn(__fmul_rn(a.b1, m), __fmul_rn(a.omb1, g));
+    float vv = __fadd_rn(__fmul_rn(a.b2, v), __fmul_rn(a.omb2, __fmul_rn(g, g)));
+    float mhat = __fdiv_rn(mm, a.q1);
+    float vhat = __fdiv_rn(vv, a.q2);
+    float d = __fdiv_rn(__fmul_rn(a.step_size, mhat), __fadd_rn(__fsqrt_rn(vhat), a.eps));
+    x = __fsub_rn(x, d);
+#else
+    volatile float t1 = a.b1 * m, t2 = a.omb1 * g;
+    float mm = t1 + t2;
+    volatile float g2 = g * g;
+    volatile float t3 = a.b2 * v, t4 = a.omb2 * g2;
+    float vv = t3 + t4;
+    volatile float mhat = mm / a.q1, vhat = vv / a.q2;
+    volatile float num = a.step_size * mhat, den = sqrtf(vhat) + a.eps;
+    volatile float d = num / den;
+    x = x - d;
+#endif
+    m = mm; v = vv;
+}
+
+// Vectorised main kernel: one thread per float4 = two (channel 0, channel 1) pairs; 7 streams of 16-byte accesses.
+__global__ void __launch_bounds__(256) k_adam(float* x, float* m, float* v, const float* g, long long n4, AdamArgs a,
                                               const float* mask) {
-    // one thread per (channel 0, channel 1) pair: n2 = n / 2 pairs (n odd handled by the host wrapper)
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < n2; i += stride) {
-        float mk_ = (mask != nullptr) ? mask[i] : 1.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-            long long j = 2 * i + c;
-            float gg = g[j];
-            float mm = a.b1 * m[j];
-            mm = mm + a.omb1 * gg;
-            float vv = a.b2 * v[j];
-            vv = vv + a.omb2 * (gg * gg);
-            float mhat = mm * a.inv_q1;
-            float vhat = vv * a.inv_q2;
-            float d = a.step_size * mhat / (sqrtf(vhat) + a.eps);
-            float xx = x[j] - d;
-            if (a.flags & 1) xx = fmaxf(xx, 0.f);
-            if ((a.flags & 2) && c == 0) xx = 0.f;
-            if ((a.flags & 4) && c == 1) xx = 0.f;
-            if (mask != nullptr) xx *= mk_;
-            x[j] = xx; m[j] = mm; v[j] = vv;
+    for (; i < n4; i += stride) {
+        float4 xx = reinterpret_cast<const float4*>(x)[i];
+        float4 mm = reinterpret_cast<const float4*>(m)[i];
+        float4 vv = reinterpret_cast<const float4*>(v)[i];
+        float4 gg = reinterpret_cast<const float4*>(g)[i];
+        adam_update(xx.x, mm.x, vv.x, gg.x, a);
+        adam_update(xx.y, mm.y, vv.y, gg.y, a);
+        adam_update(xx.z, mm.z, vv.z, gg.z, a);
+        adam_update(xx.w, mm.w, vv.w, gg.w, a);
+        if (a.flags & 1) { xx.x = fmaxf(xx.x, 0.f); xx.y = fmaxf(xx.y, 0.f); xx.z = fmaxf(xx.z, 0.f); xx.w = fmaxf(xx.w, 0.f); }
+        if (a.flags & 2) { xx.x = 0.f; xx.z = 0.f; }
+        if (a.flags & 4) { xx.y = 0.f; xx.w = 0.f; }
+        if (mask != nullptr) {
+            float2 mk_ = reinterpret_cast<const float2*>(mask)[i];
+            xx.x *= mk_.x; xx.y *= mk_.x; xx.z *= mk_.y; xx.w *= mk_.y;
         }
+        reinterpret_cast<float4*>(x)[i] = xx;
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
     }
 }
 
-__global__ void __launch_bounds__(256) k_adam_tail(float* x, float* m, float* v, const float* g, long long j, AdamArgs a) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    float gg = g[j];
-    float mm = a.b1 * m[j] + a.omb1 * gg;
-    float vv = a.b2 * v[j] + a.omb2 * (gg * gg);
-    float d = a.step_size * (mm * a.inv_q1) / (sqrtf(vv * a.inv_q2) + a.eps);
-    float xx = x[j] - d;
-    if (a.flags & 1) xx = fmaxf(xx, 0.f);
-    x[j] = xx; m[j] = mm; v[j] = vv;
+// scalar tail / unaligned path: elements [j0, n), channel = index parity
+__global__ void __launch_bounds__(256) k_adam_tail(float* x, float* m, float* v, const float* g, long long j0, long long n,
+                                                   AdamArgs a, const float* mask) {
+    long long j = j0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; j < n; j += stride) {
+        float xx = x[j], mm = m[j], vv = v[j];
+        adam_update(xx, mm, vv, g[j], a);
+        if (a.flags & 1) xx = fmaxf(xx, 0.f);
+        if ((a.flags & 2) && (j & 1) == 0) xx = 0.f;
+        if ((a.flags & 4) && (j & 1) == 1) xx = 0.f;
+        if (mask != nullptr) xx *= mask[j >> 1];
+        x[j] = xx; m[j] = mm; v[j] = vv;
+    }
 }
 
-extern "C" int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, float step_size, float b1, float b2,
-                             float eps, int step, int flags, const float* mask, void* stream) {
+extern "C" int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, double step_size, double b1, double b2,
+                             double eps, int step, int flags, const float* mask, void* stream) {
     if (!x || !m || !v || !g || n < 1 || step < 0) return ADM_ERR_ARG;
     if (((flags & 6) || mask) && (n & 1)) return ADM_ERR_ARG;
     AdamArgs a;
-    a.step_size = step_size; a.b1 = b1; a.b2 = b2; a.eps = eps; a.flags = flags;
-    a.omb1 = (float)(1.0 - (double)b1);
-    a.omb2 = (float)(1.0 - (double)b2);
-    a.inv_q1 = (float)(1.0 / (1.0 - pow((double)b1, (double)(step + 1))));
-    a.inv_q2 = (float)(1.0 / (1.0 - pow((double)b2, (double)(step + 1))));
-    long long n2 = n / 2;
-    if (n2 > 0) {
-        long long blocks = (n2 + 255) / 256;
-        if (blocks > 148LL * 32) blocks = 148LL * 32;   // grid-stride; a multiple of the SM count
-        ADM_LAUNCH(k_adam, (unsigned)blocks, 256, 0, stream, x, m, v, g, n2, a, mask);
+    // python-float (double) scalars are rounded to fp32 when they meet an fp32 tensor, as torch does
+    a.step_size = (float)step_size; a.b1 = (float)b1; a.b2 = (float)b2; a.eps = (float)eps; a.flags = flags;
+    a.omb1 = (float)(1.0 - b1);
+    a.omb2 = (float)(1.0 - b2);
+    a.q1 = (float)(1.0 - pow(b1, (double)(step + 1)));
+    a.q2 = (float)(1.0 - pow(b2, (double)(step + 1)));
+    bool aligned = ((((uintptr_t)x) | ((uintptr_t)m) | ((uintptr_t)v) | ((uintptr_t)g)) & 15) == 0 &&
+                   (mask == nullptr || (((uintptr_t)mask) & 7) == 0);
+    long long n4 = aligned ? n / 4 : 0;
+    if (n4 > 0) {
+        long long blocks = (n4 + 255) / 256;
+        if (blocks > 148LL * 16) blocks = 148LL * 16;   // grid-stride; a multiple of the SM count
+        ADM_LAUNCH(k_adam, (unsigned)blocks, 256, 0, stream, x, m, v, g, n4, a, mask);
     }
-    if (n & 1) ADM_LAUNCH(k_adam_tail, 1, 32, 0, stream, x, m, v, g, n - 1, a);
+    if (4 * n4 < n) {
+        long long rest = n - 4 * n4;
+        long long blocks = (rest + 255) / 256;
+        if (blocks > 148LL * 16) blocks = 148LL * 16;
+        ADM_LAUNCH(k_adam_tail, (unsigned)blocks, 256, 0, stream, x, m, v, g, 4 * n4, n, a, mask);
+    }
     return ADM_OK;
 }
 

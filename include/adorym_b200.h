@@ -108,12 +108,14 @@ int adm_rotate_fwd(int Y, int X, int Z, const float* obj, const float* grid, flo
 int adm_rotate_adj(int Y, int X, int Z, const float* g_rot, const float* grid, float* g_obj, void* stream);
 
 /* Fused Adam (optimizers.py:309-318) with optional epilogue.  In place on x, m, v (n floats each).
- *   step = i_batch of the reference (bias correction uses step+1)
+ *   step = i_batch of the reference (bias correction uses step+1); hyper-parameters are doubles (python floats):
+ *   1-b1, 1-b2 and the bias corrections are formed in double and then rounded to fp32, as torch does, and the
+ *   element update follows the reference's operation order with round-to-nearest fp32 ops (bit-exact vs torch CPU)
  *   flags: bit0 clip x to >= 0 (ptychography.py:1138-1139); bit1 zero channel 0 (absorption_only);
  *          bit2 zero channel 1 (phase_only) (ptychography.py:1140-1142); n must be even if bit1|bit2
  *   mask: per-voxel [n/2] multiplier applied to both channels (array_ops.py:239-244) or NULL               */
-int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, float step_size, float b1, float b2,
-                  float eps, int step, int flags, const float* mask, void* stream);
+int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, double step_size, double b1, double b2,
+                  double eps, int step, int flags, const float* mask, void* stream);
 
 /* L1 / reweighted-L1 / TV regulariser on obj [Y][X][Z][2], delta_beta type (regularizers.py:30-110).
  *   value[0] += alpha_d*mean(w0|d|) + alpha_b*mean(w1|b|) + gamma*(TV3d(d) + TV3d(b));  g_obj += gradient.
