@@ -26,6 +26,8 @@ P_CFG = ctypes.POINTER(MultisliceCfg)
 SIGNATURES = {
     'adm_abi_version': [],
     'adm_prepare_transfer_function': [c_int, c_void_p, c_int, c_float, c_void_p, c_void_p],
+    'adm_transmission_fwd': [c_int, c_float, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p],
+    'adm_transmission_adj': [c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_multislice_fwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_multislice_bwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p],
@@ -66,7 +68,7 @@ def get_lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('adorym_b200: CUDA library %s is missing; run `python -m adorym_b200.build`' % LIB_PATH)
         _lib = bind(ctypes.CDLL(LIB_PATH))
-        if _lib.adm_abi_version() != 1:
+        if _lib.adm_abi_version() != 2:
             raise RuntimeError('adorym_b200: ABI version mismatch')
     return _lib
 

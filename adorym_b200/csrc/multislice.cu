@@ -1,8 +1,14 @@
 // Fused multislice forward / adjoint kernels (sm_100a).
 //
 // One CTA owns one wavefield (pattern b, probe mode m).  The wavefield psi[P][P] lives in shared memory for the
-// whole traversal of the Nz slices; per slice the only HBM traffic is the (delta,beta) patch tile (prefetched
-// with cp.async, zero-filled outside the object = vacuum padding) and the psi checkpoint the adjoint consumes.
+// whole traversal of the Nz slices.  The object enters as the TRANSMISSION VOLUME T' = T - 1 (slice-major
+// [Nz][Y][Xp][2], written once per step by adm_transmission_fwd, so no exp/sincos runs in the per-slice loop and the
+// same kernel serves delta_beta and real_imag objects).  Per slice the only HBM traffic is
+//   forward : one TMA tile load of T' (cp.async.bulk.tensor.3d, out-of-object voxels zero-filled = vacuum),
+//             prefetched one slice ahead and signalled on an mbarrier, + the psi checkpoint store;
+//   adjoint : one cp.async.bulk of the psi checkpoint (prefetched), the T' tile (L2-resident, plain loads issued
+//             ahead of the butterfly) and ONE cp.reduce.async.bulk.tensor.3d that scatter-ADDS the [P][P] tile of
+//             dL/dT into the gradient volume (reduction done by the L2, overhang clipped by the TMA unit).
 //
 // 2-D FFT of size P = 8*R2 (R2 = 8 or 9) as an in-place mixed-radix Cooley-Tukey over shared memory:
 //   1-D forward:  pass A  radix-8 over n1 (x[R2 n1 + n2], stride R2) + twiddle W_P^{n2 k1}, stored at R2 k1 + n2
@@ -12,52 +18,31 @@
 //   pre-permuted (adm_prepare_transfer_function), so no reordering pass exists.
 // Because pass B, the H multiply and pass B^-1 act on the same R2 points, and pass A^-1, the slice modulation
 // and the next slice's pass A act on the same 8 points, a slice costs SIX shared-memory round trips:
-//   P1 [Ay^-1 . t(delta,beta) . Ay]   P2 By   P3 Ax   P4 [Bx . H . Bx^-1]   P5 Ax^-1   P6 By^-1
+//   P1 [Ay^-1 . (1 + T') . Ay]   P2 By   P3 Ax   P4 [Bx . H . Bx^-1]   P5 Ax^-1   P6 By^-1
 // y-passes run with lanes along x (row stride S = P+1 complex keeps x-passes, lanes along y, conflict free).
 //
 // Reference behaviour reproduced: adorym/propagate.py:208-258 (slice loop, last slice not propagated :253),
-// :241 transmission, :255 convolution, :263-280 detector transform; forward_model.py:313-331 + util.py:1327-1351
-// gather with vacuum padding.  The adjoint replaces the autograd tape (wrappers.py:300-331).
+// :241/:246 transmission (precomputed), :255 convolution, :263-280 detector transform; forward_model.py:313-331 +
+// util.py:1327-1351 gather with vacuum padding.  The adjoint replaces the autograd tape (wrappers.py:300-331).
 #include "fft_passes.cuh"
+#include "tma.cuh"
 #include "../../include/adorym_b200.h"
 
 struct MsParams {
-    const cpx* rot_obj;
+    const cpx* tvol;    // transmission volume T' (adjoint: plain loads of the tile)
     const cpx* probe;
     const int* pos;
     const cpx* Hp;      // prepared in-object transfer function (conj version for the adjoint)
     const cpx* Hf;      // prepared free-space transfer function (near field) or null
     cpx* ckpt;
     cpx* det;           // fwd: out ; bwd: g_det in
-    cpx* g_obj;
     cpx* g_probe;
-    int Nz, Y, X, B, M;
-    float k1, sgn;
-    int unknown_type, free_prop, probe_per_pattern;
+    int Nz, Y, X, Xp, B, M;
+    int free_prop, probe_per_pattern;
     float ff_scale;
     int ff_conj;
 };
 
-// ---- cp.async helpers -------------------------------------------------------------------------
-ADM_DEV void async_copy8(cpx* smem_dst, const cpx* gsrc, bool valid) {
-#ifndef ADM_HOST_EMU
-    unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
-    int nbytes = valid ? 8 : 0;      // src-size 0 -> the 8 destination bytes are zero-filled
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(saddr), "l"(gsrc), "r"(nbytes) : "memory");
-#else
-    *smem_dst = valid ? *gsrc : mk(0.f, 0.f);
-#endif
-}
-ADM_DEV void async_commit() {
-#ifndef ADM_HOST_EMU
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
-#endif
-}
-ADM_DEV void async_wait_all() {
-#ifndef ADM_HOST_EMU
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
-#endif
-}
 ADM_DEV void red_add2(cpx* addr, float a, float b) {
 #ifndef ADM_HOST_EMU
     asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(addr), "f"(a), "f"(b) : "memory");
@@ -67,61 +52,64 @@ ADM_DEV void red_add2(cpx* addr, float a, float b) {
 #endif
 }
 
-// transmission function of one voxel (propagate.py:241 / :246); oob real_imag voxels are vacuum (1, 0)
-ADM_DEV cpx transmission(cpx o, bool inb, int unknown_type, float k1, float sgn) {
-    if (unknown_type == ADM_DELTA_BETA) {
-        float e = expf(-k1 * o.y);
-        float s, c;
-        adm_sincos(-sgn * k1 * o.x, &s, &c);
-        return mk(e * c, e * s);
-    }
-    return inb ? o : mk(1.f, 0.f);
+// psi * (1 + T')
+ADM_DEV cpx modulate(cpx v, cpx tp) {
+    return mk(fmaf(-v.y, tp.y, fmaf(v.x, tp.x, v.x)), fmaf(v.y, tp.x, fmaf(v.x, tp.y, v.y)));
 }
+// g * conj(1 + T')
+ADM_DEV cpx modulate_conj(cpx v, cpx tp) {
+    return mk(fmaf(v.y, tp.y, fmaf(v.x, tp.x, v.x)), fmaf(v.y, tp.x, fmaf(-v.x, tp.y, v.y)));
+}
+
+// shared-memory carve-up (tile first: TMA destinations / sources need 128-byte alignment)
+template <class C> struct MsSmem {
+    static constexpr int TP = C::P + 2;      // tile row pitch: P columns + 2 (even-column TMA start, see tma.cuh)
+    static constexpr size_t TILE = sizeof(cpx) * C::P * TP;
+    static constexpr size_t PSI = sizeof(cpx) * C::P * C::S;
+    static constexpr size_t TW = sizeof(cpx) * C::P;
+    static constexpr size_t BYTES = TILE + PSI + TW + 16;
+};
 
 // ================================================================================================
 // Forward
 // ================================================================================================
-template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_fwd(MsParams p) {
+template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
-    cpx* psi = (cpx*)smem_raw;
-    cpx* tile = psi + P * S;
-    cpx* tw = tile + P * P;
+    constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
+    constexpr int TP = MsSmem<C>::TP;
+    cpx* tile = (cpx*)smem_raw;
+    cpx* psi = tile + P * TP;
+    cpx* tw = psi + P * S;
+    adm_mbar_t* bar = (adm_mbar_t*)(tw + P);
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
     const int wf = blockIdx.x;              // wavefield index b * M + m
     const int b = wf / p.M, m = wf % p.M;
     const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
-    const int gx = px + l;
-    const bool x_in = (gx >= 0) && (gx < p.X);
+    const int pxa = px & ~1, lt = l + (px & 1);     // even TMA start column, this thread's column inside the tile
     const cpx* probe = p.probe + (size_t)(p.probe_per_pattern ? wf : m) * P * P;
-    cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * P * P;
+    cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * P * TP;
     cpx* det = p.det + (size_t)wf * P * P;
-    const size_t slice_stride = (size_t)p.Y * p.X;
 
     init_twiddles<C>(tw, t);
-    // prefetch the (delta,beta) tile of slice 0: every thread copies exactly the elements it will consume
-    if (active) {
-        for (int g = q; g < R2; g += C::Q)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int y = R2 * j + g, gy = py + y;
-                bool inb = x_in && gy >= 0 && gy < p.Y;
-                const cpx* src = inb ? p.rot_obj + (size_t)gy * p.X + gx : p.rot_obj;
-                async_copy8(&tile[y * P + l], src, inb);
-            }
-        async_commit();
-    }
+    if (t == 0) mbar_init(bar, 1);
     __syncthreads();
+    if (t == 0) {   // prefetch the T' tile of slice 0
+        mbar_expect_tx(bar, TILE_BYTES);
+        tma_load_tile(tile, &tmap, 2 * pxa, py, 0, bar);
+    }
 
     for (int z = 0; z < p.Nz; ++z) {
         const bool last = (z == p.Nz - 1);
         const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
-        // ---- P1: [Ay^-1] . checkpoint . transmission . [Ay] --------------------------------------------
+        // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
         if (active) {
-            async_wait_all();
-            for (int g = q; g < R2; g += C::Q) {
+            mbar_wait(bar, z & 1);
+#pragma unroll
+            for (int gi = 0; gi < R2 / C::Q; ++gi) {
+                const int g = q + gi * C::Q;
                 cpx v[8];
                 if (z == 0) {
 #pragma unroll
@@ -133,15 +121,9 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_f
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    int y = R2 * j + g, gy = py + y;
-                    bool inb = x_in && gy >= 0 && gy < p.Y;
-                    ckpt[(size_t)z * P * P + y * P + l] = v[j];
-                    cpx o = tile[y * P + l];
-                    v[j] = cmul(v[j], transmission(o, inb, p.unknown_type, p.k1, p.sgn));
-                    if (!last) {
-                        const cpx* src = inb ? p.rot_obj + (size_t)(z + 1) * slice_stride + (size_t)gy * p.X + gx : p.rot_obj;
-                        async_copy8(&tile[y * P + l], src, inb);
-                    }
+                    const int y = R2 * j + g;
+                    ckpt[(size_t)z * P * TP + y * TP + lt] = v[j];
+                    v[j] = modulate(v[j], tile[y * TP + lt]);
                 }
                 if (go_on) {
                     if (last && p.ff_conj) {
@@ -158,9 +140,12 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_f
                     for (int j = 0; j < 8; ++j) det[(R2 * j + g) * P + l] = v[j];   // exit wave, natural order
                 }
             }
-            async_commit();
         }
         __syncthreads();
+        if (t == 0 && !last) {   // every thread has consumed tile(z): prefetch tile(z+1) behind P2..P6
+            mbar_expect_tx(bar, TILE_BYTES);
+            tma_load_tile(tile, &tmap, 2 * pxa, py, z + 1, bar);
+        }
         if (!go_on) break;
         if (last && p.free_prop == ADM_PROP_FAR) {
             // far field: finish the forward 2-D FFT (By, Ax, Bx) and store fftshift-ed, natural order
@@ -204,36 +189,35 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_f
 // ================================================================================================
 // Adjoint
 // ================================================================================================
-template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_bwd(MsParams p) {
+template <class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
-    cpx* psi = (cpx*)smem_raw;          // holds the running adjoint wavefield g
-    cpx* ckb = psi + P * S;             // checkpoint staging (cp.async)
-    cpx* tw = ckb + P * P;
+    constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
+    constexpr int TP = MsSmem<C>::TP;
+    cpx* ckb = (cpx*)smem_raw;          // psi checkpoint of the slice (bulk copy); overwritten in place by dL/dT
+    cpx* psi = ckb + P * TP;            // running adjoint wavefield g
+    cpx* tw = psi + P * S;
+    adm_mbar_t* bar = (adm_mbar_t*)(tw + P);
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
     const int wf = blockIdx.x;
     const int b = wf / p.M, m = wf % p.M;
     const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
+    const int pxa = px & ~1, lt = l + (px & 1);
     const int gx = px + l;
     const bool x_in = (gx >= 0) && (gx < p.X);
-    const cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * P * P;
+    const cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * P * TP;
     const cpx* gdet = p.det + (size_t)wf * P * P;
-    const size_t slice_stride = (size_t)p.Y * p.X;
+    const size_t slice_stride = (size_t)p.Y * p.Xp;
 
     init_twiddles<C>(tw, t);
-    // prefetch the checkpoint of the last slice
-    if (active) {
-        for (int g = q; g < R2; g += C::Q)
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                int y = R2 * j + g;
-                async_copy8(&ckb[y * P + l], &ckpt[(size_t)(p.Nz - 1) * P * P + y * P + l], true);
-            }
-        async_commit();
-    }
+    if (t == 0) mbar_init(bar, 1);
     __syncthreads();
+    if (t == 0) {   // prefetch the checkpoint of the last slice
+        mbar_expect_tx(bar, TILE_BYTES);
+        bulk_load(ckb, ckpt + (size_t)(p.Nz - 1) * P * TP, TILE_BYTES, bar);
+    }
 
     // ---- adjoint of the detector transform ---------------------------------------------------------------
     if (p.free_prop == ADM_PROP_FAR) {
@@ -275,20 +259,21 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_b
         propagate_core<C>(psi, tw, p.Hf, q, l, active);
     }
 
-    for (int z = p.Nz - 1; z >= 0; --z) {
+    int phase = 0;
+    for (int z = p.Nz - 1; z >= 0; --z, phase ^= 1) {
         const bool last = (z == p.Nz - 1);
-        // ---- P1': [Ay^-1] . gradient of the modulation . conj(t) . [Ay] ---------------------------------------
+        // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] ------------------------------
         if (active) {
-            async_wait_all();
-            for (int g = q; g < R2; g += C::Q) {
-                cpx v[8], o[8];
-                bool inb[8];
-                // object voxels of this slice (L2-resident; issued first so the butterfly hides the latency)
+#pragma unroll
+            for (int gi = 0; gi < R2 / C::Q; ++gi) {
+                const int g = q + gi * C::Q;
+                cpx v[8], tp[8];
+                // T' of this slice (L2-resident volume; issued first so the butterfly hides the latency)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    int gy = py + R2 * j + g;
-                    inb[j] = x_in && gy >= 0 && gy < p.Y;
-                    o[j] = inb[j] ? p.rot_obj[(size_t)z * slice_stride + (size_t)gy * p.X + gx] : mk(0.f, 0.f);
+                    const int gy = py + R2 * j + g;
+                    const bool inb = x_in && gy >= 0 && gy < p.Y;
+                    tp[j] = inb ? p.tvol[(size_t)z * slice_stride + (size_t)gy * p.Xp + gx] : mk(0.f, 0.f);
                 }
                 if (last && p.free_prop == ADM_PROP_NONE) {
 #pragma unroll
@@ -302,24 +287,17 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_b
                         for (int j = 0; j < 8; ++j) v[j] = cconj(v[j]);
                     }
                 }
+                if (gi == 0) {
+                    mbar_wait(bar, phase);
+                    // the two pad columns of the tile are never written by the forward pass: add zeros there
+                    if (t < 2 * P) ckb[(t >> 1) * TP + ((t & 1) ? P + 1 : ((px & 1) ? 0 : P))] = mk(0.f, 0.f);
+                }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    int y = R2 * j + g, gy = py + y;
-                    cpx w = ckb[y * P + l];                       // psi_z (wave entering the slice)
-                    if (z > 0) async_copy8(&ckb[y * P + l], &ckpt[(size_t)(z - 1) * P * P + y * P + l], true);
-                    cpx tr = transmission(o[j], inb[j], p.unknown_type, p.k1, p.sgn);
-                    cpx gt = cmulc(v[j], w);                      // g_t = g' conj(psi)
-                    float gd, gb;
-                    if (p.unknown_type == ADM_DELTA_BETA) {
-                        cpx u = cmulc(gt, tr);                    // g' conj(psi t)
-                        gd = -p.sgn * p.k1 * u.y;
-                        gb = -p.k1 * u.x;
-                    } else {
-                        gd = gt.x;
-                        gb = gt.y;
-                    }
-                    if (inb[j]) red_add2(&p.g_obj[(size_t)z * slice_stride + (size_t)gy * p.X + gx], gd, gb);
-                    v[j] = cmulc(v[j], tr);                       // g_psi = g' conj(t)
+                    const int y = R2 * j + g;
+                    const cpx w = ckb[y * TP + lt];               // psi_z (wave entering the slice)
+                    ckb[y * TP + lt] = cmulc(v[j], w);            // dL/dT = g' conj(psi_z)
+                    v[j] = modulate_conj(v[j], tp[j]);            // g_psi = g' conj(T)
                 }
                 if (z > 0) {
                     dft8<false>(v);
@@ -338,12 +316,31 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_b
                     }
                 }
             }
-            async_commit();
+            fence_proxy_async();      // the dL/dT tile is about to be read by the TMA unit
         }
         __syncthreads();
+        if (t == 0 && pxa + P >= 0 && py + P >= 0) {   // (a patch lying entirely outside contributes nothing)
+            tma_reduce_add_tile(&gmap, 2 * (pxa + P), py + P, z, ckb);   // margined volume: coordinates never negative
+            bulk_commit();
+        }
         if (z == 0) break;
-        propagate_core<C>(psi, tw, p.Hp, q, l, active);
+        if (active) pass_B_fwd<C, false>(psi, q, l);
+        __syncthreads();
+        if (t == 0) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind P3..P6
+            bulk_wait_read_all();
+            mbar_expect_tx(bar, TILE_BYTES);
+            bulk_load(ckb, ckpt + (size_t)(z - 1) * P * TP, TILE_BYTES, bar);
+        }
+        if (active) pass_A_fwd<C, true>(psi, tw, q, l);
+        __syncthreads();
+        if (active) pass_BHB_x<C>(psi, tw, p.Hp, q, l);
+        __syncthreads();
+        if (active) pass_A_inv<C, true>(psi, q, l);
+        __syncthreads();
+        if (active) pass_B_inv<C, false>(psi, tw, q, l);
+        __syncthreads();
     }
+    if (t == 0) bulk_wait_all();      // shared memory must stay valid until the last reduce has read it
 }
 
 // ================================================================================================
@@ -368,9 +365,8 @@ static int fill_params(const adm_multislice_cfg* c, MsParams& p) {
     if (c->sign_convention != 1 && c->sign_convention != -1) return ADM_ERR_ARG;
     if (c->unknown_type != ADM_DELTA_BETA && c->unknown_type != ADM_REAL_IMAG) return ADM_ERR_ARG;
     if (c->free_prop < ADM_PROP_NONE || c->free_prop > ADM_PROP_NEAR) return ADM_ERR_ARG;
-    p.Nz = c->n_slices; p.Y = c->Y; p.X = c->X; p.B = c->B; p.M = c->M;
-    p.k1 = c->k1; p.sgn = (float)c->sign_convention;
-    p.unknown_type = c->unknown_type; p.free_prop = c->free_prop; p.probe_per_pattern = c->probe_per_pattern;
+    p.Nz = c->n_slices; p.Y = c->Y; p.X = c->X; p.Xp = ADM_TVOL_PITCH(c->X); p.B = c->B; p.M = c->M;
+    p.free_prop = c->free_prop; p.probe_per_pattern = c->probe_per_pattern;
     // far field: sign +1 -> fft2 (unnormalised or 1/P), sign -1 -> ifft2 (1/P^2 or 1/P)   (propagate.py:267-270)
     float Pf = (float)c->P;
     p.ff_conj = (c->sign_convention == -1 && c->free_prop == ADM_PROP_FAR) ? 1 : 0;
@@ -389,47 +385,53 @@ extern "C" int adm_prepare_transfer_function(int P, const float* H, int conj, fl
     return ADM_OK;
 }
 
-extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* rot_obj, const float* probe, const int* pos,
+extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tvol, const float* probe, const int* pos,
                                   const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* stream) {
     MsParams p;
     int rc = fill_params(cfg, p);
     if (rc) return rc;
-    if (!rot_obj || !probe || !pos || !psi_ckpt || !det) return ADM_ERR_ARG;
+    if (!tvol || !probe || !pos || !psi_ckpt || !det) return ADM_ERR_ARG;
     if (cfg->n_slices > 1 && !Hprep) return ADM_ERR_ARG;
     if (cfg->free_prop == ADM_PROP_NEAR && !Hfree) return ADM_ERR_ARG;
-    p.rot_obj = (const cpx*)rot_obj; p.probe = (const cpx*)probe; p.pos = pos;
+    p.tvol = (const cpx*)tvol; p.probe = (const cpx*)probe; p.pos = pos;
     p.Hp = (const cpx*)Hprep; p.Hf = (const cpx*)Hfree;
-    p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)det; p.g_obj = nullptr; p.g_probe = nullptr;
+    p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)det; p.g_probe = nullptr;
+    AdmTileMap map;
+    if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;
     if (cfg->P == 72) {
-        if (set_smem(k_multislice_fwd<Cfg72>, Cfg72::SMEM)) return ADM_ERR_CUDA;
-        ADM_LAUNCH(k_multislice_fwd<Cfg72>, nwf, Cfg72::NTHREADS, Cfg72::SMEM, stream, p);
+        if (set_smem(k_multislice_fwd<Cfg72>, MsSmem<Cfg72>::BYTES)) return ADM_ERR_CUDA;
+        ADM_LAUNCH(k_multislice_fwd<Cfg72>, nwf, Cfg72::NTHREADS, MsSmem<Cfg72>::BYTES, stream, map, p);
     } else {
-        if (set_smem(k_multislice_fwd<Cfg64>, Cfg64::SMEM)) return ADM_ERR_CUDA;
-        ADM_LAUNCH(k_multislice_fwd<Cfg64>, nwf, Cfg64::NTHREADS, Cfg64::SMEM, stream, p);
+        if (set_smem(k_multislice_fwd<Cfg64>, MsSmem<Cfg64>::BYTES)) return ADM_ERR_CUDA;
+        ADM_LAUNCH(k_multislice_fwd<Cfg64>, nwf, Cfg64::NTHREADS, MsSmem<Cfg64>::BYTES, stream, map, p);
     }
     return ADM_OK;
 }
 
-extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* rot_obj, const int* pos, const float* HprepC,
-                                  const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_rot_obj,
+extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
+                                  const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol,
                                   float* g_probe, void* stream) {
     MsParams p;
     int rc = fill_params(cfg, p);
     if (rc) return rc;
-    if (!rot_obj || !pos || !psi_ckpt || !g_det || !g_rot_obj) return ADM_ERR_ARG;
+    if (!tvol || !pos || !psi_ckpt || !g_det || !g_tvol) return ADM_ERR_ARG;
     if (cfg->n_slices > 1 && !HprepC) return ADM_ERR_ARG;
     if (cfg->free_prop == ADM_PROP_NEAR && !HfreeC) return ADM_ERR_ARG;
-    p.rot_obj = (const cpx*)rot_obj; p.probe = nullptr; p.pos = pos;
+    p.tvol = (const cpx*)tvol; p.probe = nullptr; p.pos = pos;
     p.Hp = (const cpx*)HprepC; p.Hf = (const cpx*)HfreeC;
-    p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)g_det; p.g_obj = (cpx*)g_rot_obj; p.g_probe = (cpx*)g_probe;
+    p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)g_det; p.g_probe = (cpx*)g_probe;
+    AdmTileMap map;
+    if (adm_make_tile_map(&map, g_tvol, p.Nz, ADM_GVOL_ROWS(p.Y, cfg->P), p.X + ADM_GVOL_MARGIN(cfg->P),
+                          ADM_GVOL_PITCH(p.X, cfg->P), cfg->P, cfg->P + 2))
+        return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;
     if (cfg->P == 72) {
-        if (set_smem(k_multislice_bwd<Cfg72>, Cfg72::SMEM)) return ADM_ERR_CUDA;
-        ADM_LAUNCH(k_multislice_bwd<Cfg72>, nwf, Cfg72::NTHREADS, Cfg72::SMEM, stream, p);
+        if (set_smem(k_multislice_bwd<Cfg72>, MsSmem<Cfg72>::BYTES)) return ADM_ERR_CUDA;
+        ADM_LAUNCH(k_multislice_bwd<Cfg72>, nwf, Cfg72::NTHREADS, MsSmem<Cfg72>::BYTES, stream, map, p);
     } else {
-        if (set_smem(k_multislice_bwd<Cfg64>, Cfg64::SMEM)) return ADM_ERR_CUDA;
-        ADM_LAUNCH(k_multislice_bwd<Cfg64>, nwf, Cfg64::NTHREADS, Cfg64::SMEM, stream, p);
+        if (set_smem(k_multislice_bwd<Cfg64>, MsSmem<Cfg64>::BYTES)) return ADM_ERR_CUDA;
+        ADM_LAUNCH(k_multislice_bwd<Cfg64>, nwf, Cfg64::NTHREADS, MsSmem<Cfg64>::BYTES, stream, map, p);
     }
     return ADM_OK;
 }

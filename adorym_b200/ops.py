@@ -76,10 +76,25 @@ class MultislicePlan(object):
 
 
 # ------------------------------------------------------------------------------------------------------
-# multislice
+# transmission volume + multislice
 # ------------------------------------------------------------------------------------------------------
+def tvol_pitch(X):
+    """ADM_TVOL_PITCH: row pitch of the transmission volume (TMA needs a multiple of 16 bytes)."""
+    return (int(X) + 1) & ~1
+
+
+def gvol_pitch(X, P):
+    """ADM_GVOL_PITCH: row pitch of the margined gradient volume dL/dT."""
+    return (int(X) + int(P) + 1) & ~1
+
+
 class MultisliceFn(torch.autograd.Function):
-    """det[B,M,P,P,2] = multislice(rot_obj[Nz,Y,X,2], probe[M,P,P,2] | [B,M,P,P,2], pos[B,2] int32)."""
+    """det[B,M,P,P,2] = multislice(rot_obj[Nz,Y,X,2] raw (delta,beta)|(re,im), probe[M,P,P,2] | [B,M,P,P,2],
+    pos[B,2] int32).
+
+    forward : adm_transmission_fwd (T' = T - 1 volume, propagate.py:241/246) -> adm_multislice_fwd
+    backward: adm_multislice_bwd (dL/dT scattered into the margined gradient volume by TMA reduce-adds)
+              -> adm_transmission_adj (chain rule back to (delta, beta) | (re, im))."""
 
     @staticmethod
     def forward(ctx, rot_obj, probe, pos, plan):
@@ -88,36 +103,48 @@ class MultisliceFn(torch.autograd.Function):
         if pos.dtype != torch.int32 or not pos.is_cuda:
             raise RuntimeError('pos must be an int32 CUDA tensor [B, 2]')
         pos = pos.contiguous()
-        P, Nz = plan.P, plan.n_slices
-        if tuple(rot_obj.shape) != (Nz, plan.Y, plan.X, 2):
-            raise RuntimeError('rot_obj must be [Nz, Y, X, 2] = %s, got %s' % ((Nz, plan.Y, plan.X, 2), tuple(rot_obj.shape)))
+        P, Nz, Y, X = plan.P, plan.n_slices, plan.Y, plan.X
+        if tuple(rot_obj.shape) != (Nz, Y, X, 2):
+            raise RuntimeError('rot_obj must be [Nz, Y, X, 2] = %s, got %s' % ((Nz, Y, X, 2), tuple(rot_obj.shape)))
+        dev = rot_obj.device
         B = pos.shape[0]
         per_pattern = probe.dim() == 5
         M = probe.shape[1] if per_pattern else probe.shape[0]
         if tuple(probe.shape[-3:]) != (P, P, 2) or (per_pattern and probe.shape[0] != B):
             raise RuntimeError('probe must be [M,P,P,2] or [B,M,P,P,2]')
         cfg = plan.cfg(B, M, per_pattern)
-        ckpt = torch.empty((B, M, Nz, P, P, 2), dtype=torch.float32, device=rot_obj.device)
-        det = torch.empty((B, M, P, P, 2), dtype=torch.float32, device=rot_obj.device)
-        call('adm_multislice_fwd', ctypes.byref(cfg), ptr(rot_obj), ptr(probe), ptr(pos), ptr(plan.Hp), ptr(plan.Hfp),
+        tvol = torch.empty((Nz, Y, tvol_pitch(X), 2), dtype=torch.float32, device=dev)
+        call('adm_transmission_fwd', plan.unknown_type, plan.k1, plan.sign_convention, Nz * Y, X, ptr(rot_obj), ptr(tvol),
+             stream_ptr())
+        ckpt = torch.empty((B, M, Nz, P, P + 2, 2), dtype=torch.float32, device=dev)
+        det = torch.empty((B, M, P, P, 2), dtype=torch.float32, device=dev)
+        call('adm_multislice_fwd', ctypes.byref(cfg), ptr(tvol), ptr(probe), ptr(pos), ptr(plan.Hp), ptr(plan.Hfp),
              ptr(ckpt), ptr(det), stream_ptr())
         ctx.plan, ctx.cfg, ctx.per_pattern = plan, cfg, per_pattern
         ctx.probe_shape = tuple(probe.shape)
-        ctx.save_for_backward(rot_obj, pos, ckpt)
+        ctx.save_for_backward(tvol, pos, ckpt)
         return det
 
     @staticmethod
     def backward(ctx, g_det):
-        rot_obj, pos, ckpt = ctx.saved_tensors
+        tvol, pos, ckpt = ctx.saved_tensors
         plan = ctx.plan
+        P, Nz, Y, X = plan.P, plan.n_slices, plan.Y, plan.X
+        dev = tvol.device
         g_det = _f32c(g_det)
-        g_rot = torch.zeros_like(rot_obj)
+        # margined gradient volume (ADM_GVOL_MARGIN in include/adorym_b200.h)
+        g_tvol = torch.zeros((Nz, Y + P, gvol_pitch(X, P), 2), dtype=torch.float32, device=dev)
         g_probe = None
         if ctx.needs_input_grad[1]:
-            g_probe = torch.zeros(ctx.probe_shape, dtype=torch.float32, device=rot_obj.device)
-        call('adm_multislice_bwd', ctypes.byref(ctx.cfg), ptr(rot_obj), ptr(pos), ptr(plan.Hc), ptr(plan.Hfc), ptr(ckpt),
-             ptr(g_det), ptr(g_rot), ptr(g_probe), stream_ptr())
-        return (g_rot if ctx.needs_input_grad[0] else None), g_probe, None, None
+            g_probe = torch.zeros(ctx.probe_shape, dtype=torch.float32, device=dev)
+        call('adm_multislice_bwd', ctypes.byref(ctx.cfg), ptr(tvol), ptr(pos), ptr(plan.Hc), ptr(plan.Hfc), ptr(ckpt),
+             ptr(g_det), ptr(g_tvol), ptr(g_probe), stream_ptr())
+        g_rot = None
+        if ctx.needs_input_grad[0]:
+            g_rot = torch.empty((Nz, Y, X, 2), dtype=torch.float32, device=dev)
+            call('adm_transmission_adj', plan.unknown_type, plan.k1, plan.sign_convention, Nz, Y, X, P, ptr(g_tvol),
+                 ptr(tvol), ptr(g_rot), stream_ptr())
+        return g_rot, g_probe, None, None
 
 
 # ------------------------------------------------------------------------------------------------------

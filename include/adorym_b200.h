@@ -5,7 +5,8 @@
  * "FFI" it would bind is a ctypes/pybind stub called from a torch.autograd.Function that replaces
  *   - adorym/propagate.py:131-288   multislice_propagate_batch  (+ wrappers.py:699-779 fft2/ifft2/convolve,
  *                                    wrappers.py:600-608 exp_complex, forward_model.py:313-331 patch gather,
- *                                    util.py:1327-1351 pad_object)            -> adm_multislice_fwd / _bwd
+ *                                    util.py:1327-1351 pad_object)            -> adm_transmission_fwd / _adj +
+ *                                                                                adm_multislice_fwd / _bwd
  *   - adorym/forward_model.py:88-103, 353, 371-375 (norm + mismatch loss)     -> adm_detector_loss
  *   - adorym/util.py:536-552 apply_rotation / wrappers.py:1105-1147 grid_sample and its autograd transpose
  *                                                                              -> adm_rotate_fwd / adm_rotate_adj
@@ -30,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ADM_ABI_VERSION 1
+#define ADM_ABI_VERSION 2
 
 /* unknown_type */
 #define ADM_DELTA_BETA 0
@@ -67,27 +68,56 @@ int adm_abi_version(void);
  * out[px][py] = scale * (conj ? conj(H) : H)[perm(py)][perm(px)].  Use scale = 1/P^2 for a propagation step. */
 int adm_prepare_transfer_function(int P, const float* H, int conj, float scale, float* out, void* stream);
 
+/* Row pitch (in complex voxels) of the transmission volume and of its gradient: X rounded up to even, because the
+ * TMA tile loads / reduce-stores need a row pitch that is a multiple of 16 bytes.                             */
+#define ADM_TVOL_PITCH(X) (((X) + 1) & ~1)
+
+/* The gradient volume dL/dT carries a margin of P voxels on the LOW side of y and x: the TMA reduce-add that
+ * scatters the patch tiles rejects negative start coordinates (hardware probe: tools/tma_probe.cu), while overhang on
+ * the high side is clipped by the TMA unit.  Object voxel (z, y, x) lives at [z][y + P][x + P].                 */
+#define ADM_GVOL_MARGIN(P) (P)
+#define ADM_GVOL_ROWS(Y, P) ((Y) + (P))
+#define ADM_GVOL_PITCH(X, P) ((((X) + (P)) + 1) & ~1)
+
+/* Transmission volume (replaces the per-slice w.exp_complex of propagate.py:241 / the complex object of :246):
+ *   rot  [rows][X][2]   slice-major object volume (delta, beta) or (re, im), rows = Nz * Y
+ *   tvol [rows][Xp][2]  out: T' = T - 1, T = exp(-k1 beta) (cos(s k1 delta) - i sin(s k1 delta)) for delta_beta,
+ *                       T = re + i im for real_imag; pad columns x >= X are written as 0.  Xp = ADM_TVOL_PITCH(X).
+ * Vacuum outside the object is T' = 0 for both object types (util.py:1335-1350).                            */
+int adm_transmission_fwd(int unknown_type, float k1, int sign_convention, long long rows, int X, const float* rot,
+                         float* tvol, void* stream);
+/* Chain rule back to the object: g_rot [Nz][Y][X][2] (WRITTEN) from the margined gradient volume
+ * g_tvol [Nz][ADM_GVOL_ROWS(Y,P)][ADM_GVOL_PITCH(X,P)][2] = (dL/dRe T, dL/dIm T) and tvol:
+ *   dL/ddelta = -s k1 Im(g_T conj(T)), dL/dbeta = -k1 Re(g_T conj(T)); identity for real_imag.                */
+int adm_transmission_adj(int unknown_type, float k1, int sign_convention, int Nz, int Y, int X, int P,
+                         const float* g_tvol, const float* tvol, float* g_rot, void* stream);
+
 /* Forward multislice for B*M wavefields (replaces propagate.py:131-288 + the gather of forward_model.py:313-331).
- *   rot_obj  [Nz][Y][X][2]      rotated object, slice-major
+ *   tvol     [Nz][Y][Xp][2]     transmission volume T' (adm_transmission_fwd), slice-major, 16-byte aligned
  *   probe    [M][P][P][2] or [B][M][P][P][2]
  *   pos      [B][2] int32 (y, x) top-left corner of each patch in object pixels; may be negative / overhang:
- *            out-of-object voxels read as vacuum ((0,0) delta_beta, (1,0) real_imag; util.py:1335-1350)
+ *            out-of-object voxels are vacuum (TMA zero fill of T'; util.py:1335-1350)
  *   Hprep    prepared in-object transfer function (adm_prepare_transfer_function, conj=0, scale=1/P^2)
  *   Hfree    prepared free-space transfer function for ADM_PROP_NEAR, else NULL
- *   psi_ckpt [B][M][Nz][P][P][2] out: wavefield entering every slice (consumed by adm_multislice_bwd)
- *   det      [B][M][P][P][2]     out: complex wavefield on the detector (far field is fftshift-ed)        */
-int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* rot_obj, const float* probe, const int* pos,
+ *   psi_ckpt [B][M][Nz][P][P+2][2] out: wavefield entering every slice (consumed by adm_multislice_bwd), 16-byte
+ *            aligned; rows are stored with the tile pitch P+2 at column offset (x & 1) so that one bulk copy brings
+ *            a slice back in the layout the TMA reduce of the adjoint needs (pad columns are never written)
+ *   det      [B][M][P][P][2]     out: complex wavefield on the detector (far field is fftshift-ed)
+ * cfg->k1 / unknown_type are not used here (they parameterise adm_transmission_*).                          */
+int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tvol, const float* probe, const int* pos,
                        const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* stream);
 
 /* Analytic adjoint of adm_multislice_fwd (replaces torch.autograd.grad over the taped slice loop,
  * wrappers.py:300-331).
  *   g_det     [B][M][P][P][2]   dL/d(det) as (dL/dRe, dL/dIm)
  *   HprepC    prepared conj in-object transfer function (conj=1, scale=1/P^2); HfreeC likewise or NULL
- *   g_rot_obj [Nz][Y][X][2]     ACCUMULATED (+=) gradient w.r.t. the rotated object (scatter-add of patches)
+ *   g_tvol    [Nz][ADM_GVOL_ROWS(Y,P)][ADM_GVOL_PITCH(X,P)][2]  ACCUMULATED (+=) gradient w.r.t. T (dL/dRe T,
+ *             dL/dIm T), margined (see ADM_GVOL_MARGIN): per slice one TMA reduce-add of the patch tile (overlapping
+ *             patches are summed by the L2, overhang is clipped); zero it before the first call of a step
  *   g_probe   [M][P][P][2] ACCUMULATED over patterns, or [B][M][P][P][2] WRITTEN if probe_per_pattern; may be
  *             NULL when the probe gradient is not needed                                                     */
-int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* rot_obj, const int* pos, const float* HprepC,
-                       const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_rot_obj,
+int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
+                       const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol,
                        float* g_probe, void* stream);
 
 /* Detector magnitude, mismatch loss and residual (forward_model.py:88-103,353,371-375).

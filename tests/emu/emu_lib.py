@@ -67,9 +67,13 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
                         unknown_type=0 if unknown_type == 'delta_beta' else 1, free_prop=fp,
                         normalize_fft=int(normalize_fft), probe_per_pattern=ppp)
     posi = np.ascontiguousarray(pos, dtype='int32')
-    ckpt = np.zeros((B, M, Z, Pp, Pp, 2), 'float32')
+    ckpt = np.full((B, M, Z, Pp, Pp + 2, 2), np.nan, 'float32')
     det = np.zeros((B, M, Pp, Pp, 2), 'float32')
-    ck(L.adm_multislice_fwd(ctypes.byref(cfg), P(rot), P(probe_in), P(posi), P(Hp), P(Hfp), P(ckpt), P(det), None))
+    Xp = (X + 1) & ~1
+    utype = 0 if unknown_type == 'delta_beta' else 1
+    tvol = np.full((Z, Y, Xp, 2), np.nan, 'float32')
+    ck(L.adm_transmission_fwd(utype, float(np.float32(k1)), sign_convention, Z * Y, X, P(rot), P(tvol), None))
+    ck(L.adm_multislice_fwd(ctypes.byref(cfg), P(tvol), P(probe_in), P(posi), P(Hp), P(Hfp), P(ckpt), P(det), None))
     pred = np.zeros((B, Pp, Pp), 'float32')
     gdet = np.zeros_like(det)
     lpp = np.zeros((B,), 'float32')
@@ -78,10 +82,12 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
     ck(L.adm_detector_loss(B, M, Pp, 0 if loss == 'lsq' else 1, 0 if raw_data_type == 'magnitude' else 1,
                            poisson_multiplier, inv_n, P(det), P(meas), None, P(pred), P(gdet), P(lpp), None))
     loss_val = float(lpp.astype('float64').sum() * inv_n)
-    g_rot = np.zeros_like(rot)
+    g_tvol = np.zeros((Z, Y + Pp, (X + Pp + 1) & ~1, 2), 'float32')
     g_probe_in = np.zeros_like(probe_in)
-    ck(L.adm_multislice_bwd(ctypes.byref(cfg), P(rot), P(posi), P(Hc), P(Hfc), P(ckpt), P(gdet), P(g_rot),
+    ck(L.adm_multislice_bwd(ctypes.byref(cfg), P(tvol), P(posi), P(Hc), P(Hfc), P(ckpt), P(gdet), P(g_tvol),
                             P(g_probe_in), None))
+    g_rot = np.full(rot.shape, np.nan, 'float32')
+    ck(L.adm_transmission_adj(utype, float(np.float32(k1)), sign_convention, Z, Y, X, Pp, P(g_tvol), P(tvol), P(g_rot), None))
     out = {'loss': loss_val, 'pred': pred, 'det': det}
     if shift is not None:
         g_probe = np.zeros_like(probe)

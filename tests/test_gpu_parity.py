@@ -252,7 +252,10 @@ def test_full_size_properties_config_d():
     (gp,) = torch.autograd.grad((det * y).sum(), [probe])
     lhs = (det.double() * y.double()).sum().item()
     rhs = (probe.double() * gp.double()).sum().item()
-    assert abs(lhs - rhs) <= 1e-4 * abs(lhs)
+    # <A p, y> is a random-sign sum over 529 * 72 * 72 * 2 terms: the tolerance is relative to the natural scale of such
+    # a sum (its root-sum-square), not to the heavily cancelled total
+    scale = (det.double() * y.double()).norm().item()
+    assert abs(lhs - rhs) <= 1e-4 * scale
     # gradient scatter linearity on a sub-batch
     rot2 = rot.detach().requires_grad_(True)
     sub = pos_t[100:140].contiguous()
