@@ -24,6 +24,7 @@
 // Reference behaviour reproduced: adorym/propagate.py:208-258 (slice loop, last slice not propagated :253),
 // :241/:246 transmission (precomputed), :255 convolution, :263-280 detector transform; forward_model.py:313-331 +
 // util.py:1327-1351 gather with vacuum padding.  The adjoint replaces the autograd tape (wrappers.py:300-331).
+#include <stdlib.h>
 #include "fft_passes.cuh"
 #include "tma.cuh"
 #include "../../include/adorym_b200.h"
@@ -38,7 +39,7 @@ struct MsParams {
     cpx* det;           // fwd: out ; bwd: g_det in
     cpx* g_probe;
     int Nz, Y, X, Xp, B, M;
-    int free_prop, probe_per_pattern;
+    int free_prop, probe_per_pattern, h_separable;
     float ff_scale;
     int ff_conj;
 };
@@ -67,13 +68,14 @@ template <class C> struct MsSmem {
     static constexpr size_t TILE = sizeof(cpx) * C::P * TP;
     static constexpr size_t PSI = sizeof(cpx) * C::P * C::S;
     static constexpr size_t TW = sizeof(cpx) * C::P;
-    static constexpr size_t BYTES = TILE + PSI + TW + 16;
+    static constexpr size_t HS = sizeof(cpx) * 2 * C::P;     // separable transfer function tables hy | hx
+    static constexpr size_t BYTES = TILE + PSI + TW + HS + 16;
 };
 
 // ================================================================================================
 // Forward
 // ================================================================================================
-template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
@@ -81,7 +83,8 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_f
     cpx* tile = (cpx*)smem_raw;
     cpx* psi = tile + P * TP;
     cpx* tw = psi + P * S;
-    adm_mbar_t* bar = (adm_mbar_t*)(tw + P);
+    cpx* hs = tw + P;
+    adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
@@ -94,6 +97,7 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_f
     cpx* det = p.det + (size_t)wf * P * P;
 
     init_twiddles<C>(tw, t);
+    if (p.h_separable && t < 2 * P) hs[t] = p.Hp[t];
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
     if (t == 0) {   // prefetch the T' tile of slice 0
@@ -170,7 +174,8 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_f
             }
             break;
         }
-        propagate_core<C>(psi, tw, last ? p.Hf : p.Hp, q, l, active);
+        if (!last && p.h_separable) propagate_core_sep<C>(psi, tw, hs, q, l, active);
+        else propagate_core<C>(psi, tw, last ? p.Hf : p.Hp, q, l, active);
         if (last) {
             // near field: final Ay^-1, natural order store
             if (active)
@@ -189,7 +194,7 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS) k_multislice_f
 // ================================================================================================
 // Adjoint
 // ================================================================================================
-template <class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
+template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
@@ -197,7 +202,8 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_multislic
     cpx* ckb = (cpx*)smem_raw;          // psi checkpoint of the slice (bulk copy); overwritten in place by dL/dT
     cpx* psi = ckb + P * TP;            // running adjoint wavefield g
     cpx* tw = psi + P * S;
-    adm_mbar_t* bar = (adm_mbar_t*)(tw + P);
+    cpx* hs = tw + P;
+    adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
@@ -212,6 +218,7 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_multislic
     const size_t slice_stride = (size_t)p.Y * p.Xp;
 
     init_twiddles<C>(tw, t);
+    if (p.h_separable && t < 2 * P) hs[t] = p.Hp[t];
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
     if (t == 0) {   // prefetch the checkpoint of the last slice
@@ -324,7 +331,10 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_multislic
             bulk_commit();
         }
         if (z == 0) break;
-        if (active) pass_B_fwd<C, false>(psi, q, l);
+        if (active) {
+            if (p.h_separable) pass_B_fwd_y_scaled<C>(psi, hs, q, l);
+            else pass_B_fwd<C, false>(psi, q, l);
+        }
         __syncthreads();
         if (t == 0) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind P3..P6
             bulk_wait_read_all();
@@ -333,7 +343,10 @@ template <class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_multislic
         }
         if (active) pass_A_fwd<C, true>(psi, tw, q, l);
         __syncthreads();
-        if (active) pass_BHB_x<C>(psi, tw, p.Hp, q, l);
+        if (active) {
+            if (p.h_separable) pass_BHB_x_sep<C>(psi, tw, hs + P, q, l);
+            else pass_BHB_x<C>(psi, tw, p.Hp, q, l);
+        }
         __syncthreads();
         if (active) pass_A_inv<C, true>(psi, q, l);
         __syncthreads();
@@ -358,6 +371,12 @@ template <class C> __global__ void k_prepare_H(const cpx* H, int conj, float sca
 // ================================================================================================
 // host side
 // ================================================================================================
+// kernel-shape variant selection for tuning runs (0 = default)
+static int adm_variant(const char* name) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+
 static int fill_params(const adm_multislice_cfg* c, MsParams& p) {
     if (!c) return ADM_ERR_ARG;
     if (c->P != 64 && c->P != 72) return ADM_ERR_UNSUPPORTED;
@@ -366,7 +385,7 @@ static int fill_params(const adm_multislice_cfg* c, MsParams& p) {
     if (c->unknown_type != ADM_DELTA_BETA && c->unknown_type != ADM_REAL_IMAG) return ADM_ERR_ARG;
     if (c->free_prop < ADM_PROP_NONE || c->free_prop > ADM_PROP_NEAR) return ADM_ERR_ARG;
     p.Nz = c->n_slices; p.Y = c->Y; p.X = c->X; p.Xp = ADM_TVOL_PITCH(c->X); p.B = c->B; p.M = c->M;
-    p.free_prop = c->free_prop; p.probe_per_pattern = c->probe_per_pattern;
+    p.free_prop = c->free_prop; p.probe_per_pattern = c->probe_per_pattern; p.h_separable = c->h_separable ? 1 : 0;
     // far field: sign +1 -> fft2 (unnormalised or 1/P), sign -1 -> ifft2 (1/P^2 or 1/P)   (propagate.py:267-270)
     float Pf = (float)c->P;
     p.ff_conj = (c->sign_convention == -1 && c->free_prop == ADM_PROP_FAR) ? 1 : 0;
@@ -385,6 +404,23 @@ extern "C" int adm_prepare_transfer_function(int P, const float* H, int conj, fl
     return ADM_OK;
 }
 
+// separable variant: out = [hy_perm (P) | scale * hx_perm (P)], complex; conj optional
+template <class C> __global__ void k_prepare_H_sep(const cpx* hy, const cpx* hx, int conj, float scale, cpx* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * C::P) return;
+    cpx h = (i < C::P) ? hy[perm_freq<C>(i)] : cscale(hx[perm_freq<C>(i - C::P)], scale);
+    out[i] = conj ? cconj(h) : h;
+}
+
+extern "C" int adm_prepare_transfer_function_separable(int P, const float* hy, const float* hx, int conj, float scale,
+                                                       float* out, void* stream) {
+    if (!hy || !hx || !out) return ADM_ERR_ARG;
+    if (P == 72) ADM_LAUNCH(k_prepare_H_sep<Cfg72>, 1, 256, 0, stream, (const cpx*)hy, (const cpx*)hx, conj, scale, (cpx*)out);
+    else if (P == 64) ADM_LAUNCH(k_prepare_H_sep<Cfg64>, 1, 256, 0, stream, (const cpx*)hy, (const cpx*)hx, conj, scale, (cpx*)out);
+    else return ADM_ERR_UNSUPPORTED;
+    return ADM_OK;
+}
+
 extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tvol, const float* probe, const int* pos,
                                   const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* stream) {
     MsParams p;
@@ -399,12 +435,20 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     AdmTileMap map;
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;
+    int var = adm_variant("ADM_FWD_VARIANT");
+#define ADM_FWD(CFG, MINB)                                                                                         \
+    do {                                                                                                           \
+        if (set_smem(k_multislice_fwd<CFG, MINB>, MsSmem<CFG>::BYTES)) return ADM_ERR_CUDA;                        \
+        ADM_LAUNCH((k_multislice_fwd<CFG, MINB>), nwf, CFG::NTHREADS, MsSmem<CFG>::BYTES, stream, map, p);         \
+    } while (0)
     if (cfg->P == 72) {
-        if (set_smem(k_multislice_fwd<Cfg72>, MsSmem<Cfg72>::BYTES)) return ADM_ERR_CUDA;
-        ADM_LAUNCH(k_multislice_fwd<Cfg72>, nwf, Cfg72::NTHREADS, MsSmem<Cfg72>::BYTES, stream, map, p);
+        if (var == 1) ADM_FWD(Cfg72w, 1);
+        else if (var == 2) ADM_FWD(Cfg72w, 2);
+        else ADM_FWD(Cfg72, 2);
     } else {
-        if (set_smem(k_multislice_fwd<Cfg64>, MsSmem<Cfg64>::BYTES)) return ADM_ERR_CUDA;
-        ADM_LAUNCH(k_multislice_fwd<Cfg64>, nwf, Cfg64::NTHREADS, MsSmem<Cfg64>::BYTES, stream, map, p);
+        if (var == 1) ADM_FWD(Cfg64w, 1);
+        else if (var == 2) ADM_FWD(Cfg64w, 2);
+        else ADM_FWD(Cfg64, 2);
     }
     return ADM_OK;
 }
@@ -426,12 +470,20 @@ extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tv
                           ADM_GVOL_PITCH(p.X, cfg->P), cfg->P, cfg->P + 2))
         return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;
+    int var = adm_variant("ADM_BWD_VARIANT");
+#define ADM_BWD(CFG, MINB)                                                                                         \
+    do {                                                                                                           \
+        if (set_smem(k_multislice_bwd<CFG, MINB>, MsSmem<CFG>::BYTES)) return ADM_ERR_CUDA;                        \
+        ADM_LAUNCH((k_multislice_bwd<CFG, MINB>), nwf, CFG::NTHREADS, MsSmem<CFG>::BYTES, stream, map, p);         \
+    } while (0)
     if (cfg->P == 72) {
-        if (set_smem(k_multislice_bwd<Cfg72>, MsSmem<Cfg72>::BYTES)) return ADM_ERR_CUDA;
-        ADM_LAUNCH(k_multislice_bwd<Cfg72>, nwf, Cfg72::NTHREADS, MsSmem<Cfg72>::BYTES, stream, map, p);
+        if (var == 1) ADM_BWD(Cfg72w, 1);
+        else if (var == 2) ADM_BWD(Cfg72w, 2);
+        else ADM_BWD(Cfg72, 2);
     } else {
-        if (set_smem(k_multislice_bwd<Cfg64>, MsSmem<Cfg64>::BYTES)) return ADM_ERR_CUDA;
-        ADM_LAUNCH(k_multislice_bwd<Cfg64>, nwf, Cfg64::NTHREADS, MsSmem<Cfg64>::BYTES, stream, map, p);
+        if (var == 1) ADM_BWD(Cfg64w, 1);
+        else if (var == 2) ADM_BWD(Cfg64w, 2);
+        else ADM_BWD(Cfg64, 2);
     }
     return ADM_OK;
 }

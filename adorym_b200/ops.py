@@ -41,11 +41,36 @@ def prepare_transfer_function(h, device, conj=False):
     return out
 
 
+def separate_transfer_function(h, rtol=1e-6):
+    """If h[ky, kx] == hy[ky] * hx[kx] (true for the paraxial Fresnel kernel, propagate.py:72) return (hy, hx) as
+    complex128 vectors, else None."""
+    h = np.asarray(h, dtype='complex128')
+    if h.ndim != 2 or abs(h[0, 0]) < 1e-30:
+        return None
+    hy = h[:, 0].copy()
+    hx = h[0, :] / h[0, 0]
+    if np.abs(np.outer(hy, hx) - h).max() > rtol * np.abs(h).max():
+        return None
+    return hy, hx
+
+
+def prepare_transfer_function_separable(hy, hx, device, conj=False):
+    P = hy.shape[0]
+    if P not in SUPPORTED_P:
+        raise NotImplementedError('adorym_b200: transfer function of size %d (supported P: %s)' % (P, SUPPORTED_P))
+    f = lambda v: torch.from_numpy(np.stack([v.real, v.imag], -1).astype('float32')).to(device)
+    hyt, hxt = f(hy), f(hx)
+    out = torch.empty((2, P, 2), dtype=torch.float32, device=device)
+    call('adm_prepare_transfer_function_separable', P, ptr(hyt), ptr(hxt), int(bool(conj)), 1.0 / (P * P), ptr(out),
+         stream_ptr())
+    return out
+
+
 class MultislicePlan(object):
     """Static description of one multislice configuration + prepared transfer functions (cached per model)."""
 
     def __init__(self, P, n_slices, Y, X, k1, h, device, sign_convention=1, unknown_type='delta_beta', free_prop='none',
-                 normalize_fft=False, h_free=None):
+                 normalize_fft=False, h_free=None, allow_separable=True):
         if P not in SUPPORTED_P:
             raise NotImplementedError('adorym_b200: probe size %d is not supported yet (supported: %s)' % (P, SUPPORTED_P))
         self.P, self.n_slices, self.Y, self.X = int(P), int(n_slices), int(Y), int(X)
@@ -56,9 +81,16 @@ class MultislicePlan(object):
         self.normalize_fft = int(bool(normalize_fft))
         self.device = device
         self.Hp = self.Hc = self.Hfp = self.Hfc = None
+        self.h_separable = 0
         if h is not None:
-            self.Hp = prepare_transfer_function(h, device, conj=False)
-            self.Hc = prepare_transfer_function(h, device, conj=True)
+            sep = separate_transfer_function(h) if allow_separable else None
+            if sep is not None:
+                self.h_separable = 1
+                self.Hp = prepare_transfer_function_separable(sep[0], sep[1], device, conj=False)
+                self.Hc = prepare_transfer_function_separable(sep[0], sep[1], device, conj=True)
+            else:
+                self.Hp = prepare_transfer_function(h, device, conj=False)
+                self.Hc = prepare_transfer_function(h, device, conj=True)
         elif self.n_slices > 1:
             raise ValueError('a transfer function is required when n_slices > 1')
         if self.free_prop == 2:
@@ -72,7 +104,7 @@ class MultislicePlan(object):
         return MultisliceCfg(P=self.P, n_slices=self.n_slices, B=int(B), M=int(M), Y=self.Y, X=self.X, k1=self.k1,
                              sign_convention=self.sign_convention, unknown_type=self.unknown_type,
                              free_prop=self.free_prop, normalize_fft=self.normalize_fft,
-                             probe_per_pattern=int(bool(probe_per_pattern)))
+                             probe_per_pattern=int(bool(probe_per_pattern)), h_separable=self.h_separable)
 
 
 # ------------------------------------------------------------------------------------------------------

@@ -58,6 +58,7 @@ typedef struct adm_multislice_cfg {
     int free_prop;         /* ADM_PROP_*                                                                      */
     int normalize_fft;     /* far field with norm='ortho' (wrappers.py:725-756)                               */
     int probe_per_pattern; /* 0: probe is [M][P][P][2]; 1: probe is [B][M][P][P][2] (per-position shifted)    */
+    int h_separable;       /* 1: Hprep / HprepC were made by adm_prepare_transfer_function_separable ([2][P][2]) */
 } adm_multislice_cfg;
 
 /* ABI / build identification. */
@@ -67,6 +68,13 @@ int adm_abi_version(void);
  * adorym/propagate.py:62-81 get_kernel) into the layout the in-shared-memory mixed-radix FFT passes read.
  * out[px][py] = scale * (conj ? conj(H) : H)[perm(py)][perm(px)].  Use scale = 1/P^2 for a propagation step. */
 int adm_prepare_transfer_function(int P, const float* H, int conj, float scale, float* out, void* stream);
+
+/* Separable transfer function H[ky][kx] = hy[ky] * hx[kx] (the paraxial Fresnel kernel of propagate.py:72 is
+ * separable; the non-paraxial one of :76-80 is not): hy, hx are [P][2] in natural fftfreq order;
+ * out [2][P][2] = (hy | scale * hx) permuted (and conjugated if conj).  The kernels then keep H in two P-entry
+ * shared-memory tables (warp-broadcast reads) instead of reading P^2 values per slice.                        */
+int adm_prepare_transfer_function_separable(int P, const float* hy, const float* hx, int conj, float scale, float* out,
+                                            void* stream);
 
 /* Row pitch (in complex voxels) of the transmission volume and of its gradient: X rounded up to even, because the
  * TMA tile loads / reduce-stores need a row pitch that is a multiple of 16 bytes.                             */

@@ -31,7 +31,7 @@ def ck(rc):
 
 def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *, unknown_type='delta_beta',
                        free_prop='inf', sign_convention=1, normalize_fft=False, loss='lsq', raw_data_type='magnitude',
-                       poisson_multiplier=1.0, shift=None, reg=None, Hfree=None):
+                       poisson_multiplier=1.0, shift=None, reg=None, Hfree=None, separable=False):
     L = emu()
     Y, X, Z, _ = obj.shape
     M, Pp, _ = probe_real.shape
@@ -56,6 +56,17 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
     Hc = np.zeros_like(Hn)
     ck(L.adm_prepare_transfer_function(Pp, P(Hn), 0, 1.0 / (Pp * Pp), P(Hp), None))
     ck(L.adm_prepare_transfer_function(Pp, P(Hn), 1, 1.0 / (Pp * Pp), P(Hc), None))
+    hsep = 0
+    if separable:
+        hsep = 1
+        hy = H[:, 0].copy()
+        hx = H[0, :] / H[0, 0]
+        assert np.abs(np.outer(hy, hx) - H).max() < 1e-9
+        f = lambda v: np.ascontiguousarray(np.stack([v.real, v.imag], -1), dtype='float32')
+        Hp = np.zeros((2, Pp, 2), 'float32')
+        Hc = np.zeros((2, Pp, 2), 'float32')
+        ck(L.adm_prepare_transfer_function_separable(Pp, P(f(hy)), P(f(hx)), 0, 1.0 / (Pp * Pp), P(Hp), None))
+        ck(L.adm_prepare_transfer_function_separable(Pp, P(f(hy)), P(f(hx)), 1, 1.0 / (Pp * Pp), P(Hc), None))
     Hfp = Hfc = None
     fp = {'none': 0, 'inf': 1, 'near': 2}[free_prop]
     if fp == 2:
@@ -65,7 +76,7 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
         ck(L.adm_prepare_transfer_function(Pp, P(Hf), 1, 1.0 / (Pp * Pp), P(Hfc), None))
     cfg = MultisliceCfg(P=Pp, n_slices=Z, B=B, M=M, Y=Y, X=X, k1=float(np.float32(k1)), sign_convention=sign_convention,
                         unknown_type=0 if unknown_type == 'delta_beta' else 1, free_prop=fp,
-                        normalize_fft=int(normalize_fft), probe_per_pattern=ppp)
+                        normalize_fft=int(normalize_fft), probe_per_pattern=ppp, h_separable=hsep)
     posi = np.ascontiguousarray(pos, dtype='int32')
     ckpt = np.full((B, M, Z, Pp, Pp + 2, 2), np.nan, 'float32')
     det = np.zeros((B, M, Pp, Pp, 2), 'float32')
