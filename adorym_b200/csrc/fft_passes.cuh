@@ -3,7 +3,7 @@
 #pragma once
 #include "adm_common.cuh"
 
-template <int P_, int R2_, int Q_> struct MsCfg {
+template <int P_, int R2_, int Q_, bool PFA_ = false> struct MsCfg {
     static constexpr int P = P_;
     static constexpr int R1 = 8;
     static constexpr int R2 = R2_;
@@ -11,134 +11,182 @@ template <int P_, int R2_, int Q_> struct MsCfg {
     static constexpr int S = P_ + 1;        // psi row stride (complex)
     static constexpr int NACT = P_ * Q_;    // active threads
     static constexpr int NTHREADS = ((P_ * Q_ + 31) / 32) * 32;
-    static constexpr size_t SMEM = sizeof(cpx) * (size_t)(P_ * (P_ + 1) + P_ * P_ + P_);
+    static constexpr int NGA = (R2_ + Q_ - 1) / Q_;   // A-type groups per thread (radix-8 butterflies, R2 groups per line)
+    static constexpr int NGB = (8 + Q_ - 1) / Q_;     // B-type groups per thread (radix-R2 butterflies, 8 groups per line)
+    // Good-Thomas prime-factor indexing (8 and 9 are coprime): NO twiddle factors between the radix-8 and radix-9
+    // stages; only the index maps change (see Idx below).  P = 64 = 8 * 8 keeps Cooley-Tukey + twiddles.
+    static constexpr bool PFA = PFA_;
     static_assert(P_ == 8 * R2_, "P = 8 * R2");
+    static_assert(!PFA_ || (R2_ == 9 && Q_ == 3), "prime-factor path: P = 72, three thread rows");
 };
+
+// ---- index maps -------------------------------------------------------------------------------------------------
+// Along one axis a line of P points is processed by "A" butterflies (radix 8 over a, for fixed b) and "B" butterflies
+// (radix R2 over b, for fixed a); thread row q owns the groups q, q + Q, q + 2Q, ...
+//   Cooley-Tukey : position(a, b) = R2 a + b                (real space natural, spectrum X[a + 8 b] at R2 a + b)
+//   prime factor : position(a, b) = (9 a + 8 b) mod 72      (real space natural, spectrum X[(9 a + 64 b) mod 72])
+// For the prime-factor map the position of element e of group gi is c(e, gi) + r(q) (mod 72) with a compile-time c
+// and r in {0, u, 2u} (u = 8 for A, 9 for B): the wrap-around is folded into three per-thread offsets selected at
+// compile time by the range of c, so the unrolled butterflies address shared memory with immediate offsets only.
+template <class C> struct Idx {
+    int q, oa0, oa1, oa2, ob0, ob1, ob2;
+    ADM_HDM explicit Idx(int q_) : q(q_), oa0(0), oa1(0), oa2(0), ob0(0), ob1(0), ob2(0) {
+        if constexpr (C::PFA) {
+            const int ra = 8 * q, rb = 9 * q;
+            oa0 = ra; oa1 = ra - (ra >= 16 ? 72 : 0); oa2 = ra - (ra >= 8 ? 72 : 0);
+            ob0 = rb; ob1 = rb - (rb >= 18 ? 72 : 0); ob2 = rb - (rb >= 9 ? 72 : 0);
+        }
+    }
+    // group owned by this thread (b for A-type, a for B-type)
+    ADM_HDM int group(int gi) const { return q + C::Q * gi; }
+    // position of element j (0..7) of the gi-th A-type group
+    ADM_HDM int a(int j, int gi) const {
+        if constexpr (C::PFA) {
+            const int c = (9 * j + 8 * C::Q * gi) % 72;
+            return c + (c < 56 ? oa0 : (c < 64 ? oa1 : oa2));
+        } else {
+            return C::R2 * j + (q + C::Q * gi);
+        }
+    }
+    // position of element n (0..R2-1) of the gi-th B-type group
+    ADM_HDM int b(int n, int gi) const {
+        if constexpr (C::PFA) {
+            const int c = (8 * n + 9 * C::Q * gi) % 72;
+            return c + (c < 54 ? ob0 : (c < 63 ? ob1 : ob2));
+        } else {
+            return C::R2 * (q + C::Q * gi) + n;
+        }
+    }
+};
+
+// frequency index held at spectrum position p
+template <class C> ADM_DEV int perm_freq(int p) {
+    if constexpr (C::PFA) {
+        const int k1 = p % 8, k2 = (9 - p % 9) % 9;
+        return (9 * k1 + 64 * k2) % 72;
+    } else {
+        return p / C::R2 + C::R1 * (p % C::R2);
+    }
+}
 
 // ---- generic passes over the shared-memory wavefield -----------------------------------------------
 // y-direction passes: lanes along x (l = column).  x-direction passes: lanes along y (l = row).
 template <class C, bool XDIR> ADM_DEV int addr(int l, int along) {
     return XDIR ? l * C::S + along : along * C::S + l;
 }
+#define ADM_FOR_GROUPS_A(gi) _Pragma("unroll") for (int gi = 0; gi < C::NGA; ++gi) if ((C::R2 % C::Q) == 0 || I.group(gi) < C::R2)
+#define ADM_FOR_GROUPS_B(gi) _Pragma("unroll") for (int gi = 0; gi < C::NGB; ++gi) if ((C::R1 % C::Q) == 0 || I.group(gi) < C::R1)
 
-// pass A (forward radix-8 + twiddle) along one direction
+// pass A (forward radix-8 [+ twiddle]) along one direction
 template <class C, bool XDIR> ADM_DEV void pass_A_fwd(cpx* psi, const cpx* tw, int q, int l) {
-#pragma unroll
-    for (int gi = 0; gi < (C::R2 + C::Q - 1) / C::Q; ++gi) {
-        const int g = q + gi * C::Q;
-        if ((C::R2 % C::Q) != 0 && g >= C::R2) break;
+    const Idx<C> I(q);
+    ADM_FOR_GROUPS_A(gi) {
         cpx v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = psi[addr<C, XDIR>(l, C::R2 * j + g)];
+        for (int j = 0; j < 8; ++j) v[j] = psi[addr<C, XDIR>(l, I.a(j, gi))];
         dft8<false>(v);
+        if constexpr (!C::PFA) {
 #pragma unroll
-        for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+            for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[I.group(gi) * k]);
+        }
 #pragma unroll
-        for (int k = 0; k < 8; ++k) psi[addr<C, XDIR>(l, C::R2 * k + g)] = v[k];
+        for (int k = 0; k < 8; ++k) psi[addr<C, XDIR>(l, I.a(k, gi))] = v[k];
     }
 }
 // pass A^-1 (inverse radix-8), no twiddle (applied by B^-1)
 template <class C, bool XDIR> ADM_DEV void pass_A_inv(cpx* psi, int q, int l) {
-#pragma unroll
-    for (int gi = 0; gi < (C::R2 + C::Q - 1) / C::Q; ++gi) {
-        const int g = q + gi * C::Q;
-        if ((C::R2 % C::Q) != 0 && g >= C::R2) break;
+    const Idx<C> I(q);
+    ADM_FOR_GROUPS_A(gi) {
         cpx v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = psi[addr<C, XDIR>(l, C::R2 * j + g)];
+        for (int j = 0; j < 8; ++j) v[j] = psi[addr<C, XDIR>(l, I.a(j, gi))];
         dft8<true>(v);
 #pragma unroll
-        for (int k = 0; k < 8; ++k) psi[addr<C, XDIR>(l, C::R2 * k + g)] = v[k];
+        for (int k = 0; k < 8; ++k) psi[addr<C, XDIR>(l, I.a(k, gi))] = v[k];
     }
 }
-// pass B forward (radix-R2 over the contiguous index)
+// pass B forward (radix-R2)
 template <class C, bool XDIR> ADM_DEV void pass_B_fwd(cpx* psi, int q, int l) {
-#pragma unroll
-    for (int gi = 0; gi < (C::R1 + C::Q - 1) / C::Q; ++gi) {
-        const int g = q + gi * C::Q;
-        if ((C::R1 % C::Q) != 0 && g >= C::R1) break;
+    const Idx<C> I(q);
+    ADM_FOR_GROUPS_B(gi) {
         cpx v[C::R2];
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) v[n] = psi[addr<C, XDIR>(l, C::R2 * g + n)];
+        for (int n = 0; n < C::R2; ++n) v[n] = psi[addr<C, XDIR>(l, I.b(n, gi))];
         DftR<C::R2, false>::run(v);
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) psi[addr<C, XDIR>(l, C::R2 * g + n)] = v[n];
+        for (int n = 0; n < C::R2; ++n) psi[addr<C, XDIR>(l, I.b(n, gi))] = v[n];
     }
 }
-// pass B^-1 (inverse radix-R2 + conjugate twiddle)
+// pass B^-1 (inverse radix-R2 [+ conjugate twiddle])
 template <class C, bool XDIR> ADM_DEV void pass_B_inv(cpx* psi, const cpx* tw, int q, int l) {
-#pragma unroll
-    for (int gi = 0; gi < (C::R1 + C::Q - 1) / C::Q; ++gi) {
-        const int g = q + gi * C::Q;
-        if ((C::R1 % C::Q) != 0 && g >= C::R1) break;
+    const Idx<C> I(q);
+    ADM_FOR_GROUPS_B(gi) {
         cpx v[C::R2];
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) v[n] = psi[addr<C, XDIR>(l, C::R2 * g + n)];
+        for (int n = 0; n < C::R2; ++n) v[n] = psi[addr<C, XDIR>(l, I.b(n, gi))];
         DftR<C::R2, true>::run(v);
+        if constexpr (!C::PFA) {
 #pragma unroll
-        for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[g * n]);
+            for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[I.group(gi) * n]);
+        }
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) psi[addr<C, XDIR>(l, C::R2 * g + n)] = v[n];
+        for (int n = 0; n < C::R2; ++n) psi[addr<C, XDIR>(l, I.b(n, gi))] = v[n];
     }
 }
 // P4: pass B forward, multiply by the prepared transfer function, pass B^-1 (x direction, lanes along y)
 template <class C> ADM_DEV void pass_BHB_x(cpx* psi, const cpx* tw, const cpx* __restrict__ H, int q, int l) {
-#pragma unroll
-    for (int gi = 0; gi < (C::R1 + C::Q - 1) / C::Q; ++gi) {
-        const int g = q + gi * C::Q;
-        if ((C::R1 % C::Q) != 0 && g >= C::R1) break;
+    const Idx<C> I(q);
+    ADM_FOR_GROUPS_B(gi) {
         cpx v[C::R2];
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + C::R2 * g + n];
+        for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + I.b(n, gi)];
         DftR<C::R2, false>::run(v);
 #pragma unroll
-        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], H[(C::R2 * g + k) * C::P + l]);
+        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], H[I.b(k, gi) * C::P + l]);
         DftR<C::R2, true>::run(v);
+        if constexpr (!C::PFA) {
 #pragma unroll
-        for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[g * n]);
+            for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[I.group(gi) * n]);
+        }
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) psi[l * C::S + C::R2 * g + n] = v[n];
+        for (int n = 0; n < C::R2; ++n) psi[l * C::S + I.b(n, gi)] = v[n];
     }
 }
 
 // ---- separable transfer function H(ky, kx) = hy(ky) hx(kx) (Fresnel kernel, propagate.py:72) -----------------------
-// hys / hxs are P-entry shared-memory tables in the permuted spectrum order (hxs carries the 1/P^2 scale); every lane
-// of a warp reads the same entry (broadcast), so H costs no global / L1 traffic in the slice loop.
+// hys / hxs are P-entry shared-memory tables indexed by spectrum position (hxs carries the 1/P^2 scale); the lanes of a
+// warp read the same few entries (broadcast), so H costs no global / L1 traffic in the slice loop.
 // pass B forward along y with the hy factor applied to the outputs
 template <class C> ADM_DEV void pass_B_fwd_y_scaled(cpx* psi, const cpx* hys, int q, int l) {
-#pragma unroll
-    for (int gi = 0; gi < (C::R1 + C::Q - 1) / C::Q; ++gi) {
-        const int g = q + gi * C::Q;
-        if ((C::R1 % C::Q) != 0 && g >= C::R1) break;
+    const Idx<C> I(q);
+    ADM_FOR_GROUPS_B(gi) {
         cpx v[C::R2];
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) v[n] = psi[(C::R2 * g + n) * C::S + l];
+        for (int n = 0; n < C::R2; ++n) v[n] = psi[I.b(n, gi) * C::S + l];
         DftR<C::R2, false>::run(v);
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) psi[(C::R2 * g + n) * C::S + l] = cmul(v[n], hys[C::R2 * g + n]);
+        for (int n = 0; n < C::R2; ++n) psi[I.b(n, gi) * C::S + l] = cmul(v[n], hys[I.b(n, gi)]);
     }
 }
 // P4 with the hx factor
 template <class C> ADM_DEV void pass_BHB_x_sep(cpx* psi, const cpx* tw, const cpx* hxs, int q, int l) {
-#pragma unroll
-    for (int gi = 0; gi < (C::R1 + C::Q - 1) / C::Q; ++gi) {
-        const int g = q + gi * C::Q;
-        if ((C::R1 % C::Q) != 0 && g >= C::R1) break;
+    const Idx<C> I(q);
+    ADM_FOR_GROUPS_B(gi) {
         cpx v[C::R2];
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + C::R2 * g + n];
+        for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + I.b(n, gi)];
         DftR<C::R2, false>::run(v);
 #pragma unroll
-        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], hxs[C::R2 * g + k]);
+        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], hxs[I.b(k, gi)]);
         DftR<C::R2, true>::run(v);
+        if constexpr (!C::PFA) {
 #pragma unroll
-        for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[g * n]);
+            for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[I.group(gi) * n]);
+        }
 #pragma unroll
-        for (int n = 0; n < C::R2; ++n) psi[l * C::S + C::R2 * g + n] = v[n];
+        for (int n = 0; n < C::R2; ++n) psi[l * C::S + I.b(n, gi)] = v[n];
     }
 }
-
-template <class C> ADM_DEV int perm_freq(int p) { return p / C::R2 + C::R1 * (p % C::R2); }
 
 template <class C> ADM_DEV void init_twiddles(cpx* tw, int t) {
     if (t < C::P) {
@@ -183,11 +231,9 @@ template <class C> ADM_DEV void propagate_core_sep(cpx* psi, const cpx* tw, cons
     __syncthreads();
 }
 
-typedef MsCfg<72, 9, 3> Cfg72;
+typedef MsCfg<72, 9, 3, true> Cfg72;     // prime-factor indexing, no twiddles
+typedef MsCfg<72, 9, 3, false> Cfg72ct;  // Cooley-Tukey variant of the same shape (tuning / cross-check)
 typedef MsCfg<64, 8, 4> Cfg64;
-// "wide" shapes: one butterfly group per thread (three times the warps, a third of the work per thread)
-typedef MsCfg<72, 9, 9> Cfg72w;
-typedef MsCfg<64, 8, 8> Cfg64w;
 
 #ifndef ADM_HOST_EMU
 #define ADM_LAUNCH(kern, grid, block, smem, stream, ...)                                         \

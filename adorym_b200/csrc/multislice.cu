@@ -88,6 +88,7 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
+    const Idx<C> I(q);
     const int wf = blockIdx.x;              // wavefield index b * M + m
     const int b = wf / p.M, m = wf % p.M;
     const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
@@ -111,21 +112,20 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
         // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
         if (active) {
             mbar_wait(bar, z & 1);
-#pragma unroll
-            for (int gi = 0; gi < R2 / C::Q; ++gi) {
-                const int g = q + gi * C::Q;
+            ADM_FOR_GROUPS_A(gi) {
+                const int g = I.group(gi);
                 cpx v[8];
                 if (z == 0) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = probe[(R2 * j + g) * P + l];
+                    for (int j = 0; j < 8; ++j) v[j] = probe[I.a(j, gi) * P + l];
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = psi[(R2 * j + g) * S + l];
+                    for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
                     dft8<true>(v);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int y = R2 * j + g;
+                    const int y = I.a(j, gi);
                     ckpt[(size_t)z * P * TP + y * TP + lt] = v[j];
                     v[j] = modulate(v[j], tile[y * TP + lt]);
                 }
@@ -135,13 +135,15 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
                         for (int j = 0; j < 8; ++j) v[j] = cconj(v[j]);
                     }
                     dft8<false>(v);
+                    if constexpr (!C::PFA) {
 #pragma unroll
-                    for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+                        for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+                    }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) psi[(R2 * k + g) * S + l] = v[k];
+                    for (int k = 0; k < 8; ++k) psi[I.a(k, gi) * S + l] = v[k];
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) det[(R2 * j + g) * P + l] = v[j];   // exit wave, natural order
+                    for (int j = 0; j < 8; ++j) det[I.a(j, gi) * P + l] = v[j];   // exit wave, natural order
                 }
             }
         }
@@ -159,14 +161,15 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
             __syncthreads();
             if (active) {
                 const int fy = (perm_freq<C>(l) + P / 2) % P;
-                for (int g = q; g < C::R1; g += C::Q) {
+                ADM_FOR_GROUPS_B(gi) {
+                    const int g = I.group(gi);
                     cpx v[R2];
 #pragma unroll
-                    for (int n = 0; n < R2; ++n) v[n] = psi[l * S + R2 * g + n];
+                    for (int n = 0; n < R2; ++n) v[n] = psi[l * S + I.b(n, gi)];
                     DftR<R2, false>::run(v);
 #pragma unroll
                     for (int k = 0; k < R2; ++k) {
-                        int fx = (g + C::R1 * k + P / 2) % P;
+                        int fx = (perm_freq<C>(I.b(k, gi)) + P / 2) % P;
                         cpx o = cscale(v[k], p.ff_scale);
                         det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
                     }
@@ -178,15 +181,16 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
         else propagate_core<C>(psi, tw, last ? p.Hf : p.Hp, q, l, active);
         if (last) {
             // near field: final Ay^-1, natural order store
-            if (active)
-                for (int g = q; g < R2; g += C::Q) {
+            if (active) {
+                ADM_FOR_GROUPS_A(gi) {
                     cpx v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = psi[(R2 * j + g) * S + l];
+                    for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
                     dft8<true>(v);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) det[(R2 * j + g) * P + l] = v[j];
+                    for (int j = 0; j < 8; ++j) det[I.a(j, gi) * P + l] = v[j];
                 }
+            }
         }
     }
 }
@@ -207,6 +211,7 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
+    const Idx<C> I(q);
     const int wf = blockIdx.x;
     const int b = wf / p.M, m = wf % p.M;
     const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
@@ -230,19 +235,22 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
     if (p.free_prop == ADM_PROP_FAR) {
         if (active) {
             const int fy = (perm_freq<C>(l) + P / 2) % P;
-            for (int g = q; g < C::R1; g += C::Q) {
+            ADM_FOR_GROUPS_B(gi) {
+                    const int g = I.group(gi);
                 cpx v[R2];
 #pragma unroll
                 for (int k = 0; k < R2; ++k) {
-                    int fx = (g + C::R1 * k + P / 2) % P;
+                    int fx = (perm_freq<C>(I.b(k, gi)) + P / 2) % P;
                     cpx o = cscale(gdet[fy * P + fx], p.ff_scale);
                     v[k] = p.ff_conj ? cconj(o) : o;
                 }
                 DftR<R2, true>::run(v);
+                if constexpr (!C::PFA) {
 #pragma unroll
-                for (int n = 1; n < R2; ++n) v[n] = cmulc(v[n], tw[g * n]);
+                    for (int n = 1; n < R2; ++n) v[n] = cmulc(v[n], tw[g * n]);
+                }
 #pragma unroll
-                for (int n = 0; n < R2; ++n) psi[l * S + R2 * g + n] = v[n];
+                for (int n = 0; n < R2; ++n) psi[l * S + I.b(n, gi)] = v[n];
             }
         }
         __syncthreads();
@@ -251,17 +259,21 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
         if (active) pass_B_inv<C, false>(psi, tw, q, l);
         __syncthreads();
     } else if (p.free_prop == ADM_PROP_NEAR) {
-        if (active)
-            for (int g = q; g < R2; g += C::Q) {
+        if (active) {
+            ADM_FOR_GROUPS_A(gi) {
+                const int g = I.group(gi);
                 cpx v[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gdet[(R2 * j + g) * P + l];
+                for (int j = 0; j < 8; ++j) v[j] = gdet[I.a(j, gi) * P + l];
                 dft8<false>(v);
+                if constexpr (!C::PFA) {
 #pragma unroll
-                for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+                    for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+                }
 #pragma unroll
-                for (int k = 0; k < 8; ++k) psi[(R2 * k + g) * S + l] = v[k];
+                for (int k = 0; k < 8; ++k) psi[I.a(k, gi) * S + l] = v[k];
             }
+        }
         __syncthreads();
         propagate_core<C>(psi, tw, p.Hf, q, l, active);
     }
@@ -271,23 +283,22 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
         const bool last = (z == p.Nz - 1);
         // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] ------------------------------
         if (active) {
-#pragma unroll
-            for (int gi = 0; gi < R2 / C::Q; ++gi) {
-                const int g = q + gi * C::Q;
+            ADM_FOR_GROUPS_A(gi) {
+                const int g = I.group(gi);
                 cpx v[8], tp[8];
                 // T' of this slice (L2-resident volume; issued first so the butterfly hides the latency)
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int gy = py + R2 * j + g;
+                    const int gy = py + I.a(j, gi);
                     const bool inb = x_in && gy >= 0 && gy < p.Y;
                     tp[j] = inb ? p.tvol[(size_t)z * slice_stride + (size_t)gy * p.Xp + gx] : mk(0.f, 0.f);
                 }
                 if (last && p.free_prop == ADM_PROP_NONE) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = gdet[(R2 * j + g) * P + l];
+                    for (int j = 0; j < 8; ++j) v[j] = gdet[I.a(j, gi) * P + l];
                 } else {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = psi[(R2 * j + g) * S + l];
+                    for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
                     dft8<true>(v);
                     if (last && p.ff_conj) {
 #pragma unroll
@@ -301,25 +312,27 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    const int y = R2 * j + g;
+                    const int y = I.a(j, gi);
                     const cpx w = ckb[y * TP + lt];               // psi_z (wave entering the slice)
                     ckb[y * TP + lt] = cmulc(v[j], w);            // dL/dT = g' conj(psi_z)
                     v[j] = modulate_conj(v[j], tp[j]);            // g_psi = g' conj(T)
                 }
                 if (z > 0) {
                     dft8<false>(v);
+                    if constexpr (!C::PFA) {
 #pragma unroll
-                    for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+                        for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+                    }
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) psi[(R2 * k + g) * S + l] = v[k];
+                    for (int k = 0; k < 8; ++k) psi[I.a(k, gi) * S + l] = v[k];
                 } else if (p.g_probe != nullptr) {
                     if (p.probe_per_pattern) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) p.g_probe[(size_t)wf * P * P + (R2 * j + g) * P + l] = v[j];
+                        for (int j = 0; j < 8; ++j) p.g_probe[(size_t)wf * P * P + I.a(j, gi) * P + l] = v[j];
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            red_add2(&p.g_probe[(size_t)m * P * P + (R2 * j + g) * P + l], v[j].x, v[j].y);
+                            red_add2(&p.g_probe[(size_t)m * P * P + I.a(j, gi) * P + l], v[j].x, v[j].y);
                     }
                 }
             }
@@ -442,13 +455,10 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
         ADM_LAUNCH((k_multislice_fwd<CFG, MINB>), nwf, CFG::NTHREADS, MsSmem<CFG>::BYTES, stream, map, p);         \
     } while (0)
     if (cfg->P == 72) {
-        if (var == 1) ADM_FWD(Cfg72w, 1);
-        else if (var == 2) ADM_FWD(Cfg72w, 2);
+        if (var == 1) ADM_FWD(Cfg72ct, 2);
         else ADM_FWD(Cfg72, 2);
     } else {
-        if (var == 1) ADM_FWD(Cfg64w, 1);
-        else if (var == 2) ADM_FWD(Cfg64w, 2);
-        else ADM_FWD(Cfg64, 2);
+        ADM_FWD(Cfg64, 2);
     }
     return ADM_OK;
 }
@@ -477,13 +487,10 @@ extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tv
         ADM_LAUNCH((k_multislice_bwd<CFG, MINB>), nwf, CFG::NTHREADS, MsSmem<CFG>::BYTES, stream, map, p);         \
     } while (0)
     if (cfg->P == 72) {
-        if (var == 1) ADM_BWD(Cfg72w, 1);
-        else if (var == 2) ADM_BWD(Cfg72w, 2);
+        if (var == 1) ADM_BWD(Cfg72ct, 2);
         else ADM_BWD(Cfg72, 2);
     } else {
-        if (var == 1) ADM_BWD(Cfg64w, 1);
-        else if (var == 2) ADM_BWD(Cfg64w, 2);
-        else ADM_BWD(Cfg64, 2);
+        ADM_BWD(Cfg64, 2);
     }
     return ADM_OK;
 }
