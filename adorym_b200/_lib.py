@@ -22,6 +22,15 @@ class MultisliceCfg(ctypes.Structure):
 
 P_CFG = ctypes.POINTER(MultisliceCfg)
 
+
+class MultiDistCfg(ctypes.Structure):
+    """struct adm_multidist_cfg (include/adorym_b200.h)."""
+    _fields_ = [('N', c_int), ('M', c_int), ('D', c_int), ('k1', c_float), ('sign_convention', c_int),
+                ('unknown_type', c_int)]
+
+
+P_MDCFG = ctypes.POINTER(MultiDistCfg)
+
 # name -> argtypes; every entry point returns int (0 = ok).  Must list every symbol of include/adorym_b200.h.
 SIGNATURES = {
     'adm_abi_version': [],
@@ -42,6 +51,15 @@ SIGNATURES = {
                              c_void_p],
     'adm_probe_shift_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_probe_shift_bwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_lf_supported': [c_int],
+    'adm_lf_spectrum_order': [c_int, c_void_p],
+    'adm_multidist_fwd': [P_MDCFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_multidist_bwd': [P_MDCFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                          c_void_p],
+    'adm_frame_shift_fwd': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_frame_shift_bwd': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_detector_loss_large': [c_int, c_int, c_longlong, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
 }
 
 ERRORS = {1: 'bad argument', 2: 'unsupported configuration', 3: 'CUDA launch error'}
@@ -69,7 +87,7 @@ def get_lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('adorym_b200: CUDA library %s is missing; run `python -m adorym_b200.build`' % LIB_PATH)
         _lib = bind(ctypes.CDLL(LIB_PATH))
-        if _lib.adm_abi_version() != 2:
+        if _lib.adm_abi_version() != 3:
             raise RuntimeError('adorym_b200: ABI version mismatch')
     return _lib
 

@@ -326,8 +326,13 @@ class SingleBatchFullfieldModel(PtychographyModel):
 class MultiDistModel(ForwardModel):
     """adorym/forward_model.py:809-1092: one thin object, several near-field propagation distances.
 
-    Accelerated for the single-block case (n_blocks == 1, safe_zone_width == 0, forward_algorithm == 'fresnel')
-    with frame sizes the shared-memory FFT supports; everything else raises NotImplementedError."""
+    Accelerated for the single-block case (n_blocks == 1, safe_zone_width == 0, forward_algorithm == 'fresnel'):
+      * frames of 128 .. 2048 pixels per side (power of two), one object slice: the large-frame kernels
+        (ops.MultiDistFn: FFT2 of the modulated probe once for all distances, adjoint summed over distances in Fourier
+        space), incl. the refinable per-distance shift of the measured frames (forward_model.py:1079-1088,
+        ops.FrameShiftFn);
+      * frames the shared-memory FFT holds (64, 72): the multislice kernels, one call per distance.
+    Everything else raises NotImplementedError."""
 
     def __init__(self, loss_function_type='lsq', distribution_mode=None, device=None, common_vars_dict=None,
                  raw_data_type='magnitude', simulation_mode=False, *args, **kwargs):
@@ -336,12 +341,27 @@ class MultiDistModel(ForwardModel):
         a = inspect.getfullargspec(self.predict).args
         a.pop(0)
         self.argument_ls = a
+        self._md_plans = {}
+
+    def _md_plan(self, dev, N, dists):
+        cv = self.common_vars
+        key = (N, tuple(dists), str(dev))
+        plan = self._md_plans.get(key)
+        if plan is None:
+            psize_cm = cv['psize_cm'] * cv.get('ds_level', 1)
+            voxel_nm = np.array([psize_cm] * 3) * 1.e7
+            # fresnel_propagate (propagate.py:537-553): always the paraxial kernel (quirk 10), built in float64
+            hs = [get_kernel(d * 1e7, 1240. / cv['energy_ev'], voxel_nm, [N, N], sign_convention=self.sign_convention)
+                  for d in dists]
+            plan = ops.MultiDistPlan(N, hs, ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k), dev,
+                                     sign_convention=self.sign_convention, unknown_type=self.unknown_type)
+            self._md_plans[key] = plan
+        return plan
 
     def _detector_fields(self, obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj):
         cv = self.common_vars
         self._check_unsupported(['optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
-                                 'optimize_all_probe_pos', 'optimize_free_prop', 'optimize_prj_affine',
-                                 'optimize_ctf_lg_kappa'])
+                                 'optimize_free_prop', 'optimize_prj_affine', 'optimize_ctf_lg_kappa'])
         if safe_zone_width not in (0, None):
             raise NotImplementedError('adorym_b200: MultiDistModel with safe_zone_width > 0 is not accelerated yet')
         dists = [float(d) for d in np.asarray(free_prop_cm.detach().cpu() if torch.is_tensor(free_prop_cm) else free_prop_cm)]
@@ -353,10 +373,17 @@ class MultiDistModel(ForwardModel):
         P = this_obj_size[0]
         if this_obj_size[0] != this_obj_size[1]:
             raise NotImplementedError('adorym_b200: only square frames are supported')
-        rot = self._rotated_object(obj, 0)
         probe = torch.stack([probe_real, probe_imag], dim=-1)
         if probe.dim() == 3:
             probe = probe.unsqueeze(0)
+        if ops.lf_supported(P):
+            if this_obj_size[2] != 1 or not cv['two_d_mode']:
+                raise NotImplementedError('adorym_b200: large-frame MultiDistModel needs a single object slice (two_d_mode)')
+            if any(d <= 0 for d in dists):
+                raise NotImplementedError('adorym_b200: MultiDistModel needs positive propagation distances')
+            plan = self._md_plan(dev, P, dists)
+            return ops.MultiDistFn.apply(obj.reshape(P, P, 2), probe, plan)      # [n_dists, M, P, P, 2]
+        rot = self._rotated_object(obj, 0)
         pos_t = torch.zeros((1, 2), dtype=torch.int32, device=dev)
         dets = []
         for d in dists:
@@ -387,5 +414,19 @@ class MultiDistModel(ForwardModel):
             ind = np.asarray(this_ind_batch)
             full = np.concatenate([ind + i * n_blocks for i in range(n_dists)])       # forward_model.py:1058-1061
             this_prj_batch = self.get_data(this_i_theta, full, theta_downsample=theta_downsample, ds_level=1)
+            large = ops.lf_supported(det.shape[2])
+            if self.common_vars.get('optimize_all_probe_pos', False):
+                # per-distance sub-pixel shift of the measured frames, real part kept (forward_model.py:1079-1088)
+                if not large:
+                    raise NotImplementedError('adorym_b200: measured-frame shift refinement needs large-frame sizes')
+                this_prj_batch = ops.FrameShiftFn.apply(this_prj_batch, probe_pos_correction[:n_dists])
+            if large and self.common_vars.get('beamstop', None) is None:
+                loss, pred, lpp = ops.DetectorLossLargeFn.apply(det, this_prj_batch, self.loss_function_type,
+                                                                self.raw_data_type, self.poisson_multiplier)
+                self.last_pred, self.last_loss_per_pattern = pred, lpp
+                if len(self.reg_list) > 0:
+                    loss = loss + self.get_regularization_value(obj, device=self.device)
+                self._current_loss = loss.detach()
+                return loss
             return self._fused_loss(det, this_prj_batch, obj)
         return calculate_loss

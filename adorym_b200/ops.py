@@ -340,3 +340,151 @@ def k1_of(energy_ev, psize_cm, scale_ri_by_k=True, ds_level=1):
         return 1.0
     lmbda_nm = 1240. / energy_ev
     return 2. * PI * (psize_cm * ds_level * 1.e7) / lmbda_nm
+
+
+# ------------------------------------------------------------------------------------------------------
+# large frames: multi-distance near-field propagation of one thin object (MultiDistModel) + measured-frame shift
+# ------------------------------------------------------------------------------------------------------
+_LF_ORDER = {}
+
+
+def lf_supported(N):
+    return bool(_lib.get_lib().adm_lf_supported(int(N)))
+
+
+def lf_spectrum_order(N, device=None):
+    """freq index at each position of the permuted spectrum (host ndarray, or int32 device tensor if device given)."""
+    key = (int(N), str(device))
+    if key not in _LF_ORDER:
+        buf = (ctypes.c_int * int(N))()
+        _lib.check(_lib.get_lib().adm_lf_spectrum_order(int(N), ctypes.cast(buf, ctypes.c_void_p)), 'adm_lf_spectrum_order')
+        order = np.frombuffer(buf, dtype=np.int32).copy()
+        _LF_ORDER[key] = order if device is None else torch.from_numpy(order).to(device)
+    return _LF_ORDER[key]
+
+
+class MultiDistPlan(object):
+    """Prepared transfer functions of all distances for N x N frames: Hprep[d][py][px] = H_d[f(py)][f(px)] / N^2
+    (adm_lf_spectrum_order), plus its conjugate for the adjoint."""
+
+    def __init__(self, N, h_list, k1, device, sign_convention=1, unknown_type='delta_beta'):
+        if not lf_supported(N):
+            raise NotImplementedError('adorym_b200: frame size %d is not supported by the large-frame path' % N)
+        order = lf_spectrum_order(N)
+        hp = []
+        for h in h_list:
+            h = np.asarray(h)
+            if h.shape != (N, N):
+                raise ValueError('transfer function shape %s != (%d, %d)' % (h.shape, N, N))
+            hh = h[np.ix_(order, order)]
+            hp.append(np.stack([hh.real, hh.imag], -1).astype('float32'))      # f64 -> f32 as propagate.py:202-204
+        hp = torch.from_numpy(np.stack(hp)).to(device) * (1.0 / (N * N))
+        self.Hp = hp.contiguous()
+        self.Hc = (hp * torch.tensor([1.0, -1.0], device=device)).contiguous()
+        self.N, self.D = int(N), len(h_list)
+        self.k1, self.sign_convention, self.unknown_type = float(k1), int(sign_convention), UNKNOWN_TYPES[unknown_type]
+        self.device = device
+
+    def cfg(self, M):
+        return _lib.MultiDistCfg(N=self.N, M=int(M), D=self.D, k1=self.k1, sign_convention=self.sign_convention,
+                                 unknown_type=self.unknown_type)
+
+
+class MultiDistFn(torch.autograd.Function):
+    """det[D,M,N,N,2] = IFFT2(H_d . FFT2(probe_m . T(obj))): adm_multidist_fwd / adm_multidist_bwd."""
+
+    @staticmethod
+    def forward(ctx, obj2d, probe, plan):
+        obj2d = _f32c(obj2d)
+        probe = _f32c(probe)
+        N, D = plan.N, plan.D
+        M = probe.shape[0]
+        if tuple(obj2d.shape) != (N, N, 2) or tuple(probe.shape) != (M, N, N, 2):
+            raise RuntimeError('MultiDistFn: obj [N,N,2] / probe [M,N,N,2] expected, got %s / %s'
+                               % (tuple(obj2d.shape), tuple(probe.shape)))
+        dev = obj2d.device
+        cfg = plan.cfg(M)
+        work1 = torch.empty((M, N, N, 2), dtype=torch.float32, device=dev)
+        det = torch.empty((D, M, N, N, 2), dtype=torch.float32, device=dev)
+        call('adm_multidist_fwd', ctypes.byref(cfg), ptr(obj2d), ptr(probe), ptr(plan.Hp), ptr(work1), ptr(det), stream_ptr())
+        ctx.plan, ctx.cfg = plan, cfg
+        ctx.save_for_backward(obj2d, probe)
+        return det
+
+    @staticmethod
+    def backward(ctx, g_det):
+        obj2d, probe = ctx.saved_tensors
+        plan = ctx.plan
+        N, D = plan.N, plan.D
+        M = probe.shape[0]
+        dev = obj2d.device
+        g_det = _f32c(g_det)
+        work1 = torch.empty((M, N, N, 2), dtype=torch.float32, device=dev)
+        work2 = torch.empty((D, M, N, N, 2), dtype=torch.float32, device=dev)
+        g_obj = torch.empty_like(obj2d) if ctx.needs_input_grad[0] else None
+        g_probe = torch.empty_like(probe) if ctx.needs_input_grad[1] else None
+        call('adm_multidist_bwd', ctypes.byref(ctx.cfg), ptr(obj2d), ptr(probe), ptr(plan.Hc), ptr(g_det), ptr(work1),
+             ptr(work2), ptr(g_obj), ptr(g_probe), stream_ptr())
+        return g_obj, g_probe, None
+
+
+class FrameShiftFn(torch.autograd.Function):
+    """out[F,N,N] = Re realign_image_fourier(data[F,N,N], shift[F,2]) (util.py:380-397; forward_model.py:1079-1088)."""
+
+    @staticmethod
+    def forward(ctx, data, shift):
+        data = _f32c(data)
+        shift = _f32c(shift)
+        F, N = data.shape[0], data.shape[1]
+        if not lf_supported(N) or data.shape[2] != N:
+            raise NotImplementedError('adorym_b200: frame shift of %s frames' % (tuple(data.shape),))
+        dev = data.device
+        order = lf_spectrum_order(N, dev)
+        work = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        spec = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        out = torch.empty((F, N, N), dtype=torch.float32, device=dev)
+        call('adm_frame_shift_fwd', N, F, ptr(data), ptr(shift), ptr(order), ptr(work), ptr(spec), ptr(out), stream_ptr())
+        ctx.save_for_backward(spec, order)
+        ctx.dims = (F, N)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        spec, order = ctx.saved_tensors
+        F, N = ctx.dims
+        g_out = _f32c(g_out)
+        work = torch.empty((F, N, N, 2), dtype=torch.float32, device=g_out.device)
+        g_shift = torch.zeros((F, 2), dtype=torch.float32, device=g_out.device)
+        call('adm_frame_shift_bwd', N, F, ptr(g_out), ptr(spec), ptr(order), ptr(work), ptr(g_shift), stream_ptr())
+        return None, g_shift
+
+
+class DetectorLossLargeFn(torch.autograd.Function):
+    """Large-frame fused |det| + mismatch loss + residuals (adm_detector_loss_large); also differentiable with respect
+    to the measured frames (refinable data shift).  Returns (loss, pred[B,N,N], loss_per_pattern[B])."""
+
+    @staticmethod
+    def forward(ctx, det, meas, loss_function_type, raw_data_type, poisson_multiplier):
+        det = _f32c(det)
+        meas = _f32c(meas)
+        B, M = det.shape[0], det.shape[1]
+        npix = det.shape[2] * det.shape[3]
+        inv_n = 1.0 / (B * npix)
+        dev = det.device
+        pred = torch.empty((B, det.shape[2], det.shape[3]), dtype=torch.float32, device=dev)
+        lpp = torch.empty((B,), dtype=torch.float32, device=dev)
+        partial = torch.empty((B, 64), dtype=torch.float32, device=dev)
+        g_det = torch.empty_like(det)
+        g_meas = torch.empty_like(meas) if ctx.needs_input_grad[1] else None
+        call('adm_detector_loss_large', B, M, npix, LOSS_TYPES[loss_function_type], RAW_TYPES[raw_data_type],
+             float(poisson_multiplier), inv_n, ptr(det), ptr(meas), ptr(pred), ptr(g_det), ptr(g_meas), ptr(partial),
+             ptr(lpp), stream_ptr())
+        ctx.save_for_backward(g_det, g_meas)
+        loss = lpp.sum() * inv_n
+        ctx.mark_non_differentiable(pred, lpp)
+        return loss, pred, lpp
+
+    @staticmethod
+    def backward(ctx, g_loss, g_pred, g_lpp):
+        g_det, g_meas = ctx.saved_tensors
+        return g_det * g_loss, (g_meas * g_loss if g_meas is not None else None), None, None, None

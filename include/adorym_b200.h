@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ADM_ABI_VERSION 2
+#define ADM_ABI_VERSION 3
 
 /* unknown_type */
 #define ADM_DELTA_BETA 0
@@ -167,6 +167,52 @@ int adm_probe_shift_fwd(int B, int M, int P, const float* probe, const float* sh
 /* Transpose: g_probe [M][P][P][2] += sum_b S_b^H g_out[b];  g_shift [B][2] += dL/d(shift) (accumulated over modes; zero it first).        */
 int adm_probe_shift_bwd(int B, int M, int P, const float* probe, const float* shift, const float* g_out,
                         float* g_probe, float* g_shift, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Large-frame near-field path: MultiDistModel (adorym/forward_model.py:819-1092) on frames of N = 128 .. 2048 pixels
+ * per side (power of two), one thin object slice, D propagation distances, M probe modes.  Replaces, per distance and
+ * mode, multislice_propagate_batch with n_slices == 1 + fresnel_propagate (propagate.py:131-288, :537-553).
+ * --------------------------------------------------------------------------------------------------------------- */
+typedef struct adm_multidist_cfg {
+    int N;               /* frame edge; adm_lf_supported(N) != 0                                              */
+    int M;               /* probe modes                                                                        */
+    int D;               /* propagation distances                                                              */
+    float k1;            /* as adm_multislice_cfg.k1                                                           */
+    int sign_convention; /* +1 / -1                                                                            */
+    int unknown_type;    /* ADM_DELTA_BETA / ADM_REAL_IMAG                                                     */
+} adm_multidist_cfg;
+
+/* 1 if frames of edge N are handled by the large-frame kernels. */
+int adm_lf_supported(int N);
+/* HOST array freq_of_pos[N]: numpy-fftfreq index held at each position of the (digit-reversed) spectrum the large-frame
+ * FFT passes leave in place.  A transfer function H[ky][kx] (propagate.py:62-81) is prepared for the kernels as
+ * Hprep[py][px] = H[freq_of_pos[py]][freq_of_pos[px]] / N^2 (conjugated for the adjoint).                     */
+int adm_lf_spectrum_order(int N, int* freq_of_pos);
+/* det[d][m] = IFFT2(H_d . FFT2(probe_m . T(obj)))  for all d, m.
+ *   obj [N][N][2]; probe [M][N][N][2]; Hprep [D][N][N][2]; work1 [M][N][N][2]; det [D][M][N][N][2] out.       */
+int adm_multidist_fwd(const adm_multidist_cfg* cfg, const float* obj, const float* probe, const float* Hprep,
+                      float* work1, float* det, void* stream);
+/* Analytic adjoint: g_det [D][M][N][N][2] -> g_obj [N][N][2] WRITTEN (chain rule to (delta, beta) included; may be
+ * NULL), g_probe [M][N][N][2] WRITTEN (may be NULL).  HprepC = conj of Hprep; work1 [M][N][N][2], work2 [D][M][N][N][2]. */
+int adm_multidist_bwd(const adm_multidist_cfg* cfg, const float* obj, const float* probe, const float* HprepC,
+                      const float* g_det, float* work1, float* work2, float* g_obj, float* g_probe, void* stream);
+/* Sub-pixel Fourier shift of measured frames (util.py:380-397 as used on the data at forward_model.py:1079-1088):
+ *   out[f] = Re IFFT2(FFT2(data[f]) exp(-2 pi i (fx sx + fy sy))), shift [frames][2] = (sy, sx).
+ *   order [N] int32 DEVICE copy of adm_lf_spectrum_order; work [frames][N][N][2]; spec [frames][N][N][2] out (the shifted
+ *   spectrum, consumed by adm_frame_shift_bwd); out [frames][N][N].                                           */
+int adm_frame_shift_fwd(int N, int frames, const float* data, const float* shift, const int* order, float* work,
+                        float* spec, float* out, void* stream);
+/* g_shift [frames][2] += d/d(shift) of sum(g_out . out).                                                      */
+int adm_frame_shift_bwd(int N, int frames, const float* g_out, const float* spec, const int* order, float* work,
+                        float* g_shift, void* stream);
+/* adm_detector_loss for large frames (many CTAs per frame, deterministic two-stage sum) that also returns the
+ * derivative with respect to the measured frame (needed when the data are shifted by a refinable offset):
+ *   det [B][M][npix][2]; meas [B][npix] (|.| is applied, forward_model.py:1062); pred [B][npix] out;
+ *   g_det [B][M][npix][2] out or NULL; g_meas [B][npix] out or NULL; partial [B][64] workspace;
+ *   loss_per_pattern [B] out (sum, NOT divided); inv_n = 1 / (B npix) applied to the gradients only.          */
+int adm_detector_loss_large(int B, int M, long long npix, int loss_type, int raw_data_type, float poisson_multiplier,
+                            float inv_n, const float* det, const float* meas, float* pred, float* g_det, float* g_meas,
+                            float* partial, float* loss_per_pattern, void* stream);
 
 #ifdef __cplusplus
 }

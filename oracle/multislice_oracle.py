@@ -400,6 +400,32 @@ def regularization_value(obj, alpha_d=None, alpha_b=None, gamma=None, weight_l1=
     return reg
 
 
+def multidist_loss_and_grads(obj, probe_real, probe_imag, free_prop_cm_ls, prj_abs, cfg, probe_pos_correction=None,
+                             want=('obj',)):
+    """MultiDistModel.get_loss_function (adorym/forward_model.py:1039-1092) for n_blocks == 1, no affine / offset
+    refinement: predict (:819-1037), optional per-distance Fourier shift of the measured frames with the real part
+    kept (:1079-1088, optimize_all_probe_pos; probe_pos_correction is [n_dists, 2]), mismatch loss (:88-103 applies
+    abs() to the -- possibly shifted -- data).  prj_abs [n_dists, P0, P1].  Returns loss, pred, grads."""
+    leaves = {'obj': obj.clone().requires_grad_('obj' in want),
+              'probe_real': probe_real.clone().requires_grad_('probe_real' in want),
+              'probe_imag': probe_imag.clone().requires_grad_('probe_imag' in want)}
+    pred = predict_multidist(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], free_prop_cm_ls, cfg)
+    prj = prj_abs
+    if probe_pos_correction is not None:
+        leaves['probe_pos_correction'] = probe_pos_correction.clone().requires_grad_('probe_pos_correction' in want)
+        out = []
+        for i in range(len(free_prop_cm_ls)):
+            fr = prj_abs[i:i + 1]
+            sh = realign_image_fourier(torch.complex(fr, torch.zeros_like(fr)), leaves['probe_pos_correction'][i],
+                                       axes=(1, 2))
+            out.append(sh.real)
+        prj = torch.cat(out)
+    loss = mismatch_loss(pred, torch.abs(prj), cfg.get('loss_function_type', 'lsq'), cfg.get('raw_data_type', 'magnitude'),
+                         cfg.get('poisson_multiplier', 1.))
+    grads = torch.autograd.grad(loss, [leaves[k] for k in want], allow_unused=True)
+    return loss.detach(), pred.detach(), dict(zip(want, grads))
+
+
 # ----------------------------------------------------------------------------------------------
 # Adam                                                               adorym/optimizers.py:309-318
 # ----------------------------------------------------------------------------------------------

@@ -121,3 +121,60 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
         out['loss'] += float(val[0])
     out['g_obj'] = g_obj
     return out
+
+
+def multidist_loss_and_grads_emu(obj, probe_real, probe_imag, prj_abs, h_list, k1, *, unknown_type='delta_beta',
+                                 loss='lsq', raw_data_type='magnitude', shift=None):
+    """One MultiDistModel loss + gradient evaluation on the host-emulated large-frame kernels, mirroring
+    adorym_b200.ops.MultiDistFn / FrameShiftFn / DetectorLossLargeFn."""
+    from adorym_b200._lib import MultiDistCfg
+    L = emu()
+    N = obj.shape[0]
+    M = probe_real.shape[0]
+    D = len(h_list)
+    order = np.zeros(N, 'int32')
+    ck(L.adm_lf_spectrum_order(N, P(order)))
+    hp = np.stack([np.stack([h[np.ix_(order, order)].real, h[np.ix_(order, order)].imag], -1) for h in h_list])
+    Hp = np.ascontiguousarray(hp.astype('float32') * np.float32(1.0 / (N * N)))
+    Hc = np.ascontiguousarray(Hp * np.array([1, -1], 'float32'))
+    cfg = MultiDistCfg(N=N, M=M, D=D, k1=float(np.float32(k1)), sign_convention=1,
+                       unknown_type=0 if unknown_type == 'delta_beta' else 1)
+    o2 = np.ascontiguousarray(obj.reshape(N, N, 2), dtype='float32')
+    probe = np.ascontiguousarray(np.stack([probe_real, probe_imag], -1), dtype='float32')
+    work1 = np.full((M, N, N, 2), np.nan, 'float32')
+    det = np.full((D, M, N, N, 2), np.nan, 'float32')
+    ck(L.adm_multidist_fwd(ctypes.byref(cfg), P(o2), P(probe), P(Hp), P(work1), P(det), None))
+    meas = np.ascontiguousarray(prj_abs, dtype='float32')
+    out = {}
+    if shift is not None:
+        shift = np.ascontiguousarray(shift, dtype='float32')
+        work = np.full((D, N, N, 2), np.nan, 'float32')
+        spec = np.full((D, N, N, 2), np.nan, 'float32')
+        shifted = np.full((D, N, N), np.nan, 'float32')
+        ck(L.adm_frame_shift_fwd(N, D, P(meas), P(shift), P(order), P(work), P(spec), P(shifted), None))
+        out['shifted'] = shifted
+        meas_in = shifted
+    else:
+        meas_in = meas
+    pred = np.zeros((D, N, N), 'float32')
+    g_det = np.zeros_like(det)
+    g_meas = np.zeros((D, N, N), 'float32')
+    partial = np.zeros((D, 64), 'float32')
+    lpp = np.zeros((D,), 'float32')
+    inv_n = 1.0 / (D * N * N)
+    ck(L.adm_detector_loss_large(D, M, N * N, 0 if loss == 'lsq' else 1, 0 if raw_data_type == 'magnitude' else 1, 1.0,
+                                 inv_n, P(det), P(meas_in), P(pred), P(g_det), P(g_meas), P(partial), P(lpp), None))
+    out['loss'] = float(lpp.astype('float64').sum() * inv_n)
+    out['pred'] = pred
+    work2 = np.full((D, M, N, N, 2), np.nan, 'float32')
+    g_obj = np.full((N, N, 2), np.nan, 'float32')
+    g_probe = np.full((M, N, N, 2), np.nan, 'float32')
+    ck(L.adm_multidist_bwd(ctypes.byref(cfg), P(o2), P(probe), P(Hc), P(g_det), P(work1), P(work2), P(g_obj), P(g_probe), None))
+    out['g_obj'] = g_obj.reshape(obj.shape)
+    out['g_probe_real'] = g_probe[..., 0]
+    out['g_probe_imag'] = g_probe[..., 1]
+    if shift is not None:
+        g_shift = np.zeros((D, 2), 'float32')
+        ck(L.adm_frame_shift_bwd(N, D, P(g_meas), P(spec), P(order), P(work), P(g_shift), None))
+        out['g_shift'] = g_shift
+    return out

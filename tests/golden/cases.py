@@ -108,3 +108,46 @@ def make_inputs(name):
     ind = np.arange(B) + 2 if ppc is not None else np.arange(B)
     return dict(cfg=c, obj=obj, probe_real=pr, probe_imag=pi, pos=pos, prj=prj, probe_pos_correction=ppc,
                 this_ind_batch=ind)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# Multi-distance holography (MultiDistModel, BASELINE config E shape, small frames): one thin object, D distances
+# ---------------------------------------------------------------------------------------------------------
+MD_CASES = {
+    # demos/2d_multidist_holography_w_position_correction.py: real_imag object, plane probe, intensity data, lsq,
+    # refinable per-distance shift of the measured frames
+    'multidist256_shift': dict(N=256, energy_ev=17500., psize_cm=1e-4, dists=[40., 60., 80., 100.], n_modes=1,
+                               unknown_type='real_imag', delta_scale=0.4, beta_scale=0.3, seed=31, loss='lsq',
+                               raw_data_type='intensity', shift=True, optimize_probe=False),
+    # delta_beta object, structured probe, magnitude data, probe gradient (the reference's MultiDistModel indexes the
+    # imaginary probe as [i_mode] on the batch axis, forward_model.py:1005, so it only runs with one mode -- quirk 9)
+    'multidist128_probe': dict(N=128, energy_ev=17500., psize_cm=1e-4, dists=[30., 70.], n_modes=1,
+                               unknown_type='delta_beta', delta_scale=2e-7, beta_scale=2e-8, seed=32, loss='lsq',
+                               raw_data_type='magnitude', shift=False, optimize_probe=True),
+}
+
+
+def make_md_inputs(name):
+    c = dict(MD_CASES[name])
+    rs = np.random.RandomState(c['seed'])
+    N, M, D = c['N'], c['n_modes'], len(c['dists'])
+    if c['unknown_type'] == 'delta_beta':
+        d = _smooth_noise(rs, (N, N, 1), c['delta_scale'])
+        b = _smooth_noise(rs, (N, N, 1), c['beta_scale'])
+        obj = np.stack([d, b], -1).astype('float32')
+    else:
+        mag = 1.0 - _smooth_noise(rs, (N, N, 1), c['delta_scale'])
+        ph = _smooth_noise(rs, (N, N, 1), c['beta_scale'] * 3)
+        obj = np.stack([mag * np.cos(ph), mag * np.sin(ph)], -1).astype('float32')
+    if not c['optimize_probe']:
+        pr = np.ones((1, N, N), 'float32')          # probe_type='plane'
+        pi = np.zeros((1, N, N), 'float32')
+    else:
+        pr = np.stack([1.0 / (1 + m) + 0.2 * _smooth_noise(rs, (N, N), 1.0) for m in range(M)]).astype('float32')
+        pi = np.stack([0.3 * _smooth_noise(rs, (N, N), 1.0) - 0.1 * m for m in range(M)]).astype('float32')
+    amp = float(np.sqrt((pr ** 2 + pi ** 2).sum(0).mean()))
+    prj = (amp * (0.5 + 0.5 * np.stack([_smooth_noise(rs, (N, N), 1.0) for _ in range(D)]))).astype('float32')
+    if c['raw_data_type'] == 'intensity':
+        prj = (prj ** 2).astype('float32')
+    ppc = rs.uniform(-0.8, 0.8, size=(D, 2)).astype('float32') if c['shift'] else None
+    return dict(cfg=c, obj=obj, probe_real=pr, probe_imag=pi, prj=prj, probe_pos_correction=ppc)

@@ -58,3 +58,47 @@ def run_oracle_case(name, dtype=torch.float32):
         torch.tensor(inp['probe_imag']).to(dtype), inp['pos'], torch.tensor(inp['prj']).to(dtype), coord, cfg, reg=reg,
         probe_pos_correction=ppc, this_i_theta=c['i_theta'], this_ind_batch=inp['this_ind_batch'], want=tuple(want))
     return inp, float(loss), pred.numpy(), {k: v.numpy() for k, v in grads.items()}
+
+
+def md_case_cfg(name):
+    from cases import make_md_inputs
+    inp = make_md_inputs(name)
+    c = inp['cfg']
+    N = c['N']
+    cfg = dict(this_obj_size=[N, N, 1], probe_size=[N, N], energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=None,
+               unknown_type=c['unknown_type'], binning=1, sign_convention=1, scale_ri_by_k=True, fresnel_approx=True,
+               two_d_mode=True, loss_function_type=c['loss'], raw_data_type=c['raw_data_type'])
+    return inp, cfg
+
+
+def run_md_oracle_case(name, dtype=torch.float32):
+    """MultiDistModel loss + gradients from the oracle (oracle.multidist_loss_and_grads)."""
+    inp, cfg = md_case_cfg(name)
+    c = inp['cfg']
+    want = ['obj']
+    if c['optimize_probe']:
+        want += ['probe_real', 'probe_imag']
+    ppc = None
+    if inp['probe_pos_correction'] is not None:
+        ppc = torch.tensor(inp['probe_pos_correction']).to(dtype)
+        want += ['probe_pos_correction']
+    loss, pred, grads = orc.multidist_loss_and_grads(
+        torch.tensor(inp['obj']).to(dtype), torch.tensor(inp['probe_real']).to(dtype),
+        torch.tensor(inp['probe_imag']).to(dtype), c['dists'], torch.tensor(inp['prj']).to(dtype), cfg,
+        probe_pos_correction=ppc, want=tuple(want))
+    return inp, float(loss), pred.numpy(), {k: v.numpy() for k, v in grads.items()}
+
+
+def check_md_against_golden(gold, loss, pred, grads, tol=1e-4, gtol=1e-4):
+    """Compare a MultiDist result (full arrays) with the compact golden of make_golden_multidist.py."""
+    assert abs(loss - float(gold['loss'])) <= tol * abs(float(gold['loss']))
+    assert rel_err(pred[:, ::4, ::4], gold['pred_sub']) < tol
+    cg = compact_grad(grads['obj'])
+    assert abs(cg['norm'] - float(gold['gobj_norm'])) <= gtol * float(gold['gobj_norm'])
+    for k in ('proj0', 'proj1', 'proj2', 'sample'):
+        assert rel_err(cg[k], gold['gobj_' + k]) < gtol, k
+    for k in ('probe_real', 'probe_imag'):
+        if 'g_' + k + '_sub' in gold.files:
+            assert rel_err(grads[k][:, ::4, ::4], gold['g_' + k + '_sub']) < gtol, k
+    if 'g_probe_pos_correction' in gold.files:
+        assert rel_err(grads['probe_pos_correction'], gold['g_probe_pos_correction']) < gtol

@@ -61,6 +61,37 @@ def test_emulated_kernels_match_oracle_and_golden(name):
         assert rel_err(out['g_shift'], g_ref) < 1e-4
 
 
+@pytest.mark.parametrize('name', ['multidist128_probe', 'multidist256_shift'])
+def test_emulated_large_frame_kernels_match_oracle_and_golden(name):
+    """MultiDistModel path: large-frame FFT passes (digit-reversed spectrum, H permutation, adjoint summed over
+    distances), measured-frame shift and its gradient, large detector loss -- emulated kernels vs the fp64 oracle and
+    the unmodified reference's golden."""
+    from oracle_util import run_md_oracle_case, check_md_against_golden, md_case_cfg
+    inp, _ = md_case_cfg(name)
+    c = inp['cfg']
+    N = c['N']
+    voxel_nm = np.array([c['psize_cm']] * 3) * 1e7
+    lmbda_nm = 1240. / c['energy_ev']
+    hs = [orc.get_kernel(d * 1e7, lmbda_nm, voxel_nm, [N, N]) for d in c['dists']]
+    k1 = 2. * orc.PI * voxel_nm[-1] / lmbda_nm
+    out = emu_lib.multidist_loss_and_grads_emu(inp['obj'], inp['probe_real'], inp['probe_imag'], inp['prj'], hs, k1,
+                                               unknown_type=c['unknown_type'], loss=c['loss'],
+                                               raw_data_type=c['raw_data_type'], shift=inp['probe_pos_correction'])
+    _, loss, pred, grads = run_md_oracle_case(name, torch.float64)
+    assert abs(out['loss'] - loss) <= 1e-4 * abs(loss)
+    assert rel_err(out['pred'], pred) < 1e-4
+    assert rel_err(out['g_obj'], grads['obj']) < 1e-4
+    mine = {'obj': out['g_obj'], 'probe_real': out['g_probe_real'], 'probe_imag': out['g_probe_imag']}
+    if 'probe_real' in grads:
+        assert rel_err(out['g_probe_real'], grads['probe_real']) < 1e-4
+        assert rel_err(out['g_probe_imag'], grads['probe_imag']) < 1e-4
+    if 'probe_pos_correction' in grads:
+        assert rel_err(out['g_shift'], grads['probe_pos_correction']) < 1e-4
+        mine['probe_pos_correction'] = out['g_shift']
+    gold = np.load(os.path.join(GOLD, name + '.npz'))
+    check_md_against_golden(gold, out['loss'], out['pred'], mine)
+
+
 def test_emulated_adam_matches_reference_golden_bitwise():
     """adm_adam_step follows optimizers.py:309-318 op by op in fp32 (no FMA contraction, true divisions): the emulated
     kernel must reproduce the reference's three-call golden to the last bit (m, v) / 1 ulp (x)."""

@@ -5,8 +5,8 @@ import os
 import numpy as np
 import pytest
 import torch
-from cases import CASES
-from oracle_util import run_oracle_case, compact_grad, rel_err
+from cases import CASES, MD_CASES
+from oracle_util import run_oracle_case, compact_grad, rel_err, run_md_oracle_case, check_md_against_golden
 from oracle import multislice_oracle as orc
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
@@ -30,6 +30,14 @@ def test_oracle_matches_reference_golden(name):
     for k in ('probe_real', 'probe_imag', 'probe_pos_correction'):
         if 'g_' + k in gold.files:
             assert rel_err(grads[k], gold['g_' + k]) < TOL, k
+
+
+@pytest.mark.parametrize('name', sorted(MD_CASES.keys()))
+def test_oracle_multidist_matches_reference_golden(name):
+    """multidist_loss_and_grads vs the unmodified reference's MultiDistModel (make_golden_multidist.py)."""
+    gold = np.load(os.path.join(GOLD, name + '.npz'))
+    inp, loss, pred, grads = run_md_oracle_case(name, torch.float32)
+    check_md_against_golden(gold, loss, pred, grads)
 
 
 def test_oracle_adam_matches_reference_golden():
