@@ -46,49 +46,66 @@ def workload_name(mb):
 # clocks sampler (B200_PROFILING.md "clocks line")
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler(object):
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
-         'clocks_event_reasons.sw_power_cap')
+    """Samples SM clock and throttle reasons DURING the timed region through NVML (nvidia_ml_py) every 20 ms; the
+    nvidia-smi query of the recipe buffers its pipe output and returned no rows for sub-second regions."""
+    BITS = (('hw_slowdown', 0x8), ('hw_thermal_slowdown', 0x40), ('sw_thermal_slowdown', 0x20), ('sw_power_cap', 0x4))
 
     def __init__(self, gpu_index=0):
-        self.rows = []
-        self.proc = None
         self.gpu = gpu_index
+        self.sm, self.reasons, self.smax, self.power = [], set(), None, []
+        self.stop_flag = threading.Event()
+        self.th = None
+        self.err = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(',')[self.gpu])
+                except Exception:
+                    idx = self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nv = pynvml
+            self.smax = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._loop, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:      # noqa
+            self.err = repr(e)
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _loop(self):
+        nv = self.nv
+        while not self.stop_flag.is_set():
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h) if hasattr(nv, 'nvmlDeviceGetCurrentClocksEventReasons') \
+                    else nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for name, bit in self.BITS:
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception as e:      # noqa
+                self.err = repr(e)
+                break
+            time.sleep(0.02)
 
     def stop(self):
-        if self.proc is None:
-            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons = [], [], set()
-        for r in self.rows:
-            f = [x.strip() for x in r.split(',')]
-            if len(f) < 8:
-                continue
-            try:
-                sm.append(float(f[1]))
-                smax.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
-        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(smax) if smax else None,
-                'reasons': sorted(reasons), 'samples': len(sm)}
+        if self.th is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvml unavailable: %s' % self.err], 'samples': 0}
+        self.stop_flag.set()
+        self.th.join(timeout=1.0)
+        # the samples taken while the GPU was busy: the upper half of the power readings marks the loaded interval
+        sm = self.sm
+        if len(sm) >= 4 and len(self.power) == len(sm):
+            thr = 0.5 * (max(self.power) + min(self.power))
+            busy = [c for c, p in zip(sm, self.power) if p >= thr]
+            if len(busy) >= 2:
+                sm = busy
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': self.smax, 'reasons': sorted(self.reasons),
+                'samples': len(self.sm), 'samples_under_load': len(sm), 'power_w_max': max(self.power) if self.power else None}
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -369,7 +386,7 @@ def run_gpu_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--minibatch', type=int, default=529)
