@@ -28,39 +28,7 @@
 #include "fft_passes.cuh"
 #include "tma.cuh"
 #include "../../include/adorym_b200.h"
-
-struct MsParams {
-    const cpx* tvol;    // transmission volume T' (adjoint: plain loads of the tile)
-    const cpx* probe;
-    const int* pos;
-    const cpx* Hp;      // prepared in-object transfer function (conj version for the adjoint)
-    const cpx* Hf;      // prepared free-space transfer function (near field) or null
-    cpx* ckpt;
-    cpx* det;           // fwd: out ; bwd: g_det in
-    cpx* g_probe;
-    int Nz, Y, X, Xp, B, M;
-    int free_prop, probe_per_pattern, h_separable;
-    float ff_scale;
-    int ff_conj;
-};
-
-ADM_DEV void red_add2(cpx* addr, float a, float b) {
-#ifndef ADM_HOST_EMU
-    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(addr), "f"(a), "f"(b) : "memory");
-#else
-    atomicAdd(&addr->x, a);
-    atomicAdd(&addr->y, b);
-#endif
-}
-
-// psi * (1 + T')
-ADM_DEV cpx modulate(cpx v, cpx tp) {
-    return mk(fmaf(-v.y, tp.y, fmaf(v.x, tp.x, v.x)), fmaf(v.y, tp.x, fmaf(v.x, tp.y, v.y)));
-}
-// g * conj(1 + T')
-ADM_DEV cpx modulate_conj(cpx v, cpx tp) {
-    return mk(fmaf(v.y, tp.y, fmaf(v.x, tp.x, v.x)), fmaf(v.y, tp.x, fmaf(-v.x, tp.y, v.y)));
-}
+#include "ms_params.cuh"
 
 // shared-memory carve-up (tile first: TMA destinations / sources need 128-byte alignment)
 template <class C> struct MsSmem {
@@ -445,6 +413,7 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     p.tvol = (const cpx*)tvol; p.probe = (const cpx*)probe; p.pos = pos;
     p.Hp = (const cpx*)Hprep; p.Hf = (const cpx*)Hfree;
     p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)det; p.g_probe = nullptr;
+    if (adm_ms2_supported(cfg)) return adm_ms2_fwd_launch(cfg, p, tvol, stream);   // two-pass prime-factor kernels
     AdmTileMap map;
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;
@@ -475,6 +444,7 @@ extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tv
     p.tvol = (const cpx*)tvol; p.probe = nullptr; p.pos = pos;
     p.Hp = (const cpx*)HprepC; p.Hf = (const cpx*)HfreeC;
     p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)g_det; p.g_probe = (cpx*)g_probe;
+    if (adm_ms2_supported(cfg)) return adm_ms2_bwd_launch(cfg, p, tvol, g_tvol, stream);
     AdmTileMap map;
     if (adm_make_tile_map(&map, g_tvol, p.Nz, ADM_GVOL_ROWS(p.Y, cfg->P), p.X + ADM_GVOL_MARGIN(cfg->P),
                           ADM_GVOL_PITCH(p.X, cfg->P), cfg->P, cfg->P + 2))

@@ -31,11 +31,27 @@ struct EmuBarrier {
     }
 };
 
+// named barriers (bar.sync id, count): created on first use, one set per CTA
+struct EmuNamedBarriers {
+    std::mutex m;
+    std::vector<std::pair<int, EmuBarrier*>> bars;
+    EmuBarrier* get(int id, unsigned n) {
+        std::lock_guard<std::mutex> lk(m);
+        for (auto& b : bars) if (b.first == id) return b.second;
+        bars.emplace_back(id, new EmuBarrier(n));
+        return bars.back().second;
+    }
+    ~EmuNamedBarriers() { for (auto& b : bars) delete b.second; }
+};
+static thread_local EmuNamedBarriers* emu_named = nullptr;
+static inline void emu_named_sync(int id, unsigned n);
+
 static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 static thread_local EmuBarrier* emu_bar = nullptr;
 static thread_local char* emu_smem = nullptr;
 
 #define __syncthreads() emu_bar->wait()
+static inline void emu_named_sync(int id, unsigned n) { emu_named->get(id, n)->wait(); }
 #define __global__ static
 #define __device__
 #define __host__
@@ -59,6 +75,7 @@ static void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
     for (unsigned by = 0; by < grid.y; ++by)
     for (unsigned bx = 0; bx < grid.x; ++bx) {
         EmuBarrier bar(nthreads);
+        EmuNamedBarriers named;
         std::memset(smem.data(), 0xCD, smem.size());   // poison: uninitialised smem reads show up as garbage
         std::vector<std::thread> th;
         th.reserve(nthreads);
@@ -68,6 +85,7 @@ static void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
                 blockIdx = emu_dim3(bx, by, bz);
                 blockDim = block; gridDim = grid;
                 emu_bar = &bar;
+                emu_named = &named;
                 emu_smem = smem.data();
                 body();
             });

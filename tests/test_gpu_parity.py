@@ -106,6 +106,18 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
             assert rel_err(grads[k], gold['g_' + k]) < TOL, k
 
 
+@pytest.mark.parametrize('name', ['ptycho3d_p72', 'ptycho3d_p72_poisson'])
+def test_two_pass_prime_factor_kernels_match_oracle(name, monkeypatch):
+    """Opt-in kernels of multislice_pfa2.cu (ADM_MS_PFA2=1, read by the library at every call)."""
+    monkeypatch.setenv('ADM_MS_PFA2', '1')
+    inp, loss, pred, grads, fm = run_gpu_case(name)
+    _, loss64, pred64, grads64 = run_oracle_case(name, torch.float64)
+    gtol = 1e-3 if 'poisson' in name else TOL
+    assert abs(loss - loss64) <= TOL * abs(loss64)
+    assert rel_err(pred, pred64) < TOL
+    assert rel_err(grads['obj'], grads64['obj']) < gtol
+
+
 def test_per_pattern_loss_matches_oracle():
     """north_star: per-pattern loss within 1e-4 (the fused loss kernel reports one partial sum per pattern)."""
     name = 'ptycho3d_p72'

@@ -61,6 +61,21 @@ def test_emulated_kernels_match_oracle_and_golden(name):
         assert rel_err(out['g_shift'], g_ref) < 1e-4
 
 
+@pytest.mark.parametrize('name', ['ptycho3d_p72', 'ptycho3d_p72_poisson'])
+def test_emulated_two_pass_prime_factor_kernels(name, monkeypatch):
+    """The opt-in two-pass prime-factor kernels (multislice_pfa2.cu, ADM_MS_PFA2=1): even and odd patch columns,
+    patches overhanging the object, sign_convention -1 / normalize_fft -- same oracle and reference golden."""
+    monkeypatch.setenv('ADM_MS_PFA2', '1')
+    inp, out = run_emu_case(name, separable=True)
+    _, loss, pred, grads = run_oracle_case(name, torch.float64)
+    gold = np.load(os.path.join(GOLD, name + '.npz'))
+    gtol = 1e-3 if 'poisson' in name else 1e-4
+    assert abs(out['loss'] - loss) <= 1e-4 * abs(loss)
+    assert rel_err(out['pred'], pred) < 1e-4
+    assert rel_err(out['pred'], gold['pred']) < 1e-4
+    assert rel_err(out['g_obj'], grads['obj']) < gtol
+
+
 @pytest.mark.parametrize('name', ['multidist128_probe', 'multidist256_shift'])
 def test_emulated_large_frame_kernels_match_oracle_and_golden(name):
     """MultiDistModel path: large-frame FFT passes (digit-reversed spectrum, H permutation, adjoint summed over
