@@ -49,6 +49,8 @@ SIGNATURES = {
                       c_int, c_void_p, c_void_p],
     'adm_regularizer_l1tv': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
                              c_void_p],
+    'adm_regularizer_l1tv_scaled': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
+                                    c_void_p, c_int, c_void_p],
     'adm_probe_shift_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_probe_shift_bwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_lf_supported': [c_int],

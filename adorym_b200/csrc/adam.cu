@@ -109,8 +109,12 @@ extern "C" int adm_adam_step(float* x, float* m, float* v, const float* g, long 
 // ---- regulariser -------------------------------------------------------------------------------
 ADM_DEV float sgnf(float a) { return (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f); }
 
-__global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx* obj, const cpx* wl1, float ad, float ab,
-                                                  float gm, float* value, cpx* g_obj) {
+// One warp per (y, x) row, lanes along z (the contiguous axis of obj [Y][X][Z][2]): no per-element index division; the
+// six TV neighbours are the same lane of four other rows and the two neighbouring lanes.  g_scale (device scalar or
+// null) multiplies the gradient (the upstream gradient of the loss node); accumulate = 0 writes g_obj, 1 adds to it.
+__global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx* __restrict__ obj, const cpx* __restrict__ wl1,
+                                                  float ad, float ab, float gm, float* value, cpx* g_obj,
+                                                  const float* g_scale, int accumulate) {
 #ifndef ADM_HOST_EMU
     __shared__ float red[256];
 #else
@@ -118,43 +122,47 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
 #endif
     const long long N = (long long)Y * X * Z;
     const float invN = 1.0f / (float)N;
+    const float gs = (g_scale != nullptr) ? *g_scale : 1.0f;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+    const long long rows = (long long)Y * X;
+    const size_t sx = (size_t)Z, sy = (size_t)X * Z;
     float acc = 0.f;
-    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long stride = (long long)gridDim.x * blockDim.x;
-    for (; i < N; i += stride) {
-        int z = (int)(i % Z);
-        int x = (int)((i / Z) % X);
-        int y = (int)(i / ((long long)Z * X));
-        cpx c = obj[i];
-        float w0 = 1.f, w1 = 1.f;
-        if (wl1 != nullptr) { cpx w = wl1[i]; w0 = w.x; w1 = w.y; }
-        float gd = ad * w0 * sgnf(c.x) * invN;
-        float gb = ab * w1 * sgnf(c.y) * invN;
-        acc += (ad * w0 * fabsf(c.x) + ab * w1 * fabsf(c.y)) * invN;
-        if (gm != 0.f) {
-            // TV: sum over the three axes of |roll(a, 1) - a| / N (periodic), per channel
-            long long im, ip;
-            cpx a, b;
-            im = (long long)((y + Y - 1) % Y) * X * Z + (long long)x * Z + z;
-            ip = (long long)((y + 1) % Y) * X * Z + (long long)x * Z + z;
-            a = obj[im]; b = obj[ip];
-            acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-            gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-            gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-            im = (long long)y * X * Z + (long long)((x + X - 1) % X) * Z + z;
-            ip = (long long)y * X * Z + (long long)((x + 1) % X) * Z + z;
-            a = obj[im]; b = obj[ip];
-            acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-            gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-            gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-            im = (long long)y * X * Z + (long long)x * Z + (z + Z - 1) % Z;
-            ip = (long long)y * X * Z + (long long)x * Z + (z + 1) % Z;
-            a = obj[im]; b = obj[ip];
-            acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-            gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-            gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+    for (long long row = (long long)blockIdx.x * wpb + wib; row < rows; row += (long long)gridDim.x * wpb) {
+        const int y = (int)(row / X), x = (int)(row - (long long)y * X);
+        const cpx* r0 = obj + (size_t)row * sx;
+        const cpx* rym = obj + (size_t)((y + Y - 1) % Y) * sy + (size_t)x * sx;
+        const cpx* ryp = obj + (size_t)((y + 1) % Y) * sy + (size_t)x * sx;
+        const cpx* rxm = obj + (size_t)y * sy + (size_t)((x + X - 1) % X) * sx;
+        const cpx* rxp = obj + (size_t)y * sy + (size_t)((x + 1) % X) * sx;
+        for (int z = lane; z < Z; z += 32) {
+            const cpx c = r0[z];
+            float w0 = 1.f, w1 = 1.f;
+            if (wl1 != nullptr) { cpx w = wl1[(size_t)row * sx + z]; w0 = w.x; w1 = w.y; }
+            float gd = ad * w0 * sgnf(c.x) * invN;
+            float gb = ab * w1 * sgnf(c.y) * invN;
+            acc += (ad * w0 * fabsf(c.x) + ab * w1 * fabsf(c.y)) * invN;
+            if (gm != 0.f) {
+                // TV: sum over the three axes of |roll(a, 1) - a| / N (periodic), per channel
+                cpx a = rym[z], b = ryp[z];
+                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                a = rxm[z]; b = rxp[z];
+                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                a = r0[(z + Z - 1) % Z]; b = r0[(z + 1) % Z];
+                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+            }
+            if (g_obj != nullptr) {
+                cpx* o = g_obj + (size_t)row * sx + z;
+                cpx r = mk(gd * gs, gb * gs);
+                if (accumulate) { cpx t = *o; r.x += t.x; r.y += t.y; }
+                *o = r;
+            }
         }
-        if (g_obj != nullptr) { cpx o = g_obj[i]; o.x += gd; o.y += gb; g_obj[i] = o; }
     }
     red[threadIdx.x] = acc;
     __syncthreads();
@@ -165,13 +173,19 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
     if (threadIdx.x == 0 && value != nullptr) atomicAdd(value, red[0]);
 }
 
-extern "C" int adm_regularizer_l1tv(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d, float alpha_b,
-                                    float gamma, float* value, float* g_obj, void* stream) {
+extern "C" int adm_regularizer_l1tv_scaled(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
+                                           float alpha_b, float gamma, float* value, float* g_obj, const float* g_scale,
+                                           int accumulate, void* stream) {
     if (Y < 1 || X < 1 || Z < 1 || !obj) return ADM_ERR_ARG;
-    long long N = (long long)Y * X * Z;
-    long long blocks = (N + 255) / 256;
+    long long rows = (long long)Y * X;
+    long long blocks = (rows + 7) / 8;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     ADM_LAUNCH(k_reg_l1tv, (unsigned)blocks, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj, (const cpx*)weight_l1,
-               alpha_d, alpha_b, gamma, value, (cpx*)g_obj);
+               alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate);
     return ADM_OK;
+}
+
+extern "C" int adm_regularizer_l1tv(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d, float alpha_b,
+                                    float gamma, float* value, float* g_obj, void* stream) {
+    return adm_regularizer_l1tv_scaled(Y, X, Z, obj, weight_l1, alpha_d, alpha_b, gamma, value, g_obj, nullptr, 1, stream);
 }

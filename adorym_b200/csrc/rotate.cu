@@ -34,22 +34,42 @@ ADM_DEV Taps make_taps(float gz, float gx, int X, int Z) {
 
 #define ROT_YCHUNK 8
 
-// grid (ceil(X/128), Z, ceil(Y/ROT_YCHUNK)); thread -> x; loop over a chunk of y with the taps held in registers
+// Thread -> output voxel (x, z) of a compact 16 x 8 tile (each warp an 8 x 4 sub-tile): the taps of a warp then fall
+// in a ~10 x 7 patch of the source plane (a few dozen 32-byte sectors shared between the lanes) instead of along a
+// 32-voxel line (one sector per lane and tap); the stores are 64-byte runs along x.
+#define ROT_TX 16
+#define ROT_TZ 8
+ADM_DEV void rot_xz(int& x, int& z) {
+    const int t = threadIdx.x, w = t >> 5, l = t & 31;
+    x = blockIdx.x * ROT_TX + ((w & 1) << 3) + (l & 7);
+    z = blockIdx.y * ROT_TZ + ((w >> 1) << 2) + (l >> 3);
+}
+
+// grid (ceil(X/16), ceil(Z/8), ceil(Y/ROT_YCHUNK)); loop over a chunk of y with the taps held in registers
 __global__ void __launch_bounds__(128) k_rotate_fwd(int Y, int X, int Z, const cpx* obj, const float* grid, cpx* rot) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int z = blockIdx.y;
-    if (x >= X) return;
+    int x, z;
+    rot_xz(x, z);
+    if (x >= X || z >= Z) return;
     const float* g = grid + 2 * ((size_t)x * Z + z);
     Taps t = make_taps(g[0], g[1], X, Z);
-    int y0 = blockIdx.z * ROT_YCHUNK;
-    int y1 = y0 + ROT_YCHUNK < Y ? y0 + ROT_YCHUNK : Y;
-    for (int y = y0; y < y1; ++y) {
+    const int y0 = blockIdx.z * ROT_YCHUNK;
+    cpx a[ROT_YCHUNK], b[ROT_YCHUNK], c[ROT_YCHUNK], d[ROT_YCHUNK];
+    // all taps of the y chunk are requested before the first is used (8 x 4 independent loads in flight per thread)
+#pragma unroll
+    for (int k = 0; k < ROT_YCHUNK; ++k) {
+        const int y = (y0 + k < Y) ? y0 + k : Y - 1;
         const cpx* pl = obj + (size_t)y * X * Z;
-        cpx a = pl[t.i00], b = pl[t.i01], c = pl[t.i10], d = pl[t.i11];
-        cpx r;
-        r.x = a.x * t.w00 + b.x * t.w01 + c.x * t.w10 + d.x * t.w11;
-        r.y = a.y * t.w00 + b.y * t.w01 + c.y * t.w10 + d.y * t.w11;
-        rot[((size_t)z * Y + y) * X + x] = r;
+        a[k] = pl[t.i00]; b[k] = pl[t.i01]; c[k] = pl[t.i10]; d[k] = pl[t.i11];
+    }
+#pragma unroll
+    for (int k = 0; k < ROT_YCHUNK; ++k) {
+        const int y = y0 + k;
+        if (y < Y) {
+            cpx r;
+            r.x = a[k].x * t.w00 + b[k].x * t.w01 + c[k].x * t.w10 + d[k].x * t.w11;
+            r.y = a[k].y * t.w00 + b[k].y * t.w01 + c[k].y * t.w10 + d[k].y * t.w11;
+            rot[((size_t)z * Y + y) * X + x] = r;
+        }
     }
 }
 
@@ -63,15 +83,23 @@ ADM_DEV void red2(cpx* addr, float a, float b) {
 }
 
 __global__ void __launch_bounds__(128) k_rotate_adj(int Y, int X, int Z, const cpx* g_rot, const float* grid, cpx* g_obj) {
-    int x = blockIdx.x * blockDim.x + threadIdx.x;
-    int z = blockIdx.y;
-    if (x >= X) return;
+    int x, z;
+    rot_xz(x, z);
+    if (x >= X || z >= Z) return;
     const float* g = grid + 2 * ((size_t)x * Z + z);
     Taps t = make_taps(g[0], g[1], X, Z);
-    int y0 = blockIdx.z * ROT_YCHUNK;
-    int y1 = y0 + ROT_YCHUNK < Y ? y0 + ROT_YCHUNK : Y;
-    for (int y = y0; y < y1; ++y) {
-        cpx v = g_rot[((size_t)z * Y + y) * X + x];
+    const int y0 = blockIdx.z * ROT_YCHUNK;
+    cpx vv[ROT_YCHUNK];
+#pragma unroll
+    for (int k = 0; k < ROT_YCHUNK; ++k) {
+        const int y = (y0 + k < Y) ? y0 + k : Y - 1;
+        vv[k] = g_rot[((size_t)z * Y + y) * X + x];
+    }
+#pragma unroll
+    for (int k = 0; k < ROT_YCHUNK; ++k) {
+        const int y = y0 + k;
+        if (y >= Y) break;
+        const cpx v = vv[k];
         cpx* pl = g_obj + (size_t)y * X * Z;
         if (t.w00 != 0.f) red2(pl + t.i00, v.x * t.w00, v.y * t.w00);
         if (t.w01 != 0.f) red2(pl + t.i01, v.x * t.w01, v.y * t.w01);
@@ -82,16 +110,16 @@ __global__ void __launch_bounds__(128) k_rotate_adj(int Y, int X, int Z, const c
 
 extern "C" int adm_rotate_fwd(int Y, int X, int Z, const float* obj, const float* grid, float* rot, void* stream) {
     if (Y < 1 || X < 1 || Z < 1 || !obj || !grid || !rot) return ADM_ERR_ARG;
-    if (Z > 65535 || (Y + ROT_YCHUNK - 1) / ROT_YCHUNK > 65535) return ADM_ERR_UNSUPPORTED;
-    dim3 gr((X + 127) / 128, Z, (Y + ROT_YCHUNK - 1) / ROT_YCHUNK);
+    if ((Z + ROT_TZ - 1) / ROT_TZ > 65535 || (Y + ROT_YCHUNK - 1) / ROT_YCHUNK > 65535) return ADM_ERR_UNSUPPORTED;
+    dim3 gr((X + ROT_TX - 1) / ROT_TX, (Z + ROT_TZ - 1) / ROT_TZ, (Y + ROT_YCHUNK - 1) / ROT_YCHUNK);
     ADM_LAUNCH(k_rotate_fwd, gr, 128, 0, stream, Y, X, Z, (const cpx*)obj, grid, (cpx*)rot);
     return ADM_OK;
 }
 
 extern "C" int adm_rotate_adj(int Y, int X, int Z, const float* g_rot, const float* grid, float* g_obj, void* stream) {
     if (Y < 1 || X < 1 || Z < 1 || !g_rot || !grid || !g_obj) return ADM_ERR_ARG;
-    if (Z > 65535 || (Y + ROT_YCHUNK - 1) / ROT_YCHUNK > 65535) return ADM_ERR_UNSUPPORTED;
-    dim3 gr((X + 127) / 128, Z, (Y + ROT_YCHUNK - 1) / ROT_YCHUNK);
+    if ((Z + ROT_TZ - 1) / ROT_TZ > 65535 || (Y + ROT_YCHUNK - 1) / ROT_YCHUNK > 65535) return ADM_ERR_UNSUPPORTED;
+    dim3 gr((X + ROT_TX - 1) / ROT_TX, (Z + ROT_TZ - 1) / ROT_TZ, (Y + ROT_YCHUNK - 1) / ROT_YCHUNK);
     ADM_LAUNCH(k_rotate_adj, gr, 128, 0, stream, Y, X, Z, (const cpx*)g_rot, grid, (cpx*)g_obj);
     return ADM_OK;
 }

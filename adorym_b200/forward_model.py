@@ -75,11 +75,30 @@ class ForwardModel(object):
 
     def get_regularization_value(self, obj, device=None):
         reg = None
+        fused = self._fusable_regularizers()
+        if fused is not None:
+            # one L1-type and one TV term on a delta_beta object: a single pass over the volume for both
+            l1, tv = fused
+            reg = ops.RegL1TVFn.apply(obj, getattr(l1, 'weight_l1', None), l1.alpha_d, l1.alpha_b, tv.gamma)
+            self.last_reg_value = reg
+            return reg
         for r in self.reg_list:
             v = r.get_value(obj, distribution_mode=self.distribution_mode, device=device)
             reg = v if reg is None else reg + v
         self.last_reg_value = reg
         return reg
+
+    def _fusable_regularizers(self):
+        from .regularizers import L1Regularizer, ReweightedL1Regularizer, TVRegularizer
+        if len(self.reg_list) != 2:
+            return None
+        l1 = [r for r in self.reg_list if isinstance(r, (L1Regularizer, ReweightedL1Regularizer))]
+        tv = [r for r in self.reg_list if isinstance(r, TVRegularizer)]
+        if len(l1) != 1 or len(tv) != 1 or l1[0].unknown_type != 'delta_beta' or tv[0].unknown_type != 'delta_beta':
+            return None
+        if isinstance(l1[0], ReweightedL1Regularizer) and l1[0].weight_l1 is None:
+            return None
+        return l1[0], tv[0]
 
     def get_argument_index(self, arg):
         for i, a in enumerate(self.argument_ls):
@@ -256,13 +275,23 @@ class PtychographyModel(ForwardModel):
         if probe.dim() == 3:
             probe = probe.unsqueeze(0)
         # per-position probe shift: quirk 8, positive corrections only trigger it (forward_model.py:297,304)
-        if cv['optimize_all_probe_pos'] or bool((probe_pos_correction > 1e-3).any()):
+        if cv['optimize_all_probe_pos'] or self._any_positive_correction(probe_pos_correction):
             idx = torch.as_tensor(np.asarray(this_ind_batch), device=dev, dtype=torch.long)
             shift = probe_pos_correction[int(this_i_theta)].index_select(0, idx).to(torch.float32)
             probe = ops.ProbeShiftFn.apply(probe, shift)
         plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
         pos_t = torch.from_numpy(np.ascontiguousarray(pos, dtype='int32')).to(dev)
         return ops.MultisliceFn.apply(rot, probe, pos_t, plan)
+
+    def _any_positive_correction(self, ppc):
+        """forward_model.py:297,304: `any(probe_pos_correction > 1e-3)`.  The answer needs a device->host read; it is
+        remembered for as long as the same tensor has not been written to (torch's version counter)."""
+        key = (ppc.data_ptr(), ppc._version, tuple(ppc.shape))
+        hit = getattr(self, '_ppc_check', None)
+        if hit is None or hit[0] != key:
+            hit = (key, bool((ppc > 1e-3).any()))
+            self._ppc_check = hit
+        return hit[1]
 
     def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,
                 probe_pos_offset, this_i_theta, this_pos_batch, prj,

@@ -302,24 +302,38 @@ class ProbeShiftFn(torch.autograd.Function):
 # regulariser / Adam
 # ------------------------------------------------------------------------------------------------------
 class RegL1TVFn(torch.autograd.Function):
-    """alpha_d mean(w0|d|) + alpha_b mean(w1|b|) + gamma (TV3d(d) + TV3d(b)) on obj[Y,X,Z,2] (delta_beta)."""
+    """alpha_d mean(w0|d|) + alpha_b mean(w1|b|) + gamma (TV3d(d) + TV3d(b)) on obj[Y,X,Z,2] (delta_beta).
+
+    forward : value only (one read of the object).
+    backward: the gradient, already multiplied by the upstream gradient (read on the device, no host sync), written
+              in one pass -- no zero fill, no separate scaling kernel."""
 
     @staticmethod
     def forward(ctx, obj, weight_l1, alpha_d, alpha_b, gamma):
         obj = _f32c(obj)
         Y, X, Z, _ = obj.shape
         val = torch.zeros((1,), dtype=torch.float32, device=obj.device)
-        g = torch.zeros_like(obj)
         w = _f32c(weight_l1) if weight_l1 is not None else None
-        call('adm_regularizer_l1tv', Y, X, Z, ptr(obj), ptr(w), float(alpha_d or 0.), float(alpha_b or 0.),
-             float(gamma or 0.), ptr(val), ptr(g), stream_ptr())
-        ctx.save_for_backward(g)
+        ctx.coef = (float(alpha_d or 0.), float(alpha_b or 0.), float(gamma or 0.))
+        call('adm_regularizer_l1tv_scaled', Y, X, Z, ptr(obj), ptr(w), ctx.coef[0], ctx.coef[1], ctx.coef[2], ptr(val), None,
+             None, 0, stream_ptr())
+        ctx.has_w = w is not None
+        if w is not None:
+            ctx.save_for_backward(obj, w)
+        else:
+            ctx.save_for_backward(obj)
         return val[0]
 
     @staticmethod
     def backward(ctx, g_val):
-        (g,) = ctx.saved_tensors
-        return g * g_val, None, None, None, None
+        obj = ctx.saved_tensors[0]
+        w = ctx.saved_tensors[1] if ctx.has_w else None
+        Y, X, Z, _ = obj.shape
+        g = torch.empty_like(obj)
+        gs = _f32c(g_val.reshape(1))
+        call('adm_regularizer_l1tv_scaled', Y, X, Z, ptr(obj), ptr(w), ctx.coef[0], ctx.coef[1], ctx.coef[2], None, ptr(g),
+             ptr(gs), 0, stream_ptr())
+        return g, None, None, None, None
 
 
 def adam_step_(x, m, v, g, step, step_size=0.001, b1=0.9, b2=0.999, eps=1e-7, clip_nonneg=False,

@@ -375,10 +375,12 @@ def reconstruct_ptychography(
             grads = list(diff.get_gradients(**grad_func_args))
 
             if initialize_gradients:
-                gradient.arr.zero_()
+                # ptychography.py:1065-1067: zeros + grads[0] -- the buffer becomes the new gradient (no fill, no add)
+                gradient.arr = grads[0]
                 initialize_parameter_gradients(opt_ls, device_obj)
                 initialize_gradients = False
-            gradient.arr += grads[0]
+            else:
+                gradient.arr += grads[0]
             opt_ls = update_parameter_gradients(opt_ls, grads)
 
             if update_scheme == 'per angle' and not is_last_batch_of_this_theta:

@@ -267,8 +267,9 @@ class StepRunner(object):
                     probe_pos_offset=None, this_i_theta=i_theta, this_pos_batch=self.pos, prj=self.fm.prj,
                     probe_pos_correction=self.zero_ppc, this_ind_batch=self.ind, tilt_ls=None, prj_pos_offset=None)
         grads = self.diff.get_gradients(**args)
-        self.gradient.zero_()
-        self.gradient += grads[0]
+        # ptychography.py:1065-1067 (`gradient.arr = zeros; gradient.arr += grads[0]` when the buffer is re-initialised,
+        # i.e. every step at update_scheme='immediate'): 0 + g is g, so the buffer simply becomes the new gradient
+        self.gradient = grads[0]
         if self.world > 1:
             torch.distributed.all_reduce(self.gradient, op=torch.distributed.ReduceOp.SUM)
         with torch.no_grad():

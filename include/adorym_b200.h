@@ -160,6 +160,11 @@ int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, dou
  *   weight_l1 [Y][X][Z][2] or NULL; value / g_obj may be NULL.                                             */
 int adm_regularizer_l1tv(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d, float alpha_b,
                          float gamma, float* value, float* g_obj, void* stream);
+/* Same, with the gradient multiplied by the DEVICE scalar *g_scale (the upstream gradient autograd hands to the
+ * regulariser node, wrappers.py:322; NULL = 1) and written (accumulate = 0) or added (accumulate = 1) to g_obj.  */
+int adm_regularizer_l1tv_scaled(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
+                                float alpha_b, float gamma, float* value, float* g_obj, const float* g_scale,
+                                int accumulate, void* stream);
 
 /* Sub-pixel Fourier shift of the probe per pattern (util.py:380-397 as used at forward_model.py:296-303).
  *   probe [M][P][P][2]; shift [B][2] (y, x); out [B][M][P][P][2].                                          */
