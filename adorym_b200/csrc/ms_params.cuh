@@ -41,3 +41,7 @@ ADM_DEV cpx modulate_conj(cpx v, cpx tp) {
 int adm_ms2_supported(const adm_multislice_cfg* c);
 int adm_ms2_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, const float* tvol, void* stream);
 int adm_ms2_bwd_launch(const adm_multislice_cfg* c, const MsParams& p, const float* tvol, float* g_tvol, void* stream);
+
+// two wavefields per CTA on packed fp32x2 arithmetic, P = 72 (multislice_x2.cu)
+int adm_msx2_fwd_supported(const adm_multislice_cfg* c);
+int adm_msx2_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, void* stream);

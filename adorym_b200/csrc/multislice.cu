@@ -414,6 +414,7 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     p.Hp = (const cpx*)Hprep; p.Hf = (const cpx*)Hfree;
     p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)det; p.g_probe = nullptr;
     if (adm_ms2_supported(cfg)) return adm_ms2_fwd_launch(cfg, p, tvol, stream);   // two-pass prime-factor kernels
+    if (adm_msx2_fwd_supported(cfg)) return adm_msx2_fwd_launch(cfg, p, stream);   // two wavefields per CTA, packed fp32x2
     AdmTileMap map;
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;

@@ -106,10 +106,11 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
             assert rel_err(grads[k], gold['g_' + k]) < TOL, k
 
 
-@pytest.mark.parametrize('name', ['ptycho3d_p72', 'ptycho3d_p72_poisson'])
-def test_two_pass_prime_factor_kernels_match_oracle(name, monkeypatch):
-    """Opt-in kernels of multislice_pfa2.cu (ADM_MS_PFA2=1, read by the library at every call)."""
-    monkeypatch.setenv('ADM_MS_PFA2', '1')
+@pytest.mark.parametrize('name,var', [('ptycho3d_p72', 'ADM_MS_PFA2'), ('ptycho3d_p72_poisson', 'ADM_MS_PFA2'),
+                                      ('ptycho3d_p72', 'ADM_MS_X2'), ('ptycho3d_p72_poisson', 'ADM_MS_X2')])
+def test_opt_in_kernel_variants_match_oracle(name, var, monkeypatch):
+    """Opt-in kernels of multislice_pfa2.cu / multislice_x2.cu (environment switch read by the library at every call)."""
+    monkeypatch.setenv(var, '1')
     inp, loss, pred, grads, fm = run_gpu_case(name)
     _, loss64, pred64, grads64 = run_oracle_case(name, torch.float64)
     gtol = 1e-3 if 'poisson' in name else TOL

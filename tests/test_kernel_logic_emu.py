@@ -61,11 +61,13 @@ def test_emulated_kernels_match_oracle_and_golden(name):
         assert rel_err(out['g_shift'], g_ref) < 1e-4
 
 
-@pytest.mark.parametrize('name', ['ptycho3d_p72', 'ptycho3d_p72_poisson'])
-def test_emulated_two_pass_prime_factor_kernels(name, monkeypatch):
-    """The opt-in two-pass prime-factor kernels (multislice_pfa2.cu, ADM_MS_PFA2=1): even and odd patch columns,
-    patches overhanging the object, sign_convention -1 / normalize_fft -- same oracle and reference golden."""
-    monkeypatch.setenv('ADM_MS_PFA2', '1')
+@pytest.mark.parametrize('name,var', [('ptycho3d_p72', 'ADM_MS_PFA2'), ('ptycho3d_p72_poisson', 'ADM_MS_PFA2'),
+                                      ('ptycho3d_p72', 'ADM_MS_X2'), ('ptycho3d_p72_poisson', 'ADM_MS_X2')])
+def test_emulated_opt_in_kernel_variants(name, var, monkeypatch):
+    """The opt-in variants: two-pass prime-factor kernels (multislice_pfa2.cu, ADM_MS_PFA2=1) and the two-wavefield
+    packed-fp32x2 forward (multislice_x2.cu, ADM_MS_X2=1; the second case has an odd number of patterns): even and odd
+    patch columns, patches overhanging the object, sign_convention -1 / normalize_fft -- same oracle and golden."""
+    monkeypatch.setenv(var, '1')
     inp, out = run_emu_case(name, separable=True)
     _, loss, pred, grads = run_oracle_case(name, torch.float64)
     gold = np.load(os.path.join(GOLD, name + '.npz'))
