@@ -176,6 +176,13 @@ class ForwardModel(object):
         dev = self.device
         ind = np.asarray(this_ind_batch)
         it = int(this_i_theta) * theta_downsample
+        pf = getattr(self, '_prefetched', None)
+        if pf is not None:
+            self._prefetched = None
+            if pf[0] == (id(prj), it, ind.tobytes(), int(ds_level)):
+                torch.cuda.current_stream(pf[1].device).wait_event(pf[2])
+                pf[1].record_stream(torch.cuda.current_stream(pf[1].device))
+                return pf[1]
         if torch.is_tensor(prj) and prj.is_cuda:
             frames = prj[it]
             if not (len(ind) == frames.shape[0] and np.array_equal(ind, np.arange(len(ind)))):
@@ -198,6 +205,39 @@ class ForwardModel(object):
         if ds_level > 1:
             batch = batch[:, ::ds_level, ::ds_level]
         return batch
+
+    def prefetch_data(self, this_i_theta, this_ind_batch, theta_downsample=None, ds_level=1):
+        """Data path: start the host->device copy of the NEXT minibatch's measured frames on a side stream
+        while the current minibatch computes; `get_data` with the same arguments then only waits for the copy's event.
+        A no-op unless `prj` is a host tensor (the case that costs a synchronous copy inside the step)."""
+        prj = self.prj
+        if not torch.is_tensor(prj) or prj.is_cuda:
+            return
+        if theta_downsample is None:
+            theta_downsample = 1
+        dev = torch.device(self.device) if self.device is not None else torch.device('cuda', torch.cuda.current_device())
+        ind = np.asarray(this_ind_batch)
+        it = int(this_i_theta) * theta_downsample
+        if getattr(self, '_pf_stream', None) is None:
+            self._pf_stream = torch.cuda.Stream(device=dev)
+        frames = prj[it]
+        if not (len(ind) == frames.shape[0] and np.array_equal(ind, np.arange(len(ind)))):
+            shp = (len(ind),) + tuple(frames.shape[1:])
+            if getattr(self, '_pf_stage', None) is None or self._pf_stage.shape != shp or self._pf_stage.dtype != frames.dtype:
+                self._pf_stage = torch.empty(shp, dtype=frames.dtype).pin_memory()
+            elif getattr(self, '_pf_event', None) is not None:
+                self._pf_event.synchronize()          # the previous copy out of the staging buffer has finished
+            torch.index_select(frames, 0, torch.as_tensor(ind, dtype=torch.long), out=self._pf_stage)
+            frames = self._pf_stage
+        with torch.cuda.stream(self._pf_stream):
+            batch = frames.to(dev, non_blocking=True)
+            batch = (batch.abs() if batch.is_complex() else batch).to(torch.float32)
+            if ds_level > 1:
+                batch = batch[:, ::ds_level, ::ds_level]
+            ev = torch.cuda.Event()
+            ev.record(self._pf_stream)
+        self._pf_event = ev
+        self._prefetched = ((id(prj), it, ind.tobytes(), int(ds_level)), batch, ev)
 
     def _beamstop_mask(self, dev):
         bs = self.common_vars.get('beamstop', None)

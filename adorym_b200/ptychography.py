@@ -373,6 +373,11 @@ def reconstruct_ptychography(
                     grad_func_args[arg] = local_vars[arg]
             forward_model.update_loss_args(grad_func_args)
             grads = list(diff.get_gradients(**grad_func_args))
+            if i_batch + 1 < n_batch:
+                # measured frames of the next minibatch: host->device copy on a side stream under this step's kernels
+                nxt_theta, nxt_ind = rank_minibatch(ind_list_rand, i_batch + 1, rank, minibatch_size, n_ranks)
+                forward_model.prefetch_data(nxt_theta, nxt_ind, theta_downsample=forward_model.common_vars['theta_downsample'],
+                                            ds_level=forward_model.common_vars['ds_level'])
 
             if initialize_gradients:
                 # ptychography.py:1065-1067: zeros + grads[0] -- the buffer becomes the new gradient (no fill, no add)
