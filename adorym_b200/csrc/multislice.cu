@@ -189,6 +189,7 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
     const cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * P * TP;
     const cpx* gdet = p.det + (size_t)wf * P * P;
     const size_t slice_stride = (size_t)p.Y * p.Xp;
+    const cpx* tcol = p.tvol + (x_in ? gx : 0);     // this thread's column of the transmission volume
 
     init_twiddles<C>(tw, t);
     if (p.h_separable && t < 2 * P) hs[t] = p.Hp[t];
@@ -249,17 +250,19 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
     int phase = 0;
     for (int z = p.Nz - 1; z >= 0; --z, phase ^= 1) {
         const bool last = (z == p.Nz - 1);
+        const cpx* tz = tcol + (size_t)z * slice_stride;
         // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] ------------------------------
         if (active) {
             ADM_FOR_GROUPS_A(gi) {
                 const int g = I.group(gi);
                 cpx v[8], tp[8];
-                // T' of this slice (L2-resident volume; issued first so the butterfly hides the latency)
+                // T' of this slice (L2-resident volume; issued first so the butterfly hides the latency); 32-bit offsets
+                // from the per-slice column pointer, one unsigned compare per row
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int gy = py + I.a(j, gi);
-                    const bool inb = x_in && gy >= 0 && gy < p.Y;
-                    tp[j] = inb ? p.tvol[(size_t)z * slice_stride + (size_t)gy * p.Xp + gx] : mk(0.f, 0.f);
+                    const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
+                    tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : mk(0.f, 0.f);
                 }
                 if (last && p.free_prop == ADM_PROP_NONE) {
 #pragma unroll

@@ -39,6 +39,20 @@ CASES = {
                                  unknown_type='delta_beta', delta_scale=5e-4, beta_scale=5e-5, seed=12,
                                  loss='poisson', raw_data_type='intensity', sign_convention=-1, normalize_fft=True,
                                  poisson_multiplier=3.0),
+    # edge geometry: probe larger than the (non-cubic) object, a patch lying entirely outside it, odd and even columns,
+    # an odd number of patterns, two probe modes with probe + position refinement through a 3-D object, L1 + TV
+    'ptycho3d_p72_edge': dict(kind='ptycho', obj_size=(40, 48, 48), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                              theta=2.1, n_theta=5, i_theta=1,
+                              pos=[(-20, -14), (-90, -90), (-36, 11), (3, -31), (-5, -6)], n_modes=2, free_prop_cm='inf',
+                              unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=16,
+                              loss='lsq', raw_data_type='magnitude', optimize_probe=True, optimize_all_probe_pos=True,
+                              alpha_d=3e-3, alpha_b=3e-4, gamma=2e-3),
+    # no detector transform (free_prop_cm = 0: the exit wave is detected), real_imag unknown, 3-D, P = 72
+    'ptycho3d_p72_exitwave': dict(kind='ptycho', obj_size=(48, 48, 48), probe_size=(72, 72), energy_ev=5000.,
+                                  psize_cm=1e-7, theta=-0.4, n_theta=4, i_theta=2,
+                                  pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=1, free_prop_cm=0,
+                                  unknown_type='real_imag', delta_scale=0.2, beta_scale=0.2, seed=17,
+                                  loss='lsq', raw_data_type='intensity'),
     # 2-D ptychography with probe modes + probe and position refinement (BASELINE config B shape, small)
     'ptycho2d_modes': dict(kind='ptycho', obj_size=(128, 128, 1), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
                            theta=0.0, n_theta=1, i_theta=0,

@@ -107,7 +107,9 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
 
 
 @pytest.mark.parametrize('name,var', [('ptycho3d_p72', 'ADM_MS_PFA2'), ('ptycho3d_p72_poisson', 'ADM_MS_PFA2'),
-                                      ('ptycho3d_p72', 'ADM_MS_X2'), ('ptycho3d_p72_poisson', 'ADM_MS_X2')])
+                                      ('ptycho3d_p72', 'ADM_MS_X2'), ('ptycho3d_p72_poisson', 'ADM_MS_X2'),
+                                      ('ptycho3d_p72_edge', 'ADM_MS_PFA2'), ('ptycho3d_p72_exitwave', 'ADM_MS_PFA2'),
+                                      ('ptycho3d_p72_edge', 'ADM_MS_X2'), ('ptycho3d_p72_exitwave', 'ADM_MS_X2')])
 def test_opt_in_kernel_variants_match_oracle(name, var, monkeypatch):
     """Opt-in kernels of multislice_pfa2.cu / multislice_x2.cu (environment switch read by the library at every call)."""
     monkeypatch.setenv(var, '1')
@@ -117,6 +119,9 @@ def test_opt_in_kernel_variants_match_oracle(name, var, monkeypatch):
     assert abs(loss - loss64) <= TOL * abs(loss64)
     assert rel_err(pred, pred64) < TOL
     assert rel_err(grads['obj'], grads64['obj']) < gtol
+    for k in ('probe_real', 'probe_imag', 'probe_pos_correction'):
+        if k in grads:
+            assert rel_err(grads[k], grads64[k]) < TOL, k
 
 
 def test_per_pattern_loss_matches_oracle():

@@ -36,7 +36,7 @@ def run_emu_case(name, separable=False):
 
 
 @pytest.mark.parametrize('name', ['ptycho2d_modes', 'ptycho2d_realimag_p64', 'fullfield64', 'ptycho3d_p72',
-                                  'ptycho3d_p72_poisson'])
+                                  'ptycho3d_p72_poisson', 'ptycho3d_p72_edge', 'ptycho3d_p72_exitwave'])
 def test_emulated_kernels_match_oracle_and_golden(name):
     # the separable-H path (Fresnel kernel in two shared-memory tables) on the 3-D P=72 cases, the general-H path elsewhere
     inp, out = run_emu_case(name, separable=name.startswith('ptycho3d'))
@@ -62,7 +62,9 @@ def test_emulated_kernels_match_oracle_and_golden(name):
 
 
 @pytest.mark.parametrize('name,var', [('ptycho3d_p72', 'ADM_MS_PFA2'), ('ptycho3d_p72_poisson', 'ADM_MS_PFA2'),
-                                      ('ptycho3d_p72', 'ADM_MS_X2'), ('ptycho3d_p72_poisson', 'ADM_MS_X2')])
+                                      ('ptycho3d_p72', 'ADM_MS_X2'), ('ptycho3d_p72_poisson', 'ADM_MS_X2'),
+                                      ('ptycho3d_p72_edge', 'ADM_MS_PFA2'), ('ptycho3d_p72_exitwave', 'ADM_MS_PFA2'),
+                                      ('ptycho3d_p72_edge', 'ADM_MS_X2'), ('ptycho3d_p72_exitwave', 'ADM_MS_X2')])
 def test_emulated_opt_in_kernel_variants(name, var, monkeypatch):
     """The opt-in variants: two-pass prime-factor kernels (multislice_pfa2.cu, ADM_MS_PFA2=1) and the two-wavefield
     packed-fp32x2 forward (multislice_x2.cu, ADM_MS_X2=1; the second case has an odd number of patterns): even and odd
@@ -76,6 +78,12 @@ def test_emulated_opt_in_kernel_variants(name, var, monkeypatch):
     assert rel_err(out['pred'], pred) < 1e-4
     assert rel_err(out['pred'], gold['pred']) < 1e-4
     assert rel_err(out['g_obj'], grads['obj']) < gtol
+    if 'probe_real' in grads:
+        assert rel_err(out['g_probe_real'], grads['probe_real']) < 1e-4
+        assert rel_err(out['g_probe_imag'], gold['g_probe_imag']) < 1e-4
+    if 'probe_pos_correction' in grads:
+        c = inp['cfg']
+        assert rel_err(out['g_shift'], grads['probe_pos_correction'][c['i_theta'], inp['this_ind_batch']]) < 1e-4
 
 
 @pytest.mark.parametrize('name', ['multidist128_probe', 'multidist256_shift'])
