@@ -56,31 +56,44 @@ template <bool INV> ADM_HD void dft8(cpx* a) {
     cpx b1 = a[1] + a[5], c1 = a[1] - a[5];
     cpx b2 = a[2] + a[6], c2 = a[2] - a[6];
     cpx b3 = a[3] + a[7], c3 = a[3] - a[7];
-    // c_j *= W8^j  (W8 = exp(-+ i pi/4))
-    if (!INV) {
-        c1 = mk((c1.x + c1.y) * ADM_SQRT1_2, (c1.y - c1.x) * ADM_SQRT1_2);
-        c2 = mk(c2.y, -c2.x);
-        c3 = mk((c3.y - c3.x) * ADM_SQRT1_2, -(c3.x + c3.y) * ADM_SQRT1_2);
-    } else {
-        c1 = mk((c1.x - c1.y) * ADM_SQRT1_2, (c1.x + c1.y) * ADM_SQRT1_2);
-        c2 = mk(-c2.y, c2.x);
-        c3 = mk(-(c3.x + c3.y) * ADM_SQRT1_2, (c3.x - c3.y) * ADM_SQRT1_2);
-    }
     dft4<INV>(b0, b1, b2, b3);   // even outputs X[0], X[2], X[4], X[6]
-    dft4<INV>(c0, c1, c2, c3);   // odd outputs  X[1], X[3], X[5], X[7]
     a[0] = b0; a[2] = b1; a[4] = b2; a[6] = b3;
-    a[1] = c0; a[3] = c1; a[5] = c2; a[7] = c3;
+    // odd outputs: 4-point DFT of (c0, W8 c1, W8^2 c2, W8^3 c3), W8 = exp(-+ i pi/4).  With W8 c1 = s r1 and
+    // W8^3 c3 = s r3 (s = 1/sqrt 2, r1 / r3 the unscaled rotations) the factor s is folded into the last butterfly as
+    // FMAs, so the 8-point transform has no stand-alone multiplications.
+    cpx r1, r3, e0, e1;
+    if (!INV) {
+        r1 = mk(c1.x + c1.y, c1.y - c1.x);
+        r3 = mk(c3.y - c3.x, -(c3.x + c3.y));
+        e0 = mk(c0.x + c2.y, c0.y - c2.x);      // c0 + (-i) c2
+        e1 = mk(c0.x - c2.y, c0.y + c2.x);      // c0 - (-i) c2
+    } else {
+        r1 = mk(c1.x - c1.y, c1.x + c1.y);
+        r3 = mk(-(c3.x + c3.y), c3.x - c3.y);
+        e0 = mk(c0.x - c2.y, c0.y + c2.x);
+        e1 = mk(c0.x + c2.y, c0.y - c2.x);
+    }
+    const cpx e2 = r1 + r3, t = r1 - r3;
+    a[1] = mk(fmaf(ADM_SQRT1_2, e2.x, e0.x), fmaf(ADM_SQRT1_2, e2.y, e0.y));
+    a[5] = mk(fmaf(-ADM_SQRT1_2, e2.x, e0.x), fmaf(-ADM_SQRT1_2, e2.y, e0.y));
+    if (!INV) {   // e1 +- (-i) s t
+        a[3] = mk(fmaf(ADM_SQRT1_2, t.y, e1.x), fmaf(-ADM_SQRT1_2, t.x, e1.y));
+        a[7] = mk(fmaf(-ADM_SQRT1_2, t.y, e1.x), fmaf(ADM_SQRT1_2, t.x, e1.y));
+    } else {      // e1 +- (+i) s t
+        a[3] = mk(fmaf(-ADM_SQRT1_2, t.y, e1.x), fmaf(ADM_SQRT1_2, t.x, e1.y));
+        a[7] = mk(fmaf(ADM_SQRT1_2, t.y, e1.x), fmaf(-ADM_SQRT1_2, t.x, e1.y));
+    }
 }
 
 // ---- radix-3/9 -----------------------------------------------------------------------------
 template <bool INV> ADM_HD void dft3(cpx& a0, cpx& a1, cpx& a2) {
     cpx t = a1 + a2;
-    cpx u = mk(a0.x - 0.5f * t.x, a0.y - 0.5f * t.y);
-    cpx v = mk((a1.x - a2.x) * ADM_SQRT3_2, (a1.y - a2.y) * ADM_SQRT3_2);
+    cpx u = mk(fmaf(-0.5f, t.x, a0.x), fmaf(-0.5f, t.y, a0.y));
+    cpx d = a1 - a2;
     a0 = a0 + t;
-    // forward: y1 = u - i v, y2 = u + i v ; inverse swaps
-    cpx p = mk(u.x + v.y, u.y - v.x);
-    cpx q = mk(u.x - v.y, u.y + v.x);
+    // forward: y1 = u - i c d, y2 = u + i c d (c = sqrt(3)/2, folded into the FMAs); inverse swaps
+    cpx p = mk(fmaf(ADM_SQRT3_2, d.y, u.x), fmaf(-ADM_SQRT3_2, d.x, u.y));
+    cpx q = mk(fmaf(-ADM_SQRT3_2, d.y, u.x), fmaf(ADM_SQRT3_2, d.x, u.y));
     if (!INV) { a1 = p; a2 = q; } else { a1 = q; a2 = p; }
 }
 

@@ -63,23 +63,28 @@ template <bool INV> ADM_DEV void dft8_2(cx2* a) {
     cx2 b1 = a[1] + a[5], c1 = a[1] - a[5];
     cx2 b2 = a[2] + a[6], c2 = a[2] - a[6];
     cx2 b3 = a[3] + a[7], c3 = a[3] - a[7];
-    // c1 *= W8, c3 *= W8^3 (c2 *= -+i is folded into the butterflies below)
-    if (!INV) {
-        c1 = mk2(mulc(c1.x + c1.y, ADM_SQRT1_2), mulc(c1.y - c1.x, ADM_SQRT1_2));
-        c3 = mk2(mulc(c3.y - c3.x, ADM_SQRT1_2), mulc(c3.x + c3.y, -ADM_SQRT1_2));
-    } else {
-        c1 = mk2(mulc(c1.x - c1.y, ADM_SQRT1_2), mulc(c1.x + c1.y, ADM_SQRT1_2));
-        c3 = mk2(mulc(c3.x + c3.y, -ADM_SQRT1_2), mulc(c3.x - c3.y, ADM_SQRT1_2));
-    }
     // even outputs: 4-point DFT of b
     {
         cx2 e0 = b0 + b2, e1 = b0 - b2, e2 = b1 + b3, t = b1 - b3;
         a[0] = e0 + e2; a[4] = e0 - e2; a[2] = add_mi<INV>(e1, t); a[6] = sub_mi<INV>(e1, t);
     }
-    // odd outputs: 4-point DFT of (c0, c1, -+i c2, c3)
+    // odd outputs: 4-point DFT of (c0, W8 c1, -+i c2, W8^3 c3); W8 c1 = s r1, W8^3 c3 = -s r3 with the unscaled
+    // rotations r1, r3: the factor s = 1/sqrt 2 is folded into the last butterfly (FFMA2), as in dft8
     {
-        cx2 e0 = add_mi<INV>(c0, c2), e1 = sub_mi<INV>(c0, c2), e2 = c1 + c3, t = c1 - c3;
-        a[1] = e0 + e2; a[5] = e0 - e2; a[3] = add_mi<INV>(e1, t); a[7] = sub_mi<INV>(e1, t);
+        cx2 r1, r3;
+        if (!INV) { r1 = mk2(c1.x + c1.y, c1.y - c1.x); r3 = mk2(c3.x - c3.y, c3.x + c3.y); }
+        else      { r1 = mk2(c1.x - c1.y, c1.x + c1.y); r3 = mk2(c3.x + c3.y, c3.y - c3.x); }
+        cx2 e0 = add_mi<INV>(c0, c2), e1 = sub_mi<INV>(c0, c2);
+        cx2 e2 = r1 - r3, t = r1 + r3;           // (W8 c1 + W8^3 c3) / s, (W8 c1 - W8^3 c3) / s
+        a[1] = mk2(fmac(e2.x, ADM_SQRT1_2, e0.x), fmac(e2.y, ADM_SQRT1_2, e0.y));
+        a[5] = mk2(fmac(e2.x, -ADM_SQRT1_2, e0.x), fmac(e2.y, -ADM_SQRT1_2, e0.y));
+        if (!INV) {
+            a[3] = mk2(fmac(t.y, ADM_SQRT1_2, e1.x), fmac(t.x, -ADM_SQRT1_2, e1.y));
+            a[7] = mk2(fmac(t.y, -ADM_SQRT1_2, e1.x), fmac(t.x, ADM_SQRT1_2, e1.y));
+        } else {
+            a[3] = mk2(fmac(t.y, -ADM_SQRT1_2, e1.x), fmac(t.x, ADM_SQRT1_2, e1.y));
+            a[7] = mk2(fmac(t.y, ADM_SQRT1_2, e1.x), fmac(t.x, -ADM_SQRT1_2, e1.y));
+        }
     }
 }
 
@@ -87,10 +92,10 @@ template <bool INV> ADM_DEV void dft3_2(cx2& a0, cx2& a1, cx2& a2) {
     cx2 t = a1 + a2;
     cx2 u = mk2(fmac(t.x, -0.5f, a0.x), fmac(t.y, -0.5f, a0.y));
     cx2 d = a1 - a2;
-    cx2 v = mk2(mulc(d.x, ADM_SQRT3_2), mulc(d.y, ADM_SQRT3_2));
     a0 = a0 + t;
-    a1 = add_mi<INV>(u, v);
-    a2 = sub_mi<INV>(u, v);
+    cx2 p = mk2(fmac(d.y, ADM_SQRT3_2, u.x), fmac(d.x, -ADM_SQRT3_2, u.y));
+    cx2 q = mk2(fmac(d.y, -ADM_SQRT3_2, u.x), fmac(d.x, ADM_SQRT3_2, u.y));
+    if (!INV) { a1 = p; a2 = q; } else { a1 = q; a2 = p; }
 }
 
 // multiply by exp(-+ i phi), (c, s) = (cos phi, sin phi)
