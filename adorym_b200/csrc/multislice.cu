@@ -38,18 +38,23 @@ template <class C> struct MsSmem {
     static constexpr size_t TW = sizeof(cpx) * C::P;
     static constexpr size_t HS = sizeof(cpx) * 2 * C::P;     // separable transfer function tables hy | hx
     static constexpr size_t BYTES = TILE + PSI + TW + HS + 16;
+    static constexpr size_t BYTES_NOTILE = PSI + TW + HS + 16;     // forward variant that reads T' with plain loads
 };
 
 // ================================================================================================
 // Forward
 // ================================================================================================
-template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+// TILE = true : T' tile by TMA into shared memory, prefetched one slice ahead (86 KB of shared memory, 2 CTAs per SM).
+// TILE = false: T' by plain coalesced loads at the top of P1 (the volume is L2 resident); 44 KB of shared memory, so
+//               with <= 72 registers FOUR CTAs are resident per SM: 592 slots hold all 529 wavefields of config D in one
+//               wave (no tail) at twice the warps per SM.
+template <class C, int MINB, bool TILE> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
     constexpr int TP = MsSmem<C>::TP;
     cpx* tile = (cpx*)smem_raw;
-    cpx* psi = tile + P * TP;
+    cpx* psi = TILE ? tile + P * TP : (cpx*)smem_raw;
     cpx* tw = psi + P * S;
     cpx* hs = tw + P;
     adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
@@ -67,22 +72,36 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
 
     init_twiddles<C>(tw, t);
     if (p.h_separable && t < 2 * P) hs[t] = p.Hp[t];
-    if (t == 0) mbar_init(bar, 1);
+    if (TILE && t == 0) mbar_init(bar, 1);
     __syncthreads();
-    if (t == 0) {   // prefetch the T' tile of slice 0
+    if (TILE && t == 0) {   // prefetch the T' tile of slice 0
         mbar_expect_tx(bar, TILE_BYTES);
         tma_load_tile(tile, &tmap, 2 * pxa, py, 0, bar);
     }
+    // TILE = false: this thread's column of the transmission volume
+    const int gx = px + l;
+    const bool x_in = (gx >= 0) && (gx < p.X);
+    const cpx* tcol = p.tvol + (x_in ? gx : 0);
+    const size_t slice_stride = (size_t)p.Y * p.Xp;
 
     for (int z = 0; z < p.Nz; ++z) {
         const bool last = (z == p.Nz - 1);
         const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
+        const cpx* tz = tcol + (size_t)z * slice_stride;
         // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
         if (active) {
-            mbar_wait(bar, z & 1);
+            if (TILE) mbar_wait(bar, z & 1);
             ADM_FOR_GROUPS_A(gi) {
                 const int g = I.group(gi);
-                cpx v[8];
+                cpx v[8], tp[8];
+                if (!TILE) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int gy = py + I.a(j, gi);
+                        const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
+                        tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : mk(0.f, 0.f);
+                    }
+                }
                 if (z == 0) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = probe[I.a(j, gi) * P + l];
@@ -95,7 +114,7 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
                 for (int j = 0; j < 8; ++j) {
                     const int y = I.a(j, gi);
                     ckpt[(size_t)z * P * TP + y * TP + lt] = v[j];
-                    v[j] = modulate(v[j], tile[y * TP + lt]);
+                    v[j] = modulate(v[j], TILE ? tile[y * TP + lt] : tp[j]);
                 }
                 if (go_on) {
                     if (last && p.ff_conj) {
@@ -116,7 +135,7 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
             }
         }
         __syncthreads();
-        if (t == 0 && !last) {   // every thread has consumed tile(z): prefetch tile(z+1) behind P2..P6
+        if (TILE && t == 0 && !last) {   // every thread has consumed tile(z): prefetch tile(z+1) behind P2..P6
             mbar_expect_tx(bar, TILE_BYTES);
             tma_load_tile(tile, &tmap, 2 * pxa, py, z + 1, bar);
         }
@@ -422,16 +441,19 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;
     int var = adm_variant("ADM_FWD_VARIANT");
-#define ADM_FWD(CFG, MINB)                                                                                         \
+#define ADM_FWD(CFG, MINB, TILE)                                                                                   \
     do {                                                                                                           \
-        if (set_smem(k_multislice_fwd<CFG, MINB>, MsSmem<CFG>::BYTES)) return ADM_ERR_CUDA;                        \
-        ADM_LAUNCH((k_multislice_fwd<CFG, MINB>), nwf, CFG::NTHREADS, MsSmem<CFG>::BYTES, stream, map, p);         \
+        const size_t sm_ = TILE ? MsSmem<CFG>::BYTES : MsSmem<CFG>::BYTES_NOTILE;                                  \
+        if (set_smem(k_multislice_fwd<CFG, MINB, TILE>, sm_)) return ADM_ERR_CUDA;                                 \
+        ADM_LAUNCH((k_multislice_fwd<CFG, MINB, TILE>), nwf, CFG::NTHREADS, sm_, stream, map, p);                  \
     } while (0)
     if (cfg->P == 72) {
-        if (var == 1) ADM_FWD(Cfg72ct, 2);
-        else ADM_FWD(Cfg72, 2);
+        if (var == 1) ADM_FWD(Cfg72ct, 2, true);
+        else if (var == 2) ADM_FWD(Cfg72, 4, false);
+        else if (var == 3) ADM_FWD(Cfg72, 3, false);
+        else ADM_FWD(Cfg72, 2, true);
     } else {
-        ADM_FWD(Cfg64, 2);
+        ADM_FWD(Cfg64, 2, true);
     }
     return ADM_OK;
 }
