@@ -2,6 +2,7 @@
 // See multislice.cu for the description of the pass structure and the permuted spectrum order.
 #pragma once
 #include "adm_common.cuh"
+#include "cpk.cuh"
 
 template <int P_, int R2_, int Q_, bool PFA_ = false> struct MsCfg {
     static constexpr int P = P_;
@@ -78,10 +79,10 @@ template <class C, bool XDIR> ADM_DEV int addr(int l, int along) {
 #define ADM_FOR_GROUPS_B(gi) _Pragma("unroll") for (int gi = 0; gi < C::NGB; ++gi) if ((C::R1 % C::Q) == 0 || I.group(gi) < C::R1)
 
 // pass A (forward radix-8 [+ twiddle]) along one direction
-template <class C, bool XDIR> ADM_DEV void pass_A_fwd(cpx* psi, const cpx* tw, int q, int l) {
+template <class C, bool XDIR, class T> ADM_DEV void pass_A_fwd(T* psi, const T* tw, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_A(gi) {
-        cpx v[8];
+        T v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = psi[addr<C, XDIR>(l, I.a(j, gi))];
         dft8<false>(v);
@@ -94,10 +95,10 @@ template <class C, bool XDIR> ADM_DEV void pass_A_fwd(cpx* psi, const cpx* tw, i
     }
 }
 // pass A^-1 (inverse radix-8), no twiddle (applied by B^-1)
-template <class C, bool XDIR> ADM_DEV void pass_A_inv(cpx* psi, int q, int l) {
+template <class C, bool XDIR, class T> ADM_DEV void pass_A_inv(T* psi, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_A(gi) {
-        cpx v[8];
+        T v[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] = psi[addr<C, XDIR>(l, I.a(j, gi))];
         dft8<true>(v);
@@ -106,25 +107,25 @@ template <class C, bool XDIR> ADM_DEV void pass_A_inv(cpx* psi, int q, int l) {
     }
 }
 // pass B forward (radix-R2)
-template <class C, bool XDIR> ADM_DEV void pass_B_fwd(cpx* psi, int q, int l) {
+template <class C, bool XDIR, class T> ADM_DEV void pass_B_fwd(T* psi, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_B(gi) {
-        cpx v[C::R2];
+        T v[C::R2];
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) v[n] = psi[addr<C, XDIR>(l, I.b(n, gi))];
-        DftR<C::R2, false>::run(v);
+        dftr<C::R2, false>(v);
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) psi[addr<C, XDIR>(l, I.b(n, gi))] = v[n];
     }
 }
 // pass B^-1 (inverse radix-R2 [+ conjugate twiddle])
-template <class C, bool XDIR> ADM_DEV void pass_B_inv(cpx* psi, const cpx* tw, int q, int l) {
+template <class C, bool XDIR, class T> ADM_DEV void pass_B_inv(T* psi, const T* tw, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_B(gi) {
-        cpx v[C::R2];
+        T v[C::R2];
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) v[n] = psi[addr<C, XDIR>(l, I.b(n, gi))];
-        DftR<C::R2, true>::run(v);
+        dftr<C::R2, true>(v);
         if constexpr (!C::PFA) {
 #pragma unroll
             for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[I.group(gi) * n]);
@@ -134,16 +135,16 @@ template <class C, bool XDIR> ADM_DEV void pass_B_inv(cpx* psi, const cpx* tw, i
     }
 }
 // P4: pass B forward, multiply by the prepared transfer function, pass B^-1 (x direction, lanes along y)
-template <class C> ADM_DEV void pass_BHB_x(cpx* psi, const cpx* tw, const cpx* __restrict__ H, int q, int l) {
+template <class C, class T> ADM_DEV void pass_BHB_x(T* psi, const T* tw, const T* __restrict__ H, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_B(gi) {
-        cpx v[C::R2];
+        T v[C::R2];
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + I.b(n, gi)];
-        DftR<C::R2, false>::run(v);
+        dftr<C::R2, false>(v);
 #pragma unroll
         for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], H[I.b(k, gi) * C::P + l]);
-        DftR<C::R2, true>::run(v);
+        dftr<C::R2, true>(v);
         if constexpr (!C::PFA) {
 #pragma unroll
             for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[I.group(gi) * n]);
@@ -157,28 +158,28 @@ template <class C> ADM_DEV void pass_BHB_x(cpx* psi, const cpx* tw, const cpx* _
 // hys / hxs are P-entry shared-memory tables indexed by spectrum position (hxs carries the 1/P^2 scale); the lanes of a
 // warp read the same few entries (broadcast), so H costs no global / L1 traffic in the slice loop.
 // pass B forward along y with the hy factor applied to the outputs
-template <class C> ADM_DEV void pass_B_fwd_y_scaled(cpx* psi, const cpx* hys, int q, int l) {
+template <class C, class T> ADM_DEV void pass_B_fwd_y_scaled(T* psi, const T* hys, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_B(gi) {
-        cpx v[C::R2];
+        T v[C::R2];
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) v[n] = psi[I.b(n, gi) * C::S + l];
-        DftR<C::R2, false>::run(v);
+        dftr<C::R2, false>(v);
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) psi[I.b(n, gi) * C::S + l] = cmul(v[n], hys[I.b(n, gi)]);
     }
 }
 // P4 with the hx factor
-template <class C> ADM_DEV void pass_BHB_x_sep(cpx* psi, const cpx* tw, const cpx* hxs, int q, int l) {
+template <class C, class T> ADM_DEV void pass_BHB_x_sep(T* psi, const T* tw, const T* hxs, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_B(gi) {
-        cpx v[C::R2];
+        T v[C::R2];
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + I.b(n, gi)];
-        DftR<C::R2, false>::run(v);
+        dftr<C::R2, false>(v);
 #pragma unroll
         for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], hxs[I.b(k, gi)]);
-        DftR<C::R2, true>::run(v);
+        dftr<C::R2, true>(v);
         if constexpr (!C::PFA) {
 #pragma unroll
             for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[I.group(gi) * n]);
@@ -188,22 +189,22 @@ template <class C> ADM_DEV void pass_BHB_x_sep(cpx* psi, const cpx* tw, const cp
     }
 }
 
-template <class C> ADM_DEV void init_twiddles(cpx* tw, int t) {
+template <class C, class T> ADM_DEV void init_twiddles(T* tw, int t) {
     if (t < C::P) {
 #ifndef ADM_HOST_EMU
         float s, c;
         sincospif(2.0f * (float)t / (float)C::P, &s, &c);
-        tw[t] = mk(c, -s);
+        tw[t] = tmk<T>(c, -s);
 #else
         double a = 2.0 * 3.14159265358979323846 * t / C::P;
-        tw[t] = mk((float)cos(a), (float)-sin(a));
+        tw[t] = tmk<T>((float)cos(a), (float)-sin(a));
 #endif
     }
 }
 
 // P2..P6 : psi <- IFFT2(H . FFT2(psi)) given that pass A along y has already been applied, and leaving the
 // final pass A^-1 along y to the caller (fused with the next modulation).
-template <class C> ADM_DEV void propagate_core(cpx* psi, const cpx* tw, const cpx* H, int q, int l, bool active) {
+template <class C, class T> ADM_DEV void propagate_core(T* psi, const T* tw, const T* H, int q, int l, bool active) {
     if (active) pass_B_fwd<C, false>(psi, q, l);
     __syncthreads();
     if (active) pass_A_fwd<C, true>(psi, tw, q, l);
@@ -218,7 +219,7 @@ template <class C> ADM_DEV void propagate_core(cpx* psi, const cpx* tw, const cp
 
 
 // same with a separable transfer function: hs = [hy(P) | hx(P)] in shared memory
-template <class C> ADM_DEV void propagate_core_sep(cpx* psi, const cpx* tw, const cpx* hs, int q, int l, bool active) {
+template <class C, class T> ADM_DEV void propagate_core_sep(T* psi, const T* tw, const T* hs, int q, int l, bool active) {
     if (active) pass_B_fwd_y_scaled<C>(psi, hs, q, l);
     __syncthreads();
     if (active) pass_A_fwd<C, true>(psi, tw, q, l);

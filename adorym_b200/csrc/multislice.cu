@@ -48,15 +48,15 @@ template <class C> struct MsSmem {
 // TILE = false: T' by plain coalesced loads at the top of P1 (the volume is L2 resident); 44 KB of shared memory, so
 //               with <= 72 registers FOUR CTAs are resident per SM: 592 slots hold all 529 wavefields of config D in one
 //               wave (no tail) at twice the warps per SM.
-template <class C, int MINB, bool TILE> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
     constexpr int TP = MsSmem<C>::TP;
-    cpx* tile = (cpx*)smem_raw;
-    cpx* psi = TILE ? tile + P * TP : (cpx*)smem_raw;
-    cpx* tw = psi + P * S;
-    cpx* hs = tw + P;
+    T* tile = (T*)smem_raw;
+    T* psi = TILE ? tile + P * TP : (T*)smem_raw;
+    T* tw = psi + P * S;
+    T* hs = tw + P;
     adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
@@ -66,12 +66,12 @@ template <class C, int MINB, bool TILE> __global__ void __launch_bounds__(C::NTH
     const int b = wf / p.M, m = wf % p.M;
     const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
     const int pxa = px & ~1, lt = l + (px & 1);     // even TMA start column, this thread's column inside the tile
-    const cpx* probe = p.probe + (size_t)(p.probe_per_pattern ? wf : m) * P * P;
-    cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * P * TP;
-    cpx* det = p.det + (size_t)wf * P * P;
+    const T* probe = (const T*)p.probe + (size_t)(p.probe_per_pattern ? wf : m) * P * P;
+    T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * P * TP;
+    T* det = (T*)p.det + (size_t)wf * P * P;
 
     init_twiddles<C>(tw, t);
-    if (p.h_separable && t < 2 * P) hs[t] = p.Hp[t];
+    if (p.h_separable && t < 2 * P) hs[t] = ((const T*)p.Hp)[t];
     if (TILE && t == 0) mbar_init(bar, 1);
     __syncthreads();
     if (TILE && t == 0) {   // prefetch the T' tile of slice 0
@@ -81,25 +81,25 @@ template <class C, int MINB, bool TILE> __global__ void __launch_bounds__(C::NTH
     // TILE = false: this thread's column of the transmission volume
     const int gx = px + l;
     const bool x_in = (gx >= 0) && (gx < p.X);
-    const cpx* tcol = p.tvol + (x_in ? gx : 0);
+    const T* tcol = (const T*)p.tvol + (x_in ? gx : 0);
     const size_t slice_stride = (size_t)p.Y * p.Xp;
 
     for (int z = 0; z < p.Nz; ++z) {
         const bool last = (z == p.Nz - 1);
         const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
-        const cpx* tz = tcol + (size_t)z * slice_stride;
+        const T* tz = tcol + (size_t)z * slice_stride;
         // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
         if (active) {
             if (TILE) mbar_wait(bar, z & 1);
             ADM_FOR_GROUPS_A(gi) {
                 const int g = I.group(gi);
-                cpx v[8], tp[8];
+                T v[8], tp[8];
                 if (!TILE) {
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
                         const int gy = py + I.a(j, gi);
                         const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
-                        tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : mk(0.f, 0.f);
+                        tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : tmk<T>(0.f, 0.f);
                     }
                 }
                 if (z == 0) {
@@ -150,14 +150,14 @@ template <class C, int MINB, bool TILE> __global__ void __launch_bounds__(C::NTH
                 const int fy = (perm_freq<C>(l) + P / 2) % P;
                 ADM_FOR_GROUPS_B(gi) {
                     const int g = I.group(gi);
-                    cpx v[R2];
+                    T v[R2];
 #pragma unroll
                     for (int n = 0; n < R2; ++n) v[n] = psi[l * S + I.b(n, gi)];
-                    DftR<R2, false>::run(v);
+                    dftr<R2, false>(v);
 #pragma unroll
                     for (int k = 0; k < R2; ++k) {
                         int fx = (perm_freq<C>(I.b(k, gi)) + P / 2) % P;
-                        cpx o = cscale(v[k], p.ff_scale);
+                        T o = cscale(v[k], p.ff_scale);
                         det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
                     }
                 }
@@ -165,12 +165,12 @@ template <class C, int MINB, bool TILE> __global__ void __launch_bounds__(C::NTH
             break;
         }
         if (!last && p.h_separable) propagate_core_sep<C>(psi, tw, hs, q, l, active);
-        else propagate_core<C>(psi, tw, last ? p.Hf : p.Hp, q, l, active);
+        else propagate_core<C>(psi, tw, (const T*)(last ? p.Hf : p.Hp), q, l, active);
         if (last) {
             // near field: final Ay^-1, natural order store
             if (active) {
                 ADM_FOR_GROUPS_A(gi) {
-                    cpx v[8];
+                    T v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
                     dft8<true>(v);
@@ -185,15 +185,15 @@ template <class C, int MINB, bool TILE> __global__ void __launch_bounds__(C::NTH
 // ================================================================================================
 // Adjoint
 // ================================================================================================
-template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
+template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
     constexpr int TP = MsSmem<C>::TP;
-    cpx* ckb = (cpx*)smem_raw;          // psi checkpoint of the slice (bulk copy); overwritten in place by dL/dT
-    cpx* psi = ckb + P * TP;            // running adjoint wavefield g
-    cpx* tw = psi + P * S;
-    cpx* hs = tw + P;
+    T* ckb = (T*)smem_raw;          // psi checkpoint of the slice (bulk copy); overwritten in place by dL/dT
+    T* psi = ckb + P * TP;            // running adjoint wavefield g
+    T* tw = psi + P * S;
+    T* hs = tw + P;
     adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
@@ -205,13 +205,13 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
     const int pxa = px & ~1, lt = l + (px & 1);
     const int gx = px + l;
     const bool x_in = (gx >= 0) && (gx < p.X);
-    const cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * P * TP;
-    const cpx* gdet = p.det + (size_t)wf * P * P;
+    const T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * P * TP;
+    const T* gdet = (const T*)p.det + (size_t)wf * P * P;
     const size_t slice_stride = (size_t)p.Y * p.Xp;
-    const cpx* tcol = p.tvol + (x_in ? gx : 0);     // this thread's column of the transmission volume
+    const T* tcol = (const T*)p.tvol + (x_in ? gx : 0);     // this thread's column of the transmission volume
 
     init_twiddles<C>(tw, t);
-    if (p.h_separable && t < 2 * P) hs[t] = p.Hp[t];
+    if (p.h_separable && t < 2 * P) hs[t] = ((const T*)p.Hp)[t];
     if (t == 0) mbar_init(bar, 1);
     __syncthreads();
     if (t == 0) {   // prefetch the checkpoint of the last slice
@@ -225,14 +225,14 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
             const int fy = (perm_freq<C>(l) + P / 2) % P;
             ADM_FOR_GROUPS_B(gi) {
                     const int g = I.group(gi);
-                cpx v[R2];
+                T v[R2];
 #pragma unroll
                 for (int k = 0; k < R2; ++k) {
                     int fx = (perm_freq<C>(I.b(k, gi)) + P / 2) % P;
-                    cpx o = cscale(gdet[fy * P + fx], p.ff_scale);
+                    T o = cscale(gdet[fy * P + fx], p.ff_scale);
                     v[k] = p.ff_conj ? cconj(o) : o;
                 }
-                DftR<R2, true>::run(v);
+                dftr<R2, true>(v);
                 if constexpr (!C::PFA) {
 #pragma unroll
                     for (int n = 1; n < R2; ++n) v[n] = cmulc(v[n], tw[g * n]);
@@ -250,7 +250,7 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
         if (active) {
             ADM_FOR_GROUPS_A(gi) {
                 const int g = I.group(gi);
-                cpx v[8];
+                T v[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[j] = gdet[I.a(j, gi) * P + l];
                 dft8<false>(v);
@@ -263,25 +263,25 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
             }
         }
         __syncthreads();
-        propagate_core<C>(psi, tw, p.Hf, q, l, active);
+        propagate_core<C>(psi, tw, (const T*)p.Hf, q, l, active);
     }
 
     int phase = 0;
     for (int z = p.Nz - 1; z >= 0; --z, phase ^= 1) {
         const bool last = (z == p.Nz - 1);
-        const cpx* tz = tcol + (size_t)z * slice_stride;
+        const T* tz = tcol + (size_t)z * slice_stride;
         // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] ------------------------------
         if (active) {
             ADM_FOR_GROUPS_A(gi) {
                 const int g = I.group(gi);
-                cpx v[8], tp[8];
+                T v[8], tp[8];
                 // T' of this slice (L2-resident volume; issued first so the butterfly hides the latency); 32-bit offsets
                 // from the per-slice column pointer, one unsigned compare per row
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int gy = py + I.a(j, gi);
                     const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
-                    tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : mk(0.f, 0.f);
+                    tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : tmk<T>(0.f, 0.f);
                 }
                 if (last && p.free_prop == ADM_PROP_NONE) {
 #pragma unroll
@@ -298,12 +298,12 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
                 if (gi == 0) {
                     mbar_wait(bar, phase);
                     // the two pad columns of the tile are never written by the forward pass: add zeros there
-                    if (t < 2 * P) ckb[(t >> 1) * TP + ((t & 1) ? P + 1 : ((px & 1) ? 0 : P))] = mk(0.f, 0.f);
+                    if (t < 2 * P) ckb[(t >> 1) * TP + ((t & 1) ? P + 1 : ((px & 1) ? 0 : P))] = tmk<T>(0.f, 0.f);
                 }
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const int y = I.a(j, gi);
-                    const cpx w = ckb[y * TP + lt];               // psi_z (wave entering the slice)
+                    const T w = ckb[y * TP + lt];               // psi_z (wave entering the slice)
                     ckb[y * TP + lt] = cmulc(v[j], w);            // dL/dT = g' conj(psi_z)
                     v[j] = modulate_conj(v[j], tp[j]);            // g_psi = g' conj(T)
                 }
@@ -318,11 +318,11 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
                 } else if (p.g_probe != nullptr) {
                     if (p.probe_per_pattern) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) p.g_probe[(size_t)wf * P * P + I.a(j, gi) * P + l] = v[j];
+                        for (int j = 0; j < 8; ++j) ((T*)p.g_probe)[(size_t)wf * P * P + I.a(j, gi) * P + l] = v[j];
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            red_add2(&p.g_probe[(size_t)m * P * P + I.a(j, gi) * P + l], v[j].x, v[j].y);
+                            red_add2(&p.g_probe[(size_t)m * P * P + I.a(j, gi) * P + l], cx(v[j]), cy(v[j]));
                     }
                 }
             }
@@ -348,7 +348,7 @@ template <class C, int MINB> __global__ void __launch_bounds__(C::NTHREADS, MINB
         __syncthreads();
         if (active) {
             if (p.h_separable) pass_BHB_x_sep<C>(psi, tw, hs + P, q, l);
-            else pass_BHB_x<C>(psi, tw, p.Hp, q, l);
+            else pass_BHB_x<C>(psi, tw, (const T*)p.Hp, q, l);
         }
         __syncthreads();
         if (active) pass_A_inv<C, true>(psi, q, l);
@@ -441,19 +441,22 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;
     int var = adm_variant("ADM_FWD_VARIANT");
-#define ADM_FWD(CFG, MINB, TILE)                                                                                   \
+#define ADM_FWD(CFG, MINB, TILE, CT)                                                                                  \
     do {                                                                                                           \
         const size_t sm_ = TILE ? MsSmem<CFG>::BYTES : MsSmem<CFG>::BYTES_NOTILE;                                  \
-        if (set_smem(k_multislice_fwd<CFG, MINB, TILE>, sm_)) return ADM_ERR_CUDA;                                 \
-        ADM_LAUNCH((k_multislice_fwd<CFG, MINB, TILE>), nwf, CFG::NTHREADS, sm_, stream, map, p);                  \
+        if (set_smem(k_multislice_fwd<CFG, MINB, TILE, CT>, sm_)) return ADM_ERR_CUDA;                             \
+        ADM_LAUNCH((k_multislice_fwd<CFG, MINB, TILE, CT>), nwf, CFG::NTHREADS, sm_, stream, map, p);              \
     } while (0)
     if (cfg->P == 72) {
-        if (var == 1) ADM_FWD(Cfg72ct, 2, true);
-        else if (var == 2) ADM_FWD(Cfg72, 4, false);
-        else if (var == 3) ADM_FWD(Cfg72, 3, false);
-        else ADM_FWD(Cfg72, 2, true);
+        if (var == 1) ADM_FWD(Cfg72ct, 2, true, cpx);
+        else if (var == 2) ADM_FWD(Cfg72, 4, false, cpx);
+        else if (var == 3) ADM_FWD(Cfg72, 3, false, cpx);
+        else if (var == 4) ADM_FWD(Cfg72, 2, true, cpx);      // scalar butterflies (one FADD / FFMA per component)
+        else if (var == 5) ADM_FWD(Cfg72, 4, false, cpk);
+        else ADM_FWD(Cfg72, 2, true, cpk);                    // packed complex arithmetic (cpk.cuh)
     } else {
-        ADM_FWD(Cfg64, 2, true);
+        if (var == 4) ADM_FWD(Cfg64, 2, true, cpx);
+        else ADM_FWD(Cfg64, 2, true, cpk);
     }
     return ADM_OK;
 }
@@ -477,16 +480,18 @@ extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tv
         return ADM_ERR_CUDA;
     int nwf = cfg->B * cfg->M;
     int var = adm_variant("ADM_BWD_VARIANT");
-#define ADM_BWD(CFG, MINB)                                                                                         \
+#define ADM_BWD(CFG, MINB, CT)                                                                                       \
     do {                                                                                                           \
-        if (set_smem(k_multislice_bwd<CFG, MINB>, MsSmem<CFG>::BYTES)) return ADM_ERR_CUDA;                        \
-        ADM_LAUNCH((k_multislice_bwd<CFG, MINB>), nwf, CFG::NTHREADS, MsSmem<CFG>::BYTES, stream, map, p);         \
+        if (set_smem(k_multislice_bwd<CFG, MINB, CT>, MsSmem<CFG>::BYTES)) return ADM_ERR_CUDA;                    \
+        ADM_LAUNCH((k_multislice_bwd<CFG, MINB, CT>), nwf, CFG::NTHREADS, MsSmem<CFG>::BYTES, stream, map, p);     \
     } while (0)
     if (cfg->P == 72) {
-        if (var == 1) ADM_BWD(Cfg72ct, 2);
-        else ADM_BWD(Cfg72, 2);
+        if (var == 1) ADM_BWD(Cfg72ct, 2, cpx);
+        else if (var == 4) ADM_BWD(Cfg72, 2, cpx);
+        else ADM_BWD(Cfg72, 2, cpk);
     } else {
-        ADM_BWD(Cfg64, 2);
+        if (var == 4) ADM_BWD(Cfg64, 2, cpx);
+        else ADM_BWD(Cfg64, 2, cpk);
     }
     return ADM_OK;
 }
