@@ -157,20 +157,9 @@ template <class C, class T> ADM_DEV void pass_BHB_x(T* psi, const T* tw, const T
 // ---- separable transfer function H(ky, kx) = hy(ky) hx(kx) (Fresnel kernel, propagate.py:72) -----------------------
 // hys / hxs are P-entry shared-memory tables indexed by spectrum position (hxs carries the 1/P^2 scale); the lanes of a
 // warp read the same few entries (broadcast), so H costs no global / L1 traffic in the slice loop.
-// pass B forward along y with the hy factor applied to the outputs
-template <class C, class T> ADM_DEV void pass_B_fwd_y_scaled(T* psi, const T* hys, int q, int l) {
-    const Idx<C> I(q);
-    ADM_FOR_GROUPS_B(gi) {
-        T v[C::R2];
-#pragma unroll
-        for (int n = 0; n < C::R2; ++n) v[n] = psi[I.b(n, gi) * C::S + l];
-        dftr<C::R2, false>(v);
-#pragma unroll
-        for (int n = 0; n < C::R2; ++n) psi[I.b(n, gi) * C::S + l] = cmul(v[n], hys[I.b(n, gi)]);
-    }
-}
-// P4 with the hx factor
-template <class C, class T> ADM_DEV void pass_BHB_x_sep(T* psi, const T* tw, const T* hxs, int q, int l) {
+// hyl = hy at this thread's row (spectrum position l along y): the y factor of the separable transfer function is
+// constant along the row, so it is applied here from a register instead of through 24 table reads in the y pass
+template <class C, class T> ADM_DEV void pass_BHB_x_sep(T* psi, const T* tw, const T* hxs, T hyl, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_B(gi) {
         T v[C::R2];
@@ -178,7 +167,7 @@ template <class C, class T> ADM_DEV void pass_BHB_x_sep(T* psi, const T* tw, con
         for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + I.b(n, gi)];
         dftr<C::R2, false>(v);
 #pragma unroll
-        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], hxs[I.b(k, gi)]);
+        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], cmul(hxs[I.b(k, gi)], hyl));
         dftr<C::R2, true>(v);
         if constexpr (!C::PFA) {
 #pragma unroll
@@ -220,11 +209,11 @@ template <class C, class T> ADM_DEV void propagate_core(T* psi, const T* tw, con
 
 // same with a separable transfer function: hs = [hy(P) | hx(P)] in shared memory
 template <class C, class T> ADM_DEV void propagate_core_sep(T* psi, const T* tw, const T* hs, int q, int l, bool active) {
-    if (active) pass_B_fwd_y_scaled<C>(psi, hs, q, l);
+    if (active) pass_B_fwd<C, false>(psi, q, l);
     __syncthreads();
     if (active) pass_A_fwd<C, true>(psi, tw, q, l);
     __syncthreads();
-    if (active) pass_BHB_x_sep<C>(psi, tw, hs + C::P, q, l);
+    if (active) pass_BHB_x_sep<C>(psi, tw, hs + C::P, hs[l], q, l);
     __syncthreads();
     if (active) pass_A_inv<C, true>(psi, q, l);
     __syncthreads();

@@ -334,10 +334,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
             bulk_commit();
         }
         if (z == 0) break;
-        if (active) {
-            if (p.h_separable) pass_B_fwd_y_scaled<C>(psi, hs, q, l);
-            else pass_B_fwd<C, false>(psi, q, l);
-        }
+        if (active) pass_B_fwd<C, false>(psi, q, l);
         __syncthreads();
         if (t == 0) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind P3..P6
             bulk_wait_read_all();
@@ -347,7 +344,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
         if (active) pass_A_fwd<C, true>(psi, tw, q, l);
         __syncthreads();
         if (active) {
-            if (p.h_separable) pass_BHB_x_sep<C>(psi, tw, hs + P, q, l);
+            if (p.h_separable) pass_BHB_x_sep<C>(psi, tw, hs + P, hs[l], q, l);
             else pass_BHB_x<C>(psi, tw, (const T*)p.Hp, q, l);
         }
         __syncthreads();

@@ -47,16 +47,16 @@ ADM_HDM int pos72(int a, int b) { return (9 * a + 8 * b) % 72; }
 // frequency held at spectrum position (k1, k2)
 ADM_HDM int freq72(int k1, int k2) { return (9 * k1 + 64 * k2) % 72; }
 
-template <bool INV, int ST> ADM_DEV void dft9s(cpx* a) {
-    cpx t[9];
+template <bool INV, int ST, class T> ADM_DEV void dft9s(T* a) {
+    T t[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) t[i] = a[i * ST];
     dft9<INV>(t);
 #pragma unroll
     for (int i = 0; i < 9; ++i) a[i * ST] = t[i];
 }
-template <bool INV, int ST> ADM_DEV void dft8s(cpx* a) {
-    cpx t[8];
+template <bool INV, int ST, class T> ADM_DEV void dft8s(T* a) {
+    T t[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) t[i] = a[i * ST];
     dft8<INV>(t);
@@ -65,7 +65,7 @@ template <bool INV, int ST> ADM_DEV void dft8s(cpx* a) {
 }
 
 // v[9 by + bx]: 9-point transforms along bx then by (or by then bx; they commute)
-template <bool INV> ADM_DEV void dft9x9(cpx* v) {
+template <bool INV, class T> ADM_DEV void dft9x9(T* v) {
 #pragma unroll
     for (int by = 0; by < 9; ++by) dft9s<INV, 1>(v + 9 * by);
 #pragma unroll
@@ -88,16 +88,16 @@ ADM_DEV void l2_prefetch(const void* g, unsigned bytes) {
 }
 
 // S pass: u[8 jy + jx] <- IDFT8x8( H . DFT8x8(u) ) for the thread's (by, bx); hs = [hy | hx] indexed by spectrum position
-ADM_DEV void s_pass(cpx* psi, const cpx* hs, int s) {
+template <class T> ADM_DEV void s_pass(T* psi, const T* hs, int s) {
     const int by = s / 9, bx = s - 9 * by;
-    cpx u[64];
+    T u[64];
 #pragma unroll
     for (int j = 0; j < 64; ++j) u[j] = psi[j * NS + s];
 #pragma unroll
     for (int jx = 0; jx < 8; ++jx) dft8s<false, 8>(u + jx);          // along ay
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const cpx h = hs[pos72(k, by)];
+        const T h = hs[pos72(k, by)];
 #pragma unroll
         for (int jx = 0; jx < 8; ++jx) u[8 * k + jx] = cmul(u[8 * k + jx], h);
     }
@@ -105,7 +105,7 @@ ADM_DEV void s_pass(cpx* psi, const cpx* hs, int s) {
     for (int jy = 0; jy < 8; ++jy) dft8s<false, 1>(u + 8 * jy);      // along ax
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
-        const cpx h = hs[P + pos72(k, bx)];
+        const T h = hs[P + pos72(k, bx)];
 #pragma unroll
         for (int jy = 0; jy < 8; ++jy) u[8 * jy + k] = cmul(u[8 * jy + k], h);
     }
@@ -117,12 +117,12 @@ ADM_DEV void s_pass(cpx* psi, const cpx* hs, int s) {
     for (int j = 0; j < 64; ++j) psi[j * NS + s] = u[j];
 }
 
-struct Smem {
-    cpx* tile; cpx* psi; cpx* hs; adm_mbar_t* barT; adm_mbar_t* barC;
+template <class T> struct Smem {
+    T* tile; T* psi; T* hs; adm_mbar_t* barT; adm_mbar_t* barC;
     ADM_HDM explicit Smem(unsigned char* raw) {
-        tile = (cpx*)raw;
-        psi = (cpx*)(raw + OFF_PSI);
-        hs = (cpx*)(raw + OFF_HS);
+        tile = (T*)raw;
+        psi = (T*)(raw + OFF_PSI);
+        hs = (T*)(raw + OFF_HS);
         barT = (adm_mbar_t*)(raw + OFF_BAR);
         barC = barT + 1;
     }
@@ -131,10 +131,10 @@ struct Smem {
 // ================================================================================================
 // Forward
 // ================================================================================================
-__global__ void __launch_bounds__(NT, 2) k_ms2_fwd(const ADM_GRID_CONSTANT AdmTileMap map_even,
+template <class T> __global__ void __launch_bounds__(NT, 2) k_ms2_fwd(const ADM_GRID_CONSTANT AdmTileMap map_even,
                                                    const ADM_GRID_CONSTANT AdmTileMap map_odd, MsParams p) {
     ADM_SMEM_DECL
-    const Smem sm(smem_raw);
+    const Smem<T> sm(smem_raw);
     const int t = threadIdx.x;
     const int wf = blockIdx.x;
     const int b = wf / p.M, m = wf % p.M;
@@ -142,14 +142,14 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_fwd(const ADM_GRID_CONSTANT AdmTi
     const int odd = px & 1, pxa = px & ~1;
     const int TP = P + 2 * odd;
     const AdmTileMap* tmap = odd ? &map_odd : &map_even;
-    const unsigned tile_bytes = (unsigned)(sizeof(cpx) * P * TP);
-    const cpx* probe = p.probe + (size_t)(p.probe_per_pattern ? wf : m) * NPSI;
-    cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * NPSI;
-    cpx* det = p.det + (size_t)wf * NPSI;
+    const unsigned tile_bytes = (unsigned)(sizeof(T) * P * TP);
+    const T* probe = (const T*)p.probe + (size_t)(p.probe_per_pattern ? wf : m) * NPSI;
+    T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * NPSI;
+    T* det = (T*)p.det + (size_t)wf * NPSI;
     // R-thread geometry
     const int ay = (t >> 3) & 7, ax = t & 7;
 
-    for (int i = t; i < 2 * P; i += NT) sm.hs[i] = p.Hp[i];
+    for (int i = t; i < 2 * P; i += NT) sm.hs[i] = ((const T*)p.Hp)[i];
     if (t == DMA) mbar_init(sm.barT, 1);
     __syncthreads();
     if (t == DMA) {
@@ -160,7 +160,7 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_fwd(const ADM_GRID_CONSTANT AdmTi
     for (int z = 0; z < p.Nz; ++z) {
         const bool last = (z == p.Nz - 1);
         if (t < NR) {
-            cpx v[81];
+            T v[81];
             if (z == 0) {
 #pragma unroll
                 for (int by = 0; by < 9; ++by)
@@ -172,10 +172,10 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_fwd(const ADM_GRID_CONSTANT AdmTi
                 dft9x9<true>(v);
             }
             mbar_wait(sm.barT, z & 1);
-            cpx* ck = ckpt + (size_t)z * NPSI + t;
+            T* ck = ckpt + (size_t)z * NPSI + t;
 #pragma unroll
             for (int by = 0; by < 9; ++by) {
-                const cpx* row = sm.tile + pos72(ay, by) * TP + odd;
+                const T* row = sm.tile + pos72(ay, by) * TP + odd;
 #pragma unroll
                 for (int bx = 0; bx < 9; ++bx) {
                     const int e = 9 * by + bx;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_fwd(const ADM_GRID_CONSTANT AdmTi
             // far field: the remaining 8-point stages, stored fftshift-ed in natural order
             if (t < NS) {
                 const int by = t / 9, bx = t - 9 * by;
-                cpx u[64];
+                T u[64];
 #pragma unroll
                 for (int j = 0; j < 64; ++j) u[j] = sm.psi[j * NS + t];
 #pragma unroll
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_fwd(const ADM_GRID_CONSTANT AdmTi
 #pragma unroll
                     for (int kx = 0; kx < 8; ++kx) {
                         const int fx = (freq72(kx, bx) + P / 2) % P;
-                        const cpx o = cscale(u[8 * ky + kx], p.ff_scale);
+                        const T o = cscale(u[8 * ky + kx], p.ff_scale);
                         det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
                     }
                 }
@@ -236,12 +236,12 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_fwd(const ADM_GRID_CONSTANT AdmTi
 // ================================================================================================
 // Adjoint
 // ================================================================================================
-__global__ void __launch_bounds__(NT, 2) k_ms2_bwd(const ADM_GRID_CONSTANT AdmTileMap tmap_even,
+template <class T> __global__ void __launch_bounds__(NT, 2) k_ms2_bwd(const ADM_GRID_CONSTANT AdmTileMap tmap_even,
                                                    const ADM_GRID_CONSTANT AdmTileMap tmap_odd,
                                                    const ADM_GRID_CONSTANT AdmTileMap gmap_even,
                                                    const ADM_GRID_CONSTANT AdmTileMap gmap_odd, MsParams p) {
     ADM_SMEM_DECL
-    const Smem sm(smem_raw);
+    const Smem<T> sm(smem_raw);
     const int t = threadIdx.x;
     const int wf = blockIdx.x;
     const int b = wf / p.M, m = wf % p.M;
@@ -250,13 +250,13 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_bwd(const ADM_GRID_CONSTANT AdmTi
     const int TP = P + 2 * odd;
     const AdmTileMap* tmap = odd ? &tmap_odd : &tmap_even;
     const AdmTileMap* gmap = odd ? &gmap_odd : &gmap_even;
-    const unsigned tile_bytes = (unsigned)(sizeof(cpx) * P * TP);
-    const cpx* ckpt = p.ckpt + (size_t)wf * p.Nz * NPSI;
-    const cpx* gdet = p.det + (size_t)wf * NPSI;
+    const unsigned tile_bytes = (unsigned)(sizeof(T) * P * TP);
+    const T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * NPSI;
+    const T* gdet = (const T*)p.det + (size_t)wf * NPSI;
     const int ay = (t >> 3) & 7, ax = t & 7;
     const bool touches = (pxa + P >= 0) && (py + P >= 0);   // (a patch entirely outside contributes nothing)
 
-    for (int i = t; i < 2 * P; i += NT) sm.hs[i] = p.Hp[i];
+    for (int i = t; i < 2 * P; i += NT) sm.hs[i] = ((const T*)p.Hp)[i];
     if (t == DMA) { mbar_init(sm.barT, 1); mbar_init(sm.barC, 1); }
     __syncthreads();
     if (t == DMA) {
@@ -269,14 +269,14 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_bwd(const ADM_GRID_CONSTANT AdmTi
     if (p.free_prop == ADM_PROP_FAR) {
         if (t < NS) {
             const int by = t / 9, bx = t - 9 * by;
-            cpx u[64];
+            T u[64];
 #pragma unroll
             for (int ky = 0; ky < 8; ++ky) {
                 const int fy = (freq72(ky, by) + P / 2) % P;
 #pragma unroll
                 for (int kx = 0; kx < 8; ++kx) {
                     const int fx = (freq72(kx, bx) + P / 2) % P;
-                    const cpx o = cscale(gdet[fy * P + fx], p.ff_scale);
+                    const T o = cscale(gdet[fy * P + fx], p.ff_scale);
                     u[8 * ky + kx] = p.ff_conj ? cconj(o) : o;
                 }
             }
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_bwd(const ADM_GRID_CONSTANT AdmTi
     for (int z = p.Nz - 1; z >= 0; --z, ++it) {
         const bool last = (z == p.Nz - 1);
         if (t < NR) {
-            cpx v[81];
+            T v[81];
             const bool from_det = last && p.free_prop == ADM_PROP_NONE;
             if (from_det) {
 #pragma unroll
@@ -320,18 +320,18 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_bwd(const ADM_GRID_CONSTANT AdmTi
             }
             mbar_wait(sm.barT, it & 1);
             if (odd) {   // the two pad columns of the 74-wide tile hold neighbouring T' values: nothing to add there
-                for (int i = t; i < 2 * P; i += NR) sm.tile[(i >> 1) * TP + ((i & 1) ? P + 1 : 0)] = mk(0.f, 0.f);
+                for (int i = t; i < 2 * P; i += NR) sm.tile[(i >> 1) * TP + ((i & 1) ? P + 1 : 0)] = tmk<T>(0.f, 0.f);
             }
             mbar_wait(sm.barC, it & 1);
 #pragma unroll
             for (int by = 0; by < 9; ++by) {
-                cpx* row = sm.tile + pos72(ay, by) * TP + odd;
+                T* row = sm.tile + pos72(ay, by) * TP + odd;
 #pragma unroll
                 for (int bx = 0; bx < 9; ++bx) {
                     const int e = 9 * by + bx;
-                    const cpx w = sm.psi[e * NR + t];        // psi_z (wave entering the slice)
+                    const T w = sm.psi[e * NR + t];        // psi_z (wave entering the slice)
                     const int x = pos72(ax, bx);
-                    const cpx tp = row[x];
+                    const T tp = row[x];
                     row[x] = cmulc(v[e], w);                 // dL/dT = g' conj(psi_z)
                     v[e] = modulate_conj(v[e], tp);          // g_psi = g' conj(1 + T')
                 }
@@ -348,9 +348,9 @@ __global__ void __launch_bounds__(NT, 2) k_ms2_bwd(const ADM_GRID_CONSTANT AdmTi
 #pragma unroll
                     for (int bx = 0; bx < 9; ++bx) {
                         const int o = pos72(ay, by) * P + pos72(ax, bx);
-                        const cpx g = v[9 * by + bx];
-                        if (p.probe_per_pattern) p.g_probe[(size_t)wf * NPSI + o] = g;
-                        else red_add2(&p.g_probe[(size_t)m * NPSI + o], g.x, g.y);
+                        const T g = v[9 * by + bx];
+                        if (p.probe_per_pattern) ((T*)p.g_probe)[(size_t)wf * NPSI + o] = g;
+                        else red_add2(&p.g_probe[(size_t)m * NPSI + o], cx(g), cy(g));
                     }
             }
         }
@@ -385,12 +385,13 @@ int adm_ms2_supported(const adm_multislice_cfg* c) {
     return c->P == 72 && c->h_separable && c->n_slices > 1 && c->free_prop != ADM_PROP_NEAR;
 }
 
+// (instantiated on the scalar complex type: with packed register pairs the 81-value blocks spill more, 8.3 / 7.1 ms)
 int adm_ms2_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, const float* tvol, void* stream) {
     AdmTileMap me, mo;
     if (adm_make_tile_map(&me, tvol, p.Nz, p.Y, p.X, p.Xp, ms2::P, ms2::P)) return ADM_ERR_CUDA;
     if (adm_make_tile_map(&mo, tvol, p.Nz, p.Y, p.X, p.Xp, ms2::P, ms2::P + 2)) return ADM_ERR_CUDA;
-    if (set_smem(ms2::k_ms2_fwd, ms2::SMEM_BYTES)) return ADM_ERR_CUDA;
-    ADM_LAUNCH(ms2::k_ms2_fwd, c->B * c->M, ms2::NT, ms2::SMEM_BYTES, stream, me, mo, p);
+    if (set_smem(ms2::k_ms2_fwd<cpx>, ms2::SMEM_BYTES)) return ADM_ERR_CUDA;
+    ADM_LAUNCH(ms2::k_ms2_fwd<cpx>, c->B * c->M, ms2::NT, ms2::SMEM_BYTES, stream, me, mo, p);
     return ADM_OK;
 }
 
@@ -401,7 +402,7 @@ int adm_ms2_bwd_launch(const adm_multislice_cfg* c, const MsParams& p, const flo
     const int rows = ADM_GVOL_ROWS(p.Y, ms2::P), gx = p.X + ADM_GVOL_MARGIN(ms2::P), gp = ADM_GVOL_PITCH(p.X, ms2::P);
     if (adm_make_tile_map(&ge, g_tvol, p.Nz, rows, gx, gp, ms2::P, ms2::P)) return ADM_ERR_CUDA;
     if (adm_make_tile_map(&go, g_tvol, p.Nz, rows, gx, gp, ms2::P, ms2::P + 2)) return ADM_ERR_CUDA;
-    if (set_smem(ms2::k_ms2_bwd, ms2::SMEM_BYTES)) return ADM_ERR_CUDA;
-    ADM_LAUNCH(ms2::k_ms2_bwd, c->B * c->M, ms2::NT, ms2::SMEM_BYTES, stream, te, to, ge, go, p);
+    if (set_smem(ms2::k_ms2_bwd<cpx>, ms2::SMEM_BYTES)) return ADM_ERR_CUDA;
+    ADM_LAUNCH(ms2::k_ms2_bwd<cpx>, c->B * c->M, ms2::NT, ms2::SMEM_BYTES, stream, te, to, ge, go, p);
     return ADM_OK;
 }
