@@ -450,6 +450,8 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
         else if (var == 3) ADM_FWD(Cfg72, 3, false, cpx);
         else if (var == 4) ADM_FWD(Cfg72, 2, true, cpx);      // scalar butterflies (one FADD / FFMA per component)
         else if (var == 5) ADM_FWD(Cfg72, 4, false, cpk);
+        else if (var == 6) ADM_FWD(Cfg72, 2, false, cpk);
+        else if (var == 7) ADM_FWD(Cfg72, 3, false, cpk);
         else ADM_FWD(Cfg72, 2, true, cpk);                    // packed complex arithmetic (cpk.cuh)
     } else {
         if (var == 4) ADM_FWD(Cfg64, 2, true, cpx);
