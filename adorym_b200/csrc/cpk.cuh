@@ -61,7 +61,15 @@ template <bool INV> ADM_DEV cpk kmi(cpk a) { return INV ? kswp_np(a) : kswp_pn(a
 template <bool INV> ADM_DEV cpk add_mi(cpk a, cpk w) { return a + kmi<INV>(w); }
 template <bool INV> ADM_DEV cpk sub_mi(cpk a, cpk w) { return a + kmi<!INV>(w); }
 
-ADM_DEV cpk cconj(cpk a) { float x, y; kun(a, x, y); return kmk(x, -y); }
+#ifndef ADM_HOST_EMU
+ADM_DEV cpk cconj(cpk a) {      // explicit FMUL2 by (1, -1)
+    cpk r, b = kmk(1.0f, -1.0f);
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+#else
+static inline cpk cconj(cpk a) { return kmk(a.x, -a.y); }
+#endif
 ADM_DEV cpk cscale(cpk a, float s) { return kscale(a, s); }
 ADM_DEV cpk cmul(cpk a, cpk b) { float bx, by; kun(b, bx, by); return kfmas(kswp_np(a), by, kscale(a, bx)); }
 // a * conj(b)

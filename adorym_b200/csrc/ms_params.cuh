@@ -45,3 +45,8 @@ int adm_ms2_bwd_launch(const adm_multislice_cfg* c, const MsParams& p, const flo
 // two wavefields per CTA on packed fp32x2 arithmetic, P = 72 (multislice_x2.cu)
 int adm_msx2_fwd_supported(const adm_multislice_cfg* c);
 int adm_msx2_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, void* stream);
+
+// register-resident line FFTs, two passes per slice, P = 72 (multislice_col.cu)
+int adm_msc_supported(const adm_multislice_cfg* c);
+int adm_msc_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, const float* tvol, void* stream);
+int adm_msc_bwd_launch(const adm_multislice_cfg* c, const MsParams& p, float* g_tvol, void* stream);

@@ -432,6 +432,7 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     p.tvol = (const cpx*)tvol; p.probe = (const cpx*)probe; p.pos = pos;
     p.Hp = (const cpx*)Hprep; p.Hf = (const cpx*)Hfree;
     p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)det; p.g_probe = nullptr;
+    if (adm_msc_supported(cfg)) return adm_msc_fwd_launch(cfg, p, tvol, stream);   // register-resident line FFTs
     if (adm_ms2_supported(cfg)) return adm_ms2_fwd_launch(cfg, p, tvol, stream);   // two-pass prime-factor kernels
     if (adm_msx2_fwd_supported(cfg)) return adm_msx2_fwd_launch(cfg, p, stream);   // two wavefields per CTA, packed fp32x2
     AdmTileMap map;
@@ -472,6 +473,7 @@ extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tv
     p.tvol = (const cpx*)tvol; p.probe = nullptr; p.pos = pos;
     p.Hp = (const cpx*)HprepC; p.Hf = (const cpx*)HfreeC;
     p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)g_det; p.g_probe = (cpx*)g_probe;
+    if (adm_msc_supported(cfg)) return adm_msc_bwd_launch(cfg, p, g_tvol, stream);
     if (adm_ms2_supported(cfg)) return adm_ms2_bwd_launch(cfg, p, tvol, g_tvol, stream);
     AdmTileMap map;
     if (adm_make_tile_map(&map, g_tvol, p.Nz, ADM_GVOL_ROWS(p.Y, cfg->P), p.X + ADM_GVOL_MARGIN(cfg->P),

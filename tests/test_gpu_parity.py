@@ -109,7 +109,9 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
 @pytest.mark.parametrize('name,var', [('ptycho3d_p72', 'ADM_MS_PFA2'), ('ptycho3d_p72_poisson', 'ADM_MS_PFA2'),
                                       ('ptycho3d_p72', 'ADM_MS_X2'), ('ptycho3d_p72_poisson', 'ADM_MS_X2'),
                                       ('ptycho3d_p72_edge', 'ADM_MS_PFA2'), ('ptycho3d_p72_exitwave', 'ADM_MS_PFA2'),
-                                      ('ptycho3d_p72_edge', 'ADM_MS_X2'), ('ptycho3d_p72_exitwave', 'ADM_MS_X2')])
+                                      ('ptycho3d_p72_edge', 'ADM_MS_X2'), ('ptycho3d_p72_exitwave', 'ADM_MS_X2'),
+                                      ('ptycho3d_p72', 'ADM_MS_COL'), ('ptycho3d_p72_poisson', 'ADM_MS_COL'),
+                                      ('ptycho3d_p72_edge', 'ADM_MS_COL'), ('ptycho3d_p72_exitwave', 'ADM_MS_COL')])
 def test_opt_in_kernel_variants_match_oracle(name, var, monkeypatch):
     """Opt-in kernels of multislice_pfa2.cu / multislice_x2.cu (environment switch read by the library at every call)."""
     monkeypatch.setenv(var, '1')

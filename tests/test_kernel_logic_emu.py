@@ -64,7 +64,9 @@ def test_emulated_kernels_match_oracle_and_golden(name):
 @pytest.mark.parametrize('name,var', [('ptycho3d_p72', 'ADM_MS_PFA2'), ('ptycho3d_p72_poisson', 'ADM_MS_PFA2'),
                                       ('ptycho3d_p72', 'ADM_MS_X2'), ('ptycho3d_p72_poisson', 'ADM_MS_X2'),
                                       ('ptycho3d_p72_edge', 'ADM_MS_PFA2'), ('ptycho3d_p72_exitwave', 'ADM_MS_PFA2'),
-                                      ('ptycho3d_p72_edge', 'ADM_MS_X2'), ('ptycho3d_p72_exitwave', 'ADM_MS_X2')])
+                                      ('ptycho3d_p72_edge', 'ADM_MS_X2'), ('ptycho3d_p72_exitwave', 'ADM_MS_X2'),
+                                      ('ptycho3d_p72', 'ADM_MS_COL'), ('ptycho3d_p72_poisson', 'ADM_MS_COL'),
+                                      ('ptycho3d_p72_edge', 'ADM_MS_COL'), ('ptycho3d_p72_exitwave', 'ADM_MS_COL')])
 def test_emulated_opt_in_kernel_variants(name, var, monkeypatch):
     """The opt-in variants: two-pass prime-factor kernels (multislice_pfa2.cu, ADM_MS_PFA2=1) and the two-wavefield
     packed-fp32x2 forward (multislice_x2.cu, ADM_MS_X2=1; the second case has an odd number of patterns): even and odd
