@@ -319,6 +319,12 @@ int adm_msc_supported(const adm_multislice_cfg* c) {
 int adm_msc_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, const float* tvol, void* stream) {
     AdmTileMap map;
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, msc::P, msc::TP)) return ADM_ERR_CUDA;
+    const char* e = getenv("ADM_MSC_SCALAR");
+    if (e && atoi(e)) {      // scalar instantiation for A/B runs
+        if (set_smem(msc::k_msc_fwd<cpx>, msc::SMEM_BYTES)) return ADM_ERR_CUDA;
+        ADM_LAUNCH(msc::k_msc_fwd<cpx>, c->B * c->M, msc::NT, msc::SMEM_BYTES, stream, map, p);
+        return ADM_OK;
+    }
     if (set_smem(msc::k_msc_fwd<cpk>, msc::SMEM_BYTES)) return ADM_ERR_CUDA;
     ADM_LAUNCH(msc::k_msc_fwd<cpk>, c->B * c->M, msc::NT, msc::SMEM_BYTES, stream, map, p);
     return ADM_OK;
