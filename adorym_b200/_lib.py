@@ -38,9 +38,11 @@ SIGNATURES = {
     'adm_prepare_transfer_function_separable': [c_int, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p],
     'adm_transmission_fwd': [c_int, c_float, c_int, c_longlong, c_int, c_void_p, c_void_p, c_void_p],
     'adm_transmission_adj': [c_int, c_float, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
-    'adm_multislice_fwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
-    'adm_multislice_bwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+    'adm_multislice_workspace_bytes': [c_int],
+    'adm_multislice_fwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p],
+    'adm_multislice_bwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                           c_void_p, c_void_p],
     'adm_detector_loss': [c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p],
     'adm_rotate_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -51,6 +53,11 @@ SIGNATURES = {
                              c_void_p],
     'adm_regularizer_l1tv_scaled': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
                                     c_void_p, c_int, c_void_p],
+    'adm_regularizer_l1tv_range': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int, c_int, c_void_p],
+    'adm_object_to_transmission': [c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p],
+    'adm_transmission_to_object_adj': [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int,
+                                       c_void_p, c_int, c_int, c_void_p],
     'adm_probe_shift_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_probe_shift_bwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_lf_supported': [c_int],
@@ -64,6 +71,7 @@ SIGNATURES = {
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
 }
 
+RETURNS_LONGLONG = ('adm_multislice_workspace_bytes',)
 ERRORS = {1: 'bad argument', 2: 'unsupported configuration', 3: 'CUDA launch error'}
 
 
@@ -72,7 +80,7 @@ def bind(cdll):
     for name, argtypes in SIGNATURES.items():
         fn = getattr(cdll, name)
         fn.argtypes = argtypes
-        fn.restype = c_int
+        fn.restype = c_longlong if name in RETURNS_LONGLONG else c_int
     return cdll
 
 
@@ -89,7 +97,7 @@ def get_lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('adorym_b200: CUDA library %s is missing; run `python -m adorym_b200.build`' % LIB_PATH)
         _lib = bind(ctypes.CDLL(LIB_PATH))
-        if _lib.adm_abi_version() != 3:
+        if _lib.adm_abi_version() != 4:
             raise RuntimeError('adorym_b200: ABI version mismatch')
     return _lib
 

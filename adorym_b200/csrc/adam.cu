@@ -114,7 +114,8 @@ ADM_DEV float sgnf(float a) { return (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f);
 // null) multiplies the gradient (the upstream gradient of the loss node); accumulate = 0 writes g_obj, 1 adds to it.
 __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx* __restrict__ obj, const cpx* __restrict__ wl1,
                                                   float ad, float ab, float gm, float* value, cpx* g_obj,
-                                                  const float* g_scale, int accumulate) {
+                                                  const float* g_scale, int accumulate, long long row_begin,
+                                                  long long row_end) {
 #ifndef ADM_HOST_EMU
     __shared__ float red[256];
 #else
@@ -124,10 +125,9 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
     const float invN = 1.0f / (float)N;
     const float gs = (g_scale != nullptr) ? *g_scale : 1.0f;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
-    const long long rows = (long long)Y * X;
     const size_t sx = (size_t)Z, sy = (size_t)X * Z;
     float acc = 0.f;
-    for (long long row = (long long)blockIdx.x * wpb + wib; row < rows; row += (long long)gridDim.x * wpb) {
+    for (long long row = row_begin + (long long)blockIdx.x * wpb + wib; row < row_end; row += (long long)gridDim.x * wpb) {
         const int y = (int)(row / X), x = (int)(row - (long long)y * X);
         const cpx* r0 = obj + (size_t)row * sx;
         const cpx* rym = obj + (size_t)((y + Y - 1) % Y) * sy + (size_t)x * sx;
@@ -173,16 +173,24 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
     if (threadIdx.x == 0 && value != nullptr) atomicAdd(value, red[0]);
 }
 
-extern "C" int adm_regularizer_l1tv_scaled(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
-                                           float alpha_b, float gamma, float* value, float* g_obj, const float* g_scale,
-                                           int accumulate, void* stream) {
+extern "C" int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
+                                          float alpha_b, float gamma, float* value, float* g_obj, const float* g_scale,
+                                          int accumulate, int y_begin, int y_end, void* stream) {
     if (Y < 1 || X < 1 || Z < 1 || !obj) return ADM_ERR_ARG;
-    long long rows = (long long)Y * X;
+    if (y_begin < 0 || y_end > Y || y_begin >= y_end) return ADM_ERR_ARG;
+    long long rows = (long long)(y_end - y_begin) * X;
     long long blocks = (rows + 7) / 8;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
     ADM_LAUNCH(k_reg_l1tv, (unsigned)blocks, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj, (const cpx*)weight_l1,
-               alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate);
+               alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate, (long long)y_begin * X, (long long)y_end * X);
     return ADM_OK;
+}
+
+extern "C" int adm_regularizer_l1tv_scaled(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
+                                           float alpha_b, float gamma, float* value, float* g_obj, const float* g_scale,
+                                           int accumulate, void* stream) {
+    return adm_regularizer_l1tv_range(Y, X, Z, obj, weight_l1, alpha_d, alpha_b, gamma, value, g_obj, g_scale, accumulate, 0, Y,
+                                      stream);
 }
 
 extern "C" int adm_regularizer_l1tv(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d, float alpha_b,

@@ -16,6 +16,13 @@ struct MsParams {
     int free_prop, probe_per_pattern, h_separable;
     float ff_scale;
     int ff_conj;
+    // persistent balanced schedule (multislice.cu): the nwf * Nz slice steps of a launch are laid end to end and cut in
+    // gridDim.x intervals of T steps; a wavefield cut by an interval boundary is handed from one CTA to the next through
+    // a raw copy of the shared-memory wavefield (handoff slot) and a flag.  split = 0: one wavefield per CTA.
+    int split, T;
+    int* flags;          // [slots] hand-off flags, 0 outside a launch
+    float4* handoff;     // [slots][slot_f4] raw copies of the psi buffer
+    int slot_f4;
 };
 
 ADM_DEV void red_add2(cpx* addr, float a, float b) {
@@ -37,16 +44,3 @@ ADM_DEV cpx modulate_conj(cpx v, cpx tp) {
 }
 
 
-// two-pass prime-factor kernels for P = 72 (multislice_pfa2.cu); selected by adm_ms2_supported()
-int adm_ms2_supported(const adm_multislice_cfg* c);
-int adm_ms2_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, const float* tvol, void* stream);
-int adm_ms2_bwd_launch(const adm_multislice_cfg* c, const MsParams& p, const float* tvol, float* g_tvol, void* stream);
-
-// two wavefields per CTA on packed fp32x2 arithmetic, P = 72 (multislice_x2.cu)
-int adm_msx2_fwd_supported(const adm_multislice_cfg* c);
-int adm_msx2_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, void* stream);
-
-// register-resident line FFTs, two passes per slice, P = 72 (multislice_col.cu)
-int adm_msc_supported(const adm_multislice_cfg* c);
-int adm_msc_fwd_launch(const adm_multislice_cfg* c, const MsParams& p, const float* tvol, void* stream);
-int adm_msc_bwd_launch(const adm_multislice_cfg* c, const MsParams& p, float* g_tvol, void* stream);

@@ -38,23 +38,86 @@ template <class C> struct MsSmem {
     static constexpr size_t TW = sizeof(cpx) * C::P;
     static constexpr size_t HS = sizeof(cpx) * 2 * C::P;     // separable transfer function tables hy | hx
     static constexpr size_t BYTES = TILE + PSI + TW + HS + 16;
-    static constexpr size_t BYTES_NOTILE = PSI + TW + HS + 16;     // forward variant that reads T' with plain loads
+    static constexpr int PSI_F4 = (int)(PSI / 16);           // the psi buffer as float4 (hand-off copies)
+    static_assert(PSI % 16 == 0 && TILE % 16 == 0, "16-byte granularity");
 };
+
+// ---- persistent balanced schedule ---------------------------------------------------------------------------------
+// A launch owns nwf = B * M independent wavefields, each a strictly sequential chain of Nz slice steps.  With one
+// CTA per wavefield and two CTAs resident per SM, 529 wavefields on 296 slots run as 1.79 "waves": the second wave
+// leaves a fifth of the slots idle.  Instead the nwf * Nz slice steps are laid end to end and cut into gridDim.x
+// intervals of T steps (McNaughton's wrap-around rule): every CTA does the same number of slice steps, and a
+// wavefield cut by an interval boundary is handed from one CTA to the other through a raw copy of the shared-memory
+// wavefield (42 KB, once per CTA) and a flag.  The CTA that holds the EARLY part of a cut chain processes it FIRST, the
+// CTA that holds the late part processes it LAST (T >= Nz), so the consumer practically never waits; the dependency
+// always points to a lower blockIdx, and the grid never exceeds the number of co-resident CTAs.
+struct MsSeg { int wf, zb, ze; };
+// c: logical CTA index, i: position in this CTA's processing order (0 = first).  fwd: chains run z upwards, the cut
+// wavefield at the END of the interval is its early part -> processed first; bwd: chains run z downwards, the cut
+// wavefield at the START of the interval is its early part -> processed first.
+ADM_DEV int ms_nseg(const MsParams& p, int c, int& wf_first, int& wf_last, long long& s0, long long& s1) {
+    const long long total = (long long)p.B * p.M * p.Nz;
+    if (!p.split) { s0 = (long long)c * p.Nz; s1 = s0 + p.Nz; }
+    else { s0 = (long long)c * p.T; s1 = s0 + p.T; if (s1 > total) s1 = total; }
+    wf_first = (int)(s0 / p.Nz); wf_last = (int)((s1 - 1) / p.Nz);
+    return wf_last - wf_first + 1;
+}
+ADM_DEV MsSeg ms_seg(const MsParams& p, int wf, long long s0, long long s1) {
+    MsSeg s; s.wf = wf;
+    long long lo = s0 - (long long)wf * p.Nz, hi = s1 - (long long)wf * p.Nz;
+    s.zb = lo > 0 ? (int)lo : 0; s.ze = hi < p.Nz ? (int)hi : p.Nz;
+    return s;
+}
+ADM_DEV void flag_set(int* f) {
+#ifndef ADM_HOST_EMU
+    asm volatile("st.release.gpu.global.s32 [%0], %1;\n" ::"l"(f), "r"(1) : "memory");
+#else
+    std::atomic_ref<int>(*f).store(1);
+#endif
+}
+ADM_DEV void flag_wait_and_clear(int* f) {
+#ifndef ADM_HOST_EMU
+    int v;
+    do { asm volatile("ld.acquire.gpu.global.s32 %0, [%1];\n" : "=r"(v) : "l"(f) : "memory"); } while (v == 0);
+    asm volatile("st.relaxed.gpu.global.s32 [%0], %1;\n" ::"l"(f), "r"(0) : "memory");
+#else
+    std::atomic_ref<int> r(*f);
+    while (r.load() == 0) std::this_thread::yield();
+    r.store(0);
+#endif
+}
+// raw copy of the shared-memory wavefield to / from a hand-off slot (all threads; barriers by the caller)
+template <class C> ADM_DEV void handoff_store(const MsParams& p, int slot, const void* psi) {
+    float4* dst = p.handoff + (size_t)slot * p.slot_f4;
+    const float4* src = (const float4*)psi;
+    for (int i = threadIdx.x; i < MsSmem<C>::PSI_F4; i += C::NTHREADS) dst[i] = src[i];
+#ifndef ADM_HOST_EMU
+    __threadfence();
+#endif
+}
+template <class C> ADM_DEV void handoff_load(const MsParams& p, int slot, void* psi) {
+    const float4* src = p.handoff + (size_t)slot * p.slot_f4;
+    float4* dst = (float4*)psi;
+    for (int i = threadIdx.x; i < MsSmem<C>::PSI_F4; i += C::NTHREADS) {
+#ifndef ADM_HOST_EMU
+        dst[i] = __ldcg(src + i);
+#else
+        dst[i] = src[i];
+#endif
+    }
+}
 
 // ================================================================================================
 // Forward
 // ================================================================================================
-// TILE = true : T' tile by TMA into shared memory, prefetched one slice ahead (86 KB of shared memory, 2 CTAs per SM).
-// TILE = false: T' by plain coalesced loads at the top of P1 (the volume is L2 resident); 44 KB of shared memory, so
-//               with <= 72 registers FOUR CTAs are resident per SM: 592 slots hold all 529 wavefields of config D in one
-//               wave (no tail) at twice the warps per SM.
-template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+// T' tile by TMA into shared memory, prefetched one slice ahead (86 KB of shared memory, 2 CTAs per SM).
+template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
     constexpr int TP = MsSmem<C>::TP;
     T* tile = (T*)smem_raw;
-    T* psi = TILE ? tile + P * TP : (T*)smem_raw;
+    T* psi = tile + P * TP;
     T* tw = psi + P * S;
     T* hs = tw + P;
     adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
@@ -62,122 +125,129 @@ template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
     const Idx<C> I(q);
-    const int wf = blockIdx.x;              // wavefield index b * M + m
-    const int b = wf / p.M, m = wf % p.M;
-    const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
-    const int pxa = px & ~1, lt = l + (px & 1);     // even TMA start column, this thread's column inside the tile
-    const T* probe = (const T*)p.probe + (size_t)(p.probe_per_pattern ? wf : m) * P * P;
-    T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * P * TP;
-    T* det = (T*)p.det + (size_t)wf * P * P;
+    const int c = blockIdx.x;               // logical CTA index (dependencies point to c - 1)
 
     init_twiddles<C>(tw, t);
     if (p.h_separable && t < 2 * P) hs[t] = ((const T*)p.Hp)[t];
-    if (TILE && t == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (TILE && t == 0) {   // prefetch the T' tile of slice 0
-        mbar_expect_tx(bar, TILE_BYTES);
-        tma_load_tile(tile, &tmap, 2 * pxa, py, 0, bar);
-    }
-    // TILE = false: this thread's column of the transmission volume
-    const int gx = px + l;
-    const bool x_in = (gx >= 0) && (gx < p.X);
-    const T* tcol = (const T*)p.tvol + (x_in ? gx : 0);
-    const size_t slice_stride = (size_t)p.Y * p.Xp;
+    if (t == 0) mbar_init(bar, 1);
+    unsigned ph = 0;                        // parity of the next tile completion
 
-    for (int z = 0; z < p.Nz; ++z) {
-        const bool last = (z == p.Nz - 1);
-        const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
-        const T* tz = tcol + (size_t)z * slice_stride;
-        // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
-        if (active) {
-            if (TILE) mbar_wait(bar, z & 1);
-            ADM_FOR_GROUPS_A(gi) {
-                const int g = I.group(gi);
-                T v[8], tp[8];
-                if (!TILE) {
+    int wf_first, wf_last;
+    long long s0, s1;
+    ms_nseg(p, c, wf_first, wf_last, s0, s1);
+    for (int wfi = wf_last; wfi >= wf_first; --wfi) {
+        const MsSeg sg = ms_seg(p, wfi, s0, s1);
+        const int wf = sg.wf;               // wavefield index b * M + m
+        const int b = wf / p.M, m = wf % p.M;
+        const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
+        const int pxa = px & ~1, lt = l + (px & 1);     // even TMA start column, this thread's column inside the tile
+        const T* probe = (const T*)p.probe + (size_t)(p.probe_per_pattern ? wf : m) * P * P;
+        T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * P * TP;
+        T* det = (T*)p.det + (size_t)wf * P * P;
+
+        __syncthreads();                    // the previous segment is done with the tile and the wavefield
+        if (t == 0) {                       // prefetch the T' tile of the first slice of the segment
+            mbar_expect_tx(bar, TILE_BYTES);
+            tma_load_tile(tile, &tmap, 2 * pxa, py, sg.zb, bar);
+        }
+        if (sg.zb > 0) {                    // late part of a cut chain: the wavefield comes from CTA c - 1
+            if (t == 0) flag_wait_and_clear(p.flags + c);
+            __syncthreads();
+            handoff_load<C>(p, c, psi);
+            __syncthreads();
+        }
+
+        for (int z = sg.zb; z < sg.ze; ++z) {
+            const bool last = (z == p.Nz - 1);
+            const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
+            // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
+            if (active) {
+                mbar_wait(bar, ph);
+                ADM_FOR_GROUPS_A(gi) {
+                    const int g = I.group(gi);
+                    T v[8];
+                    if (z == 0) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = probe[I.a(j, gi) * P + l];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
+                        dft8<true>(v);
+                    }
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const int gy = py + I.a(j, gi);
-                        const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
-                        tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : tmk<T>(0.f, 0.f);
+                        const int y = I.a(j, gi);
+                        ckpt[(size_t)z * P * TP + y * TP + lt] = v[j];
+                        v[j] = modulate(v[j], tile[y * TP + lt]);
                     }
-                }
-                if (z == 0) {
+                    if (go_on) {
+                        if (last && p.ff_conj) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = probe[I.a(j, gi) * P + l];
-                } else {
+                            for (int j = 0; j < 8; ++j) v[j] = cconj(v[j]);
+                        }
+                        dft8<false>(v);
+                        if constexpr (!C::PFA) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
-                    dft8<true>(v);
-                }
+                            for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+                        }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int y = I.a(j, gi);
-                    ckpt[(size_t)z * P * TP + y * TP + lt] = v[j];
-                    v[j] = modulate(v[j], TILE ? tile[y * TP + lt] : tp[j]);
-                }
-                if (go_on) {
-                    if (last && p.ff_conj) {
+                        for (int k = 0; k < 8; ++k) psi[I.a(k, gi) * S + l] = v[k];
+                    } else {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = cconj(v[j]);
+                        for (int j = 0; j < 8; ++j) det[I.a(j, gi) * P + l] = v[j];   // exit wave, natural order
                     }
-                    dft8<false>(v);
-                    if constexpr (!C::PFA) {
-#pragma unroll
-                        for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
-                    }
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) psi[I.a(k, gi) * S + l] = v[k];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) det[I.a(j, gi) * P + l] = v[j];   // exit wave, natural order
                 }
             }
-        }
-        __syncthreads();
-        if (TILE && t == 0 && !last) {   // every thread has consumed tile(z): prefetch tile(z+1) behind P2..P6
-            mbar_expect_tx(bar, TILE_BYTES);
-            tma_load_tile(tile, &tmap, 2 * pxa, py, z + 1, bar);
-        }
-        if (!go_on) break;
-        if (last && p.free_prop == ADM_PROP_FAR) {
-            // far field: finish the forward 2-D FFT (By, Ax, Bx) and store fftshift-ed, natural order
-            if (active) pass_B_fwd<C, false>(psi, q, l);
+            ph ^= 1;
             __syncthreads();
-            if (active) pass_A_fwd<C, true>(psi, tw, q, l);
-            __syncthreads();
-            if (active) {
-                const int fy = (perm_freq<C>(l) + P / 2) % P;
-                ADM_FOR_GROUPS_B(gi) {
-                    const int g = I.group(gi);
-                    T v[R2];
+            if (t == 0 && z + 1 < sg.ze) {   // every thread has consumed tile(z): prefetch tile(z+1) behind P2..P6
+                mbar_expect_tx(bar, TILE_BYTES);
+                tma_load_tile(tile, &tmap, 2 * pxa, py, z + 1, bar);
+            }
+            if (!go_on) break;
+            if (last && p.free_prop == ADM_PROP_FAR) {
+                // far field: finish the forward 2-D FFT (By, Ax, Bx) and store fftshift-ed, natural order
+                if (active) pass_B_fwd<C, false>(psi, q, l);
+                __syncthreads();
+                if (active) pass_A_fwd<C, true>(psi, tw, q, l);
+                __syncthreads();
+                if (active) {
+                    const int fy = (perm_freq<C>(l) + P / 2) % P;
+                    ADM_FOR_GROUPS_B(gi) {
+                        T v[R2];
 #pragma unroll
-                    for (int n = 0; n < R2; ++n) v[n] = psi[l * S + I.b(n, gi)];
-                    dftr<R2, false>(v);
+                        for (int n = 0; n < R2; ++n) v[n] = psi[l * S + I.b(n, gi)];
+                        dftr<R2, false>(v);
 #pragma unroll
-                    for (int k = 0; k < R2; ++k) {
-                        int fx = (perm_freq<C>(I.b(k, gi)) + P / 2) % P;
-                        T o = cscale(v[k], p.ff_scale);
-                        det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
+                        for (int k = 0; k < R2; ++k) {
+                            int fx = (perm_freq<C>(I.b(k, gi)) + P / 2) % P;
+                            T o = cscale(v[k], p.ff_scale);
+                            det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
+                        }
+                    }
+                }
+                break;
+            }
+            if (!last && p.h_separable) propagate_core_sep<C>(psi, tw, hs, q, l, active);
+            else propagate_core<C>(psi, tw, (const T*)(last ? p.Hf : p.Hp), q, l, active);
+            if (last) {
+                // near field: final Ay^-1, natural order store
+                if (active) {
+                    ADM_FOR_GROUPS_A(gi) {
+                        T v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
+                        dft8<true>(v);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) det[I.a(j, gi) * P + l] = v[j];
                     }
                 }
             }
-            break;
         }
-        if (!last && p.h_separable) propagate_core_sep<C>(psi, tw, hs, q, l, active);
-        else propagate_core<C>(psi, tw, (const T*)(last ? p.Hf : p.Hp), q, l, active);
-        if (last) {
-            // near field: final Ay^-1, natural order store
-            if (active) {
-                ADM_FOR_GROUPS_A(gi) {
-                    T v[8];
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
-                    dft8<true>(v);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) det[I.a(j, gi) * P + l] = v[j];
-                }
-            }
+        if (sg.ze < p.Nz) {                 // early part of a cut chain: hand the wavefield to CTA c + 1
+            handoff_store<C>(p, c + 1, psi);
+            __syncthreads();
+            if (t == 0) flag_set(p.flags + c + 1);
         }
     }
 }
@@ -199,115 +269,77 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
     const Idx<C> I(q);
-    const int wf = blockIdx.x;
-    const int b = wf / p.M, m = wf % p.M;
-    const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
-    const int pxa = px & ~1, lt = l + (px & 1);
-    const int gx = px + l;
-    const bool x_in = (gx >= 0) && (gx < p.X);
-    const T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * P * TP;
-    const T* gdet = (const T*)p.det + (size_t)wf * P * P;
-    const size_t slice_stride = (size_t)p.Y * p.Xp;
-    const T* tcol = (const T*)p.tvol + (x_in ? gx : 0);     // this thread's column of the transmission volume
+    const int c = gridDim.x - 1 - blockIdx.x;   // logical CTA index; the chains run downwards, so CTA c depends on the
+                                                // FIRST segment of CTA c + 1 = a lower blockIdx
 
     init_twiddles<C>(tw, t);
     if (p.h_separable && t < 2 * P) hs[t] = ((const T*)p.Hp)[t];
     if (t == 0) mbar_init(bar, 1);
-    __syncthreads();
-    if (t == 0) {   // prefetch the checkpoint of the last slice
-        mbar_expect_tx(bar, TILE_BYTES);
-        bulk_load(ckb, ckpt + (size_t)(p.Nz - 1) * P * TP, TILE_BYTES, bar);
-    }
+    unsigned phase = 0;
 
-    // ---- adjoint of the detector transform ---------------------------------------------------------------
-    if (p.free_prop == ADM_PROP_FAR) {
-        if (active) {
-            const int fy = (perm_freq<C>(l) + P / 2) % P;
-            ADM_FOR_GROUPS_B(gi) {
+    int wf_first, wf_last;
+    long long s0, s1;
+    ms_nseg(p, c, wf_first, wf_last, s0, s1);
+    for (int wfi = wf_first; wfi <= wf_last; ++wfi) {
+        const MsSeg sg = ms_seg(p, wfi, s0, s1);
+        const int wf = sg.wf;
+        const int b = wf / p.M, m = wf % p.M;
+        const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
+        const int pxa = px & ~1, lt = l + (px & 1);
+        const int gx = px + l;
+        const bool x_in = (gx >= 0) && (gx < p.X);
+        const T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * P * TP;
+        const T* gdet = (const T*)p.det + (size_t)wf * P * P;
+        const size_t slice_stride = (size_t)p.Y * p.Xp;
+        const T* tcol = (const T*)p.tvol + (x_in ? gx : 0);     // this thread's column of the transmission volume
+
+        __syncthreads();                    // the previous segment is done with the wavefield
+        if (t == 0) {   // prefetch the checkpoint of the first (highest) slice of the segment
+            bulk_wait_read_all();           // ... and its last reduce has drained the tile
+            mbar_expect_tx(bar, TILE_BYTES);
+            bulk_load(ckb, ckpt + (size_t)(sg.ze - 1) * P * TP, TILE_BYTES, bar);
+        }
+
+        if (sg.ze < p.Nz) {
+            // late part of a cut chain: the adjoint wavefield comes from CTA c + 1
+            if (t == 0) flag_wait_and_clear(p.flags + c + 1);
+            __syncthreads();
+            handoff_load<C>(p, c + 1, psi);
+            __syncthreads();
+        } else if (p.free_prop == ADM_PROP_FAR) {
+            // ---- adjoint of the detector transform -------------------------------------------------------
+            if (active) {
+                const int fy = (perm_freq<C>(l) + P / 2) % P;
+                ADM_FOR_GROUPS_B(gi) {
                     const int g = I.group(gi);
-                T v[R2];
+                    T v[R2];
 #pragma unroll
-                for (int k = 0; k < R2; ++k) {
-                    int fx = (perm_freq<C>(I.b(k, gi)) + P / 2) % P;
-                    T o = cscale(gdet[fy * P + fx], p.ff_scale);
-                    v[k] = p.ff_conj ? cconj(o) : o;
+                    for (int k = 0; k < R2; ++k) {
+                        int fx = (perm_freq<C>(I.b(k, gi)) + P / 2) % P;
+                        T o = cscale(gdet[fy * P + fx], p.ff_scale);
+                        v[k] = p.ff_conj ? cconj(o) : o;
+                    }
+                    dftr<R2, true>(v);
+                    if constexpr (!C::PFA) {
+#pragma unroll
+                        for (int n = 1; n < R2; ++n) v[n] = cmulc(v[n], tw[g * n]);
+                    }
+#pragma unroll
+                    for (int n = 0; n < R2; ++n) psi[l * S + I.b(n, gi)] = v[n];
                 }
-                dftr<R2, true>(v);
-                if constexpr (!C::PFA) {
-#pragma unroll
-                    for (int n = 1; n < R2; ++n) v[n] = cmulc(v[n], tw[g * n]);
-                }
-#pragma unroll
-                for (int n = 0; n < R2; ++n) psi[l * S + I.b(n, gi)] = v[n];
             }
-        }
-        __syncthreads();
-        if (active) pass_A_inv<C, true>(psi, q, l);
-        __syncthreads();
-        if (active) pass_B_inv<C, false>(psi, tw, q, l);
-        __syncthreads();
-    } else if (p.free_prop == ADM_PROP_NEAR) {
-        if (active) {
-            ADM_FOR_GROUPS_A(gi) {
-                const int g = I.group(gi);
-                T v[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) v[j] = gdet[I.a(j, gi) * P + l];
-                dft8<false>(v);
-                if constexpr (!C::PFA) {
-#pragma unroll
-                    for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
-                }
-#pragma unroll
-                for (int k = 0; k < 8; ++k) psi[I.a(k, gi) * S + l] = v[k];
-            }
-        }
-        __syncthreads();
-        propagate_core<C>(psi, tw, (const T*)p.Hf, q, l, active);
-    }
-
-    int phase = 0;
-    for (int z = p.Nz - 1; z >= 0; --z, phase ^= 1) {
-        const bool last = (z == p.Nz - 1);
-        const T* tz = tcol + (size_t)z * slice_stride;
-        // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] ------------------------------
-        if (active) {
-            ADM_FOR_GROUPS_A(gi) {
-                const int g = I.group(gi);
-                T v[8], tp[8];
-                // T' of this slice (L2-resident volume; issued first so the butterfly hides the latency); 32-bit offsets
-                // from the per-slice column pointer, one unsigned compare per row
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int gy = py + I.a(j, gi);
-                    const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
-                    tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : tmk<T>(0.f, 0.f);
-                }
-                if (last && p.free_prop == ADM_PROP_NONE) {
+            __syncthreads();
+            if (active) pass_A_inv<C, true>(psi, q, l);
+            __syncthreads();
+            if (active) pass_B_inv<C, false>(psi, tw, q, l);
+            __syncthreads();
+        } else if (p.free_prop == ADM_PROP_NEAR) {
+            if (active) {
+                ADM_FOR_GROUPS_A(gi) {
+                    const int g = I.group(gi);
+                    T v[8];
 #pragma unroll
                     for (int j = 0; j < 8; ++j) v[j] = gdet[I.a(j, gi) * P + l];
-                } else {
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
-                    dft8<true>(v);
-                    if (last && p.ff_conj) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = cconj(v[j]);
-                    }
-                }
-                if (gi == 0) {
-                    mbar_wait(bar, phase);
-                    // the two pad columns of the tile are never written by the forward pass: add zeros there
-                    if (t < 2 * P) ckb[(t >> 1) * TP + ((t & 1) ? P + 1 : ((px & 1) ? 0 : P))] = tmk<T>(0.f, 0.f);
-                }
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    const int y = I.a(j, gi);
-                    const T w = ckb[y * TP + lt];               // psi_z (wave entering the slice)
-                    ckb[y * TP + lt] = cmulc(v[j], w);            // dL/dT = g' conj(psi_z)
-                    v[j] = modulate_conj(v[j], tp[j]);            // g_psi = g' conj(T)
-                }
-                if (z > 0) {
                     dft8<false>(v);
                     if constexpr (!C::PFA) {
 #pragma unroll
@@ -315,43 +347,103 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                     }
 #pragma unroll
                     for (int k = 0; k < 8; ++k) psi[I.a(k, gi) * S + l] = v[k];
-                } else if (p.g_probe != nullptr) {
-                    if (p.probe_per_pattern) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) ((T*)p.g_probe)[(size_t)wf * P * P + I.a(j, gi) * P + l] = v[j];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            red_add2(&p.g_probe[(size_t)m * P * P + I.a(j, gi) * P + l], cx(v[j]), cy(v[j]));
-                    }
                 }
             }
-            fence_proxy_async();      // the dL/dT tile is about to be read by the TMA unit
+            __syncthreads();
+            propagate_core<C>(psi, tw, (const T*)p.Hf, q, l, active);
         }
-        __syncthreads();
-        if (t == 0 && pxa + P >= 0 && py + P >= 0) {   // (a patch lying entirely outside contributes nothing)
-            tma_reduce_add_tile(&gmap, 2 * (pxa + P), py + P, z, ckb);   // margined volume: coordinates never negative
-            bulk_commit();
+
+        for (int z = sg.ze - 1; z >= sg.zb; --z, phase ^= 1) {
+            const bool last = (z == p.Nz - 1);
+            const T* tz = tcol + (size_t)z * slice_stride;
+            // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] --------------------------
+            if (active) {
+                ADM_FOR_GROUPS_A(gi) {
+                    const int g = I.group(gi);
+                    T v[8], tp[8];
+                    // T' of this slice (L2-resident volume; issued first so the butterfly hides the latency); 32-bit
+                    // offsets from the per-slice column pointer, one unsigned compare per row
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int gy = py + I.a(j, gi);
+                        const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
+                        tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : tmk<T>(0.f, 0.f);
+                    }
+                    if (last && p.free_prop == ADM_PROP_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = gdet[I.a(j, gi) * P + l];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) v[j] = psi[I.a(j, gi) * S + l];
+                        dft8<true>(v);
+                        if (last && p.ff_conj) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = cconj(v[j]);
+                        }
+                    }
+                    if (gi == 0) {
+                        mbar_wait(bar, phase);
+                        // the two pad columns of the tile are never written by the forward pass: add zeros there
+                        if (t < 2 * P) ckb[(t >> 1) * TP + ((t & 1) ? P + 1 : ((px & 1) ? 0 : P))] = tmk<T>(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const int y = I.a(j, gi);
+                        const T w = ckb[y * TP + lt];               // psi_z (wave entering the slice)
+                        ckb[y * TP + lt] = cmulc(v[j], w);            // dL/dT = g' conj(psi_z)
+                        v[j] = modulate_conj(v[j], tp[j]);            // g_psi = g' conj(T)
+                    }
+                    if (z > 0) {
+                        dft8<false>(v);
+                        if constexpr (!C::PFA) {
+#pragma unroll
+                            for (int k = 1; k < 8; ++k) v[k] = cmul(v[k], tw[g * k]);
+                        }
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) psi[I.a(k, gi) * S + l] = v[k];
+                    } else if (p.g_probe != nullptr) {
+                        if (p.probe_per_pattern) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) ((T*)p.g_probe)[(size_t)wf * P * P + I.a(j, gi) * P + l] = v[j];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                red_add2(&p.g_probe[(size_t)m * P * P + I.a(j, gi) * P + l], cx(v[j]), cy(v[j]));
+                        }
+                    }
+                }
+                fence_proxy_async();      // the dL/dT tile is about to be read by the TMA unit
+            }
+            __syncthreads();
+            if (t == 0 && pxa + P >= 0 && py + P >= 0) {   // (a patch lying entirely outside contributes nothing)
+                tma_reduce_add_tile(&gmap, 2 * (pxa + P), py + P, z, ckb);   // margined volume: coordinates never negative
+                bulk_commit();
+            }
+            if (z == 0) { phase ^= 1; break; }
+            if (active) pass_B_fwd<C, false>(psi, q, l);
+            __syncthreads();
+            if (t == 0 && z > sg.zb) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind P3..P6
+                bulk_wait_read_all();
+                mbar_expect_tx(bar, TILE_BYTES);
+                bulk_load(ckb, ckpt + (size_t)(z - 1) * P * TP, TILE_BYTES, bar);
+            }
+            if (active) pass_A_fwd<C, true>(psi, tw, q, l);
+            __syncthreads();
+            if (active) {
+                if (p.h_separable) pass_BHB_x_sep<C>(psi, tw, hs + P, hs[l], q, l);
+                else pass_BHB_x<C>(psi, tw, (const T*)p.Hp, q, l);
+            }
+            __syncthreads();
+            if (active) pass_A_inv<C, true>(psi, q, l);
+            __syncthreads();
+            if (active) pass_B_inv<C, false>(psi, tw, q, l);
+            __syncthreads();
         }
-        if (z == 0) break;
-        if (active) pass_B_fwd<C, false>(psi, q, l);
-        __syncthreads();
-        if (t == 0) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind P3..P6
-            bulk_wait_read_all();
-            mbar_expect_tx(bar, TILE_BYTES);
-            bulk_load(ckb, ckpt + (size_t)(z - 1) * P * TP, TILE_BYTES, bar);
+        if (sg.zb > 0) {                    // early part of a cut chain: hand the adjoint wavefield to CTA c - 1
+            handoff_store<C>(p, c, psi);
+            __syncthreads();
+            if (t == 0) flag_set(p.flags + c);
         }
-        if (active) pass_A_fwd<C, true>(psi, tw, q, l);
-        __syncthreads();
-        if (active) {
-            if (p.h_separable) pass_BHB_x_sep<C>(psi, tw, hs + P, hs[l], q, l);
-            else pass_BHB_x<C>(psi, tw, (const T*)p.Hp, q, l);
-        }
-        __syncthreads();
-        if (active) pass_A_inv<C, true>(psi, q, l);
-        __syncthreads();
-        if (active) pass_B_inv<C, false>(psi, tw, q, l);
-        __syncthreads();
     }
     if (t == 0) bulk_wait_all();      // shared memory must stay valid until the last reduce has read it
 }
@@ -375,6 +467,50 @@ template <class C> __global__ void k_prepare_H(const cpx* H, int conj, float sca
 static int adm_variant(const char* name) {
     const char* e = getenv(name);
     return e ? atoi(e) : 0;
+}
+
+// number of CTAs of `kern` that are co-resident on the device (SM count x occupancy); ADM_MS_GRID overrides it (tests)
+template <class K> static int ms_resident_ctas(K kern, int threads, size_t smem) {
+    int forced = adm_variant("ADM_MS_GRID");
+    if (forced > 0) return forced;
+#ifndef ADM_HOST_EMU
+    static int cached = 0;      // per kernel instantiation (all devices of a node are the same part)
+    if (cached > 0) return cached;
+    int dev = 0, sms = 0, occ = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) return 0;
+    cached = sms * occ;
+    return cached;
+#else
+    return 8;
+#endif
+}
+
+#define ADM_MS_MAX_SLOTS 1024
+// workspace: [ADM_MS_MAX_SLOTS] int flags | pad to 256 B | [ADM_MS_MAX_SLOTS][slot] raw wavefield copies
+static size_t ms_slot_bytes(int P) { return (size_t)P * (P + 1) * sizeof(cpx); }
+
+// schedule: one wavefield per CTA while they all fit; otherwise (and only with a workspace) equal intervals of slice steps
+static int ms_schedule(MsParams& p, int cap, void* workspace, int P, int& grid) {
+    const int nwf = p.B * p.M;
+    p.split = 0; p.T = p.Nz; p.flags = nullptr; p.handoff = nullptr; p.slot_f4 = (int)(ms_slot_bytes(P) / 16);
+    grid = nwf;
+    if (cap <= 0) return ADM_ERR_CUDA;
+    if (workspace != nullptr && nwf > cap && cap + 1 <= ADM_MS_MAX_SLOTS) {
+        const long long total = (long long)nwf * p.Nz;
+        const long long T = (total + cap - 1) / cap;          // >= Nz because nwf > cap
+        p.split = 1; p.T = (int)T;
+        grid = (int)((total + T - 1) / T);
+        p.flags = (int*)workspace;
+        p.handoff = (float4*)((char*)workspace + 4096);
+    }
+    return ADM_OK;
+}
+
+extern "C" long long adm_multislice_workspace_bytes(int P) {
+    if (P != 64 && P != 72) return 0;
+    return 4096 + (long long)ADM_MS_MAX_SLOTS * (long long)ms_slot_bytes(P);
 }
 
 static int fill_params(const adm_multislice_cfg* c, MsParams& p) {
@@ -422,7 +558,8 @@ extern "C" int adm_prepare_transfer_function_separable(int P, const float* hy, c
 }
 
 extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tvol, const float* probe, const int* pos,
-                                  const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* stream) {
+                                  const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* workspace,
+                                  void* stream) {
     MsParams p;
     int rc = fill_params(cfg, p);
     if (rc) return rc;
@@ -432,38 +569,32 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     p.tvol = (const cpx*)tvol; p.probe = (const cpx*)probe; p.pos = pos;
     p.Hp = (const cpx*)Hprep; p.Hf = (const cpx*)Hfree;
     p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)det; p.g_probe = nullptr;
-    if (adm_msc_supported(cfg)) return adm_msc_fwd_launch(cfg, p, tvol, stream);   // register-resident line FFTs
-    if (adm_ms2_supported(cfg)) return adm_ms2_fwd_launch(cfg, p, tvol, stream);   // two-pass prime-factor kernels
-    if (adm_msx2_fwd_supported(cfg)) return adm_msx2_fwd_launch(cfg, p, stream);   // two wavefields per CTA, packed fp32x2
     AdmTileMap map;
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
-    int nwf = cfg->B * cfg->M;
     int var = adm_variant("ADM_FWD_VARIANT");
-#define ADM_FWD(CFG, MINB, TILE, CT)                                                                                  \
+#define ADM_FWD(CFG, MINB, CT)                                                                                        \
     do {                                                                                                           \
-        const size_t sm_ = TILE ? MsSmem<CFG>::BYTES : MsSmem<CFG>::BYTES_NOTILE;                                  \
-        if (set_smem(k_multislice_fwd<CFG, MINB, TILE, CT>, sm_)) return ADM_ERR_CUDA;                             \
-        ADM_LAUNCH((k_multislice_fwd<CFG, MINB, TILE, CT>), nwf, CFG::NTHREADS, sm_, stream, map, p);              \
+        const size_t sm_ = MsSmem<CFG>::BYTES;                                                                     \
+        if (set_smem(k_multislice_fwd<CFG, MINB, CT>, sm_)) return ADM_ERR_CUDA;                                   \
+        int grid_;                                                                                                 \
+        if (ms_schedule(p, ms_resident_ctas(k_multislice_fwd<CFG, MINB, CT>, CFG::NTHREADS, sm_), workspace,       \
+                        CFG::P, grid_))                                                                            \
+            return ADM_ERR_CUDA;                                                                                   \
+        ADM_LAUNCH((k_multislice_fwd<CFG, MINB, CT>), grid_, CFG::NTHREADS, sm_, stream, map, p);                  \
     } while (0)
     if (cfg->P == 72) {
-        if (var == 1) ADM_FWD(Cfg72ct, 2, true, cpx);
-        else if (var == 2) ADM_FWD(Cfg72, 4, false, cpx);
-        else if (var == 3) ADM_FWD(Cfg72, 3, false, cpx);
-        else if (var == 4) ADM_FWD(Cfg72, 2, true, cpx);      // scalar butterflies (one FADD / FFMA per component)
-        else if (var == 5) ADM_FWD(Cfg72, 4, false, cpk);
-        else if (var == 6) ADM_FWD(Cfg72, 2, false, cpk);
-        else if (var == 7) ADM_FWD(Cfg72, 3, false, cpk);
-        else ADM_FWD(Cfg72, 2, true, cpk);                    // packed complex arithmetic (cpk.cuh)
+        if (var == 4) ADM_FWD(Cfg72, 2, cpx);      // scalar butterflies (one FADD / FFMA per component)
+        else ADM_FWD(Cfg72, 2, cpk);               // packed complex arithmetic (cpk.cuh)
     } else {
-        if (var == 4) ADM_FWD(Cfg64, 2, true, cpx);
-        else ADM_FWD(Cfg64, 2, true, cpk);
+        if (var == 4) ADM_FWD(Cfg64, 2, cpx);
+        else ADM_FWD(Cfg64, 2, cpk);
     }
     return ADM_OK;
 }
 
 extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
                                   const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol,
-                                  float* g_probe, void* stream) {
+                                  float* g_probe, void* workspace, void* stream) {
     MsParams p;
     int rc = fill_params(cfg, p);
     if (rc) return rc;
@@ -473,22 +604,23 @@ extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tv
     p.tvol = (const cpx*)tvol; p.probe = nullptr; p.pos = pos;
     p.Hp = (const cpx*)HprepC; p.Hf = (const cpx*)HfreeC;
     p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)g_det; p.g_probe = (cpx*)g_probe;
-    if (adm_msc_supported(cfg)) return adm_msc_bwd_launch(cfg, p, g_tvol, stream);
-    if (adm_ms2_supported(cfg)) return adm_ms2_bwd_launch(cfg, p, tvol, g_tvol, stream);
     AdmTileMap map;
     if (adm_make_tile_map(&map, g_tvol, p.Nz, ADM_GVOL_ROWS(p.Y, cfg->P), p.X + ADM_GVOL_MARGIN(cfg->P),
                           ADM_GVOL_PITCH(p.X, cfg->P), cfg->P, cfg->P + 2))
         return ADM_ERR_CUDA;
-    int nwf = cfg->B * cfg->M;
     int var = adm_variant("ADM_BWD_VARIANT");
 #define ADM_BWD(CFG, MINB, CT)                                                                                       \
     do {                                                                                                           \
-        if (set_smem(k_multislice_bwd<CFG, MINB, CT>, MsSmem<CFG>::BYTES)) return ADM_ERR_CUDA;                    \
-        ADM_LAUNCH((k_multislice_bwd<CFG, MINB, CT>), nwf, CFG::NTHREADS, MsSmem<CFG>::BYTES, stream, map, p);     \
+        const size_t sm_ = MsSmem<CFG>::BYTES;                                                                     \
+        if (set_smem(k_multislice_bwd<CFG, MINB, CT>, sm_)) return ADM_ERR_CUDA;                                   \
+        int grid_;                                                                                                 \
+        if (ms_schedule(p, ms_resident_ctas(k_multislice_bwd<CFG, MINB, CT>, CFG::NTHREADS, sm_), workspace,       \
+                        CFG::P, grid_))                                                                            \
+            return ADM_ERR_CUDA;                                                                                   \
+        ADM_LAUNCH((k_multislice_bwd<CFG, MINB, CT>), grid_, CFG::NTHREADS, sm_, stream, map, p);                  \
     } while (0)
     if (cfg->P == 72) {
-        if (var == 1) ADM_BWD(Cfg72ct, 2, cpx);
-        else if (var == 4) ADM_BWD(Cfg72, 2, cpx);
+        if (var == 4) ADM_BWD(Cfg72, 2, cpx);
         else ADM_BWD(Cfg72, 2, cpk);
     } else {
         if (var == 4) ADM_BWD(Cfg64, 2, cpx);

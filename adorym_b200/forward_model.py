@@ -76,10 +76,9 @@ class ForwardModel(object):
     def get_regularization_value(self, obj, device=None):
         reg = None
         fused = self._fusable_regularizers()
-        if fused is not None:
-            # one L1-type and one TV term on a delta_beta object: a single pass over the volume for both
-            l1, tv = fused
-            reg = ops.RegL1TVFn.apply(obj, getattr(l1, 'weight_l1', None), l1.alpha_d, l1.alpha_b, tv.gamma)
+        if fused is not None and obj.dim() == 4:
+            # L1-type and / or TV terms on a delta_beta object: a single pass over the volume for all of them
+            reg = ops.RegL1TVFn.apply(obj, *fused)
             self.last_reg_value = reg
             return reg
         for r in self.reg_list:
@@ -89,16 +88,24 @@ class ForwardModel(object):
         return reg
 
     def _fusable_regularizers(self):
+        """-> (weight_l1|None, alpha_d, alpha_b, gamma) when the regulariser list is any combination of at most one
+        L1-type and at most one TV term on a delta_beta object (one fused kernel pass, ops.MultisliceFn `reg`), else
+        None (the terms are then evaluated one by one through their get_value)."""
         from .regularizers import L1Regularizer, ReweightedL1Regularizer, TVRegularizer
-        if len(self.reg_list) != 2:
+        if len(self.reg_list) == 0 or len(self.reg_list) > 2:
             return None
         l1 = [r for r in self.reg_list if isinstance(r, (L1Regularizer, ReweightedL1Regularizer))]
         tv = [r for r in self.reg_list if isinstance(r, TVRegularizer)]
-        if len(l1) != 1 or len(tv) != 1 or l1[0].unknown_type != 'delta_beta' or tv[0].unknown_type != 'delta_beta':
+        if len(l1) + len(tv) != len(self.reg_list) or len(l1) > 1 or len(tv) > 1:
             return None
-        if isinstance(l1[0], ReweightedL1Regularizer) and l1[0].weight_l1 is None:
+        if any(r.unknown_type != 'delta_beta' for r in self.reg_list) or self.unknown_type != 'delta_beta':
             return None
-        return l1[0], tv[0]
+        w = None
+        if l1 and isinstance(l1[0], ReweightedL1Regularizer):
+            if l1[0].weight_l1 is None:
+                return None
+            w = l1[0].weight_l1
+        return (w, l1[0].alpha_d if l1 else 0., l1[0].alpha_b if l1 else 0., tv[0].gamma if tv else 0.)
 
     def get_argument_index(self, arg):
         for i, a in enumerate(self.argument_ls):
@@ -135,16 +142,25 @@ class ForwardModel(object):
                                             src_folder=folder if cv.get('precalculate_rotation_coords', True) else None)
         return self._rot_table.grid(this_i_theta)
 
-    def _rotated_object(self, obj, this_i_theta):
-        """-> slice-major [Nz, Y, X, 2] view/copy of the object at angle this_i_theta."""
+    def _object_grid(self, obj, this_i_theta):
+        """Normalised rotation grid for ops.MultisliceFn (layout 'yxz'), or None when the object already is in the beam
+        frame: two_d_mode, or rotate_out_of_loop (the driver rotates once per angle and hands over obj.arr_rot,
+        ptychography.py:918-943,1011; forward_model.py:266)."""
         cv = self.common_vars
         dev = self._device(obj)
-        if cv['two_d_mode']:
-            Y, X, Z = obj.shape[:3]
-            return obj.reshape(Y, X, 2).unsqueeze(0) if Z == 1 else obj.permute(2, 0, 1, 3).contiguous()
-        if self.rotate_out_of_loop:
-            raise NotImplementedError('adorym_b200: rotate_out_of_loop is not on the accelerated path yet')
-        return ops.RotateFn.apply(obj, self._rotation_grid(this_i_theta, dev))
+        if cv['two_d_mode'] or self.rotate_out_of_loop:
+            return None
+        return self._rotation_grid(this_i_theta, dev)
+
+    def _multislice(self, obj, this_i_theta, probe, pos_t, plan, with_reg):
+        """fused rotate + transmission + gather + multislice; with_reg: also the fused regulariser value (None when the
+        regulariser list is not fusable) -> (det, reg_value | None, reg_was_fused)."""
+        reg = self._fusable_regularizers() if with_reg else None
+        grid = self._object_grid(obj, this_i_theta)
+        if reg is not None:
+            det, reg_val = ops.MultisliceFn.apply(obj, grid, probe, pos_t, plan, reg, 'yxz')
+            return det, reg_val, True
+        return ops.MultisliceFn.apply(obj, grid, probe, pos_t, plan, None, 'yxz'), None, False
 
     def _plan(self, dev, P, Nz, Y, X, free_prop_cm):
         cv = self.common_vars
@@ -258,14 +274,18 @@ class ForwardModel(object):
         self._current_loss = loss.detach()
         return loss
 
-    def _fused_loss(self, det, this_prj_batch, obj):
-        """detector magnitude + mismatch + residual in one kernel, then the regularisers."""
+    def _fused_loss(self, det, this_prj_batch, obj, reg_val=None, reg_done=False):
+        """detector magnitude + mismatch + residual in one kernel, then the regularisers (reg_done: their value came out
+        of the fused object chain already)."""
         mask = self._beamstop_mask(det.device)
         loss, pred, lpp = ops.DetectorLossFn.apply(det, this_prj_batch, mask, self.loss_function_type,
                                                    self.raw_data_type, self.poisson_multiplier)
         self.last_pred = pred
         self.last_loss_per_pattern = lpp
-        if len(self.reg_list) > 0:
+        if reg_done:
+            self.last_reg_value = reg_val
+            loss = loss + reg_val
+        elif len(self.reg_list) > 0:
             loss = loss + self.get_regularization_value(obj, device=self.device)
         self._current_loss = loss.detach()
         return loss
@@ -299,8 +319,9 @@ class PtychographyModel(ForwardModel):
         self.run_float64 = run_float64
 
     def _detector_field(self, obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                        this_ind_batch):
-        """rotate -> (shift probe) -> fused gather + multislice -> complex detector field [B, M, P, P, 2]."""
+                        this_ind_batch, with_reg=False):
+        """(shift probe) -> fused rotate + transmission + gather + multislice -> complex detector field [B, M, P, P, 2]
+        (, regulariser value, fused flag)."""
         cv = self.common_vars
         self._check_unsupported(['optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
                                  'optimize_tilt'])
@@ -310,7 +331,6 @@ class PtychographyModel(ForwardModel):
             raise NotImplementedError('adorym_b200: only square probes are supported')
         this_obj_size = cv['this_obj_size']
         pos = _np_int_positions(this_pos_batch)
-        rot = self._rotated_object(obj, this_i_theta)
         probe = torch.stack([probe_real, probe_imag], dim=-1)
         if probe.dim() == 3:
             probe = probe.unsqueeze(0)
@@ -321,7 +341,8 @@ class PtychographyModel(ForwardModel):
             probe = ops.ProbeShiftFn.apply(probe, shift)
         plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
         pos_t = torch.from_numpy(np.ascontiguousarray(pos, dtype='int32')).to(dev)
-        return ops.MultisliceFn.apply(rot, probe, pos_t, plan)
+        out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg)
+        return out if with_reg else out[0]
 
     def _any_positive_correction(self, ppc):
         """forward_model.py:297,304: `any(probe_pos_correction > 1e-3)`.  The answer needs a device->host read; it is
@@ -348,11 +369,11 @@ class PtychographyModel(ForwardModel):
                            probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
             theta_downsample = self.common_vars['theta_downsample']
             ds_level = self.common_vars['ds_level']
-            det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                                       this_ind_batch)
+            det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch,
+                                                          probe_pos_correction, this_ind_batch, with_reg=True)
             self.i_call += 1
             this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
-            return self._fused_loss(det, this_prj_batch, obj)
+            return self._fused_loss(det, this_prj_batch, obj, reg_val, reg_done)
         return calculate_loss
 
 
@@ -365,7 +386,7 @@ class SingleBatchFullfieldModel(PtychographyModel):
                                                         raw_data_type, simulation_mode=simulation_mode, *args, **kwargs)
 
     def _detector_field(self, obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                        this_ind_batch):
+                        this_ind_batch, with_reg=False):
         cv = self.common_vars
         self._check_unsupported(['optimize_prj_pos_offset'])
         dev = self._device(obj)
@@ -373,13 +394,13 @@ class SingleBatchFullfieldModel(PtychographyModel):
         this_obj_size = cv['this_obj_size']
         if list(probe_size) != list(this_obj_size[:2]):
             raise ValueError('SingleBatchFullfieldModel needs probe_size == obj_size[:2]')
-        rot = self._rotated_object(obj, this_i_theta)
         probe = torch.stack([probe_real, probe_imag], dim=-1)
         if probe.dim() == 3:
             probe = probe.unsqueeze(0)
         plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
         pos_t = torch.zeros((1, 2), dtype=torch.int32, device=dev)
-        return ops.MultisliceFn.apply(rot, probe, pos_t, plan)
+        out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg)
+        return out if with_reg else out[0]
 
     def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,
                 probe_pos_offset, this_i_theta, this_pos_batch, prj,
@@ -452,12 +473,11 @@ class MultiDistModel(ForwardModel):
                 raise NotImplementedError('adorym_b200: MultiDistModel needs positive propagation distances')
             plan = self._md_plan(dev, P, dists)
             return ops.MultiDistFn.apply(obj.reshape(P, P, 2), probe, plan)      # [n_dists, M, P, P, 2]
-        rot = self._rotated_object(obj, 0)
         pos_t = torch.zeros((1, 2), dtype=torch.int32, device=dev)
         dets = []
         for d in dists:
             plan = self._plan(dev, P, this_obj_size[2], this_obj_size[0], this_obj_size[1], d)
-            dets.append(ops.MultisliceFn.apply(rot, probe, pos_t, plan))
+            dets.append(self._multislice(obj, 0, probe, pos_t, plan, False)[0])
         return torch.cat(dets, 0)      # [n_dists, M, P, P, 2]
 
     def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,

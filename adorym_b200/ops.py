@@ -120,25 +120,64 @@ def gvol_pitch(X, P):
     return (int(X) + int(P) + 1) & ~1
 
 
-class MultisliceFn(torch.autograd.Function):
-    """det[B,M,P,P,2] = multislice(rot_obj[Nz,Y,X,2] raw (delta,beta)|(re,im), probe[M,P,P,2] | [B,M,P,P,2],
-    pos[B,2] int32).
+_MS_WORKSPACE = {}
 
-    forward : adm_transmission_fwd (T' = T - 1 volume, propagate.py:241/246) -> adm_multislice_fwd
-    backward: adm_multislice_bwd (dL/dT scattered into the margined gradient volume by TMA reduce-adds)
-              -> adm_transmission_adj (chain rule back to (delta, beta) | (re, im))."""
+
+def multislice_workspace(device, P):
+    """Persistent, zero-initialised scratch of the balanced multislice schedule (include/adorym_b200.h:
+    adm_multislice_workspace_bytes), one per (device, stream, P): hand-off slots + flags for wavefields that migrate
+    between CTAs.  The kernels leave the flags zero, so it is allocated and cleared once."""
+    key = (str(device), int(torch.cuda.current_stream(device).cuda_stream), int(P))
+    ws = _MS_WORKSPACE.get(key)
+    if ws is None:
+        n = int(_lib.get_lib().adm_multislice_workspace_bytes(int(P)))
+        ws = torch.zeros((n,), dtype=torch.uint8, device=device)
+        _MS_WORKSPACE[key] = ws
+    return ws
+
+
+# Gradient slabs: with GRAD_SLABS > 1 the object gradient of MultisliceFn.backward is produced in that many y slabs (the
+# rotation is about y, so the planes are independent) and a CUDA event is recorded after each; the driver starts the
+# NCCL all-reduce of a slab as soon as its event has fired (dist.Comm.allreduce_slabs) instead of after the whole volume.
+GRAD_SLABS = 1
+last_obj_grad_slabs = None       # [(y0, y1, event)] of the most recent backward, or None
+
+
+def slab_ranges(Y, n):
+    n = max(1, min(int(n), int(Y)))
+    edges = [int(round(i * Y / n)) for i in range(n + 1)]
+    return [(edges[i], edges[i + 1]) for i in range(n) if edges[i + 1] > edges[i]]
+
+
+class MultisliceFn(torch.autograd.Function):
+    """det[B,M,P,P,2] (, reg) = multislice(obj, probe[M,P,P,2] | [B,M,P,P,2], pos[B,2] int32).
+
+    layout 'yxz': obj is the reference-layout object [Y,X,Z,2]; `grid` (normalized_grid) rotates it about y, grid=None
+                  means it already is in the beam frame.  One fused kernel makes the slice-major transmission volume
+                  T' = T - 1 (adm_object_to_transmission: util.py:536-552 + propagate.py:241/246), and one fused kernel
+                  takes dL/dT back to the object (adm_transmission_to_object_adj).  `reg` = None or
+                  (weight_l1|None, alpha_d, alpha_b, gamma): the L1 / TV regulariser of the object
+                  (regularizers.py:30-110); its value is returned as a second output and its gradient INITIALISES the
+                  object-gradient buffer that the transpose rotation then accumulates into (no zero fill, no add).
+    layout 'zyx': obj is an explicit slice-major volume [Nz,Y,X,2] (propagate.py:131 drop-in); reg must be None.
+
+    forward : transmission volume -> adm_multislice_fwd
+    backward: adm_multislice_bwd (dL/dT scattered into the margined gradient volume by TMA reduce-adds) -> chain rule."""
 
     @staticmethod
-    def forward(ctx, rot_obj, probe, pos, plan):
-        rot_obj = _f32c(rot_obj)
+    def forward(ctx, obj, grid, probe, pos, plan, reg=None, layout='zyx'):
+        obj = _f32c(obj)
         probe = _f32c(probe)
         if pos.dtype != torch.int32 or not pos.is_cuda:
             raise RuntimeError('pos must be an int32 CUDA tensor [B, 2]')
         pos = pos.contiguous()
         P, Nz, Y, X = plan.P, plan.n_slices, plan.Y, plan.X
-        if tuple(rot_obj.shape) != (Nz, Y, X, 2):
-            raise RuntimeError('rot_obj must be [Nz, Y, X, 2] = %s, got %s' % ((Nz, Y, X, 2), tuple(rot_obj.shape)))
-        dev = rot_obj.device
+        want = (Y, X, Nz, 2) if layout == 'yxz' else (Nz, Y, X, 2)
+        if tuple(obj.shape) != want:
+            raise RuntimeError('object must be %s for layout %s, got %s' % (want, layout, tuple(obj.shape)))
+        if layout != 'yxz' and (reg is not None or grid is not None):
+            raise RuntimeError('rotation / fused regulariser need the reference layout [Y,X,Z,2]')
+        dev = obj.device
         B = pos.shape[0]
         per_pattern = probe.dim() == 5
         M = probe.shape[1] if per_pattern else probe.shape[0]
@@ -146,37 +185,85 @@ class MultisliceFn(torch.autograd.Function):
             raise RuntimeError('probe must be [M,P,P,2] or [B,M,P,P,2]')
         cfg = plan.cfg(B, M, per_pattern)
         tvol = torch.empty((Nz, Y, tvol_pitch(X), 2), dtype=torch.float32, device=dev)
-        call('adm_transmission_fwd', plan.unknown_type, plan.k1, plan.sign_convention, Nz * Y, X, ptr(rot_obj), ptr(tvol),
-             stream_ptr())
+        if layout == 'yxz':
+            call('adm_object_to_transmission', Y, X, Nz, ptr(obj), ptr(grid), plan.unknown_type, plan.k1,
+                 plan.sign_convention, ptr(tvol), stream_ptr())
+        else:
+            call('adm_transmission_fwd', plan.unknown_type, plan.k1, plan.sign_convention, Nz * Y, X, ptr(obj), ptr(tvol),
+                 stream_ptr())
+        reg_val = None
+        if reg is not None:
+            w, ad, ab, gm = reg
+            w = _f32c(w) if w is not None else None
+            reg = (w, float(ad or 0.), float(ab or 0.), float(gm or 0.))
+            val = torch.zeros((1,), dtype=torch.float32, device=dev)
+            call('adm_regularizer_l1tv_scaled', Y, X, Nz, ptr(obj), ptr(w), reg[1], reg[2], reg[3], ptr(val), None, None, 0,
+                 stream_ptr())
+            reg_val = val[0]
         ckpt = torch.empty((B, M, Nz, P, P + 2, 2), dtype=torch.float32, device=dev)
         det = torch.empty((B, M, P, P, 2), dtype=torch.float32, device=dev)
         call('adm_multislice_fwd', ctypes.byref(cfg), ptr(tvol), ptr(probe), ptr(pos), ptr(plan.Hp), ptr(plan.Hfp),
-             ptr(ckpt), ptr(det), stream_ptr())
-        ctx.plan, ctx.cfg, ctx.per_pattern = plan, cfg, per_pattern
+             ptr(ckpt), ptr(det), ptr(multislice_workspace(dev, P)), stream_ptr())
+        ctx.plan, ctx.cfg, ctx.per_pattern, ctx.layout, ctx.reg = plan, cfg, per_pattern, layout, reg
         ctx.probe_shape = tuple(probe.shape)
-        ctx.save_for_backward(tvol, pos, ckpt)
+        ctx.has_grid = grid is not None
+        saved = [tvol, pos, ckpt]
+        if grid is not None:
+            saved.append(grid)
+        if reg is not None:
+            saved.append(obj)
+            if reg[0] is not None:
+                saved.append(reg[0])
+        ctx.save_for_backward(*saved)
+        if reg is not None:
+            return det, reg_val
         return det
 
     @staticmethod
-    def backward(ctx, g_det):
-        tvol, pos, ckpt = ctx.saved_tensors
+    def backward(ctx, g_det, g_reg=None):
+        global last_obj_grad_slabs
+        saved = list(ctx.saved_tensors)
+        tvol, pos, ckpt = saved[:3]
+        rest = saved[3:]
+        grid = rest.pop(0) if ctx.has_grid else None
+        obj = rest.pop(0) if ctx.reg is not None else None
+        w = rest.pop(0) if (ctx.reg is not None and ctx.reg[0] is not None) else None
         plan = ctx.plan
         P, Nz, Y, X = plan.P, plan.n_slices, plan.Y, plan.X
         dev = tvol.device
         g_det = _f32c(g_det)
-        # margined gradient volume (ADM_GVOL_MARGIN in include/adorym_b200.h)
+        # margined gradient volume (ADM_GVOL_MARGIN in include/adorym_b200.h); the adjoint kernel reduce-adds into it
         g_tvol = torch.zeros((Nz, Y + P, gvol_pitch(X, P), 2), dtype=torch.float32, device=dev)
         g_probe = None
-        if ctx.needs_input_grad[1]:
+        if ctx.needs_input_grad[2]:
             g_probe = torch.zeros(ctx.probe_shape, dtype=torch.float32, device=dev)
         call('adm_multislice_bwd', ctypes.byref(ctx.cfg), ptr(tvol), ptr(pos), ptr(plan.Hc), ptr(plan.Hfc), ptr(ckpt),
-             ptr(g_det), ptr(g_tvol), ptr(g_probe), stream_ptr())
-        g_rot = None
+             ptr(g_det), ptr(g_tvol), ptr(g_probe), ptr(multislice_workspace(dev, P)), stream_ptr())
+        g_obj = None
         if ctx.needs_input_grad[0]:
-            g_rot = torch.empty((Nz, Y, X, 2), dtype=torch.float32, device=dev)
-            call('adm_transmission_adj', plan.unknown_type, plan.k1, plan.sign_convention, Nz, Y, X, P, ptr(g_tvol),
-                 ptr(tvol), ptr(g_rot), stream_ptr())
-        return g_rot, g_probe, None, None
+            if ctx.layout == 'yxz':
+                g_obj = torch.empty((Y, X, Nz, 2), dtype=torch.float32, device=dev)
+                use_reg = ctx.reg is not None and g_reg is not None
+                gs = _f32c(g_reg.reshape(1)) if use_reg else None
+                slabs = []
+                for (y0, y1) in slab_ranges(Y, GRAD_SLABS):
+                    if use_reg:
+                        call('adm_regularizer_l1tv_range', Y, X, Nz, ptr(obj), ptr(w), ctx.reg[1], ctx.reg[2], ctx.reg[3], None,
+                             ptr(g_obj), ptr(gs), 0, y0, y1, stream_ptr())
+                    else:
+                        g_obj[y0:y1].zero_()
+                    call('adm_transmission_to_object_adj', Y, X, Nz, P, ptr(g_tvol), ptr(tvol), ptr(grid), plan.unknown_type,
+                         plan.k1, plan.sign_convention, ptr(g_obj), y0, y1, stream_ptr())
+                    if GRAD_SLABS > 1:
+                        ev = torch.cuda.Event()
+                        ev.record()
+                        slabs.append((y0, y1, ev))
+                last_obj_grad_slabs = (g_obj, slabs) if slabs else None
+            else:
+                g_obj = torch.empty((Nz, Y, X, 2), dtype=torch.float32, device=dev)
+                call('adm_transmission_adj', plan.unknown_type, plan.k1, plan.sign_convention, Nz, Y, X, P, ptr(g_tvol),
+                     ptr(tvol), ptr(g_obj), stream_ptr())
+        return g_obj, None, g_probe, None, None, None, None
 
 
 # ------------------------------------------------------------------------------------------------------

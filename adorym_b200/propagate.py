@@ -94,7 +94,7 @@ def multislice_propagate_batch(grid_batch, probe_real, probe_imag, energy_ev, ps
         probe = torch.stack([probe_real, probe_imag], -1).unsqueeze(0)          # [1, P, P, 2]
     else:
         probe = torch.stack([probe_real, probe_imag], -1).unsqueeze(1)          # [B, 1, P, P, 2]
-    det = ops.MultisliceFn.apply(rot, probe, pos, plan)
+    det = ops.MultisliceFn.apply(rot, None, probe, pos, plan, None, 'zyx')
     ret = [det[:, 0, :, :, 0], det[:, 0, :, :, 1]]
     if return_fft_time:
         ret.append(0.)

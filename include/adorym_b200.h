@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ADM_ABI_VERSION 3
+#define ADM_ABI_VERSION 4
 
 /* unknown_type */
 #define ADM_DELTA_BETA 0
@@ -111,9 +111,16 @@ int adm_transmission_adj(int unknown_type, float k1, int sign_convention, int Nz
  *            aligned; rows are stored with the tile pitch P+2 at column offset (x & 1) so that one bulk copy brings
  *            a slice back in the layout the TMA reduce of the adjoint needs (pad columns are never written)
  *   det      [B][M][P][P][2]     out: complex wavefield on the detector (far field is fftshift-ed)
+ *   workspace  adm_multislice_workspace_bytes(P) bytes, zero-filled ONCE after allocation (the kernels leave its
+ *            flags zero), private to the stream, or NULL.  With a workspace and more wavefields than co-resident CTAs
+ *            the launch is persistent: the B*M*Nz slice steps are cut into equal intervals, one per CTA, and a wavefield
+ *            cut by a boundary is handed from CTA to CTA through the workspace (no idle tail of a partial last wave).
+ *            NULL (or few wavefields): one CTA per wavefield.
  * cfg->k1 / unknown_type are not used here (they parameterise adm_transmission_*).                          */
+long long adm_multislice_workspace_bytes(int P);
 int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tvol, const float* probe, const int* pos,
-                       const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* stream);
+                       const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* workspace,
+                       void* stream);
 
 /* Analytic adjoint of adm_multislice_fwd (replaces torch.autograd.grad over the taped slice loop,
  * wrappers.py:300-331).
@@ -123,10 +130,11 @@ int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tvol, const f
  *             dL/dIm T), margined (see ADM_GVOL_MARGIN): per slice one TMA reduce-add of the patch tile (overlapping
  *             patches are summed by the L2, overhang is clipped); zero it before the first call of a step
  *   g_probe   [M][P][P][2] ACCUMULATED over patterns, or [B][M][P][P][2] WRITTEN if probe_per_pattern; may be
- *             NULL when the probe gradient is not needed                                                     */
+ *             NULL when the probe gradient is not needed
+ *   workspace as for adm_multislice_fwd (the same buffer may serve both calls of a step)                    */
 int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
                        const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol,
-                       float* g_probe, void* stream);
+                       float* g_probe, void* workspace, void* stream);
 
 /* Detector magnitude, mismatch loss and residual (forward_model.py:88-103,353,371-375).
  *   det [B][M][P][P][2]; meas [B][P][P] = |prj| as stored (magnitude or intensity, see raw_data_type);
@@ -144,6 +152,19 @@ int adm_detector_loss(int B, int M, int P, int loss_type, int raw_data_type, flo
 int adm_rotate_fwd(int Y, int X, int Z, const float* obj, const float* grid, float* rot, void* stream);
 /* Exact transpose: g_obj [Y][X][Z][2] += R^T g_rot  (g_rot [Z][Y][X][2]).                                   */
 int adm_rotate_adj(int Y, int X, int Z, const float* g_rot, const float* grid, float* g_obj, void* stream);
+
+/* Object -> transmission volume in one pass (adm_rotate_fwd + adm_transmission_fwd without the intermediate rotated
+ * volume): tvol [Z][Y][Xp][2] = T'( R_grid obj [Y][X][Z][2] ).  grid == NULL: no rotation, a pure
+ * [Y][X][Z] -> [Z][Y][X] transposition (the object is already in the beam frame: rotate_out_of_loop,
+ * ptychography.py:1011, or a single angle).                                                                    */
+int adm_object_to_transmission(int Y, int X, int Z, const float* obj, const float* grid, int unknown_type, float k1,
+                               int sign_convention, float* tvol, void* stream);
+/* Its transpose on the planes y in [y_begin, y_end) (adm_transmission_adj + adm_rotate_adj without the intermediate):
+ * g_obj [Y][X][Z][2] += R^T chain(g_tvol, tvol).  g_obj is NOT cleared: initialise it with zeros or with the
+ * regulariser gradient (adm_regularizer_l1tv_range, accumulate = 0).  tvol may be NULL for ADM_REAL_IMAG.        */
+int adm_transmission_to_object_adj(int Y, int X, int Z, int P, const float* g_tvol, const float* tvol, const float* grid,
+                                   int unknown_type, float k1, int sign_convention, float* g_obj, int y_begin, int y_end,
+                                   void* stream);
 
 /* Fused Adam (optimizers.py:309-318) with optional epilogue.  In place on x, m, v (n floats each).
  *   step = i_batch of the reference (bias correction uses step+1); hyper-parameters are doubles (python floats):
@@ -165,6 +186,12 @@ int adm_regularizer_l1tv(int Y, int X, int Z, const float* obj, const float* wei
 int adm_regularizer_l1tv_scaled(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
                                 float alpha_b, float gamma, float* value, float* g_obj, const float* g_scale,
                                 int accumulate, void* stream);
+
+/* Same on the planes y in [y_begin, y_end) only (value and gradient restricted to those planes; the TV neighbours are
+ * read from the whole object): lets the driver produce the object gradient slab by slab under the all-reduce.     */
+int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d, float alpha_b,
+                               float gamma, float* value, float* g_obj, const float* g_scale, int accumulate, int y_begin,
+                               int y_end, void* stream);
 
 /* Sub-pixel Fourier shift of the probe per pattern (util.py:380-397 as used at forward_model.py:296-303).
  *   probe [M][P][P][2]; shift [B][2] (y, x); out [B][M][P][P][2].                                          */

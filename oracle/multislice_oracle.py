@@ -9,8 +9,8 @@ may import this module, and only as the checker / the reported CPU baseline.
 Pinning: the reference (mdw771/adorym @ efbb333b) has NO golden vectors or assertions of its own
 (SURVEY.md section 4), so this restatement is pinned against outputs of the reference itself,
 imported in the build container through the I/O shims in `oracle/ref_shims`
-(`tests/golden/make_golden.py` -> `tests/golden/*.npz`, and `tests/test_oracle_vs_reference.py`
-when /root/reference is present).  Parity against the numpy/HIPS-autograd backend is UNPINNED
+(`tests/golden/make_golden.py`, `make_golden_multidist.py`, `make_golden_driver.py` -> `tests/golden/*.npz`,
+checked by `tests/test_oracle_golden.py` on every CPU run).  Parity against the numpy/HIPS-autograd backend is UNPINNED
 (the `autograd` package is not installable here); the PyTorch backend is the pinned one.
 
 Every function cites the reference file:line it follows (paths relative to the reference root).
@@ -457,7 +457,14 @@ def ptycho_loss_and_grads(obj, probe_real, probe_imag, pos_batch, prj_abs, coord
         leaves['probe_pos_correction'] = ppc
     pred = predict_ptycho(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], pos_batch, coord_old, cfg,
                           probe_pos_correction=ppc, this_i_theta=this_i_theta, this_ind_batch=this_ind_batch)
-    loss = mismatch_loss(pred, prj_abs, cfg.get('loss_function_type', 'lsq'), cfg.get('raw_data_type', 'magnitude'),
+    pred_l, prj_l = pred, prj_abs
+    if cfg.get('beamstop', None) is not None:
+        # forward_model.py:128-136: pixels with beamstop < 1e-5 are dropped from the mean
+        bs = torch.as_tensor(np.asarray(cfg['beamstop']) >= 1e-5)
+        sel = bs.unsqueeze(0).expand_as(pred)
+        pred_l = pred[sel].reshape(pred.shape[0], -1)
+        prj_l = prj_abs[sel].reshape(pred.shape[0], -1)
+    loss = mismatch_loss(pred_l, prj_l, cfg.get('loss_function_type', 'lsq'), cfg.get('raw_data_type', 'magnitude'),
                          cfg.get('poisson_multiplier', 1.))
     data_loss = loss.detach().clone()
     if reg:

@@ -31,13 +31,18 @@ def ck(rc):
 
 def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *, unknown_type='delta_beta',
                        free_prop='inf', sign_convention=1, normalize_fft=False, loss='lsq', raw_data_type='magnitude',
-                       poisson_multiplier=1.0, shift=None, reg=None, Hfree=None, separable=False):
+                       poisson_multiplier=1.0, shift=None, reg=None, Hfree=None, separable=False, fused_chain=True,
+                       grad_slabs=1, weight_l1=None, beamstop=None):
+    """fused_chain: object -> transmission volume and back through the fused kernels (object_chain.cu), as
+    ops.MultisliceFn layout 'yxz' does; False: the separate rotate / transmission kernels (rotate.cu, transmission.cu)."""
     L = emu()
     Y, X, Z, _ = obj.shape
     M, Pp, _ = probe_real.shape
     B = len(pos)
     obj = np.ascontiguousarray(obj, dtype='float32')
-    if grid is not None:
+    if fused_chain:
+        rot = None
+    elif grid is not None:
         rot = np.zeros((Z, Y, X, 2), 'float32')
         ck(L.adm_rotate_fwd(Y, X, Z, P(obj), P(grid), P(rot), None))
     else:
@@ -83,23 +88,36 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
     Xp = (X + 1) & ~1
     utype = 0 if unknown_type == 'delta_beta' else 1
     tvol = np.full((Z, Y, Xp, 2), np.nan, 'float32')
-    ck(L.adm_transmission_fwd(utype, float(np.float32(k1)), sign_convention, Z * Y, X, P(rot), P(tvol), None))
-    ck(L.adm_multislice_fwd(ctypes.byref(cfg), P(tvol), P(probe_in), P(posi), P(Hp), P(Hfp), P(ckpt), P(det), None))
+    if fused_chain:
+        ck(L.adm_object_to_transmission(Y, X, Z, P(obj), P(grid), utype, float(np.float32(k1)), sign_convention, P(tvol), None))
+    else:
+        ck(L.adm_transmission_fwd(utype, float(np.float32(k1)), sign_convention, Z * Y, X, P(rot), P(tvol), None))
+    ws = np.zeros(int(L.adm_multislice_workspace_bytes(Pp)), 'uint8')
+    ck(L.adm_multislice_fwd(ctypes.byref(cfg), P(tvol), P(probe_in), P(posi), P(Hp), P(Hfp), P(ckpt), P(det), P(ws), None))
     pred = np.zeros((B, Pp, Pp), 'float32')
     gdet = np.zeros_like(det)
     lpp = np.zeros((B,), 'float32')
     meas = np.ascontiguousarray(prj_abs, dtype='float32')
-    inv_n = 1.0 / (B * Pp * Pp)
+    mask = None
+    n_valid = Pp * Pp
+    if beamstop is not None:
+        mask = np.ascontiguousarray((np.asarray(beamstop) >= 1e-5).astype('float32'))
+        n_valid = int(mask.sum())
+    inv_n = 1.0 / (B * n_valid)
     ck(L.adm_detector_loss(B, M, Pp, 0 if loss == 'lsq' else 1, 0 if raw_data_type == 'magnitude' else 1,
-                           poisson_multiplier, inv_n, P(det), P(meas), None, P(pred), P(gdet), P(lpp), None))
+                           poisson_multiplier, inv_n, P(det), P(meas), P(mask), P(pred), P(gdet), P(lpp), None))
     loss_val = float(lpp.astype('float64').sum() * inv_n)
     g_tvol = np.zeros((Z, Y + Pp, (X + Pp + 1) & ~1, 2), 'float32')
     g_probe_in = np.zeros_like(probe_in)
     ck(L.adm_multislice_bwd(ctypes.byref(cfg), P(tvol), P(posi), P(Hc), P(Hfc), P(ckpt), P(gdet), P(g_tvol),
-                            P(g_probe_in), None))
-    g_rot = np.full(rot.shape, np.nan, 'float32')
-    ck(L.adm_transmission_adj(utype, float(np.float32(k1)), sign_convention, Z, Y, X, Pp, P(g_tvol), P(tvol), P(g_rot), None))
+                            P(g_probe_in), P(ws), None))
+    assert not ws[:4096].any(), 'hand-off flags must be left zero'
+    g_rot = None
+    if not fused_chain:
+        g_rot = np.full(rot.shape, np.nan, 'float32')
+        ck(L.adm_transmission_adj(utype, float(np.float32(k1)), sign_convention, Z, Y, X, Pp, P(g_tvol), P(tvol), P(g_rot), None))
     out = {'loss': loss_val, 'pred': pred, 'det': det}
+    wl1 = None if weight_l1 is None else np.ascontiguousarray(weight_l1, dtype='float32')
     if shift is not None:
         g_probe = np.zeros_like(probe)
         g_shift = np.zeros((B, 2), 'float32')
@@ -109,16 +127,39 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
         g_probe = g_probe_in
     out['g_probe_real'] = g_probe[..., 0]
     out['g_probe_imag'] = g_probe[..., 1]
-    if grid is not None:
-        g_obj = np.zeros_like(obj)
-        ck(L.adm_rotate_adj(Y, X, Z, P(g_rot), P(grid), P(g_obj), None))
+    if fused_chain:
+        # the regulariser gradient INITIALISES the buffer (accumulate = 0), the transpose chain accumulates into it, per slab
+        g_obj = np.full(obj.shape, np.nan, 'float32')
+        one = np.ones((1,), 'float32')
+        edges = [int(round(i * Y / grad_slabs)) for i in range(grad_slabs + 1)]
+        for y0, y1 in zip(edges[:-1], edges[1:]):
+            if y1 <= y0:
+                continue
+            if reg:
+                ck(L.adm_regularizer_l1tv_range(Y, X, Z, P(obj), P(wl1), float(reg.get('alpha_d') or 0.),
+                                                float(reg.get('alpha_b') or 0.), float(reg.get('gamma') or 0.), None, P(g_obj),
+                                                P(one), 0, y0, y1, None))
+            else:
+                g_obj[y0:y1] = 0
+            ck(L.adm_transmission_to_object_adj(Y, X, Z, Pp, P(g_tvol), P(tvol), P(grid), utype, float(np.float32(k1)),
+                                                sign_convention, P(g_obj), y0, y1, None))
+        if reg:
+            val = np.zeros((1,), 'float32')
+            ck(L.adm_regularizer_l1tv_scaled(Y, X, Z, P(obj), P(wl1), float(reg.get('alpha_d') or 0.),
+                                             float(reg.get('alpha_b') or 0.), float(reg.get('gamma') or 0.), P(val), None, None,
+                                             0, None))
+            out['loss'] += float(val[0])
     else:
-        g_obj = np.ascontiguousarray(g_rot.transpose(1, 2, 0, 3))
-    if reg:
-        val = np.zeros((1,), 'float32')
-        ck(L.adm_regularizer_l1tv(Y, X, Z, P(obj), None, float(reg.get('alpha_d') or 0.), float(reg.get('alpha_b') or 0.),
-                                  float(reg.get('gamma') or 0.), P(val), P(g_obj), None))
-        out['loss'] += float(val[0])
+        if grid is not None:
+            g_obj = np.zeros_like(obj)
+            ck(L.adm_rotate_adj(Y, X, Z, P(g_rot), P(grid), P(g_obj), None))
+        else:
+            g_obj = np.ascontiguousarray(g_rot.transpose(1, 2, 0, 3))
+        if reg:
+            val = np.zeros((1,), 'float32')
+            ck(L.adm_regularizer_l1tv(Y, X, Z, P(obj), P(wl1), float(reg.get('alpha_d') or 0.), float(reg.get('alpha_b') or 0.),
+                                      float(reg.get('gamma') or 0.), P(val), P(g_obj), None))
+            out['loss'] += float(val[0])
     out['g_obj'] = g_obj
     return out
 

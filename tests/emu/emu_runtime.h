@@ -52,6 +52,7 @@ static thread_local char* emu_smem = nullptr;
 
 #define __syncthreads() emu_bar->wait()
 static inline void emu_named_sync(int id, unsigned n) { emu_named->get(id, n)->wait(); }
+#define __threadfence() std::atomic_thread_fence(std::memory_order_seq_cst)
 #define __global__ static
 #define __device__
 #define __host__

@@ -53,6 +53,26 @@ CASES = {
                                   pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=1, free_prop_cm=0,
                                   unknown_type='real_imag', delta_scale=0.2, beta_scale=0.2, seed=17,
                                   loss='lsq', raw_data_type='intensity'),
+    # regulariser-dominated gradient: L1 + TV weights chosen so that |g_reg| is a large fraction of |g| (a wrong sign, a
+    # missing TV neighbour or a wrong 1/N in the fused regulariser kernel cannot hide below the tolerance); non-cubic
+    'ptycho3d_p72_strongreg': dict(kind='ptycho', obj_size=(40, 56, 48), probe_size=(72, 72), energy_ev=5000.,
+                                   psize_cm=1e-7, theta=1.3, n_theta=5, i_theta=2,
+                                   pos=[(-20, -14), (-30, 3), (3, -17)], n_modes=1, free_prop_cm='inf',
+                                   unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=18,
+                                   loss='lsq', raw_data_type='magnitude', alpha_d=4e4, alpha_b=2e4, gamma=3e4),
+    # reweighted L1 (weights as the driver forms them, ptychography.py:995-999) + TV, also regulariser-dominated
+    'ptycho3d_p72_rwl1': dict(kind='ptycho', obj_size=(40, 48, 56), probe_size=(72, 72), energy_ev=5000.,
+                              psize_cm=1e-7, theta=-0.9, n_theta=5, i_theta=4,
+                              pos=[(-16, -20), (-32, 0), (5, -11)], n_modes=1, free_prop_cm='inf',
+                              unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=19,
+                              loss='lsq', raw_data_type='magnitude', alpha_d=2e3, alpha_b=1e3, gamma=2e4,
+                              reweighted=True),
+    # beamstop: the central detector pixels are excluded from the loss (forward_model.py:128-136)
+    'ptycho3d_p72_beamstop': dict(kind='ptycho', obj_size=(48, 48, 48), probe_size=(72, 72), energy_ev=5000.,
+                                  psize_cm=1e-7, theta=0.5, n_theta=4, i_theta=1,
+                                  pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=2, free_prop_cm='inf',
+                                  unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=20,
+                                  loss='lsq', raw_data_type='magnitude', optimize_probe=True, beamstop_radius=7.5),
     # 2-D ptychography with probe modes + probe and position refinement (BASELINE config B shape, small)
     'ptycho2d_modes': dict(kind='ptycho', obj_size=(128, 128, 1), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
                            theta=0.0, n_theta=1, i_theta=0,
@@ -120,8 +140,15 @@ def make_inputs(name):
     if c.get('optimize_all_probe_pos', False):
         ppc = rs.uniform(-0.6, 0.6, size=(n_theta, 16, 2)).astype('float32')
     ind = np.arange(B) + 2 if ppc is not None else np.arange(B)
-    return dict(cfg=c, obj=obj, probe_real=pr, probe_imag=pi, pos=pos, prj=prj, probe_pos_correction=ppc,
-                this_ind_batch=ind)
+    out = dict(cfg=c, obj=obj, probe_real=pr, probe_imag=pi, pos=pos, prj=prj, probe_pos_correction=ppc,
+               this_ind_batch=ind, weight_l1=None, beamstop=None)
+    if c.get('reweighted', False):
+        # ptychography.py:995-999: weight_l1 = max(obj) / (|obj| + 1e-4 mean(obj)), in fp32 as the driver does
+        out['weight_l1'] = (obj.max() / (np.abs(obj) + np.float32(1e-4) * obj.mean())).astype('float32')
+    if c.get('beamstop_radius'):
+        yy, xx = np.meshgrid(np.arange(P[0]) - P[0] // 2, np.arange(P[1]) - P[1] // 2, indexing='ij')
+        out['beamstop'] = (np.sqrt(yy ** 2 + xx ** 2) > c['beamstop_radius']).astype('float32')   # 1 = valid pixel
+    return out
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -38,7 +38,7 @@ def run_reference(name):
     from adorym.forward_model import PtychographyModel, SingleBatchFullfieldModel
     from adorym.propagate import get_kernel
     from adorym.util import save_rotation_lookup
-    from adorym.regularizers import L1Regularizer, TVRegularizer
+    from adorym.regularizers import L1Regularizer, TVRegularizer, ReweightedL1Regularizer
     gs.backend = 'pytorch'
     inp = make_inputs(name)
     c = inp['cfg']
@@ -72,12 +72,17 @@ def run_reference(name):
                   optimize_probe_defocusing=False, optimize_probe_pos_offset=False, optimize_prj_pos_offset=False,
                   optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=False, initial_tilt=None,
                   debug=False, output_folder=tmp, n_probe_modes=c['n_modes'], n_theta=n_theta,
-                  precalculate_rotation_coords=True, theta_ls=theta_ls, theta_downsample=None, beamstop=None)
+                  precalculate_rotation_coords=True, theta_ls=theta_ls, theta_downsample=None,
+                  beamstop=None if inp['beamstop'] is None else torch.tensor(inp['beamstop'].copy()))
         Model = SingleBatchFullfieldModel if c['kind'] == 'fullfield' else PtychographyModel
         fm = Model(loss_function_type=c['loss'], distribution_mode=None, device=None, common_vars_dict=cv,
                    raw_data_type=c['raw_data_type'])
         regs = []
-        if c.get('alpha_d'):
+        if c.get('alpha_d') and c.get('reweighted', False):
+            r = ReweightedL1Regularizer(c['alpha_d'], c['alpha_b'], unknown_type=c['unknown_type'])
+            r.update_l1_weight(torch.tensor(inp['weight_l1']))
+            regs.append(r)
+        elif c.get('alpha_d'):
             regs.append(L1Regularizer(c['alpha_d'], c['alpha_b'], unknown_type=c['unknown_type']))
         if c.get('gamma'):
             regs.append(TVRegularizer(c['gamma'], unknown_type=c['unknown_type']))

@@ -40,6 +40,9 @@ def case_cfg(name):
     reg = None
     if c.get('alpha_d') or c.get('gamma'):
         reg = dict(alpha_d=c.get('alpha_d'), alpha_b=c.get('alpha_b'), gamma=c.get('gamma'))
+        if inp.get('weight_l1') is not None:
+            reg['weight_l1'] = inp['weight_l1']
+    cfg['beamstop'] = inp.get('beamstop')
     return inp, cfg, coord, reg
 
 
@@ -53,6 +56,8 @@ def run_oracle_case(name, dtype=torch.float32):
     if inp['probe_pos_correction'] is not None:
         ppc = torch.tensor(inp['probe_pos_correction']).to(dtype)
         want += ['probe_pos_correction']
+    if reg is not None and reg.get('weight_l1') is not None:
+        reg = dict(reg, weight_l1=torch.tensor(reg['weight_l1']).to(dtype))
     loss, data_loss, pred, grads = orc.ptycho_loss_and_grads(
         torch.tensor(inp['obj']).to(dtype), torch.tensor(inp['probe_real']).to(dtype),
         torch.tensor(inp['probe_imag']).to(dtype), inp['pos'], torch.tensor(inp['prj']).to(dtype), coord, cfg, reg=reg,
