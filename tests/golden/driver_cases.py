@@ -1,0 +1,62 @@
+"""Seeded inputs of the driver goldens (shared by make_golden_driver.py, the oracle driver test and the GPU test):
+a small 3-D ptychotomography reconstruction that switches on everything the batch loop of
+adorym/ptychography.py:859-1271 does around the hot path -- probe refinement, probe-position refinement with drift
+removal, finite-support mask, reweighted L1 + TV, non-negativity, per-angle Adam step index."""
+import numpy as np
+from cases import _smooth_noise, _gaussian_probe
+
+DRIVER_CASES = {
+    'driver_immediate': dict(update_scheme='immediate', n_epochs=2),
+    'driver_per_angle': dict(update_scheme='per angle', n_epochs=2),
+}
+OBJ_SIZE = (32, 40, 40)
+P = 72
+N_THETA = 3
+POS = [(-20.3, -18.6), (-24.8, -6.1), (-16.2, 1.4), (-9.7, -21.2), (-30.4, -30.9), (-12.5, -11.3)]
+
+
+def driver_params(name):
+    c = DRIVER_CASES[name]
+    rs = np.random.RandomState(77)
+    init = [_smooth_noise(rs, OBJ_SIZE, 3e-4), _smooth_noise(rs, OBJ_SIZE, 3e-5)]
+    return dict(obj_size=OBJ_SIZE, probe_pos=POS, theta_st=0, theta_end=2 * np.pi, n_theta=N_THETA, energy_ev=5000.,
+                psize_cm=1e-7, free_prop_cm='inf', minibatch_size=2, n_epochs=c['n_epochs'], alpha_d=2e-2, alpha_b=2e-3,
+                gamma=5e-2, reweighted_l1=True, learning_rate=2e-5, optimizer='adam', update_scheme=c['update_scheme'],
+                probe_type='gaussian', probe_mag_sigma=6, probe_phase_sigma=6, probe_phase_max=0.5,
+                optimize_probe=True, probe_learning_rate=1e-3, optimize_all_probe_pos=True, all_probe_pos_learning_rate=1e-2,
+                non_negativity=True, initial_guess=init, unknown_type='delta_beta', loss_function_type='lsq',
+                raw_data_type='magnitude', randomize_probe_pos=False, shared_probe_among_angles=True)
+
+
+def driver_truth():
+    rs = np.random.RandomState(78)
+    return np.stack([_smooth_noise(rs, OBJ_SIZE, 6e-4), _smooth_noise(rs, OBJ_SIZE, 6e-5)], -1)
+
+
+def driver_mask():
+    Y, X, Z = OBJ_SIZE
+    yy, xx, zz = np.meshgrid(np.arange(Y) - Y / 2 + 0.5, np.arange(X) - X / 2 + 0.5, np.arange(Z) - Z / 2 + 0.5, indexing='ij')
+    return ((xx ** 2 + zz ** 2) < (0.45 * X) ** 2).astype('float32')
+
+
+def driver_data():
+    """Measured magnitudes [n_theta, n_pos, P, P] (complex64, as exchange/data stores them): the oracle's forward model on
+    the true object at the ROUNDED positions with the initial Gaussian probe (adorym/simulation.py:659-671 recipe)."""
+    import torch
+    from oracle import multislice_oracle as orc
+    Y, X, Z = OBJ_SIZE
+    theta_ls = np.linspace(0, 2 * np.pi, N_THETA, dtype='float32')
+    voxel_nm = np.array([1e-7] * 3) * 1e7
+    h = orc.get_kernel(voxel_nm[-1], 1240. / 5000., voxel_nm, [P, P])
+    cfg = dict(this_obj_size=[Y, X, Z], probe_size=[P, P], energy_ev=5000., psize_cm=1e-7, h=h, free_prop_cm='inf',
+               unknown_type='delta_beta')
+    pr, pi = orc.gaussian_probe([P, P], 1, 6, 0.5, 6)
+    pr = torch.tensor(pr[None], dtype=torch.float32) * 1.1      # the "true" probe differs from the initial guess
+    pi = torch.tensor(pi[None], dtype=torch.float32) * 0.9
+    pos = np.round(np.array(POS)).astype(int)
+    tr = torch.tensor(driver_truth(), dtype=torch.float32)
+    data = np.zeros([N_THETA, len(pos), P, P], dtype='complex64')
+    with torch.no_grad():
+        for i in range(N_THETA):
+            data[i] = orc.predict_ptycho(tr, pr, pi, pos, orc.rotation_coords([Y, X, Z], theta_ls[i]), cfg).numpy()
+    return data

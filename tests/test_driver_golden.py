@@ -1,0 +1,57 @@
+"""The DRIVER against the unmodified reference's own reconstruct_ptychography (tests/golden/make_golden_driver.py):
+2 epochs x 3 angles x 3 minibatches of a small 3-D ptychotomography reconstruction with probe refinement, probe-position
+refinement (drift removal), finite-support mask, reweighted L1 + TV, non-negativity; update_scheme 'immediate' and
+'per angle' (ref adorym/ptychography.py:859-1271, optimizers.py:993-1089).
+
+Stated tolerance for a reconstruction after a fixed number of updates: first loss (precedes every update) 1e-4; loss
+history 1.5e-2 relative; final object / probe / position corrections 3e-2 of their norm.  These are 3x the reference's
+OWN sensitivity, measured with the unmodified reference in the build container: perturbing its initial guess by 1e-7
+relative moves its loss history by up to 4.8e-3 (growing with the update count) and its final object by 8.4e-3 -- Adam's
+first steps are sign-like (m / (sqrt(v) + eps) ~ sign(g) where |g| >> eps), so roundoff in near-zero gradient voxels
+flips whole steps and any two correct fp32 evaluations drift apart at that rate."""
+import os
+import numpy as np
+import pytest
+import torch
+
+from driver_cases import DRIVER_CASES, driver_params, driver_mask
+from oracle_util import rel_err
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
+
+
+def _data():
+    return np.load(os.path.join(GOLD, 'driver_data.npz'))['data'].astype('float32')
+
+
+def _check(name, hist, obj, pr, pi, ppc):
+    gold = np.load(os.path.join(GOLD, name + '.npz'))
+    gh = gold['loss_history']
+    assert len(hist) == len(gh)
+    assert np.array_equal(np.asarray(hist)[:, :2].astype(int), gh[:, :2].astype(int))       # same (epoch, batch) sequence
+    lh = np.asarray(hist)[:, 2]
+    assert abs(lh[0] - gh[0, 2]) <= 1e-4 * gh[0, 2]
+    np.testing.assert_allclose(lh, gh[:, 2], rtol=1.5e-2)
+    assert rel_err(obj, gold['obj']) < 3e-2
+    assert rel_err(pr, gold['probe_real']) < 3e-2
+    assert rel_err(pi, gold['probe_imag']) < 3e-2
+    assert rel_err(ppc, gold['probe_pos_correction']) < 3e-2
+
+
+@pytest.mark.parametrize('name', sorted(DRIVER_CASES))
+def test_oracle_driver_matches_reference_driver_golden(name):
+    from oracle_driver import oracle_reconstruct_full
+    hist, obj, pr, pi, ppc = oracle_reconstruct_full(_data(), driver_mask(), **driver_params(name))
+    _check(name, hist, obj, pr, pi, ppc)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize('name', sorted(DRIVER_CASES))
+def test_reconstruct_ptychography_matches_reference_driver_golden(name):
+    import adorym_b200 as ab
+    params = driver_params(name)
+    out = ab.reconstruct_ptychography(_data(), **params, finite_support_mask_path=driver_mask(), verbose=False,
+                                      save_outputs=False, output_folder='/tmp/adm_test_driver_' + name)
+    hist = [(e, b, l) for (e, b, l, t) in out['loss_history']]
+    _check(name, hist, out['obj'].cpu().numpy(), out['probe_real'].cpu().numpy(), out['probe_imag'].cpu().numpy(),
+           out['probe_pos_correction'].cpu().numpy())

@@ -295,8 +295,12 @@ def _config_d_model(dev, pos, prj, theta, reg=True):
 
 def test_config_d_full_size_matches_oracle(monkeypatch):
     """BASELINE config D at FULL size (256^3 object, P = 72, 256 slices, far field, lsq + L1 + TV, rotation).
-    (a) six of the 529 positions (two overhanging corners, the centre, interior ones): loss, magnitudes and the object
-        gradient vs the oracle evaluated in fp64 on the same inputs, 1e-4 relative;
+    (a) six of the 529 positions (two overhanging corners, the centre, interior ones): loss, per-pattern loss and
+        magnitudes vs the oracle evaluated in fp64 on the same inputs, 1e-4 relative.  Object gradient: through 256
+        slices dL/ddelta = -k1 Im(g conj(psi)) cancels heavily and the reference algorithm's OWN fp32 evaluation sits
+        4.9e-3 (delta channel 1.1e-2) away from its fp64 evaluation (measured with the oracle at this size), so the bar
+        is: at least as close to the fp64 gradient as 1.2x the reference algorithm in fp32 (the kernels carry T - 1
+        instead of T and land at 3.8e-3);
     (b) all 529 positions of the angle (the benchmark's minibatch, which runs on the persistent balanced schedule with
         wavefields migrating between CTAs): per-pattern loss and magnitudes of the six positions vs the oracle, and the
         whole gradient vs the one-CTA-per-wavefield launch of the same kernels (ADM_MS_GRID forces it)."""
@@ -344,8 +348,13 @@ def test_config_d_full_size_matches_oracle(monkeypatch):
     np.testing.assert_allclose(lpp6, ref_lpp, rtol=TOL)
     for b in range(len(sel)):
         assert rel_err(pred6[b], p64[b]) < TOL, 'pattern %d' % sel[b]
-    assert rel_err(g6.cpu().numpy(), gr64['obj'].numpy()) < TOL
-    del g6
+    _, _, _, gr32 = orc.ptycho_loss_and_grads(torch.tensor(obj), torch.tensor(pr), torch.tensor(pi), pos_all[sel],
+                                              torch.tensor(prj_all[sel]), lut, cfg, reg=reg, want=('obj',))
+    ref32_err = rel_err(gr32['obj'].numpy(), gr64['obj'].numpy())
+    gpu_err = rel_err(g6.cpu().numpy(), gr64['obj'].numpy())
+    print('config D full size: |g_gpu - g_64| / |g_64| = %.3e, reference algorithm in fp32: %.3e' % (gpu_err, ref32_err))
+    assert gpu_err < max(TOL, 1.2 * ref32_err)
+    del g6, gr32
 
     # ---- (b) the whole angle on the balanced schedule ----
     ind = np.arange(529)
