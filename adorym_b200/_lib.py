@@ -49,6 +49,7 @@ SIGNATURES = {
     'adm_rotate_adj': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_adam_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double, c_double, c_int,
                       c_int, c_void_p, c_void_p],
+    'adm_sgd_step': [c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_int, c_void_p, c_void_p],
     'adm_regularizer_l1tv': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
                              c_void_p],
     'adm_regularizer_l1tv_scaled': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
@@ -129,9 +130,23 @@ def timing_summary():
     return out
 
 
+_ptr_devices = set()     # devices of the tensors whose pointers were taken since the last call()
+
+
 def call(name, *args):
+    """Invoke one ABI entry point.  The kernels launch on the CURRENT device / stream of the calling thread, so every
+    tensor handed over through ptr() since the previous call must live on that device: anything else would make the
+    kernel dereference another GPU's memory on an unrelated stream."""
     global launch_count
     fn = getattr(get_lib(), name)
+    if _ptr_devices:
+        import torch
+        cur = torch.cuda.current_device()
+        bad = [d for d in _ptr_devices if d != cur]
+        _ptr_devices.clear()
+        if bad:
+            raise RuntimeError('adorym_b200.%s: tensors live on cuda:%s but the current device is cuda:%d; wrap the call in '
+                               '`with torch.cuda.device(tensor.device):` (or torch.cuda.set_device)' % (name, bad, cur))
     if _timing is not None:
         import torch
         e0 = torch.cuda.Event(enable_timing=True)
@@ -154,6 +169,7 @@ def ptr(t):
         raise RuntimeError('adorym_b200: expected a CUDA tensor (there is no CPU path)')
     if not t.is_contiguous():
         raise RuntimeError('adorym_b200: expected a contiguous tensor')
+    _ptr_devices.add(t.device.index)
     return ctypes.c_void_p(t.data_ptr())
 
 

@@ -106,6 +106,47 @@ extern "C" int adm_adam_step(float* x, float* m, float* v, const float* g, long 
     return ADM_OK;
 }
 
+// ---- gradient descent / momentum (adorym/optimizers.py:366-411, :432-464) ----------------------------------------
+// GD: x <- x - step g;  Momentum: v <- gamma v + step g, x <- x - v.  Every product / sum individually rounded, as torch
+// evaluates the reference's expressions; same epilogue flags / mask as k_adam.
+struct SgdArgs {
+    float step_size, gamma;
+    int flags, momentum;
+};
+__global__ void __launch_bounds__(256) k_sgd(float* x, float* v, const float* g, long long n, SgdArgs a, const float* mask) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long stride = (long long)gridDim.x * blockDim.x;
+    for (; j < n; j += stride) {
+        float xx = x[j];
+#ifndef ADM_HOST_EMU
+        float d = __fmul_rn(a.step_size, g[j]);
+        if (a.momentum) { d = __fadd_rn(__fmul_rn(a.gamma, v[j]), d); v[j] = d; }
+        xx = __fsub_rn(xx, d);
+#else
+        volatile float d = a.step_size * g[j];
+        if (a.momentum) { volatile float t = a.gamma * v[j]; d = t + d; v[j] = d; }
+        xx = xx - d;
+#endif
+        if (a.flags & 1) xx = fmaxf(xx, 0.f);
+        if ((a.flags & 2) && (j & 1) == 0) xx = 0.f;
+        if ((a.flags & 4) && (j & 1) == 1) xx = 0.f;
+        if (mask != nullptr) xx *= mask[j >> 1];
+        x[j] = xx;
+    }
+}
+
+extern "C" int adm_sgd_step(float* x, float* v, const float* g, long long n, double step_size, double gamma, int flags,
+                            const float* mask, void* stream) {
+    if (!x || !g || n < 1) return ADM_ERR_ARG;
+    if (((flags & 6) || mask) && (n & 1)) return ADM_ERR_ARG;
+    SgdArgs a;
+    a.step_size = (float)step_size; a.gamma = (float)gamma; a.flags = flags; a.momentum = v != nullptr ? 1 : 0;
+    long long blocks = (n + 255) / 256;
+    if (blocks > 148LL * 32) blocks = 148LL * 32;
+    ADM_LAUNCH(k_sgd, (unsigned)blocks, 256, 0, stream, x, v, g, n, a, mask);
+    return ADM_OK;
+}
+
 // ---- regulariser -------------------------------------------------------------------------------
 ADM_DEV float sgnf(float a) { return (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f); }
 

@@ -58,6 +58,44 @@ class Comm(object):
         return t.numpy()
 
 
+_comm_stream = {}
+
+
+def allreduce_update_pipelined(opt, x, gradient, i_batch, slabs, **options):
+    """SUM all-reduce of the object gradient + fused Adam, pipelined over the y slabs the backward pass produced
+    (ops.last_obj_grad_slabs: [(y0, y1, event)]; the tomographic rotation is about y, so the transpose rotation, the
+    regulariser and Adam are all independent per y plane).  Slab k is all-reduced on a side stream as soon as its event
+    has fired -- while the adjoint kernels still produce slab k+1 -- and Adam runs on slab k while slab k+1 is on the
+    wire.  Same sums and the same update as `gradient = comm.allreduce(gradient); opt.apply_gradient(...)`
+    (adorym/ptychography.py:1113-1125): only the order in time changes.  Returns the updated x."""
+    dev = x.device
+    cs = _comm_stream.get(dev)
+    if cs is None:
+        cs = _comm_stream[dev] = torch.cuda.Stream(device=dev)
+    main = torch.cuda.current_stream(dev)
+    g = gradient.arr if hasattr(gradient, 'arr') else gradient
+    if 'm' not in opt.params_whole_array_dict or opt.params_whole_array_dict['m'].shape != x.shape:
+        opt.create_param_arrays(list(x.shape), device=dev)
+    m, v = opt.params_whole_array_dict['m'], opt.params_whole_array_dict['v']
+    mask = options.pop('mask', None)
+    done = []
+    for (y0, y1, ev) in slabs:
+        cs.wait_event(ev)
+        with torch.cuda.stream(cs):
+            dist.all_reduce(g[y0:y1], op=dist.ReduceOp.SUM)
+            e2 = torch.cuda.Event()
+            e2.record(cs)
+        done.append((y0, y1, e2))
+    g.record_stream(cs)
+    xd = x.detach()
+    for (y0, y1, e2) in done:
+        main.wait_event(e2)
+        opt.apply_gradient(xd[y0:y1], g[y0:y1], i_batch, m=m[y0:y1], v=v[y0:y1], update_batch_count=False,
+                           mask=None if mask is None else mask[y0:y1], **options)
+    opt.i_batch += 1
+    return xd
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).
     Returns (rank, world_size, local_rank).  A no-op for single-process runs."""

@@ -211,9 +211,15 @@ class ForwardModel(object):
                 shp = (len(ind),) + tuple(frames.shape[1:])
                 if getattr(self, '_stage', None) is None or self._stage.shape != shp or self._stage.dtype != frames.dtype:
                     self._stage = torch.empty(shp, dtype=frames.dtype).pin_memory()
+                ev = getattr(self, '_stage_event', None)
+                if ev is not None:
+                    ev.synchronize()          # the previous copy out of the staging buffer has finished
                 torch.index_select(frames, 0, torch.as_tensor(ind, dtype=torch.long), out=self._stage)
                 frames = self._stage
             batch = frames.to(dev, non_blocking=True)
+            if frames is getattr(self, '_stage', None):
+                self._stage_event = torch.cuda.Event()
+                self._stage_event.record(torch.cuda.current_stream(dev))
             batch = (batch.abs() if batch.is_complex() else batch).to(torch.float32)
         else:
             a = np.abs(np.asarray(prj[it, ind]))

@@ -426,12 +426,41 @@ class RegL1TVFn(torch.autograd.Function):
 def adam_step_(x, m, v, g, step, step_size=0.001, b1=0.9, b2=0.999, eps=1e-7, clip_nonneg=False,
                zero_channel=None, mask=None):
     """In-place fused Adam on fp32 CUDA tensors (optimizers.py:309-318) + optional epilogue."""
-    for t in (x, m, v, g):
+    for name, t in (('x', x), ('m', m), ('v', v), ('g', g)):
         if t.dtype != torch.float32:
-            raise RuntimeError('adam_step_: fp32 tensors required')
+            raise RuntimeError('adam_step_: fp32 tensors required (%s is %s)' % (name, t.dtype))
+        if t.device != x.device or t.numel() != x.numel():
+            raise RuntimeError('adam_step_: %s must live on %s and hold %d elements (got %s, %d)'
+                               % (name, x.device, x.numel(), t.device, t.numel()))
+    for name, t in (('x', x), ('m', m), ('v', v)):
+        if not t.is_contiguous():
+            raise RuntimeError('adam_step_: %s must be contiguous (it is updated in place)' % name)
+    if mask is not None:
+        # the reference multiplies obj [..., 2] by mask [..., 1] (array_ops.py:239-244): a broadcast error there, a
+        # silent out-of-bounds read here unless checked
+        if mask.dtype != torch.float32 or mask.device != x.device or not mask.is_contiguous() \
+                or mask.numel() * 2 != x.numel():
+            raise RuntimeError('adam_step_: mask must be a contiguous fp32 tensor on %s with %d elements (one per voxel); got '
+                               '%s %s %s' % (x.device, x.numel() // 2, mask.dtype, mask.device, tuple(mask.shape)))
     flags = (1 if clip_nonneg else 0) | (2 if zero_channel == 0 else 0) | (4 if zero_channel == 1 else 0)
     call('adm_adam_step', ptr(x), ptr(m), ptr(v), ptr(_f32c(g)), x.numel(), float(step_size), float(b1), float(b2),
          float(eps), int(step), flags, ptr(mask), stream_ptr())
+    return x
+
+
+def sgd_step_(x, v, g, step_size=0.001, gamma=0.9, clip_nonneg=False, zero_channel=None, mask=None):
+    """In-place gradient descent (v is None) or momentum update on fp32 CUDA tensors (optimizers.py:366-464)."""
+    for name, t in (('x', x), ('g', g)) + ((('v', v),) if v is not None else ()):
+        if t.dtype != torch.float32 or t.device != x.device or t.numel() != x.numel():
+            raise RuntimeError('sgd_step_: %s must be fp32 on %s with %d elements' % (name, x.device, x.numel()))
+    if not x.is_contiguous() or (v is not None and not v.is_contiguous()):
+        raise RuntimeError('sgd_step_: x and v must be contiguous (they are updated in place)')
+    if mask is not None and (mask.dtype != torch.float32 or mask.device != x.device or not mask.is_contiguous()
+                             or mask.numel() * 2 != x.numel()):
+        raise RuntimeError('sgd_step_: mask must be a contiguous fp32 tensor with one element per voxel')
+    flags = (1 if clip_nonneg else 0) | (2 if zero_channel == 0 else 0) | (4 if zero_channel == 1 else 0)
+    call('adm_sgd_step', ptr(x), ptr(v), ptr(_f32c(g)), x.numel(), float(step_size), float(gamma), flags, ptr(mask),
+         stream_ptr())
     return x
 
 

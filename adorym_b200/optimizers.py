@@ -85,14 +85,17 @@ class AdamOptimizer(Optimizer):
 
 
 class GDOptimizer(Optimizer):
-    """adorym/optimizers.py:440-464 without the dynamic-rate schedule options beyond the defaults."""
+    """adorym/optimizers.py:432-464; the update runs as one fused kernel (adm_sgd_step) in place on x."""
 
     def __init__(self, name, output_folder='.', distribution_mode=None, options_dict=None, forward_model=None):
         super(GDOptimizer, self).__init__(name, output_folder=output_folder, params_list=[],
                                           distribution_mode=distribution_mode, options_dict=options_dict,
                                           forward_model=forward_model)
 
-    def apply_gradient(self, x, gradient, i_batch, step_size=0.001, dynamic_rate=True, first_downrate_iteration=92, **kwargs):
+    def apply_gradient(self, x, gradient, i_batch, step_size=0.001, dynamic_rate=True, first_downrate_iteration=92,
+                       use_numpy=False, verbose=False, **kwargs):
+        if use_numpy:
+            raise NotImplementedError('adorym_b200.GDOptimizer: numpy updates are out of scope')
         g = self.convert_gradient(gradient)
         if dynamic_rate:
             threshold_iteration = first_downrate_iteration
@@ -102,7 +105,33 @@ class GDOptimizer(Optimizer):
                 i += 1
                 step_size /= 2.
         with torch.no_grad():
-            return x.detach() - step_size * g
+            xd = x.detach()
+            ops.sgd_step_(xd, None, g.detach(), step_size=step_size, clip_nonneg=kwargs.get('clip_nonneg', False),
+                          zero_channel=kwargs.get('zero_channel', None), mask=kwargs.get('mask', None))
+        return xd
+
+
+class MomentumOptimizer(Optimizer):
+    """adorym/optimizers.py:366-411: v <- gamma v + step g, x <- x - v (fused kernel, in place on x and v)."""
+
+    def __init__(self, name, output_folder='.', distribution_mode=None, options_dict=None, forward_model=None):
+        super(MomentumOptimizer, self).__init__(name, output_folder=output_folder, params_list=['v'],
+                                                distribution_mode=distribution_mode, options_dict=options_dict,
+                                                forward_model=forward_model)
+
+    def apply_gradient(self, x, gradient, i_batch, step_size=0.001, gamma=0.9, use_numpy=False, params_slicer=None,
+                       **kwargs):
+        if use_numpy or params_slicer is not None:
+            raise NotImplementedError('adorym_b200.MomentumOptimizer: numpy / sliced updates are out of scope')
+        g = self.convert_gradient(gradient)
+        if 'v' not in self.params_whole_array_dict or self.params_whole_array_dict['v'].shape != x.shape:
+            self.create_param_arrays(list(x.shape), device=x.device)
+        v = self.params_whole_array_dict['v']
+        with torch.no_grad():
+            xd = x.detach()
+            ops.sgd_step_(xd, v, g.detach(), step_size=step_size, gamma=gamma, clip_nonneg=kwargs.get('clip_nonneg', False),
+                          zero_channel=kwargs.get('zero_channel', None), mask=kwargs.get('mask', None))
+        return xd
 
 
 # ------------------------------------------------------------------------------------------------------

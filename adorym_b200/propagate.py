@@ -40,6 +40,15 @@ def _free_prop_mode(free_prop_cm):
 _plan_cache = {}
 
 
+def _kernel_digest(kernel):
+    """Content hash of a user-supplied transfer function (an id() can be recycled by the allocator and would then hit
+    a stale plan)."""
+    if kernel is None:
+        return None
+    import hashlib
+    return hashlib.sha1(np.ascontiguousarray(np.asarray(kernel)).tobytes()).hexdigest()
+
+
 def multislice_propagate_batch(grid_batch, probe_real, probe_imag, energy_ev, psize_cm, delta_cm=None,
                                free_prop_cm=None, obj_batch_shape=None, kernel=None, fresnel_approx=True,
                                pure_projection=False, binning=1, device=None, type='delta_beta',
@@ -81,12 +90,14 @@ def multislice_propagate_batch(grid_batch, probe_real, probe_imag, energy_ev, ps
         h_free = get_kernel(float(free_prop_cm) * 1e7, lmbda_nm, voxel_nm, [P0, P1], sign_convention=sign_convention)
     key = (P0, Nz, B, float(energy_ev), float(psize_cm), mode, float(free_prop_cm) if mode == 'near' else 0., type,
            bool(normalize_fft), int(sign_convention), bool(scale_ri_by_k), bool(fresnel_approx),
-           id(kernel) if kernel is not None else None, str(grid_batch.device))
+           _kernel_digest(kernel), str(grid_batch.device))
     plan = _plan_cache.get(key)
     if plan is None:
         plan = ops.MultislicePlan(P0, Nz, B * P0, P1, ops.k1_of(energy_ev, psize_cm, scale_ri_by_k), h, grid_batch.device,
                                   sign_convention=sign_convention, unknown_type=type, free_prop=mode,
                                   normalize_fft=normalize_fft, h_free=h_free)
+        if len(_plan_cache) >= 32:          # bounded: drop the oldest plan
+            _plan_cache.pop(next(iter(_plan_cache)))
         _plan_cache[key] = plan
     rot = grid_batch.permute(3, 0, 1, 2, 4).reshape(Nz, B * P0, P1, 2).contiguous()
     pos = torch.stack([torch.arange(B, dtype=torch.int32) * P0, torch.zeros(B, dtype=torch.int32)], 1).to(grid_batch.device)

@@ -17,11 +17,12 @@ from .array_ops import ObjectFunction, Gradient, Mask
 from .differentiator import Differentiator
 from .dist import Comm, epoch_task_list, rank_minibatch
 from .forward_model import ForwardModel, PtychographyModel, SingleBatchFullfieldModel, MultiDistModel
-from .optimizers import (Optimizer, AdamOptimizer, GDOptimizer, create_and_initialize_parameter_optimizers,
+from .optimizers import (Optimizer, AdamOptimizer, GDOptimizer, MomentumOptimizer,
+                         create_and_initialize_parameter_optimizers,
                          initialize_parameter_gradients, update_parameter_gradients, update_parameters)
 from .propagate import get_kernel
 from .regularizers import L1Regularizer, ReweightedL1Regularizer, TVRegularizer
-from .util import initialize_probe, save_rotation_lookup
+from .util import initialize_probe, save_rotation_lookup, apply_rotation, RotationTable
 
 PI = 3.1415927   # default of theta_end only (adorym/ptychography.py:52, quirk 11)
 
@@ -111,7 +112,7 @@ def reconstruct_ptychography(
     if distribution_mode is not None:
         raise NotImplementedError('adorym_b200: distribution_mode=%r is replaced by NCCL data parallelism' % (distribution_mode,))
     for name, val in (('use_epie', use_epie), ('pure_projection', pure_projection), ('xpu', xpu),
-                      ('run_bfloat16', run_bfloat16), ('run_float64', run_float64), ('rotate_out_of_loop', rotate_out_of_loop),
+                      ('run_bfloat16', run_bfloat16), ('run_float64', run_float64),
                       ('fourier_disparity', fourier_disparity), ('dynamic_dropping', dynamic_dropping)):
         if val:
             raise NotImplementedError('adorym_b200: %s is not on the accelerated path' % name)
@@ -126,6 +127,7 @@ def reconstruct_ptychography(
 
     comm = Comm()
     n_ranks, rank = comm.Get_size(), comm.Get_rank()
+    ops.GRAD_SLABS = 4 if n_ranks > 1 else 1
     if not torch.cuda.is_available():
         raise RuntimeError('adorym_b200 needs a CUDA device (B200); there is no CPU fallback')
     if n_ranks > 1:
@@ -215,8 +217,10 @@ def reconstruct_ptychography(
     elif optimizer == 'gd':
         opt = GDOptimizer('obj', output_folder=output_folder,
                           options_dict={'step_size': learning_rate, 'dynamic_rate': True, 'first_downrate_iteration': 20})
+    elif optimizer == 'momentum':
+        opt = MomentumOptimizer('obj', output_folder=output_folder, options_dict={'step_size': learning_rate})
     else:
-        raise NotImplementedError('adorym_b200: optimizer=%r (adam and gd are on the accelerated path)' % (optimizer,))
+        raise NotImplementedError('adorym_b200: optimizer=%r (adam, gd and momentum are on the accelerated path)' % (optimizer,))
     opt.create_container([*this_obj_size, 2], use_checkpoint, device_obj)
     opt.set_index_in_grad_return(0)
     opt_ls = [opt]
@@ -270,6 +274,9 @@ def reconstruct_ptychography(
         else:
             from PIL import Image, ImageSequence
             mask_arr = np.stack([np.array(fr) for fr in ImageSequence.Iterator(Image.open(finite_support_mask_path))])
+        if tuple(np.asarray(mask_arr).shape) != tuple(this_obj_size):
+            raise ValueError('finite-support mask has shape %s, the object is %s' % (tuple(np.asarray(mask_arr).shape),
+                                                                                     tuple(this_obj_size)))
         mask.initialize_array_with_values(mask_arr, device=device_obj)
 
     # ---- probe (ptychography.py:607-667) ---------------------------------------------------------------------------
@@ -323,6 +330,7 @@ def reconstruct_ptychography(
     diff.create_loss_node(forward_model.get_loss_function(), opt_args_ls)
 
     loss_history = []
+    rot_table = None
     n_pos = len(probe_pos)
     cont = True
     i_epoch = 0
@@ -350,6 +358,16 @@ def reconstruct_ptychography(
             this_i_theta, this_ind_batch = rank_minibatch(ind_list_rand, i_batch, rank, minibatch_size, n_ranks)
             this_pos_batch = probe_pos_int[this_ind_batch]
             is_last_batch_of_this_theta = i_batch == n_batch - 1 or ind_list_rand[i_batch + 1][0, 0] != this_i_theta
+            if rotate_out_of_loop and not two_d_mode and this_i_theta != current_i_theta:
+                # ptychography.py:918-943: the object is rotated ONCE when the angle changes; the minibatches of the angle
+                # then work on obj.arr_rot (even after an immediate update of obj.arr: reference behaviour)
+                if rot_table is None:
+                    folder = 'arrsize_{}_{}_{}_ntheta_{}'.format(*this_obj_size, n_theta)
+                    rot_table = RotationTable(this_obj_size, theta_ls, device_obj,
+                                              src_folder=folder if precalculate_rotation_coords else None)
+                with torch.no_grad():
+                    obj.arr_rot = apply_rotation(obj.arr.detach(), rot_table.lut(this_i_theta))
+                obj.arr_rot.requires_grad_(True)
             current_i_theta = this_i_theta
 
             if reweighted_l1:
@@ -366,7 +384,7 @@ def reconstruct_ptychography(
             grad_func_args = {}
             for arg in forward_model.argument_ls:
                 if arg == 'obj':
-                    grad_func_args[arg] = obj.arr
+                    grad_func_args[arg] = obj.arr_rot if (rotate_out_of_loop and not two_d_mode) else obj.arr
                 elif arg in optimizable_params:
                     grad_func_args[arg] = optimizable_params[arg]
                 else:
@@ -386,6 +404,12 @@ def reconstruct_ptychography(
                 initialize_gradients = False
             else:
                 gradient.arr += grads[0]
+            if rotate_out_of_loop and not two_d_mode:
+                # ptychography.py:1067-1078: the (accumulated) gradient lives in the beam frame and is rotated back with the
+                # inverse-angle lookup table -- a forward interpolation, not the transpose -- after EVERY minibatch
+                # (reference behaviour, flagged by its own TODO at :1075)
+                with torch.no_grad():
+                    gradient.arr = apply_rotation(gradient.arr, rot_table.lut(this_i_theta, reverse=True))
             opt_ls = update_parameter_gradients(opt_ls, grads)
 
             if update_scheme == 'per angle' and not is_last_batch_of_this_theta:
@@ -393,12 +417,16 @@ def reconstruct_ptychography(
             initialize_gradients = True
 
             # ---- all-reduce (SUM) + update (ptychography.py:1113-1163) ----
-            if n_ranks > 1:
+            slabs = ops.last_obj_grad_slabs
+            pipelined = (n_ranks > 1 and slabs is not None and slabs[0].data_ptr() == gradient.arr.data_ptr() and isinstance(opt, AdamOptimizer)
+                         and optimize_object and not fix_object)
+            if n_ranks > 1 and not pipelined:
                 gradient.arr = comm.allreduce(gradient.arr)
             with torch.no_grad():
                 if optimize_object and not fix_object:
                     extra = {}
-                    if isinstance(opt, AdamOptimizer):
+                    fused_opt = isinstance(opt, (AdamOptimizer, GDOptimizer, MomentumOptimizer))
+                    if fused_opt:
                         # constraints fused into the Adam epilogue (ptychography.py:1138-1142, array_ops.py:239-244)
                         extra['clip_nonneg'] = bool(non_negativity and unknown_type != 'real_imag')
                         if unknown_type == 'delta_beta' and object_type == 'absorption_only':
@@ -407,8 +435,14 @@ def reconstruct_ptychography(
                             extra['zero_channel'] = 1
                         if mask is not None and unknown_type == 'delta_beta':
                             extra['mask'] = mask.mask
-                    new = opt.apply_gradient(obj.arr, gradient, i_opt_batch, **opt.options_dict, **extra)
-                    if not isinstance(opt, AdamOptimizer):
+                    if pipelined:
+                        # the all-reduce runs slab by slab under the adjoint kernels and under Adam (dist.py)
+                        from .dist import allreduce_update_pipelined
+                        new = allreduce_update_pipelined(opt, obj.arr, gradient, i_opt_batch, slabs[1], **opt.options_dict,
+                                                         **extra)
+                    else:
+                        new = opt.apply_gradient(obj.arr, gradient, i_opt_batch, **opt.options_dict, **extra)
+                    if not fused_opt:
                         if non_negativity and unknown_type != 'real_imag':
                             new = new.clamp_(min=0)
                         if unknown_type == 'delta_beta' and object_type == 'absorption_only':
@@ -423,8 +457,8 @@ def reconstruct_ptychography(
                             new = torch.stack([new[..., 0] / nrm, new[..., 1] / nrm], -1)
                     obj.arr = new.requires_grad_(True)
             optimizable_params = update_parameters(opt_ls, optimizable_params, locals())
-            if mask is not None and not (isinstance(opt, AdamOptimizer) and unknown_type == 'delta_beta'
-                                         and optimize_object and not fix_object):
+            if mask is not None and not (isinstance(opt, (AdamOptimizer, GDOptimizer, MomentumOptimizer))
+                                         and unknown_type == 'delta_beta' and optimize_object and not fix_object):
                 obj.apply_finite_support_mask_to_array(mask, unknown_type=unknown_type, device=device_obj)
             if mask is not None and shrink_cycle is not None and i_batch % shrink_cycle == 0 and i_batch > 0:
                 mask.update_mask_array(obj, shrink_threshold)

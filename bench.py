@@ -285,13 +285,59 @@ class StepRunner(object):
         # ptychography.py:1065-1067 (`gradient.arr = zeros; gradient.arr += grads[0]` when the buffer is re-initialised,
         # i.e. every step at update_scheme='immediate'): 0 + g is g, so the buffer simply becomes the new gradient
         self.gradient = grads[0]
-        if self.world > 1:
-            torch.distributed.all_reduce(self.gradient, op=torch.distributed.ReduceOp.SUM)
+        from adorym_b200 import ops as _ops, dist as _adist
+        slabs = _ops.last_obj_grad_slabs
         with torch.no_grad():
-            new = self.opt.apply_gradient(self.obj, self.gradient, self.i_step, **self.opt.options_dict)
+            if self.world > 1 and slabs is not None and slabs[0].data_ptr() == self.gradient.data_ptr():
+                # gradient all-reduce pipelined by y slabs with the adjoint rotation and with Adam
+                new = _adist.allreduce_update_pipelined(self.opt, self.obj, self.gradient, self.i_step, slabs[1],
+                                                        **self.opt.options_dict)
+            else:
+                if self.world > 1:
+                    torch.distributed.all_reduce(self.gradient, op=torch.distributed.ReduceOp.SUM)
+                new = self.opt.apply_gradient(self.obj, self.gradient, self.i_step, **self.opt.options_dict)
         self.obj = new.requires_grad_(True)
         self.i_step += 1
         return self.fm.current_loss if host_data else None
+
+
+def dp_check(torch, ab, runner, dev, rank, world):
+    """On-hardware check of the data-parallel semantics (untimed, N > 1):
+    (1) one DP step's all-reduced object gradient equals the SUM of the single-rank gradients of all ranks' minibatches,
+        recomputed serially on rank 0 from the gathered frames (SUM, not mean: adorym/ptychography.py:1113-1114);
+    (2) after the timed steps every replica of the object is bit-identical to rank 0's (checked by the caller)."""
+    import torch.distributed as dist
+    runner.reset()
+    i_theta = 0
+    runner.fm.prj = runner.prj_dev
+    args = dict(obj=runner.obj, probe_real=runner.probe_real, probe_imag=runner.probe_imag, probe_defocus_mm=None,
+                probe_pos_offset=None, this_i_theta=i_theta, this_pos_batch=runner.pos, prj=runner.fm.prj,
+                probe_pos_correction=runner.zero_ppc, this_ind_batch=runner.ind, tilt_ls=None, prj_pos_offset=None)
+    g = runner.diff.get_gradients(**args)[0].clone()
+    dist.all_reduce(g, op=dist.ReduceOp.SUM)
+    frames = [torch.empty_like(runner.prj_dev[0]) for _ in range(world)]
+    dist.all_gather(frames, runner.prj_dev[0].contiguous())
+    thetas = [torch.zeros(1, device=dev) for _ in range(world)]
+    dist.all_gather(thetas, torch.tensor([float(runner.theta_ls[0])], device=dev))
+    out = None
+    if rank == 0:
+        cv = dict(runner.fm.common_vars)
+        cv['theta_ls'] = np.array([float(t.item()) for t in thetas], dtype='float32')
+        cv['n_theta'] = world
+        fm = ab.PtychographyModel(loss_function_type='lsq', device=dev, common_vars_dict=cv, raw_data_type='magnitude')
+        fm.add_regularizers(runner.fm.reg_list)
+        fm.prj = torch.stack(frames)
+        diff = ab.Differentiator()
+        diff.create_loss_node(fm.get_loss_function(), [0])
+        zero = torch.zeros([world, len(runner.pos), 2], device=dev)
+        gs = None
+        for r in range(world):
+            a = dict(args, this_i_theta=r, prj=fm.prj, probe_pos_correction=zero)
+            gr = diff.get_gradients(**a)[0]
+            gs = gr.clone() if gs is None else gs + gr
+        out = float((g - gs).double().norm() / gs.double().norm())
+    runner.reset()
+    return out
 
 
 def run_gpu_arm(args):
@@ -308,6 +354,8 @@ def run_gpu_arm(args):
     from adorym_b200 import _lib
     mb = args.minibatch
     K, W = args.steps, max(args.warmup, 3)
+    from adorym_b200 import ops as _ops
+    _ops.GRAD_SLABS = args.grad_slabs if world > 1 else 1
     runner = StepRunner(torch, ab, dev, rank, world, K + W, mb)
 
     def barrier():
@@ -347,6 +395,16 @@ def run_gpu_arm(args):
     clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _, _ = timed(True, False)
     frame_bytes = runner.frame_bytes
+    dp = None
+    if world > 1:
+        # replicas after the timed steps: every rank's object must equal rank 0's bit for bit
+        ref = runner.obj.detach().clone()
+        torch.distributed.broadcast(ref, src=0)
+        d = (ref - runner.obj.detach()).abs().max().reshape(1)
+        torch.distributed.all_reduce(d, op=torch.distributed.ReduceOp.MAX)
+        sum_err = dp_check(torch, ab, runner, dev, rank, world)
+        dp = {'max_abs_replica_difference': float(d.item()), 'allreduced_vs_summed_single_rank_gradient_rel': sum_err,
+              'grad_slabs': _ops.GRAD_SLABS}
 
     # ---- secondary figure: the reference demo's own schedule (minibatch_size = 2, update after every minibatch,
     # demos/multislice_ptycho_256_theta.py:63,93); every step still rotates and Adam-updates the whole 256^3 volume, so
@@ -426,8 +484,34 @@ def run_gpu_arm(args):
             'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
             'e2e': {'value': e2e, 'unit': UNIT, 'h2d_bytes_per_step': frame_bytes + mb * 8,
                     'd2h_bytes_per_step': 4, 'ms_per_step': ms_e2e / K},
-            'gpu_launches': launches, 'reference_default_schedule': ref_sched}
+            'gpu_launches': launches, 'reference_default_schedule': ref_sched, 'dp_check': dp}
     print(json.dumps(line), flush=True)
+
+
+def run_other_configs(args):
+    """The other named shapes of BASELINE.json (configs A, B, C, E) on one GPU, with the same clocks sampler as the
+    headline line: one JSON line per configuration (secondary figures; `python bench.py` without --config is the
+    driver's contract line on config D)."""
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError('bench.py --config: no CUDA device (there is no CPU fallback)')
+    sys.path.insert(0, os.path.join(ROOT, 'tools'))
+    import bench_configs as bc
+    for cfg in args.config:
+        sampler = ClockSampler(0)
+        sampler.start()
+        lines = bc.run([cfg], steps=args.steps, warmup=max(args.warmup, 3))
+        clocks = sampler.stop()
+        for l in lines:
+            out = {'metric': METRIC.replace('at 256^3', 'config ' + l['config']), 'value': l['value'], 'unit': UNIT, 'n_gpus': 1,
+                   'steps': l['steps'], 'warmup': l['warmup'], 'ms_per_step': l['ms_per_step'], 'higher_is_better': True,
+                   'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                   'config': {'workload': l['workload'], 'patterns_per_step': l['patterns_per_step'],
+                              'l2_policy': 'working set is L2 resident by construction (<= 8 MB): launch / latency bound'},
+                   'roofline': {'bound': 'hbm', 'achieved': l['algorithmic_bytes_per_step'] / (l['ms_per_step'] * 1e-3) / 1e9,
+                                'peak': l['peak_gbs'], 'unit': 'GB/s', 'frac': l['hbm_roofline_frac'], 'traffic': None},
+                   'clocks': clocks}
+            print(json.dumps(out), flush=True)
 
 
 def main():
@@ -437,11 +521,16 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--minibatch', type=int, default=529)
+    ap.add_argument('--grad-slabs', type=int, default=4, help='y slabs of the pipelined gradient all-reduce (N > 1)')
+    ap.add_argument('--config', nargs='*', default=None, choices=['A', 'B', 'C', 'E'],
+                    help='secondary lines for the other named shapes (default: the contract line on config D)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-reference-schedule', action='store_true')
     args = ap.parse_args()
     if args.impl == 'reference':
         run_reference_arm(args)
+    elif args.config:
+        run_other_configs(args)
     else:
         run_gpu_arm(args)
     try:

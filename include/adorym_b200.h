@@ -176,6 +176,12 @@ int adm_transmission_to_object_adj(int Y, int X, int Z, int P, const float* g_tv
 int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, double step_size, double b1, double b2,
                   double eps, int step, int flags, const float* mask, void* stream);
 
+/* Gradient descent (optimizers.py:432-464: x <- x - step g) and momentum (optimizers.py:366-411: v <- gamma v + step g,
+ * x <- x - v; v == NULL selects plain GD), in place, with the flags / mask epilogue of adm_adam_step.  The dynamic
+ * step-size schedule of GDOptimizer is host arithmetic on `step_size`.                                          */
+int adm_sgd_step(float* x, float* v, const float* g, long long n, double step_size, double gamma, int flags,
+                 const float* mask, void* stream);
+
 /* L1 / reweighted-L1 / TV regulariser on obj [Y][X][Z][2], delta_beta type (regularizers.py:30-110).
  *   value[0] += alpha_d*mean(w0|d|) + alpha_b*mean(w1|b|) + gamma*(TV3d(d) + TV3d(b));  g_obj += gradient.
  *   weight_l1 [Y][X][Z][2] or NULL; value / g_obj may be NULL.                                             */

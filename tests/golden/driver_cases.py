@@ -8,6 +8,9 @@ from cases import _smooth_noise, _gaussian_probe
 DRIVER_CASES = {
     'driver_immediate': dict(update_scheme='immediate', n_epochs=2),
     'driver_per_angle': dict(update_scheme='per angle', n_epochs=2),
+    # rotate_out_of_loop (ptychography.py:918-943,1011,1067-1078): the object is rotated once per angle, the minibatches work
+    # on obj.arr_rot, the gradient is rotated back with the inverse-angle table after every minibatch
+    'driver_rot_out_of_loop': dict(update_scheme='immediate', n_epochs=1, rotate_out_of_loop=True),
 }
 OBJ_SIZE = (32, 40, 40)
 P = 72
@@ -25,7 +28,8 @@ def driver_params(name):
                 probe_type='gaussian', probe_mag_sigma=6, probe_phase_sigma=6, probe_phase_max=0.5,
                 optimize_probe=True, probe_learning_rate=1e-3, optimize_all_probe_pos=True, all_probe_pos_learning_rate=1e-2,
                 non_negativity=True, initial_guess=init, unknown_type='delta_beta', loss_function_type='lsq',
-                raw_data_type='magnitude', randomize_probe_pos=False, shared_probe_among_angles=True)
+                raw_data_type='magnitude', randomize_probe_pos=False, shared_probe_among_angles=True,
+                rotate_out_of_loop=c.get('rotate_out_of_loop', False))
 
 
 def driver_truth():

@@ -67,6 +67,7 @@ def oracle_reconstruct_full(data_abs, mask, obj_size, probe_pos, theta_st, theta
     pr = torch.tensor(pr[None], dtype=dtype)
     pi = torch.tensor(pi[None], dtype=dtype)
     luts = [orc.rotation_coords([Y, X, Z], th) for th in theta_ls]
+    luts_rev = [orc.rotation_coords([Y, X, Z], -th) for th in theta_ls]      # util.py:505-512: the '_'-prefixed tables
     ppc = torch.tensor(np.tile(probe_pos - pos_int, [n_theta, 1, 1]), dtype=dtype)
     obj = torch.tensor(np.stack(initial_guess, -1), dtype=dtype)
     mask_t = None if mask is None else torch.tensor(mask, dtype=dtype).unsqueeze(-1)
@@ -85,8 +86,14 @@ def oracle_reconstruct_full(data_abs, mask, obj_size, probe_pos, theta_st, theta
         n_batch = len(chunks)
         i_opt = 0
         init_grads = True
+        current_i_theta = -1
+        obj_rot = None
         for i_batch in range(n_batch):
             i_theta, ind = orc.rank_slice_of_chunk(chunks, i_batch, 0, minibatch_size, 1)
+            if rotate_out_of_loop and i_theta != current_i_theta:
+                with torch.no_grad():
+                    obj_rot = orc.apply_rotation(obj, luts[i_theta])       # ptychography.py:918-943, once per angle
+            current_i_theta = i_theta
             last_of_theta = i_batch == n_batch - 1 or chunks[i_batch + 1][0, 0] != i_theta
             reg = dict(alpha_d=alpha_d, alpha_b=alpha_b, gamma=gamma)
             if reweighted_l1:
@@ -94,7 +101,8 @@ def oracle_reconstruct_full(data_abs, mask, obj_size, probe_pos, theta_st, theta
                     weight_l1 = obj.max() / (obj.abs() + 1e-4 * obj.mean())
                 reg['weight_l1'] = weight_l1
             loss, _, _, grads = orc.ptycho_loss_and_grads(
-                obj, pr, pi, pos_int[ind], torch.tensor(data_abs[i_theta, ind], dtype=dtype), luts[i_theta], cfg, reg=reg,
+                obj_rot if rotate_out_of_loop else obj, pr, pi, pos_int[ind],
+                torch.tensor(data_abs[i_theta, ind], dtype=dtype), None if rotate_out_of_loop else luts[i_theta], cfg, reg=reg,
                 probe_pos_correction=ppc if optimize_all_probe_pos else None, this_i_theta=i_theta, this_ind_batch=ind,
                 want=tuple(want))
             if init_grads:
@@ -103,6 +111,8 @@ def oracle_reconstruct_full(data_abs, mask, obj_size, probe_pos, theta_st, theta
                 g_ppc = torch.zeros_like(ppc)
                 init_grads = False
             g_obj = g_obj + grads['obj']
+            if rotate_out_of_loop:
+                g_obj = orc.apply_rotation(g_obj, luts_rev[i_theta])        # ptychography.py:1067-1078, every minibatch
             if optimize_probe:
                 g_probe = g_probe + torch.stack([grads['probe_real'], grads['probe_imag']], -1)
             if optimize_all_probe_pos:

@@ -92,6 +92,9 @@ def test_signatures_against_reference_source():
     assert _ref_args(REF + '/util.py', None, 'pad_object') == _args(ab.pad_object)
     ref = _ref_args(REF + '/optimizers.py', 'AdamOptimizer', 'apply_gradient')
     assert ref[:7] == _args(ab.AdamOptimizer.apply_gradient)[:7]
+    assert _ref_args(REF + '/optimizers.py', 'GDOptimizer', 'apply_gradient')[:6] == _args(ab.GDOptimizer.apply_gradient)[:6]
+    assert _ref_args(REF + '/optimizers.py', 'MomentumOptimizer', 'apply_gradient')[:5] == \
+        _args(ab.MomentumOptimizer.apply_gradient)[:5]
     ours = set(inspect.signature(ab.reconstruct_ptychography).parameters)
     ref = _ref_args(REF + '/ptychography.py', None, 'reconstruct_ptychography')
     missing = [a for a in ref if a not in ours]
@@ -102,7 +105,7 @@ def test_c_abi_library_builds_loads_and_exports_header_symbols():
     lib = abuild.build()
     assert os.path.exists(lib)
     hdr = open(os.path.join(ROOT, 'include', 'adorym_b200.h')).read()
-    declared = sorted(set(re.findall(r'^int\s+(adm_\w+)\s*\(', hdr, flags=re.M)))
+    declared = sorted(set(re.findall(r'^(?:int|long long)\s+(adm_\w+)\s*\(', hdr, flags=re.M)))
     assert len(declared) >= 14
     # every declared symbol has a ctypes signature and vice versa
     assert declared == sorted(_lib.SIGNATURES.keys())

@@ -226,6 +226,44 @@ def test_adam_epilogue_flags_and_mask():
     np.testing.assert_allclose(out.cpu().numpy(), xr.numpy(), rtol=2e-6, atol=1e-12)
 
 
+def test_gd_and_momentum_optimizers_match_reference_update():
+    """GDOptimizer / MomentumOptimizer (fused adm_sgd_step) vs the reference's expressions evaluated by torch on the CPU
+    (adorym/optimizers.py:432-464: x - step g with the halving schedule; :366-411: v = gamma v + step g, x = x - v),
+    bit for bit, over three consecutive calls; plus the constraint epilogue."""
+    import adorym_b200 as ab
+    dev = torch.device('cuda', 0)
+    rs = np.random.RandomState(4)
+    x0 = torch.tensor(rs.normal(size=(6, 5, 7, 2)).astype('float32') * 1e-3)
+    gs = [torch.tensor((rs.normal(size=(6, 5, 7, 2)) * 10.0 ** rs.uniform(-6, 0, size=(6, 5, 7, 2))).astype('float32'))
+          for _ in range(3)]
+    # gradient descent, dynamic rate: halved once past first_downrate_iteration
+    opt = ab.GDOptimizer('obj', options_dict={'step_size': 1e-2})
+    x, xr = x0.clone().to(dev), x0.clone()
+    for i, g in zip((0, 5, 200), gs):
+        x = opt.apply_gradient(x, g.to(dev), i, step_size=1e-2, dynamic_rate=True, first_downrate_iteration=92)
+        ss = 1e-2 / 2. if i > 92 else 1e-2
+        xr = xr - ss * g
+        assert torch.equal(x.cpu(), xr)
+    # momentum
+    opt = ab.MomentumOptimizer('obj', options_dict={'step_size': 1e-2})
+    opt.create_container(list(x0.shape), False, dev)
+    x, xr, vr = x0.clone().to(dev), x0.clone(), torch.zeros_like(x0)
+    for i, g in enumerate(gs):
+        x = opt.apply_gradient(x, g.to(dev), i, step_size=1e-2, gamma=0.9)
+        vr = 0.9 * vr + 1e-2 * g
+        xr = xr - vr
+        assert torch.equal(x.cpu(), xr)
+        assert torch.equal(opt.params_whole_array_dict['v'].cpu(), vr)
+    # epilogue: non-negativity, phase-only, mask
+    mask = torch.tensor((rs.uniform(size=(6, 5, 7)) > 0.4).astype('float32'))
+    x = opt.apply_gradient(x0.clone().to(dev), gs[0].to(dev), 3, step_size=1e-2, gamma=0.0, clip_nonneg=True, zero_channel=1,
+                           mask=mask.to(dev))
+    ref = (x0 - 1e-2 * gs[0]).clamp(min=0)
+    ref[..., 1] = 0
+    ref = ref * mask.unsqueeze(-1)
+    assert torch.equal(x.cpu(), ref)
+
+
 def test_full_size_properties_config_d():
     """BASELINE config D at full size (256^3, P=72, 529 positions, one angle): size-independent properties.
     (1) Parseval / unit-modulus transmission: with beta = 0, sum|det|^2 == P^2 sum|probe|^2 for every pattern.

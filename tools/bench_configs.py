@@ -37,7 +37,14 @@ def base_cv(**kw):
     return cv
 
 
+STEPS = None      # overridden by bench.py --config (steps, warmup)
+WARMUP = None
+LINES = []
+
+
 def time_steps(step, n_warm=5, n=30):
+    n_warm = WARMUP if WARMUP is not None else n_warm
+    n = STEPS if STEPS is not None else n
     for _ in range(n_warm):
         step()
     torch.cuda.synchronize()
@@ -47,14 +54,19 @@ def time_steps(step, n_warm=5, n=30):
         step()
     e1.record()
     torch.cuda.synchronize()
+    time_steps.last = (n, n_warm)
     return e0.elapsed_time(e1) / n
 
 
 def report(name, workload, patterns_per_step, ms, alg_bytes):
-    print(json.dumps({'config': name, 'workload': workload, 'patterns_per_step': patterns_per_step, 'ms_per_step': ms,
-                      'value': patterns_per_step / (ms * 1e-3), 'unit': 'patterns/s',
-                      'algorithmic_bytes_per_step': alg_bytes,
-                      'hbm_roofline_frac': alg_bytes / (ms * 1e-3) / 1e9 / PEAK, 'peak_gbs': PEAK}), flush=True)
+    n, n_warm = getattr(time_steps, 'last', (None, None))
+    line = {'config': name, 'workload': workload, 'patterns_per_step': patterns_per_step, 'ms_per_step': ms,
+            'value': patterns_per_step / (ms * 1e-3), 'unit': 'patterns/s', 'steps': n, 'warmup': n_warm,
+            'algorithmic_bytes_per_step': alg_bytes,
+            'hbm_roofline_frac': alg_bytes / (ms * 1e-3) / 1e9 / PEAK, 'peak_gbs': PEAK}
+    LINES.append(line)
+    if STEPS is None:
+        print(json.dumps(line), flush=True)
 
 
 def ptycho_runner(obj_size, P, pos, M, unknown_type, energy_ev, psize_cm, raw_data_type, mb, refine, lr_obj, seed=0):
@@ -235,7 +247,15 @@ def config_E():
            D, ms, 92e6)
 
 
-if __name__ == '__main__':
-    which = sys.argv[1:] or ['A', 'B', 'C', 'E']
+def run(which, steps=None, warmup=None):
+    """-> list of result dicts (bench.py --config adds the clocks record and prints them)."""
+    global STEPS, WARMUP
+    STEPS, WARMUP = steps, warmup
+    del LINES[:]
     for w in which:
         {'A': config_A, 'B': config_B, 'C': config_C, 'E': config_E}[w]()
+    return list(LINES)
+
+
+if __name__ == '__main__':
+    run(sys.argv[1:] or ['A', 'B', 'C', 'E'])
