@@ -4,7 +4,8 @@ AdamOptimizer).  See DESIGN.md / INTEGRATION.md.  There is no CPU fallback."""
 from .propagate import multislice_propagate_batch, get_kernel, gen_freq_mesh
 from .util import (apply_rotation, pad_object, calculate_pad_len, save_rotation_lookup, read_origin_coords,
                    initialize_probe, generate_gaussian_map)
-from .forward_model import ForwardModel, PtychographyModel, SingleBatchFullfieldModel, MultiDistModel
+from .forward_model import (ForwardModel, PtychographyModel, SingleBatchFullfieldModel, SingleBatchPtychographyModel,
+                            SparseMultisliceModel, MultiDistModel)
 from .optimizers import Optimizer, AdamOptimizer, GDOptimizer, MomentumOptimizer
 from .regularizers import Regularizer, L1Regularizer, ReweightedL1Regularizer, TVRegularizer
 from .array_ops import ObjectFunction, Gradient, Mask
@@ -13,6 +14,7 @@ from .ptychography import reconstruct_ptychography
 
 __all__ = ['multislice_propagate_batch', 'get_kernel', 'gen_freq_mesh', 'apply_rotation', 'pad_object',
            'calculate_pad_len', 'save_rotation_lookup', 'read_origin_coords', 'initialize_probe',
-           'ForwardModel', 'PtychographyModel', 'SingleBatchFullfieldModel', 'MultiDistModel',
+           'ForwardModel', 'PtychographyModel', 'SingleBatchFullfieldModel', 'SingleBatchPtychographyModel',
+           'SparseMultisliceModel', 'MultiDistModel',
            'Optimizer', 'AdamOptimizer', 'GDOptimizer', 'MomentumOptimizer', 'Regularizer', 'L1Regularizer', 'ReweightedL1Regularizer',
            'TVRegularizer', 'ObjectFunction', 'Gradient', 'Mask', 'Differentiator', 'reconstruct_ptychography']

@@ -17,7 +17,7 @@ class MultisliceCfg(ctypes.Structure):
     """struct adm_multislice_cfg (include/adorym_b200.h)."""
     _fields_ = [('P', c_int), ('n_slices', c_int), ('B', c_int), ('M', c_int), ('Y', c_int), ('X', c_int),
                 ('k1', c_float), ('sign_convention', c_int), ('unknown_type', c_int), ('free_prop', c_int),
-                ('normalize_fft', c_int), ('probe_per_pattern', c_int), ('h_separable', c_int)]
+                ('normalize_fft', c_int), ('probe_per_pattern', c_int), ('h_separable', c_int), ('h_per_slice', c_int)]
 
 
 P_CFG = ctypes.POINTER(MultisliceCfg)

@@ -13,7 +13,7 @@ struct MsParams {
     cpx* det;           // fwd: out ; bwd: g_det in
     cpx* g_probe;
     int Nz, Y, X, Xp, B, M;
-    int free_prop, probe_per_pattern, h_separable;
+    int free_prop, probe_per_pattern, h_separable, h_per_slice;
     float ff_scale;
     int ff_conj;
     // persistent balanced schedule (multislice.cu): the nwf * Nz slice steps of a launch are laid end to end and cut in

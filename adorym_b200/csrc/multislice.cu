@@ -228,6 +228,8 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                 }
                 break;
             }
+            if (!last && p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)z * 2 * P + t];   // gap z -> z+1 (read
+                                                                          // by P4, two barriers further down)
             if (!last && p.h_separable) propagate_core_sep<C>(psi, tw, hs, q, l, active);
             else propagate_core<C>(psi, tw, (const T*)(last ? p.Hf : p.Hp), q, l, active);
             if (last) {
@@ -420,6 +422,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                 bulk_commit();
             }
             if (z == 0) { phase ^= 1; break; }
+            if (p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)(z - 1) * 2 * P + t];     // gap z-1 -> z
             if (active) pass_B_fwd<C, false>(psi, q, l);
             __syncthreads();
             if (t == 0 && z > sg.zb) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind P3..P6
@@ -522,6 +525,8 @@ static int fill_params(const adm_multislice_cfg* c, MsParams& p) {
     if (c->free_prop < ADM_PROP_NONE || c->free_prop > ADM_PROP_NEAR) return ADM_ERR_ARG;
     p.Nz = c->n_slices; p.Y = c->Y; p.X = c->X; p.Xp = ADM_TVOL_PITCH(c->X); p.B = c->B; p.M = c->M;
     p.free_prop = c->free_prop; p.probe_per_pattern = c->probe_per_pattern; p.h_separable = c->h_separable ? 1 : 0;
+    p.h_per_slice = c->h_per_slice ? 1 : 0;
+    if (p.h_per_slice && !p.h_separable) return ADM_ERR_UNSUPPORTED;
     // far field: sign +1 -> fft2 (unnormalised or 1/P), sign -1 -> ifft2 (1/P^2 or 1/P)   (propagate.py:267-270)
     float Pf = (float)c->P;
     p.ff_conj = (c->sign_convention == -1 && c->free_prop == ADM_PROP_FAR) ? 1 : 0;

@@ -341,7 +341,8 @@ class PtychographyModel(ForwardModel):
         if probe.dim() == 3:
             probe = probe.unsqueeze(0)
         # per-position probe shift: quirk 8, positive corrections only trigger it (forward_model.py:297,304)
-        if cv['optimize_all_probe_pos'] or self._any_positive_correction(probe_pos_correction):
+        if probe_pos_correction is not None and (cv['optimize_all_probe_pos']
+                                                 or self._any_positive_correction(probe_pos_correction)):
             idx = torch.as_tensor(np.asarray(this_ind_batch), device=dev, dtype=torch.long)
             shift = probe_pos_correction[int(this_i_theta)].index_select(0, idx).to(torch.float32)
             probe = ops.ProbeShiftFn.apply(probe, shift)
@@ -375,6 +376,112 @@ class PtychographyModel(ForwardModel):
                            probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
             theta_downsample = self.common_vars['theta_downsample']
             ds_level = self.common_vars['ds_level']
+            det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch,
+                                                          probe_pos_correction, this_ind_batch, with_reg=True)
+            self.i_call += 1
+            this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
+            return self._fused_loss(det, this_prj_batch, obj, reg_val, reg_done)
+        return calculate_loss
+
+
+class SingleBatchPtychographyModel(PtychographyModel):
+    """adorym/forward_model.py:493-586: the reference's single-pattern fast path (it only avoids a stack / concatenate
+    in Python); on the fused kernels a minibatch of one pattern is the general path with B = 1."""
+
+    def __init__(self, loss_function_type='lsq', distribution_mode=None, device=None, common_vars_dict=None,
+                 raw_data_type='magnitude', simulation_mode=False, *args, **kwargs):
+        super(SingleBatchPtychographyModel, self).__init__(loss_function_type, distribution_mode, device, common_vars_dict,
+                                                           raw_data_type, simulation_mode=simulation_mode, *args, **kwargs)
+
+    def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,
+                probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
+        if len(np.asarray(this_pos_batch)) != 1:
+            raise ValueError('SingleBatchPtychographyModel takes one probe position per call')
+        # forward_model.py:493-586 never shifts the probe (no probe_pos_correction branch)
+        det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, None, this_ind_batch)
+        self.i_call += 1
+        return ops.DetectorMagnitudeFn.apply(det)
+
+    def get_loss_function(self):
+        def calculate_loss(obj, probe_real, probe_imag, probe_defocus_mm,
+                           probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                           probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
+            theta_downsample = self.common_vars['theta_downsample']
+            ds_level = self.common_vars['ds_level']
+            det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, None,
+                                                          this_ind_batch, with_reg=True)
+            self.i_call += 1
+            this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
+            return self._fused_loss(det, this_prj_batch, obj, reg_val, reg_done)
+        return calculate_loss
+
+
+class SparseMultisliceModel(PtychographyModel):
+    """adorym/forward_model.py:589-806: a few thin slices at arbitrary positions `slice_pos_cm_ls`; the wave is propagated
+    by the paraxial Fresnel kernel over each gap slice_pos[i+1] - slice_pos[i] (propagate.py:479-534,
+    fresnel_propagate_wrapped :556-568), the transmission of every slice still uses the voxel size as its thickness
+    (propagate.py:505).  Same fused kernels as PtychographyModel with one separable transfer function per gap
+    (adm_multislice_cfg.h_per_slice).  Refinement of the slice positions (optimize_slice_pos) is not accelerated."""
+
+    def __init__(self, loss_function_type='lsq', distribution_mode=None, device=None, common_vars_dict=None,
+                 raw_data_type='magnitude', simulation_mode=False, *args, **kwargs):
+        super(SparseMultisliceModel, self).__init__(loss_function_type, distribution_mode, device, common_vars_dict,
+                                                    raw_data_type, simulation_mode=simulation_mode, *args, **kwargs)
+        a = inspect.getfullargspec(self.predict).args
+        a.pop(0)
+        self.argument_ls = a
+        self._sparse_plans = {}
+
+    def _sparse_plan(self, dev, slice_pos_cm_ls):
+        cv = self.common_vars
+        if cv.get('optimize_slice_pos', False):
+            raise NotImplementedError('adorym_b200: optimize_slice_pos is not on the accelerated path yet')
+        pos = np.asarray(slice_pos_cm_ls.detach().cpu() if torch.is_tensor(slice_pos_cm_ls) else slice_pos_cm_ls, dtype='float64')
+        P = cv['probe_size'][0]
+        Y, X, Z = cv['this_obj_size']
+        if len(pos) != Z:
+            raise ValueError('slice_pos_cm_ls must hold one position per object slice')
+        key = (tuple(pos.tolist()), str(dev), str(cv['free_prop_cm']))
+        plan = self._sparse_plans.get(key)
+        if plan is None:
+            psize_cm = cv['psize_cm'] * cv.get('ds_level', 1)
+            voxel_nm = np.array([psize_cm] * 3) * 1.e7
+            lmbda_nm = 1240. / cv['energy_ev']
+            gaps_nm = np.diff(pos) * 1e7
+            # fresnel_propagate_wrapped -> get_kernel_wrapped with its default fresnel_approx=True (propagate.py:84-103)
+            h_gaps = [get_kernel(float(d), lmbda_nm, voxel_nm, [P, P], sign_convention=self.sign_convention) for d in gaps_nm]
+            mode = _free_prop_mode(cv['free_prop_cm'])
+            h_free = None
+            if mode == 'near':
+                h_free = get_kernel(float(cv['free_prop_cm']) * 1e7, lmbda_nm, voxel_nm, [P, P],
+                                    sign_convention=self.sign_convention)
+            plan = ops.MultislicePlan(P, Z, Y, X, ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k), None, dev,
+                                      sign_convention=self.sign_convention, unknown_type=self.unknown_type, free_prop=mode,
+                                      normalize_fft=self.normalize_fft, h_free=h_free, h_gaps=h_gaps)
+            self._sparse_plans[key] = plan
+        return plan
+
+    def _plan(self, dev, P, Nz, Y, X, free_prop_cm):
+        return self._sparse_plan(dev, self._slice_pos)
+
+    def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,
+                probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                probe_pos_correction, this_ind_batch, slice_pos_cm_ls,
+                prj_pos_offset):
+        self._slice_pos = slice_pos_cm_ls
+        det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
+                                   this_ind_batch)
+        self.i_call += 1
+        return ops.DetectorMagnitudeFn.apply(det)
+
+    def get_loss_function(self):
+        def calculate_loss(obj, probe_real, probe_imag, probe_defocus_mm,
+                           probe_pos_offset, this_i_theta, this_pos_batch, prj,
+                           probe_pos_correction, this_ind_batch, slice_pos_cm_ls, prj_pos_offset):
+            theta_downsample = self.common_vars['theta_downsample']
+            ds_level = self.common_vars['ds_level']
+            self._slice_pos = slice_pos_cm_ls
             det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch,
                                                           probe_pos_correction, this_ind_batch, with_reg=True)
             self.i_call += 1

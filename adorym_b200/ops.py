@@ -70,7 +70,9 @@ class MultislicePlan(object):
     """Static description of one multislice configuration + prepared transfer functions (cached per model)."""
 
     def __init__(self, P, n_slices, Y, X, k1, h, device, sign_convention=1, unknown_type='delta_beta', free_prop='none',
-                 normalize_fft=False, h_free=None, allow_separable=True):
+                 normalize_fft=False, h_free=None, allow_separable=True, h_gaps=None):
+        """h: the in-object transfer function [P,P] (all gaps equal), or h_gaps: a list of n_slices-1 separable transfer
+        functions, one per gap between consecutive slices (sparse multislice, propagate.py:479-534)."""
         if P not in SUPPORTED_P:
             raise NotImplementedError('adorym_b200: probe size %d is not supported yet (supported: %s)' % (P, SUPPORTED_P))
         self.P, self.n_slices, self.Y, self.X = int(P), int(n_slices), int(Y), int(X)
@@ -82,7 +84,18 @@ class MultislicePlan(object):
         self.device = device
         self.Hp = self.Hc = self.Hfp = self.Hfc = None
         self.h_separable = 0
-        if h is not None:
+        self.h_per_slice = 0
+        if h_gaps is not None:
+            if len(h_gaps) != self.n_slices - 1:
+                raise ValueError('h_gaps must hold n_slices - 1 transfer functions')
+            seps = [separate_transfer_function(hg) for hg in h_gaps]
+            if any(sp is None for sp in seps):
+                raise NotImplementedError('adorym_b200: per-gap transfer functions must be separable (paraxial Fresnel kernel)')
+            self.h_separable, self.h_per_slice = 1, 1
+            if seps:
+                self.Hp = torch.stack([prepare_transfer_function_separable(a, b, device, conj=False) for a, b in seps]).contiguous()
+                self.Hc = torch.stack([prepare_transfer_function_separable(a, b, device, conj=True) for a, b in seps]).contiguous()
+        elif h is not None:
             sep = separate_transfer_function(h) if allow_separable else None
             if sep is not None:
                 self.h_separable = 1
@@ -104,7 +117,8 @@ class MultislicePlan(object):
         return MultisliceCfg(P=self.P, n_slices=self.n_slices, B=int(B), M=int(M), Y=self.Y, X=self.X, k1=self.k1,
                              sign_convention=self.sign_convention, unknown_type=self.unknown_type,
                              free_prop=self.free_prop, normalize_fft=self.normalize_fft,
-                             probe_per_pattern=int(bool(probe_per_pattern)), h_separable=self.h_separable)
+                             probe_per_pattern=int(bool(probe_per_pattern)), h_separable=self.h_separable,
+                             h_per_slice=self.h_per_slice)
 
 
 # ------------------------------------------------------------------------------------------------------

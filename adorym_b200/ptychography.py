@@ -16,7 +16,8 @@ from . import ops
 from .array_ops import ObjectFunction, Gradient, Mask
 from .differentiator import Differentiator
 from .dist import Comm, epoch_task_list, rank_minibatch
-from .forward_model import ForwardModel, PtychographyModel, SingleBatchFullfieldModel, MultiDistModel
+from .forward_model import (ForwardModel, PtychographyModel, SingleBatchFullfieldModel, SingleBatchPtychographyModel,
+                            SparseMultisliceModel, MultiDistModel)
 from .optimizers import (Optimizer, AdamOptimizer, GDOptimizer, MomentumOptimizer,
                          create_and_initialize_parameter_optimizers,
                          initialize_parameter_gradients, update_parameter_gradients, update_parameters)
@@ -122,8 +123,10 @@ def reconstruct_ptychography(
         raise ValueError('backend')
     if not shared_probe_among_angles or not common_probe_pos:
         raise NotImplementedError('adorym_b200: per-angle probes / per-angle probe positions')
-    if update_using_external_algorithm is not None or slice_pos_cm_ls is not None and len(slice_pos_cm_ls) > 1:
-        raise NotImplementedError('adorym_b200: external update algorithms / sparse multislice')
+    if update_using_external_algorithm is not None:
+        raise NotImplementedError('adorym_b200: external update algorithms')
+    if optimize_slice_pos:
+        raise NotImplementedError('adorym_b200: optimize_slice_pos is not on the accelerated path yet')
 
     comm = Comm()
     n_ranks, rank = comm.Get_size(), comm.Get_rank()
@@ -192,7 +195,9 @@ def reconstruct_ptychography(
         minibatch_size = 1      # ptychography.py:342-346
     ds_level = 1
     this_obj_size = obj_size
-    is_sparse_multislice = False
+    is_sparse_multislice = slice_pos_cm_ls is not None and len(slice_pos_cm_ls) > 1      # ptychography.py:285-289
+    if is_sparse_multislice:
+        slice_pos_cm_ls = np.asarray(slice_pos_cm_ls, dtype='float64')
     if rank == 0:
         os.makedirs(output_folder, exist_ok=True)
     comm.Barrier()
@@ -236,8 +241,12 @@ def reconstruct_ptychography(
     if forward_model == 'auto':
         if is_multi_dist:
             forward_model = MultiDistModel(**forwardmodel_args)
+        elif is_sparse_multislice:
+            forward_model = SparseMultisliceModel(**forwardmodel_args)
         elif minibatch_size == 1 and len(probe_pos) == 1 and np.allclose(probe_pos[0], 0):
             forward_model = SingleBatchFullfieldModel(**forwardmodel_args)
+        elif common_probe_pos and minibatch_size == 1 and len(probe_pos) > 1 and n_probe_modes == 1:
+            forward_model = SingleBatchPtychographyModel(**forwardmodel_args)         # ptychography.py:540-541
         else:
             forward_model = PtychographyModel(**forwardmodel_args)
     else:
@@ -380,6 +389,7 @@ def reconstruct_ptychography(
             # ---- gradients (ptychography.py:1008-1042) ----
             local_vars = {'this_i_theta': this_i_theta, 'this_pos_batch': this_pos_batch, 'prj': prj,
                           'this_ind_batch': this_ind_batch, 'tilt_ls': tilt_ls, 'free_prop_cm': free_prop_cm,
+                          'slice_pos_cm_ls': slice_pos_cm_ls,
                           'safe_zone_width': safe_zone_width, 'ctf_lg_kappa': ctf_lg_kappa}
             grad_func_args = {}
             for arg in forward_model.argument_ls:

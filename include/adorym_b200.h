@@ -59,6 +59,9 @@ typedef struct adm_multislice_cfg {
     int normalize_fft;     /* far field with norm='ortho' (wrappers.py:725-756)                               */
     int probe_per_pattern; /* 0: probe is [M][P][P][2]; 1: probe is [B][M][P][P][2] (per-position shifted)    */
     int h_separable;       /* 1: Hprep / HprepC were made by adm_prepare_transfer_function_separable ([2][P][2]) */
+    int h_per_slice;       /* 1 (needs h_separable): Hprep / HprepC are [n_slices-1][2][P][2], one separable transfer
+                              function per gap between slices z and z+1 -- sparse multislice with unequal slice
+                              spacings (propagate.py:479-534 sparse_multislice_propagate_batch)                 */
 } adm_multislice_cfg;
 
 /* ABI / build identification. */
