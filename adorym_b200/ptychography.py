@@ -45,11 +45,10 @@ class _Dataset(object):
                 self.meta = {k.split('/')[-1]: z[k] for k in z.files if k.startswith('metadata/')}
             else:
                 try:
-                    import h5py
+                    import h5py as h5
                 except ImportError:
-                    raise ImportError('adorym_b200: reading %s needs h5py (not installed); pass a .npy/.npz file or '
-                                      'an array instead' % path)
-                f = h5py.File(path, 'r')
+                    from . import h5lite as h5      # contiguous exchange/data through np.memmap, no h5py needed
+                f = h5.File(path, 'r')
                 self.data = f['exchange/data']
                 if 'metadata' in f:
                     self.meta = {k: f['metadata'][k][...] for k in f['metadata'].keys()}

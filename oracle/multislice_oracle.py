@@ -211,8 +211,12 @@ def realign_image_fourier(a, shift, axes=(-2, -1)):
 def multislice_propagate_batch(grid_batch, probe, energy_ev, psize_cm, free_prop_cm=None, kernel=None,
                                fresnel_approx=True, binning=1, type='delta_beta', normalize_fft=False,
                                sign_convention=1, scale_ri_by_k=True, shift_exit_wave=None,
-                               return_intermediate=False):
+                               return_intermediate=False, slice_pos_cm_ls=None):
     """adorym/propagate.py:131-288 for pure_projection=False, kappa=None, repeating_slice=None.
+
+    slice_pos_cm_ls given: sparse_multislice_propagate_batch (propagate.py:479-534) -- the propagation after slice i
+    uses the paraxial kernel of the gap slice_pos[i+1] - slice_pos[i] (fresnel_propagate_wrapped, :556-568 ->
+    get_kernel_wrapped, :84-103), the transmission still uses the voxel size as thickness (:505).
 
     grid_batch [B, P0, P1, Nz, 2] real; probe complex [P0, P1] or [B, P0, P1]. Returns the
     complex detector-plane wavefield [B, P0, P1] (far field is fftshift-ed, :267-270).
@@ -253,7 +257,11 @@ def multislice_propagate_batch(grid_batch, probe, energy_ev, psize_cm, free_prop
         else:
             c = torch.prod(torch.complex(d, b), dim=3) if this_step > 1 else torch.complex(d[..., 0], b[..., 0])
         psi = psi * c
-        if i_step < n_steps - 1:
+        if i_step < n_steps - 1 and slice_pos_cm_ls is not None:
+            gap_nm = float(slice_pos_cm_ls[i_step + 1] - slice_pos_cm_ls[i_step]) * 1e7
+            hg = get_kernel(gap_nm, lmbda_nm, voxel_nm, grid_shape, sign_convention=sign_convention)
+            psi = torch.fft.ifft2(torch.fft.fft2(psi) * torch.tensor(hg).to(cdt))
+        elif i_step < n_steps - 1:
             if this_step == binning:
                 psi = torch.fft.ifft2(torch.fft.fft2(psi) * h)
             else:
@@ -318,7 +326,8 @@ def predict_ptycho(obj, probe_real, probe_imag, pos_batch, coord_old, cfg, probe
                                          binning=cfg.get('binning', 1), type=unknown_type,
                                          normalize_fft=cfg.get('normalize_fft', False),
                                          sign_convention=cfg.get('sign_convention', 1),
-                                         scale_ri_by_k=cfg.get('scale_ri_by_k', True))
+                                         scale_ri_by_k=cfg.get('scale_ri_by_k', True),
+                                         slice_pos_cm_ls=cfg.get('slice_pos_cm_ls'))
         if M == 1:
             # w.norm -> torch.norm(stack) (wrappers.py:1062-1067): zero subgradient at 0
             return torch.norm(torch.stack([psi.real, psi.imag], dim=0), dim=0)

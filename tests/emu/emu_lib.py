@@ -32,7 +32,7 @@ def ck(rc):
 def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *, unknown_type='delta_beta',
                        free_prop='inf', sign_convention=1, normalize_fft=False, loss='lsq', raw_data_type='magnitude',
                        poisson_multiplier=1.0, shift=None, reg=None, Hfree=None, separable=False, fused_chain=True,
-                       grad_slabs=1, weight_l1=None, beamstop=None):
+                       grad_slabs=1, weight_l1=None, beamstop=None, h_gaps=None):
     """fused_chain: object -> transmission volume and back through the fused kernels (object_chain.cu), as
     ops.MultisliceFn layout 'yxz' does; False: the separate rotate / transmission kernels (rotate.cu, transmission.cu)."""
     L = emu()
@@ -72,6 +72,18 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
         Hc = np.zeros((2, Pp, 2), 'float32')
         ck(L.adm_prepare_transfer_function_separable(Pp, P(f(hy)), P(f(hx)), 0, 1.0 / (Pp * Pp), P(Hp), None))
         ck(L.adm_prepare_transfer_function_separable(Pp, P(f(hy)), P(f(hx)), 1, 1.0 / (Pp * Pp), P(Hc), None))
+    hps = 0
+    if h_gaps is not None:
+        # sparse multislice: one separable transfer function per gap, [Nz-1][2][P][2]
+        hsep, hps = 1, 1
+        f = lambda v: np.ascontiguousarray(np.stack([v.real, v.imag], -1), dtype='float32')
+        Hp = np.zeros((len(h_gaps), 2, Pp, 2), 'float32')
+        Hc = np.zeros((len(h_gaps), 2, Pp, 2), 'float32')
+        for i, hg in enumerate(h_gaps):
+            hy, hx = hg[:, 0].copy(), hg[0, :] / hg[0, 0]
+            assert np.abs(np.outer(hy, hx) - hg).max() < 1e-9
+            ck(L.adm_prepare_transfer_function_separable(Pp, P(f(hy)), P(f(hx)), 0, 1.0 / (Pp * Pp), P(Hp[i]), None))
+            ck(L.adm_prepare_transfer_function_separable(Pp, P(f(hy)), P(f(hx)), 1, 1.0 / (Pp * Pp), P(Hc[i]), None))
     Hfp = Hfc = None
     fp = {'none': 0, 'inf': 1, 'near': 2}[free_prop]
     if fp == 2:
@@ -81,7 +93,7 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
         ck(L.adm_prepare_transfer_function(Pp, P(Hf), 1, 1.0 / (Pp * Pp), P(Hfc), None))
     cfg = MultisliceCfg(P=Pp, n_slices=Z, B=B, M=M, Y=Y, X=X, k1=float(np.float32(k1)), sign_convention=sign_convention,
                         unknown_type=0 if unknown_type == 'delta_beta' else 1, free_prop=fp,
-                        normalize_fft=int(normalize_fft), probe_per_pattern=ppp, h_separable=hsep)
+                        normalize_fft=int(normalize_fft), probe_per_pattern=ppp, h_separable=hsep, h_per_slice=hps)
     posi = np.ascontiguousarray(pos, dtype='int32')
     ckpt = np.full((B, M, Z, Pp, Pp + 2, 2), np.nan, 'float32')
     det = np.zeros((B, M, Pp, Pp, 2), 'float32')

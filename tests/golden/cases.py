@@ -73,6 +73,13 @@ CASES = {
                                   pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=2, free_prop_cm='inf',
                                   unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=20,
                                   loss='lsq', raw_data_type='magnitude', optimize_probe=True, beamstop_radius=7.5),
+    # sparse multislice (SparseMultisliceModel, forward_model.py:589-806): three thin slices at unequal positions, one
+    # paraxial transfer function per gap; the object is handed over in the beam frame (rotate_out_of_loop)
+    'sparse3_p72': dict(kind='sparse', obj_size=(90, 84, 3), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                        theta=0.0, n_theta=1, i_theta=0, pos=[(-10, -10), (20, 13), (9, -12), (0, 4)], n_modes=2,
+                        free_prop_cm='inf', unknown_type='delta_beta', delta_scale=3e-2, beta_scale=3e-3, seed=23,
+                        loss='lsq', raw_data_type='magnitude', optimize_probe=True, optimize_all_probe_pos=True,
+                        slice_pos_cm=[0., 2.0e-6, 7.5e-6], rotate_out_of_loop=True),
     # 2-D ptychography with probe modes + probe and position refinement (BASELINE config B shape, small)
     'ptycho2d_modes': dict(kind='ptycho', obj_size=(128, 128, 1), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
                            theta=0.0, n_theta=1, i_theta=0,

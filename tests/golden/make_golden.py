@@ -35,7 +35,8 @@ def run_reference(name):
     import adorym
     import adorym.global_settings as gs
     import adorym.wrappers as w
-    from adorym.forward_model import PtychographyModel, SingleBatchFullfieldModel
+    from adorym.forward_model import PtychographyModel, SingleBatchFullfieldModel, SparseMultisliceModel
+    from adorym.propagate import gen_freq_mesh
     from adorym.propagate import get_kernel
     from adorym.util import save_rotation_lookup
     from adorym.regularizers import L1Regularizer, TVRegularizer, ReweightedL1Regularizer
@@ -63,7 +64,7 @@ def run_reference(name):
         os.makedirs('arrsize_{}_{}_{}_ntheta_{}'.format(Y, X, Z, n_theta))
         save_rotation_lookup([Y, X, Z], theta_ls)
         cv = dict(unknown_type=c['unknown_type'], normalize_fft=c.get('normalize_fft', False), sign_convention=sign,
-                  rotate_out_of_loop=False, scale_ri_by_k=True, is_minus_logged=False, forward_algorithm='fresnel',
+                  rotate_out_of_loop=c.get('rotate_out_of_loop', False), scale_ri_by_k=True, is_minus_logged=False, forward_algorithm='fresnel',
                   stdout_options={'save_stdout': False, 'output_folder': tmp, 'timestamp': ''},
                   poisson_multiplier=c.get('poisson_multiplier', 1.), common_probe_pos=True, binning=1, prj=prj_full,
                   device_obj=None, lmbda_nm=lmbda_nm, voxel_nm=voxel_nm, probe_size=P, fresnel_approx=True,
@@ -74,7 +75,10 @@ def run_reference(name):
                   debug=False, output_folder=tmp, n_probe_modes=c['n_modes'], n_theta=n_theta,
                   precalculate_rotation_coords=True, theta_ls=theta_ls, theta_downsample=None,
                   beamstop=None if inp['beamstop'] is None else torch.tensor(inp['beamstop'].copy()))
-        Model = SingleBatchFullfieldModel if c['kind'] == 'fullfield' else PtychographyModel
+        Model = {'fullfield': SingleBatchFullfieldModel, 'sparse': SparseMultisliceModel}.get(c['kind'], PtychographyModel)
+        if c['kind'] == 'sparse':
+            u, v = gen_freq_mesh(voxel_nm, P)                    # ptychography.py:289-292
+            cv['u'], cv['v'] = w.create_variable(u, requires_grad=False), w.create_variable(v, requires_grad=False)
         fm = Model(loss_function_type=c['loss'], distribution_mode=None, device=None, common_vars_dict=cv,
                    raw_data_type=c['raw_data_type'])
         regs = []
@@ -99,6 +103,9 @@ def run_reference(name):
                     this_pos_batch=inp['pos'], prj=prj_full, probe_pos_correction=ppc,
                     this_ind_batch=inp['this_ind_batch'], tilt_ls=np.zeros([3, n_theta]),
                     prj_pos_offset=w.zeros([n_theta, 2], requires_grad=True))
+        if c['kind'] == 'sparse':
+            del args['tilt_ls']
+            args['slice_pos_cm_ls'] = w.create_variable(np.array(c['slice_pos_cm']), requires_grad=False)
         opt_args = [0]
         names = ['obj']
         if c.get('optimize_probe', False):

@@ -43,6 +43,10 @@ def case_cfg(name):
         if inp.get('weight_l1') is not None:
             reg['weight_l1'] = inp['weight_l1']
     cfg['beamstop'] = inp.get('beamstop')
+    if c.get('slice_pos_cm') is not None:
+        cfg['slice_pos_cm_ls'] = np.array(c['slice_pos_cm'])
+    if c.get('rotate_out_of_loop', False):
+        coord = None
     return inp, cfg, coord, reg
 
 

@@ -21,7 +21,8 @@ def _common_vars(inp, cfg, dev, prj_full, theta_ls, n_theta):
     c = inp['cfg']
     Y, X, Z = c['obj_size']
     return dict(unknown_type=c['unknown_type'], normalize_fft=c.get('normalize_fft', False),
-                sign_convention=c.get('sign_convention', 1), rotate_out_of_loop=False, scale_ri_by_k=True,
+                sign_convention=c.get('sign_convention', 1), rotate_out_of_loop=c.get('rotate_out_of_loop', False),
+                scale_ri_by_k=True,
                 is_minus_logged=False, forward_algorithm='fresnel', stdout_options={},
                 poisson_multiplier=c.get('poisson_multiplier', 1.), common_probe_pos=True, binning=1, prj=prj_full,
                 device_obj=dev, probe_size=list(c['probe_size']), fresnel_approx=True, two_d_mode=(Z == 1),
@@ -46,7 +47,7 @@ def run_gpu_case(name):
     prj_full = np.zeros([n_theta, 16, P[0], P[1]], dtype='float32')
     prj_full[c['i_theta'], inp['this_ind_batch']] = inp['prj']
     cv = _common_vars(inp, cfg, dev, prj_full, theta_ls, n_theta)
-    Model = ab.SingleBatchFullfieldModel if c['kind'] == 'fullfield' else ab.PtychographyModel
+    Model = {'fullfield': ab.SingleBatchFullfieldModel, 'sparse': ab.SparseMultisliceModel}.get(c['kind'], ab.PtychographyModel)
     fm = Model(loss_function_type=c['loss'], distribution_mode=None, device=dev, common_vars_dict=cv,
                raw_data_type=c['raw_data_type'])
     regs = []
@@ -67,6 +68,9 @@ def run_gpu_case(name):
                 probe_pos_offset=torch.zeros([n_theta, 2], device=dev), this_i_theta=c['i_theta'],
                 this_pos_batch=inp['pos'], prj=prj_full, probe_pos_correction=ppc, this_ind_batch=inp['this_ind_batch'],
                 tilt_ls=np.zeros([3, n_theta]), prj_pos_offset=torch.zeros([n_theta, 2], device=dev))
+    if c['kind'] == 'sparse':
+        del args['tilt_ls']
+        args['slice_pos_cm_ls'] = np.array(c['slice_pos_cm'])
     opt_args, names = [0], ['obj']
     if c.get('optimize_probe', False):
         opt_args += [fm.get_argument_index('probe_real'), fm.get_argument_index('probe_imag')]

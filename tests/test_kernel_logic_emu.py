@@ -28,6 +28,10 @@ def run_emu_case(name, separable=False, **kw):
     if inp['probe_pos_correction'] is not None:
         shift = inp['probe_pos_correction'][c['i_theta'], inp['this_ind_batch']]
     fp = 'inf' if c['free_prop_cm'] == 'inf' else ('none' if c['free_prop_cm'] in (0, None) else 'near')
+    if c.get('slice_pos_cm') is not None:
+        gaps = np.diff(np.array(c['slice_pos_cm'])) * 1e7
+        kw = dict(kw, h_gaps=[orc.get_kernel(float(g), 1240. / c['energy_ev'], np.array([voxel_nm] * 3), c['probe_size'])
+                              for g in gaps])
     return inp, emu_lib.loss_and_grads_emu(
         inp['obj'], inp['probe_real'], inp['probe_imag'], inp['pos'], inp['prj'], grid, cfg['h'], k1,
         unknown_type=c['unknown_type'], free_prop=fp, sign_convention=c.get('sign_convention', 1),
@@ -38,7 +42,8 @@ def run_emu_case(name, separable=False, **kw):
 
 @pytest.mark.parametrize('name', ['ptycho2d_modes', 'ptycho2d_realimag_p64', 'fullfield64', 'ptycho3d_p72',
                                   'ptycho3d_p72_poisson', 'ptycho3d_p72_edge', 'ptycho3d_p72_exitwave',
-                                  'ptycho3d_p72_strongreg', 'ptycho3d_p72_rwl1', 'ptycho3d_p72_beamstop'])
+                                  'ptycho3d_p72_strongreg', 'ptycho3d_p72_rwl1', 'ptycho3d_p72_beamstop',
+                                  'sparse3_p72'])
 def test_emulated_kernels_match_oracle_and_golden(name):
     # the separable-H path (Fresnel kernel in two shared-memory tables) on the 3-D P=72 cases, the general-H path elsewhere
     inp, out = run_emu_case(name, separable=name.startswith('ptycho3d'))
