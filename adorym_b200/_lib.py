@@ -49,6 +49,8 @@ SIGNATURES = {
     'adm_rotate_adj': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_adam_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double, c_double, c_int,
                       c_int, c_void_p, c_void_p],
+    'adm_p2p_reduce_adam': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double,
+                            c_double, c_int, c_int, c_void_p, c_void_p],
     'adm_sgd_step': [c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_int, c_void_p, c_void_p],
     'adm_regularizer_l1tv': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
                              c_void_p],

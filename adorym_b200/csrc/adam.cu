@@ -106,6 +106,89 @@ extern "C" int adm_adam_step(float* x, float* m, float* v, const float* g, long 
     return ADM_OK;
 }
 
+// ---- data-parallel update over NVLink peer memory ------------------------------------------------------------------
+// Replaces `gradient = allreduce(gradient); x = adam(x, gradient)` (adorym/ptychography.py:1113-1125) for G ranks on one
+// NVSwitch node by ONE kernel per rank: rank r owns the r-th contiguous shard of the volume, PULLS that shard of the
+// gradient from every rank's gradient buffer through NVLink peer loads (rank order 0..G-1, so the sum is the same
+// whichever rank computes it), applies Adam to its shard of x with its shard of (m, v), and PUSHES the updated shard
+// into every rank's copy of x with peer stores.  Wire traffic equals a reduce-scatter + all-gather, the inbound and
+// outbound directions of the links run at the same time, Adam's own HBM traffic shrinks to 1/G and hides under the
+// transfers, and there is no separate collective launch.  The caller brackets the kernel with two cross-GPU barriers
+// (all gradients complete before the pull; all pushes complete before x is read again).
+#define ADM_P2P_MAX_RANKS 8
+struct P2PPtrs {
+    float* x[ADM_P2P_MAX_RANKS];
+    const float* g[ADM_P2P_MAX_RANKS];
+};
+__global__ void __launch_bounds__(256) k_p2p_reduce_adam(P2PPtrs pp, int world, const float* x_self, float* m, float* v, long long i4_begin,
+                                                         long long i4_end, AdamArgs a, const float* mask) {
+    long long i = i4_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (; i < i4_end; i += stride) {
+        float4 gg[ADM_P2P_MAX_RANKS];
+#pragma unroll
+        for (int r = 0; r < ADM_P2P_MAX_RANKS; ++r)
+            if (r < world) gg[r] = reinterpret_cast<const float4*>(pp.g[r])[i];      // all peer loads in flight together
+        float4 gs = gg[0];
+#pragma unroll
+        for (int r = 1; r < ADM_P2P_MAX_RANKS; ++r)
+            if (r < world) {
+#ifndef ADM_HOST_EMU
+                gs.x = __fadd_rn(gs.x, gg[r].x); gs.y = __fadd_rn(gs.y, gg[r].y);
+                gs.z = __fadd_rn(gs.z, gg[r].z); gs.w = __fadd_rn(gs.w, gg[r].w);
+#else
+                gs.x += gg[r].x; gs.y += gg[r].y; gs.z += gg[r].z; gs.w += gg[r].w;
+#endif
+            }
+        float4 xx = reinterpret_cast<const float4*>(x_self)[i];
+        float4 mm = reinterpret_cast<const float4*>(m)[i];
+        float4 vv = reinterpret_cast<const float4*>(v)[i];
+        adam_update(xx.x, mm.x, vv.x, gs.x, a);
+        adam_update(xx.y, mm.y, vv.y, gs.y, a);
+        adam_update(xx.z, mm.z, vv.z, gs.z, a);
+        adam_update(xx.w, mm.w, vv.w, gs.w, a);
+        if (a.flags & 1) { xx.x = fmaxf(xx.x, 0.f); xx.y = fmaxf(xx.y, 0.f); xx.z = fmaxf(xx.z, 0.f); xx.w = fmaxf(xx.w, 0.f); }
+        if (a.flags & 2) { xx.x = 0.f; xx.z = 0.f; }
+        if (a.flags & 4) { xx.y = 0.f; xx.w = 0.f; }
+        if (mask != nullptr) {
+            float2 mk_ = reinterpret_cast<const float2*>(mask)[i];
+            xx.x *= mk_.x; xx.y *= mk_.x; xx.z *= mk_.y; xx.w *= mk_.y;
+        }
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+#pragma unroll
+        for (int r = 0; r < ADM_P2P_MAX_RANKS; ++r)
+            if (r < world) reinterpret_cast<float4*>(pp.x[r])[i] = xx;
+    }
+}
+
+extern "C" int adm_p2p_reduce_adam(float* const* x_ptrs, const float* const* g_ptrs, int world, int rank, float* m, float* v,
+                                   long long n, double step_size, double b1, double b2, double eps, int step, int flags,
+                                   const float* mask, void* stream) {
+    if (!x_ptrs || !g_ptrs || !m || !v || n < 4 || (n & 3) || step < 0) return ADM_ERR_ARG;
+    if (world < 1 || world > ADM_P2P_MAX_RANKS || rank < 0 || rank >= world) return ADM_ERR_ARG;
+    P2PPtrs pp;
+    for (int r = 0; r < ADM_P2P_MAX_RANKS; ++r) {
+        pp.x[r] = r < world ? x_ptrs[r] : nullptr;
+        pp.g[r] = r < world ? g_ptrs[r] : nullptr;
+        if (r < world && (!pp.x[r] || !pp.g[r] || ((((uintptr_t)pp.x[r]) | ((uintptr_t)pp.g[r])) & 15))) return ADM_ERR_ARG;
+    }
+    if (((((uintptr_t)m) | ((uintptr_t)v)) & 15) || (mask && (((uintptr_t)mask) & 7))) return ADM_ERR_ARG;
+    AdamArgs a;
+    a.step_size = (float)step_size; a.b1 = (float)b1; a.b2 = (float)b2; a.eps = (float)eps; a.flags = flags;
+    a.omb1 = (float)(1.0 - b1);
+    a.omb2 = (float)(1.0 - b2);
+    a.q1 = (float)(1.0 - pow(b1, (double)(step + 1)));
+    a.q2 = (float)(1.0 - pow(b2, (double)(step + 1)));
+    const long long n4 = n / 4;
+    const long long i0 = n4 * rank / world, i1 = n4 * (rank + 1) / world;       // this rank's shard (float4 units)
+    if (i1 <= i0) return ADM_OK;
+    long long blocks = (i1 - i0 + 255) / 256;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    ADM_LAUNCH(k_p2p_reduce_adam, (unsigned)blocks, 256, 0, stream, pp, world, (const float*)pp.x[rank], m, v, i0, i1, a, mask);
+    return ADM_OK;
+}
+
 // ---- gradient descent / momentum (adorym/optimizers.py:366-411, :432-464) ----------------------------------------
 // GD: x <- x - step g;  Momentum: v <- gamma v + step g, x <- x - v.  Every product / sum individually rounded, as torch
 // evaluates the reference's expressions; same epilogue flags / mask as k_adam.
@@ -150,13 +233,15 @@ extern "C" int adm_sgd_step(float* x, float* v, const float* g, long long n, dou
 // ---- regulariser -------------------------------------------------------------------------------
 ADM_DEV float sgnf(float a) { return (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f); }
 
-// One warp per (y, x) row, lanes along z (the contiguous axis of obj [Y][X][Z][2]): no per-element index division; the
-// six TV neighbours are the same lane of four other rows and the two neighbouring lanes.  g_scale (device scalar or
-// null) multiplies the gradient (the upstream gradient of the loss node); accumulate = 0 writes g_obj, 1 adds to it.
+// A warp owns one x column of a chunk of REG_YC planes and STREAMS along y with a three-plane sliding window in
+// registers (prev / cur / next), lanes along z (the contiguous axis of obj [Y][X][Z][2]): per voxel one new coalesced
+// load from the streamed row plus the x neighbours, which the neighbouring warps of the CTA have just brought into L1
+// -- instead of five row loads from L2 (y-1, y, y+1, x-1, x+1).  g_scale (device scalar or null) multiplies the
+// gradient (the upstream gradient of the loss node); accumulate = 0 writes g_obj, 1 adds to it.  Planes [y_begin, y_end).
+#define REG_YC 16
 __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx* __restrict__ obj, const cpx* __restrict__ wl1,
                                                   float ad, float ab, float gm, float* value, cpx* g_obj,
-                                                  const float* g_scale, int accumulate, long long row_begin,
-                                                  long long row_end) {
+                                                  const float* g_scale, int accumulate, int y_begin, int y_end) {
 #ifndef ADM_HOST_EMU
     __shared__ float red[256];
 #else
@@ -167,51 +252,60 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
     const float gs = (g_scale != nullptr) ? *g_scale : 1.0f;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const size_t sx = (size_t)Z, sy = (size_t)X * Z;
+    const int x = blockIdx.x * wpb + wib;
+    const int y0 = y_begin + blockIdx.y * REG_YC;
+    const int y1 = (y0 + REG_YC < y_end) ? y0 + REG_YC : y_end;
     float acc = 0.f;
-    for (long long row = row_begin + (long long)blockIdx.x * wpb + wib; row < row_end; row += (long long)gridDim.x * wpb) {
-        const int y = (int)(row / X), x = (int)(row - (long long)y * X);
-        const cpx* r0 = obj + (size_t)row * sx;
-        const cpx* rym = obj + (size_t)((y + Y - 1) % Y) * sy + (size_t)x * sx;
-        const cpx* ryp = obj + (size_t)((y + 1) % Y) * sy + (size_t)x * sx;
-        const cpx* rxm = obj + (size_t)y * sy + (size_t)((x + X - 1) % X) * sx;
-        const cpx* rxp = obj + (size_t)y * sy + (size_t)((x + 1) % X) * sx;
-        for (int z = lane; z < Z; z += 32) {
-            const cpx c = r0[z];
-            float w0 = 1.f, w1 = 1.f;
-            if (wl1 != nullptr) { cpx w = wl1[(size_t)row * sx + z]; w0 = w.x; w1 = w.y; }
-            float gd = ad * w0 * sgnf(c.x) * invN;
-            float gb = ab * w1 * sgnf(c.y) * invN;
-            acc += (ad * w0 * fabsf(c.x) + ab * w1 * fabsf(c.y)) * invN;
-            if (gm != 0.f) {
-                // TV: sum over the three axes of |roll(a, 1) - a| / N (periodic), per channel
-                cpx a = rym[z], b = ryp[z];
-                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-                a = rxm[z]; b = rxp[z];
-                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-                a = r0[(z + Z - 1) % Z]; b = r0[(z + 1) % Z];
-                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-            }
-            if (g_obj != nullptr) {
-                cpx* o = g_obj + (size_t)row * sx + z;
-                cpx r = mk(gd * gs, gb * gs);
-                if (accumulate) { cpx t = *o; r.x += t.x; r.y += t.y; }
-                *o = r;
+    if (x < X) {
+        const size_t oxm = (size_t)((x + X - 1) % X) * sx, oxp = (size_t)((x + 1) % X) * sx, ox = (size_t)x * sx;
+        for (int zb = 0; zb < Z; zb += 32) {
+            const int z = zb + lane;
+            if (z >= Z) continue;
+            const int zm = (z + Z - 1) % Z, zp = (z + 1) % Z;
+            cpx prev = obj[(size_t)((y0 + Y - 1) % Y) * sy + ox + z];
+            cpx c = obj[(size_t)y0 * sy + ox + z];
+            for (int y = y0; y < y1; ++y) {
+                const cpx* pl = obj + (size_t)y * sy;
+                const cpx next = obj[(size_t)((y + 1) % Y) * sy + ox + z];
+                float w0 = 1.f, w1 = 1.f;
+                if (wl1 != nullptr) { cpx w = wl1[(size_t)y * sy + ox + z]; w0 = w.x; w1 = w.y; }
+                float gd = ad * w0 * sgnf(c.x) * invN;
+                float gb = ab * w1 * sgnf(c.y) * invN;
+                acc += (ad * w0 * fabsf(c.x) + ab * w1 * fabsf(c.y)) * invN;
+                if (gm != 0.f) {
+                    // TV: sum over the three axes of |roll(a, 1) - a| / N (periodic), per channel
+                    cpx a = prev, b = next;
+                    acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                    a = pl[oxm + z]; b = pl[oxp + z];
+                    acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                    a = pl[ox + zm]; b = pl[ox + zp];
+                    acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                }
+                if (g_obj != nullptr) {
+                    cpx* o = g_obj + (size_t)y * sy + ox + z;
+                    cpx r = mk(gd * gs, gb * gs);
+                    if (accumulate) { cpx t = *o; r.x += t.x; r.y += t.y; }
+                    *o = r;
+                }
+                prev = c; c = next;
             }
         }
     }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    if (value != nullptr) {           // (uniform across the grid: every thread reaches the barriers)
+        red[threadIdx.x] = acc;
         __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) atomicAdd(value, red[0]);
     }
-    if (threadIdx.x == 0 && value != nullptr) atomicAdd(value, red[0]);
 }
 
 extern "C" int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
@@ -219,11 +313,11 @@ extern "C" int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj,
                                           int accumulate, int y_begin, int y_end, void* stream) {
     if (Y < 1 || X < 1 || Z < 1 || !obj) return ADM_ERR_ARG;
     if (y_begin < 0 || y_end > Y || y_begin >= y_end) return ADM_ERR_ARG;
-    long long rows = (long long)(y_end - y_begin) * X;
-    long long blocks = (rows + 7) / 8;
-    if (blocks > 148LL * 16) blocks = 148LL * 16;
-    ADM_LAUNCH(k_reg_l1tv, (unsigned)blocks, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj, (const cpx*)weight_l1,
-               alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate, (long long)y_begin * X, (long long)y_end * X);
+    const int nych = (y_end - y_begin + REG_YC - 1) / REG_YC;
+    if (nych > 65535) return ADM_ERR_UNSUPPORTED;
+    dim3 gr((X + 7) / 8, nych);
+    ADM_LAUNCH(k_reg_l1tv, gr, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj, (const cpx*)weight_l1,
+               alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate, y_begin, y_end);
     return ADM_OK;
 }
 

@@ -96,6 +96,68 @@ def allreduce_update_pipelined(opt, x, gradient, i_batch, slabs, **options):
     return xd
 
 
+class PeerUpdate(object):
+    """Data-parallel object update over NVLink peer memory for the ranks of one NVSwitch node (adm_p2p_reduce_adam).
+
+    Owns two SYMMETRIC buffers (torch.distributed._symmetric_memory: every rank's copy is mapped into every process):
+    the object `x` and the object gradient `g`.  The forward / adjoint kernels work on the local copies as usual
+    (ops.OBJ_GRAD_OUT makes the adjoint write its gradient straight into `g`); `update()` then replaces
+    `gradient = comm.allreduce(gradient); x = opt.apply_gradient(x, gradient, ...)` (adorym/ptychography.py:1113-1125) by
+    barrier -> one fused kernel (pull my shard of every rank's g, sum in rank order, Adam on my shard, push the new shard
+    into every rank's x) -> barrier.  Same SUM semantics, bit-identical replicas."""
+
+    def __init__(self, shape, device, group=None):
+        import ctypes
+        import torch.distributed._symmetric_memory as symm
+        group = group if group is not None else dist.group.WORLD
+        try:
+            symm.enable_symm_mem_for_group(group.group_name)
+        except Exception:
+            pass
+        self.shape = tuple(int(s) for s in shape)
+        n = int(np.prod(self.shape))
+        if n % 4:
+            raise ValueError('PeerUpdate needs a volume whose element count is a multiple of 4')
+        self.n = n
+        self.x = symm.empty(n, dtype=torch.float32, device=device)
+        self.g = symm.empty(n, dtype=torch.float32, device=device)
+        self.hx = symm.rendezvous(self.x, group)
+        self.hg = symm.rendezvous(self.g, group)
+        self.world, self.rank = int(self.hx.world_size), int(self.hx.rank)
+        if self.world > 8:
+            raise NotImplementedError('PeerUpdate: at most 8 ranks (one NVSwitch node)')
+        self._xp = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hx.buffer_ptrs])
+        self._gp = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hg.buffer_ptrs])
+        self.x.zero_()
+        self.g.zero_()
+
+    def object_tensor(self):
+        return self.x.view(self.shape)
+
+    def gradient_tensor(self):
+        return self.g.view(self.shape)
+
+    def update(self, opt, i_batch, step_size=0.001, b1=0.9, b2=0.999, eps=1e-7, clip_nonneg=False, zero_channel=None,
+               mask=None, **unused):
+        """One data-parallel Adam step on the symmetric object from the symmetric gradients of all ranks."""
+        import ctypes
+        from . import ops
+        shape = list(self.shape)
+        if 'm' not in opt.params_whole_array_dict or list(opt.params_whole_array_dict['m'].shape) != shape:
+            opt.create_param_arrays(shape, device=self.x.device)
+        m, v = opt.params_whole_array_dict['m'], opt.params_whole_array_dict['v']
+        if mask is not None and (mask.dtype != torch.float32 or not mask.is_contiguous() or mask.numel() * 2 != self.n):
+            raise RuntimeError('PeerUpdate.update: mask must be a contiguous fp32 tensor with one element per voxel')
+        flags = (1 if clip_nonneg else 0) | (2 if zero_channel == 0 else 0) | (4 if zero_channel == 1 else 0)
+        self.hg.barrier(channel=0)          # every rank's gradient is complete (and its reads of x are done)
+        ops.call('adm_p2p_reduce_adam', ctypes.cast(self._xp, ctypes.c_void_p), ctypes.cast(self._gp, ctypes.c_void_p),
+                 self.world, self.rank, ops.ptr(m), ops.ptr(v), self.n, float(step_size), float(b1), float(b2), float(eps),
+                 int(i_batch), flags, ops.ptr(mask), ops.stream_ptr())
+        self.hx.barrier(channel=1)          # every rank's shard has landed in every copy of x
+        opt.i_batch += 1
+        return self.object_tensor()
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).
     Returns (rank, world_size, local_rank).  A no-op for single-process runs."""

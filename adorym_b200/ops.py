@@ -10,7 +10,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import MultisliceCfg, call, ptr, stream_ptr
+from ._lib import MultisliceCfg, call, ptr, stream_ptr  # noqa: F401  (re-exported: dist.PeerUpdate uses ops.call / ops.ptr)
 
 PI = 3.14159265359          # adorym/constants.py
 UNKNOWN_TYPES = {'delta_beta': 0, 'real_imag': 1}
@@ -155,6 +155,9 @@ def multislice_workspace(device, P):
 # NCCL all-reduce of a slab as soon as its event has fired (dist.Comm.allreduce_slabs) instead of after the whole volume.
 GRAD_SLABS = 1
 last_obj_grad_slabs = None       # [(y0, y1, event)] of the most recent backward, or None
+# Optional preallocated output of the object gradient [Y,X,Z,2] (e.g. the symmetric, peer-mapped gradient buffer of
+# dist.PeerUpdate): MultisliceFn.backward then writes the gradient there instead of into a fresh tensor.
+OBJ_GRAD_OUT = None
 
 
 def slab_ranges(Y, n):
@@ -256,7 +259,10 @@ class MultisliceFn(torch.autograd.Function):
         g_obj = None
         if ctx.needs_input_grad[0]:
             if ctx.layout == 'yxz':
-                g_obj = torch.empty((Y, X, Nz, 2), dtype=torch.float32, device=dev)
+                if OBJ_GRAD_OUT is not None and tuple(OBJ_GRAD_OUT.shape) == (Y, X, Nz, 2) and OBJ_GRAD_OUT.device == dev:
+                    g_obj = OBJ_GRAD_OUT
+                else:
+                    g_obj = torch.empty((Y, X, Nz, 2), dtype=torch.float32, device=dev)
                 use_reg = ctx.reg is not None and g_reg is not None
                 gs = _f32c(g_reg.reshape(1)) if use_reg else None
                 slabs = []

@@ -206,7 +206,7 @@ class StepRunner(object):
     """One data-parallel rank of the reference's batch loop (ptychography.py:859-1271), through the public classes
     (PtychographyModel.get_loss_function + Differentiator.get_gradients + AdamOptimizer.apply_gradient)."""
 
-    def __init__(self, torch, ab, dev, rank, world, n_steps_total, mb):
+    def __init__(self, torch, ab, dev, rank, world, n_steps_total, mb, dp_mode='nccl'):
         self.torch, self.ab, self.dev, self.rank, self.world = torch, ab, dev, rank, world
         c = CFG_D
         Y, X, Z = c['obj_size']
@@ -255,11 +255,23 @@ class StepRunner(object):
         self.fm.add_regularizers([ab.L1Regularizer(c['alpha_d'], c['alpha_b']), ab.TVRegularizer(c['gamma'])])
         self.diff = ab.Differentiator()
         self.diff.create_loss_node(self.fm.get_loss_function(), [0])
+        # N > 1 on one NVSwitch node: the object and its gradient live in symmetric (peer-mapped) memory and the update is
+        # ONE fused kernel per rank (pull-reduce over NVLink + Adam + push); NCCL all-reduce is the fallback
+        self.peer = None
+        if world > 1 and dp_mode == 'p2p':
+            from adorym_b200 import dist as _adist, ops as _ops
+            self.peer = _adist.PeerUpdate([Y, X, Z, 2], dev)
+            _ops.OBJ_GRAD_OUT = self.peer.gradient_tensor()
         self.reset()
 
     def reset(self):
         torch, ab = self.torch, self.ab
-        self.obj = self.obj0.clone().requires_grad_(True)
+        if self.peer is not None:
+            with torch.no_grad():
+                self.peer.object_tensor().copy_(self.obj0)
+            self.obj = self.peer.object_tensor().requires_grad_(True)
+        else:
+            self.obj = self.obj0.clone().requires_grad_(True)
         self.opt = ab.AdamOptimizer('obj', options_dict={'step_size': CFG_D['learning_rate']})
         self.opt.create_container(list(self.obj.shape), False, self.dev)
         self.gradient = torch.zeros_like(self.obj0)
@@ -288,7 +300,11 @@ class StepRunner(object):
         from adorym_b200 import ops as _ops, dist as _adist
         slabs = _ops.last_obj_grad_slabs
         with torch.no_grad():
-            if self.world > 1 and slabs is not None and slabs[0].data_ptr() == self.gradient.data_ptr():
+            if self.peer is not None:
+                if self.gradient.data_ptr() != self.peer.g.data_ptr():
+                    self.peer.gradient_tensor().copy_(self.gradient)
+                new = self.peer.update(self.opt, self.i_step, **self.opt.options_dict)
+            elif self.world > 1 and slabs is not None and slabs[0].data_ptr() == self.gradient.data_ptr():
                 # gradient all-reduce pipelined by y slabs with the adjoint rotation and with Adam
                 new = _adist.allreduce_update_pipelined(self.opt, self.obj, self.gradient, self.i_step, slabs[1],
                                                         **self.opt.options_dict)
@@ -337,7 +353,29 @@ def dp_check(torch, ab, runner, dev, rank, world):
             gs = gr.clone() if gs is None else gs + gr
         out = float((g - gs).double().norm() / gs.double().norm())
     runner.reset()
-    return out
+    p2p = None
+    if runner.peer is not None:
+        # (3) the fused peer-memory update (adm_p2p_reduce_adam) against all_gather + rank-ordered sum + the single-GPU
+        # Adam kernel on rank 0: the same fp32 operations in the same order, so the objects must agree bit for bit
+        g = runner.diff.get_gradients(**dict(args, obj=runner.obj))[0]
+        gl = [torch.empty_like(g) for _ in range(world)]
+        dist.all_gather(gl, g.contiguous())
+        x0 = runner.obj.detach().clone()
+        opt_p = ab.AdamOptimizer('obj', options_dict=dict(runner.opt.options_dict))
+        with torch.no_grad():
+            if g.data_ptr() != runner.peer.g.data_ptr():
+                runner.peer.gradient_tensor().copy_(g)
+            xn = runner.peer.update(opt_p, 0, **opt_p.options_dict)
+        if rank == 0:
+            gs = gl[0].clone()
+            for r in range(1, world):
+                gs += gl[r]
+            opt_r = ab.AdamOptimizer('obj', options_dict=dict(runner.opt.options_dict))
+            with torch.no_grad():
+                xr = opt_r.apply_gradient(x0, gs, 0, **opt_r.options_dict)
+            p2p = float((xr - xn.detach()).abs().max().item())
+        runner.reset()
+    return out, p2p
 
 
 def run_gpu_arm(args):
@@ -355,8 +393,8 @@ def run_gpu_arm(args):
     mb = args.minibatch
     K, W = args.steps, max(args.warmup, 3)
     from adorym_b200 import ops as _ops
-    _ops.GRAD_SLABS = args.grad_slabs if world > 1 else 1
-    runner = StepRunner(torch, ab, dev, rank, world, K + W, mb)
+    _ops.GRAD_SLABS = args.grad_slabs if (world > 1 and args.dp == 'nccl') else 1
+    runner = StepRunner(torch, ab, dev, rank, world, K + W, mb, dp_mode=args.dp)
 
     def barrier():
         if world > 1:
@@ -402,9 +440,11 @@ def run_gpu_arm(args):
         torch.distributed.broadcast(ref, src=0)
         d = (ref - runner.obj.detach()).abs().max().reshape(1)
         torch.distributed.all_reduce(d, op=torch.distributed.ReduceOp.MAX)
-        sum_err = dp_check(torch, ab, runner, dev, rank, world)
+        sum_err, p2p_err = dp_check(torch, ab, runner, dev, rank, world)
         dp = {'max_abs_replica_difference': float(d.item()), 'allreduced_vs_summed_single_rank_gradient_rel': sum_err,
-              'grad_slabs': _ops.GRAD_SLABS}
+              'p2p_update_vs_allgather_sum_adam_max_abs': p2p_err,
+              'grad_slabs': _ops.GRAD_SLABS, 'update': 'p2p fused pull-reduce + Adam + push (adm_p2p_reduce_adam)'
+              if runner.peer is not None else 'NCCL all-reduce (slab pipelined) + Adam'}
 
     # ---- secondary figure: the reference demo's own schedule (minibatch_size = 2, update after every minibatch,
     # demos/multislice_ptycho_256_theta.py:63,93); every step still rotates and Adam-updates the whole 256^3 volume, so
@@ -414,6 +454,7 @@ def run_gpu_arm(args):
         del runner
         torch.cuda.empty_cache()
         K2 = min(K, 20)
+        _ops.OBJ_GRAD_OUT = None
         runner = StepRunner(torch, ab, dev, rank, world, K2 + W, 2)
         mbk, Kk = mb, K
         mb, K = 2, K2
@@ -477,8 +518,10 @@ def run_gpu_arm(args):
             'ms_per_step': ms_dev / K, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
             'data': 'synthetic',
             'config': {'workload': workload_name(mb), 'obj_size': [256, 256, 256], 'probe_size': [72, 72],
-                       'minibatch_size': mb, 'n_slices': 256, 'parallelism': 'dp%d (angles sharded, NCCL all-reduce SUM of '
-                       'the object gradient)' % world,
+                       'minibatch_size': mb, 'n_slices': 256,
+                       'parallelism': 'dp%d (angles sharded; object gradient summed over ranks %s)'
+                                      % (world, 'by the fused NVLink peer-memory update kernel' if (world > 1 and args.dp == 'p2p')
+                                         else 'with an NCCL all-reduce'),
                        'l2_policy': 'inputs larger than L2: 134 MB volumes, %.1f GB psi checkpoints per step vs 126 MB L2'
                                     % (mb * p8 / 1e9)},
             'roofline': roofline, 'cpu_baseline': cpu, 'clocks': clocks,
@@ -521,7 +564,9 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--minibatch', type=int, default=529)
-    ap.add_argument('--grad-slabs', type=int, default=4, help='y slabs of the pipelined gradient all-reduce (N > 1)')
+    ap.add_argument('--dp', default='p2p', choices=['p2p', 'nccl'],
+                    help='N > 1: fused peer-memory update kernel (default) or NCCL all-reduce + Adam')
+    ap.add_argument('--grad-slabs', type=int, default=2, help='y slabs of the pipelined gradient all-reduce (N > 1)')
     ap.add_argument('--config', nargs='*', default=None, choices=['A', 'B', 'C', 'E'],
                     help='secondary lines for the other named shapes (default: the contract line on config D)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

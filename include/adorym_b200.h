@@ -179,6 +179,16 @@ int adm_transmission_to_object_adj(int Y, int X, int Z, int P, const float* g_tv
 int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, double step_size, double b1, double b2,
                   double eps, int step, int flags, const float* mask, void* stream);
 
+/* Data-parallel object update over NVLink peer memory (replaces comm.allreduce + AdamOptimizer.apply_gradient,
+ * ptychography.py:1113-1125, for `world` <= 8 ranks of one NVSwitch node).  x_ptrs / g_ptrs: HOST arrays of `world` DEVICE
+ * pointers -- every rank's object x [n] and gradient g [n] buffers, peer-mapped into this process (symmetric memory /
+ * CUDA IPC); m, v: this rank's Adam moments [n] (only its shard is touched).  Rank r pulls its shard of every g (summed in
+ * rank order), applies adm_adam_step's update to its shard of x and pushes the result into every rank's x.  The caller
+ * must place a cross-GPU barrier before the call (all g complete) and after it (all pushes complete).  n % 4 == 0.   */
+int adm_p2p_reduce_adam(float* const* x_ptrs, const float* const* g_ptrs, int world, int rank, float* m, float* v,
+                        long long n, double step_size, double b1, double b2, double eps, int step, int flags,
+                        const float* mask, void* stream);
+
 /* Gradient descent (optimizers.py:432-464: x <- x - step g) and momentum (optimizers.py:366-411: v <- gamma v + step g,
  * x <- x - v; v == NULL selects plain GD), in place, with the flags / mask epilogue of adm_adam_step.  The dynamic
  * step-size schedule of GDOptimizer is host arithmetic on `step_size`.                                          */
