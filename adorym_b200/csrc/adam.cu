@@ -262,12 +262,21 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
             const int z = blockIdx.z * 32 + lane;       // one 32-voxel z chunk per CTA layer: 8x more warps in flight
             if (z < Z) {
             const int zm = (z + Z - 1) % Z, zp = (z + 1) % Z;
-            cpx prev = obj[(size_t)((y0 + Y - 1) % Y) * sy + ox + z];
-            cpx c = obj[(size_t)y0 * sy + ox + z];
-#pragma unroll 4
-            for (int y = y0; y < y1; ++y) {
+            // the whole y column of this chunk (+ one halo plane on each side) is requested up front: REG_YC + 2
+            // independent coalesced loads in flight per thread
+            cpx col[REG_YC + 2];
+#pragma unroll
+            for (int k = 0; k < REG_YC + 2; ++k) {
+                int yy = y0 - 1 + k;
+                yy = (yy < 0) ? yy + Y : ((yy >= Y) ? yy - Y : yy);
+                if (k <= y1 - y0 + 1) col[k] = obj[(size_t)yy * sy + ox + z];
+            }
+#pragma unroll
+            for (int k = 0; k < REG_YC; ++k) {
+                const int y = y0 + k;
+                if (y >= y1) break;
                 const cpx* pl = obj + (size_t)y * sy;
-                const cpx next = obj[(size_t)((y + 1) % Y) * sy + ox + z];
+                const cpx prev = col[k], c = col[k + 1], next = col[k + 2];
                 float w0 = 1.f, w1 = 1.f;
                 if (wl1 != nullptr) { cpx w = wl1[(size_t)y * sy + ox + z]; w0 = w.x; w1 = w.y; }
                 float gd = ad * w0 * sgnf(c.x) * invN;
@@ -294,12 +303,21 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
                     if (accumulate) { cpx t = *o; r.x += t.x; r.y += t.y; }
                     *o = r;
                 }
-                prev = c; c = next;
             }
             }
         }
     }
-    if (value != nullptr) {           // (uniform across the grid: every thread reaches the barriers)
+    if (value != nullptr) {           // (uniform across the grid: every thread reaches the barrier)
+#ifndef ADM_HOST_EMU
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+        if (lane == 0) red[wib] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < wpb; ++w) t += red[w];
+            atomicAdd(value, t);
+        }
+#else
         red[threadIdx.x] = acc;
         __syncthreads();
         for (int s = blockDim.x / 2; s > 0; s >>= 1) {
@@ -307,6 +325,7 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
             __syncthreads();
         }
         if (threadIdx.x == 0) atomicAdd(value, red[0]);
+#endif
     }
 }
 
