@@ -258,8 +258,8 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
     float acc = 0.f;
     if (x < X) {
         const size_t oxm = (size_t)((x + X - 1) % X) * sx, oxp = (size_t)((x + 1) % X) * sx, ox = (size_t)x * sx;
-        {
-            const int z = blockIdx.z * 32 + lane;       // one 32-voxel z chunk per CTA layer: 8x more warps in flight
+        for (int zb = 0; zb < Z; zb += 32) {             // the CTA sweeps 8 x rows x the whole z extent of every plane:
+            const int z = zb + lane;                     // 16 KB contiguous per plane (DRAM page locality)
             if (z < Z) {
             const int zm = (z + Z - 1) % Z, zp = (z + 1) % Z;
             // the whole y column of this chunk (+ one halo plane on each side) is requested up front: REG_YC + 2
@@ -336,8 +336,7 @@ extern "C" int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj,
     if (y_begin < 0 || y_end > Y || y_begin >= y_end) return ADM_ERR_ARG;
     const int nych = (y_end - y_begin + REG_YC - 1) / REG_YC;
     if (nych > 65535) return ADM_ERR_UNSUPPORTED;
-    if ((Z + 31) / 32 > 65535) return ADM_ERR_UNSUPPORTED;
-    dim3 gr((X + 7) / 8, nych, (Z + 31) / 32);
+    dim3 gr((X + 7) / 8, nych);
     ADM_LAUNCH(k_reg_l1tv, gr, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj, (const cpx*)weight_l1,
                alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate, y_begin, y_end);
     return ADM_OK;
