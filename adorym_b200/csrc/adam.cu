@@ -233,15 +233,13 @@ extern "C" int adm_sgd_step(float* x, float* v, const float* g, long long n, dou
 // ---- regulariser -------------------------------------------------------------------------------
 ADM_DEV float sgnf(float a) { return (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f); }
 
-// A warp owns one x column of a chunk of REG_YC planes and STREAMS along y with a three-plane sliding window in
-// registers (prev / cur / next), lanes along z (the contiguous axis of obj [Y][X][Z][2]): per voxel one new coalesced
-// load from the streamed row plus the x neighbours, which the neighbouring warps of the CTA have just brought into L1
-// -- instead of five row loads from L2 (y-1, y, y+1, x-1, x+1).  g_scale (device scalar or null) multiplies the
-// gradient (the upstream gradient of the loss node); accumulate = 0 writes g_obj, 1 adds to it.  Planes [y_begin, y_end).
-#define REG_YC 16
+// One warp per (y, x) row, lanes along z (the contiguous axis of obj [Y][X][Z][2]): no per-element index division; the
+// six TV neighbours are the same lane of four other rows and the two neighbouring lanes.  g_scale (device scalar or
+// null) multiplies the gradient (the upstream gradient of the loss node); accumulate = 0 writes g_obj, 1 adds to it.
 __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx* __restrict__ obj, const cpx* __restrict__ wl1,
                                                   float ad, float ab, float gm, float* value, cpx* g_obj,
-                                                  const float* g_scale, int accumulate, int y_begin, int y_end) {
+                                                  const float* g_scale, int accumulate, long long row_begin,
+                                                  long long row_end) {
 #ifndef ADM_HOST_EMU
     __shared__ float red[256];
 #else
@@ -252,81 +250,51 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
     const float gs = (g_scale != nullptr) ? *g_scale : 1.0f;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const size_t sx = (size_t)Z, sy = (size_t)X * Z;
-    const int x = blockIdx.x * wpb + wib;
-    const int y0 = y_begin + blockIdx.y * REG_YC;
-    const int y1 = (y0 + REG_YC < y_end) ? y0 + REG_YC : y_end;
     float acc = 0.f;
-    if (x < X) {
-        const size_t oxm = (size_t)((x + X - 1) % X) * sx, oxp = (size_t)((x + 1) % X) * sx, ox = (size_t)x * sx;
-        for (int zb = 0; zb < Z; zb += 32) {             // the CTA sweeps 8 x rows x the whole z extent of every plane:
-            const int z = zb + lane;                     // 16 KB contiguous per plane (DRAM page locality)
-            if (z < Z) {
-            const int zm = (z + Z - 1) % Z, zp = (z + 1) % Z;
-            // the whole y column of this chunk (+ one halo plane on each side) is requested up front: REG_YC + 2
-            // independent coalesced loads in flight per thread
-            cpx col[REG_YC + 2];
-#pragma unroll
-            for (int k = 0; k < REG_YC + 2; ++k) {
-                int yy = y0 - 1 + k;
-                yy = (yy < 0) ? yy + Y : ((yy >= Y) ? yy - Y : yy);
-                if (k <= y1 - y0 + 1) col[k] = obj[(size_t)yy * sy + ox + z];
+    for (long long row = row_begin + (long long)blockIdx.x * wpb + wib; row < row_end; row += (long long)gridDim.x * wpb) {
+        const int y = (int)(row / X), x = (int)(row - (long long)y * X);
+        const cpx* r0 = obj + (size_t)row * sx;
+        const cpx* rym = obj + (size_t)((y + Y - 1) % Y) * sy + (size_t)x * sx;
+        const cpx* ryp = obj + (size_t)((y + 1) % Y) * sy + (size_t)x * sx;
+        const cpx* rxm = obj + (size_t)y * sy + (size_t)((x + X - 1) % X) * sx;
+        const cpx* rxp = obj + (size_t)y * sy + (size_t)((x + 1) % X) * sx;
+        for (int z = lane; z < Z; z += 32) {
+            const cpx c = r0[z];
+            float w0 = 1.f, w1 = 1.f;
+            if (wl1 != nullptr) { cpx w = wl1[(size_t)row * sx + z]; w0 = w.x; w1 = w.y; }
+            float gd = ad * w0 * sgnf(c.x) * invN;
+            float gb = ab * w1 * sgnf(c.y) * invN;
+            acc += (ad * w0 * fabsf(c.x) + ab * w1 * fabsf(c.y)) * invN;
+            if (gm != 0.f) {
+                // TV: sum over the three axes of |roll(a, 1) - a| / N (periodic), per channel
+                cpx a = rym[z], b = ryp[z];
+                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                a = rxm[z]; b = rxp[z];
+                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                a = r0[(z + Z - 1) % Z]; b = r0[(z + 1) % Z];
+                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
             }
-#pragma unroll
-            for (int k = 0; k < REG_YC; ++k) {
-                const int y = y0 + k;
-                if (y >= y1) break;
-                const cpx* pl = obj + (size_t)y * sy;
-                const cpx prev = col[k], c = col[k + 1], next = col[k + 2];
-                float w0 = 1.f, w1 = 1.f;
-                if (wl1 != nullptr) { cpx w = wl1[(size_t)y * sy + ox + z]; w0 = w.x; w1 = w.y; }
-                float gd = ad * w0 * sgnf(c.x) * invN;
-                float gb = ab * w1 * sgnf(c.y) * invN;
-                acc += (ad * w0 * fabsf(c.x) + ab * w1 * fabsf(c.y)) * invN;
-                if (gm != 0.f) {
-                    // TV: sum over the three axes of |roll(a, 1) - a| / N (periodic), per channel
-                    cpx a = prev, b = next;
-                    acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-                    a = pl[oxm + z]; b = pl[oxp + z];
-                    acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-                    a = pl[ox + zm]; b = pl[ox + zp];
-                    acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-                }
-                if (g_obj != nullptr) {
-                    cpx* o = g_obj + (size_t)y * sy + ox + z;
-                    cpx r = mk(gd * gs, gb * gs);
-                    if (accumulate) { cpx t = *o; r.x += t.x; r.y += t.y; }
-                    *o = r;
-                }
-            }
+            if (g_obj != nullptr) {
+                cpx* o = g_obj + (size_t)row * sx + z;
+                cpx r = mk(gd * gs, gb * gs);
+                if (accumulate) { cpx t = *o; r.x += t.x; r.y += t.y; }
+                *o = r;
             }
         }
     }
-    if (value != nullptr) {           // (uniform across the grid: every thread reaches the barrier)
-#ifndef ADM_HOST_EMU
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
-        if (lane == 0) red[wib] = acc;
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
         __syncthreads();
-        if (threadIdx.x == 0) {
-            float t = 0.f;
-            for (int w = 0; w < wpb; ++w) t += red[w];
-            atomicAdd(value, t);
-        }
-#else
-        red[threadIdx.x] = acc;
-        __syncthreads();
-        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
-            __syncthreads();
-        }
-        if (threadIdx.x == 0) atomicAdd(value, red[0]);
-#endif
     }
+    if (threadIdx.x == 0 && value != nullptr) atomicAdd(value, red[0]);
 }
 
 extern "C" int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
@@ -334,11 +302,11 @@ extern "C" int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj,
                                           int accumulate, int y_begin, int y_end, void* stream) {
     if (Y < 1 || X < 1 || Z < 1 || !obj) return ADM_ERR_ARG;
     if (y_begin < 0 || y_end > Y || y_begin >= y_end) return ADM_ERR_ARG;
-    const int nych = (y_end - y_begin + REG_YC - 1) / REG_YC;
-    if (nych > 65535) return ADM_ERR_UNSUPPORTED;
-    dim3 gr((X + 7) / 8, nych);
-    ADM_LAUNCH(k_reg_l1tv, gr, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj, (const cpx*)weight_l1,
-               alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate, y_begin, y_end);
+    long long rows = (long long)(y_end - y_begin) * X;
+    long long blocks = (rows + 7) / 8;
+    if (blocks > 148LL * 16) blocks = 148LL * 16;
+    ADM_LAUNCH(k_reg_l1tv, (unsigned)blocks, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj, (const cpx*)weight_l1,
+               alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate, (long long)y_begin * X, (long long)y_end * X);
     return ADM_OK;
 }
 
