@@ -129,7 +129,6 @@ def reconstruct_ptychography(
 
     comm = Comm()
     n_ranks, rank = comm.Get_size(), comm.Get_rank()
-    ops.GRAD_SLABS = 4 if n_ranks > 1 else 1
     if not torch.cuda.is_available():
         raise RuntimeError('adorym_b200 needs a CUDA device (B200); there is no CPU fallback')
     if n_ranks > 1:
@@ -271,6 +270,22 @@ def reconstruct_ptychography(
 
     gradient = Gradient(obj, forward_model=forward_model)
     gradient.arr = torch.zeros([*this_obj_size, 2], dtype=torch.float32, device=device_obj)
+
+    # N > 1 ranks on one NVSwitch node: the object and its gradient live in symmetric (peer-mapped) memory and
+    # "all-reduce + Adam" (ptychography.py:1113-1125) is one fused kernel per rank (dist.PeerUpdate).  ADM_DP=nccl selects
+    # the NCCL all-reduce (pipelined by y slabs) instead; so do the option combinations whose constraints are not fused.
+    peer = None
+    ops.OBJ_GRAD_OUT = None
+    if (n_ranks > 1 and n_ranks <= 8 and os.environ.get('ADM_DP', 'p2p') == 'p2p' and isinstance(opt, AdamOptimizer)
+            and unknown_type == 'delta_beta' and optimize_object and not fix_object and int(np.prod(this_obj_size)) % 2 == 0):
+        from .dist import PeerUpdate
+        peer = PeerUpdate([*this_obj_size, 2], device_obj)
+        with torch.no_grad():
+            peer.object_tensor().copy_(obj.arr.detach())
+        obj.arr = peer.object_tensor().requires_grad_(True)
+        if update_scheme == 'immediate' and not rotate_out_of_loop:
+            ops.OBJ_GRAD_OUT = peer.gradient_tensor()        # the adjoint writes straight into the symmetric buffer
+    ops.GRAD_SLABS = 4 if (n_ranks > 1 and peer is None) else 1
 
     mask = None
     if finite_support_mask_path is not None:
@@ -427,9 +442,10 @@ def reconstruct_ptychography(
 
             # ---- all-reduce (SUM) + update (ptychography.py:1113-1163) ----
             slabs = ops.last_obj_grad_slabs
-            pipelined = (n_ranks > 1 and slabs is not None and slabs[0].data_ptr() == gradient.arr.data_ptr() and isinstance(opt, AdamOptimizer)
+            pipelined = (n_ranks > 1 and peer is None and slabs is not None
+                         and slabs[0].data_ptr() == gradient.arr.data_ptr() and isinstance(opt, AdamOptimizer)
                          and optimize_object and not fix_object)
-            if n_ranks > 1 and not pipelined:
+            if n_ranks > 1 and not pipelined and peer is None:
                 gradient.arr = comm.allreduce(gradient.arr)
             with torch.no_grad():
                 if optimize_object and not fix_object:
@@ -444,7 +460,12 @@ def reconstruct_ptychography(
                             extra['zero_channel'] = 1
                         if mask is not None and unknown_type == 'delta_beta':
                             extra['mask'] = mask.mask
-                    if pipelined:
+                    if peer is not None:
+                        # pull-reduce over NVLink + Adam + push, one kernel (dist.PeerUpdate / adm_p2p_reduce_adam)
+                        if gradient.arr.data_ptr() != peer.g.data_ptr():
+                            peer.gradient_tensor().copy_(gradient.arr)
+                        new = peer.update(opt, i_opt_batch, **opt.options_dict, **extra)
+                    elif pipelined:
                         # the all-reduce runs slab by slab under the adjoint kernels and under Adam (dist.py)
                         from .dist import allreduce_update_pipelined
                         new = allreduce_update_pipelined(opt, obj.arr, gradient, i_opt_batch, slabs[1], **opt.options_dict,
@@ -492,6 +513,7 @@ def reconstruct_ptychography(
             np.save(os.path.join(output_folder, 'probe_ds_1.npy'),
                     torch.stack([optimizable_params['probe_real'], optimizable_params['probe_imag']], -1).detach().cpu().numpy())
     comm.Barrier()
+    ops.OBJ_GRAD_OUT = None
     return {'obj': obj.arr.detach(), 'probe_real': optimizable_params['probe_real'].detach(),
             'probe_imag': optimizable_params['probe_imag'].detach(),
             'probe_pos_correction': optimizable_params['probe_pos_correction'].detach(),
