@@ -285,7 +285,7 @@ def reconstruct_ptychography(
         obj.arr = peer.object_tensor().requires_grad_(True)
         if update_scheme == 'immediate' and not rotate_out_of_loop:
             ops.OBJ_GRAD_OUT = peer.gradient_tensor()        # the adjoint writes straight into the symmetric buffer
-    ops.GRAD_SLABS = 4 if (n_ranks > 1 and peer is None) else 1
+    ops.GRAD_SLABS = int(os.environ.get('ADM_GRAD_SLABS', '4')) if (n_ranks > 1 and peer is None) else 1
 
     mask = None
     if finite_support_mask_path is not None:

@@ -21,8 +21,9 @@ torch.cuda.set_device(local)
 data = np.load(os.path.join(ROOT, 'tests', 'golden', 'driver_data.npz'))['data'].astype('float32')
 out = {}
 res = {}
-for mode in ('p2p', 'nccl'):
-    os.environ['ADM_DP'] = mode
+for mode in ('p2p', 'nccl', 'nccl1'):
+    os.environ['ADM_DP'] = mode[:4]
+    os.environ['ADM_GRAD_SLABS'] = '1' if mode == 'nccl1' else '4'
     params = driver_params('driver_immediate')
     params['minibatch_size'] = 1 if world > 2 else 2
     r = ab.reconstruct_ptychography(data, **params, finite_support_mask_path=driver_mask(), verbose=False, save_outputs=False,
@@ -38,6 +39,8 @@ lp, ln = np.array(out['p2p_losses']), np.array(out['nccl_losses'])
 out['loss_history_rel_diff_p2p_vs_nccl'] = float(np.max(np.abs(lp - ln) / np.abs(ln)))
 out['obj_rel_diff_p2p_vs_nccl'] = float((res['p2p']['obj'] - res['nccl']['obj']).double().norm() / res['nccl']['obj'].double().norm())
 out['world'] = world
+l1 = np.array(out['nccl1_losses'])
+out['loss_history_rel_diff_p2p_vs_nccl1'] = float(np.max(np.abs(lp - l1) / np.abs(l1)))
 if rank == 0:
     print(json.dumps(out))
 torch.distributed.destroy_process_group()
