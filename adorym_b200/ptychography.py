@@ -499,7 +499,12 @@ def reconstruct_ptychography(
                 i_epoch, i_batch, n_batch, this_i_theta, current_loss, time.time() - t00,
                 minibatch_size * n_ranks / (time.time() - t00)), rank, verbose)
             if optimizer_batch_number_increment == 'angle':
-                if i_batch == n_batch - 1 or ind_list_rand[i_batch + 1][0, 0] != current_i_theta:
+                # ptychography.py:1267-1271 compares with the rank-local current_i_theta; ranks that hold different angles
+                # of one chunk would then advance their Adam step index at different times and the replicas of the object
+                # would drift apart (measured: 3e-5 absolute after 10 minibatches on 2 ranks).  The step index follows the
+                # FIRST angle of the chunk on every rank: identical to the reference for one rank, consistent for N.
+                chunk_theta = int(ind_list_rand[i_batch][0, 0])
+                if i_batch == n_batch - 1 or ind_list_rand[i_batch + 1][0, 0] != chunk_theta:
                     i_opt_batch += 1
             elif optimizer_batch_number_increment == 'batch':
                 i_opt_batch += 1
