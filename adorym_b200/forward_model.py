@@ -152,6 +152,53 @@ class ForwardModel(object):
             return None
         return self._rotation_grid(this_i_theta, dev)
 
+    def _large_frame_multislice(self, obj, this_i_theta, probe):
+        """Full-field multislice on frames the shared-memory FFT cannot hold (128 .. 2048 pixels per side): the slice loop
+        of propagate.py:208-258 with one fused large-frame step per slice -- psi <- IFFT2(H . FFT2(psi . T(slice))) is
+        exactly the thin-object near-field kernel chain of ops.MultiDistFn (row pass: modulation + FFT, column pass:
+        FFT . H . IFFT, row pass: IFFT) with the running wavefield in the role of the probe; autograd chains the per-slice
+        analytic adjoints.  The last slice is not propagated inside the object (:253); a finite free_prop_cm is one more
+        fused step with the free-space kernel (:271-280)."""
+        cv = self.common_vars
+        dev = self._device(obj)
+        Y, X, Z = cv['this_obj_size']
+        mode = _free_prop_mode(cv['free_prop_cm'])
+        if mode == 'inf':
+            raise NotImplementedError('adorym_b200: far-field detection of %d-pixel full-field frames is not accelerated' % Y)
+        grid = self._object_grid(obj, this_i_theta)
+        if grid is not None:
+            rot = ops.RotateFn.apply(obj, grid)                                  # [Z, Y, X, 2]
+        else:
+            rot = obj.permute(2, 0, 1, 3).contiguous()
+        key = ('lf', Y, mode, float(cv['free_prop_cm']) if mode == 'near' else 0., str(dev))
+        plans = self._plans.get(key)
+        if plans is None:
+            psize_cm = cv['psize_cm'] * cv.get('ds_level', 1)
+            voxel_nm = np.array([psize_cm] * 3) * 1.e7
+            k1 = ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k)
+            mk = lambda h: ops.MultiDistPlan(Y, [h], k1, dev, sign_convention=self.sign_convention, unknown_type=self.unknown_type)
+            p_in = mk(cv['h']) if Z > 1 else None
+            p_free = None
+            if mode == 'near':
+                p_free = mk(get_kernel(float(cv['free_prop_cm']) * 1e7, 1240. / cv['energy_ev'], voxel_nm, [Y, X],
+                                       sign_convention=self.sign_convention))          # quirk 10: always paraxial
+            plans = self._plans[key] = (p_in, p_free, k1)
+        p_in, p_free, k1 = plans
+        psi = probe
+        for z in range(Z - 1):
+            psi = ops.MultiDistFn.apply(rot[z], psi, p_in)[0]
+        if p_free is not None:
+            return ops.MultiDistFn.apply(rot[Z - 1], psi, p_free)                  # [1, M, N, N, 2]
+        last = rot[Z - 1]
+        if self.unknown_type == 'delta_beta':                                       # propagate.py:241
+            e = torch.exp(-k1 * last[..., 1])
+            ph = -self.sign_convention * k1 * last[..., 0]
+            tr, ti = e * torch.cos(ph), e * torch.sin(ph)
+        else:
+            tr, ti = last[..., 0], last[..., 1]
+        out = torch.stack([psi[..., 0] * tr - psi[..., 1] * ti, psi[..., 0] * ti + psi[..., 1] * tr], -1)
+        return out.unsqueeze(0)
+
     def _multislice(self, obj, this_i_theta, probe, pos_t, plan, with_reg):
         """fused rotate + transmission + gather + multislice; with_reg: also the fused regulariser value (None when the
         regulariser list is not fusable) -> (det, reg_value | None, reg_was_fused)."""
@@ -510,6 +557,10 @@ class SingleBatchFullfieldModel(PtychographyModel):
         probe = torch.stack([probe_real, probe_imag], dim=-1)
         if probe.dim() == 3:
             probe = probe.unsqueeze(0)
+        if probe_size[0] not in ops.SUPPORTED_P and probe_size[0] == probe_size[1] and ops.lf_supported(probe_size[0]):
+            self._check_unsupported([])
+            det = self._large_frame_multislice(obj, this_i_theta, probe.contiguous())
+            return (det, None, False) if with_reg else det
         plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
         pos_t = torch.zeros((1, 2), dtype=torch.int32, device=dev)
         out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg)

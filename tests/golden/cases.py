@@ -73,6 +73,16 @@ CASES = {
                                   pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=2, free_prop_cm='inf',
                                   unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=20,
                                   loss='lsq', raw_data_type='magnitude', optimize_probe=True, beamstop_radius=7.5),
+    # full-field multislice tomography on frames the shared-memory FFT cannot hold (128 pixels): large-frame row / column
+    # kernels, one fused step per slice; exit wave (free_prop_cm = 0) and near-field detection
+    'fullfield128': dict(kind='fullfield', obj_size=(128, 128, 10), probe_size=(128, 128), energy_ev=800., psize_cm=0.67e-7,
+                         theta=0.0, n_theta=3, i_theta=0, pos=[(0, 0)], n_modes=1, free_prop_cm=0,
+                         unknown_type='delta_beta', delta_scale=2e-3, beta_scale=3e-4, seed=24,
+                         loss='lsq', raw_data_type='magnitude', rotate_out_of_loop=True),
+    'fullfield128_near': dict(kind='fullfield', obj_size=(128, 128, 6), probe_size=(128, 128), energy_ev=800.,
+                              psize_cm=0.67e-7, theta=0.0, n_theta=3, i_theta=0, pos=[(0, 0)], n_modes=1,
+                              free_prop_cm=2e-5, unknown_type='real_imag', delta_scale=0.2, beta_scale=0.2, seed=25,
+                              loss='lsq', raw_data_type='intensity', rotate_out_of_loop=True),
     # sparse multislice (SparseMultisliceModel, forward_model.py:589-806): three thin slices at unequal positions, one
     # paraxial transfer function per gap; the object is handed over in the beam frame (rotate_out_of_loop)
     'sparse3_p72': dict(kind='sparse', obj_size=(90, 84, 3), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,

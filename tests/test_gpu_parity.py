@@ -114,6 +114,44 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
             assert rel_err(grads[k], gold['g_' + k]) < TOL, k
 
 
+def test_single_batch_ptychography_model_matches_oracle():
+    """SingleBatchPtychographyModel (forward_model.py:493-586: one probe position per call, no probe shift) on the fused
+    kernels vs the oracle for single positions of the 3-D P = 72 case."""
+    import adorym_b200 as ab
+    dev = torch.device('cuda', 0)
+    name = 'ptycho3d_p72'
+    inp, cfg, coord, reg = case_cfg(name)
+    c = inp['cfg']
+    n_theta = c['n_theta']
+    P = c['probe_size']
+    theta_ls = np.linspace(0, 2 * np.pi, n_theta, dtype='float32')
+    theta_ls[c['i_theta']] = c['theta']
+    prj_full = np.zeros([n_theta, 16, P[0], P[1]], dtype='float32')
+    prj_full[c['i_theta'], inp['this_ind_batch']] = inp['prj']
+    cv = _common_vars(inp, cfg, dev, prj_full, theta_ls, n_theta)
+    cv['minibatch_size'] = 1
+    fm = ab.SingleBatchPtychographyModel(loss_function_type=c['loss'], device=dev, common_vars_dict=cv,
+                                         raw_data_type=c['raw_data_type'])
+    t = lambda a, rg=True: torch.tensor(a, dtype=torch.float32, device=dev, requires_grad=rg)
+    for j in (0, 2):
+        obj, pr, pi = t(inp['obj']), t(inp['probe_real']), t(inp['probe_imag'])
+        args = dict(obj=obj, probe_real=pr, probe_imag=pi, probe_defocus_mm=None, probe_pos_offset=None,
+                    this_i_theta=c['i_theta'], this_pos_batch=inp['pos'][j:j + 1], prj=prj_full,
+                    probe_pos_correction=torch.zeros([n_theta, 16, 2], device=dev),
+                    this_ind_batch=inp['this_ind_batch'][j:j + 1], tilt_ls=None, prj_pos_offset=None)
+        diff = ab.Differentiator()
+        diff.create_loss_node(fm.get_loss_function(), [0, fm.get_argument_index('probe_real')])
+        g_obj, g_pr = diff.get_gradients(**args)
+        l64, _, _, gr64 = orc.ptycho_loss_and_grads(torch.tensor(inp['obj'], dtype=torch.float64),
+                                                    torch.tensor(inp['probe_real'], dtype=torch.float64),
+                                                    torch.tensor(inp['probe_imag'], dtype=torch.float64), inp['pos'][j:j + 1],
+                                                    torch.tensor(inp['prj'][j:j + 1], dtype=torch.float64), coord, cfg,
+                                                    want=('obj', 'probe_real'))
+        assert abs(fm.current_loss - float(l64)) <= TOL * abs(float(l64))
+        assert rel_err(g_obj.cpu().numpy(), gr64['obj'].numpy()) < TOL
+        assert rel_err(g_pr.cpu().numpy(), gr64['probe_real'].numpy()) < TOL
+
+
 def test_per_pattern_loss_matches_oracle():
     """north_star: per-pattern loss within 1e-4 (the fused loss kernel reports one partial sum per pattern)."""
     name = 'ptycho3d_p72'
