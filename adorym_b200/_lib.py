@@ -49,7 +49,7 @@ SIGNATURES = {
     'adm_rotate_adj': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_adam_step': [c_void_p, c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double, c_double, c_int,
                       c_int, c_void_p, c_void_p],
-    'adm_p2p_reduce_adam': [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double,
+    'adm_p2p_reduce_adam': [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_longlong, c_double, c_double, c_double,
                             c_double, c_int, c_int, c_void_p, c_void_p],
     'adm_sgd_step': [c_void_p, c_void_p, c_void_p, c_longlong, c_double, c_double, c_int, c_void_p, c_void_p],
     'adm_regularizer_l1tv': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
@@ -58,9 +58,9 @@ SIGNATURES = {
                                     c_void_p, c_int, c_void_p],
     'adm_regularizer_l1tv_range': [c_int, c_int, c_int, c_void_p, c_void_p, c_float, c_float, c_float, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int, c_int, c_void_p],
-    'adm_object_to_transmission': [c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_void_p, c_void_p],
+    'adm_object_to_transmission': [c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_float, c_int, c_int, c_void_p, c_void_p],
     'adm_transmission_to_object_adj': [c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_float, c_int,
-                                       c_void_p, c_int, c_int, c_void_p],
+                                       c_int, c_void_p, c_int, c_int, c_void_p],
     'adm_probe_shift_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_probe_shift_bwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_lf_supported': [c_int],

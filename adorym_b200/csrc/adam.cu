@@ -119,27 +119,51 @@ extern "C" int adm_adam_step(float* x, float* m, float* v, const float* g, long 
 struct P2PPtrs {
     float* x[ADM_P2P_MAX_RANKS];
     const float* g[ADM_P2P_MAX_RANKS];
+    float* mc_x;            // NVLS multicast mappings of the two symmetric buffers, or null: the switch then performs the
+    const float* mc_g;      // reduction (multimem.ld_reduce) and the replication (multimem.st)
 };
+#ifndef ADM_HOST_EMU
+// sum over all ranks of the 16 bytes at the same offset of every rank's buffer, reduced inside the NVSwitch
+ADM_DEV float4 mc_ld_reduce_add(const float* p) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];\n"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
+// one store replicated by the NVSwitch into every rank's buffer
+ADM_DEV void mc_st(float* p, float4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+                 : "memory");
+}
+#endif
 __global__ void __launch_bounds__(256) k_p2p_reduce_adam(P2PPtrs pp, int world, const float* x_self, float* m, float* v, long long i4_begin,
                                                          long long i4_end, AdamArgs a, const float* mask) {
     long long i = i4_begin + (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (; i < i4_end; i += stride) {
-        float4 gg[ADM_P2P_MAX_RANKS];
-#pragma unroll
-        for (int r = 0; r < ADM_P2P_MAX_RANKS; ++r)
-            if (r < world) gg[r] = reinterpret_cast<const float4*>(pp.g[r])[i];      // all peer loads in flight together
-        float4 gs = gg[0];
-#pragma unroll
-        for (int r = 1; r < ADM_P2P_MAX_RANKS; ++r)
-            if (r < world) {
+        float4 gs;
 #ifndef ADM_HOST_EMU
-                gs.x = __fadd_rn(gs.x, gg[r].x); gs.y = __fadd_rn(gs.y, gg[r].y);
-                gs.z = __fadd_rn(gs.z, gg[r].z); gs.w = __fadd_rn(gs.w, gg[r].w);
-#else
-                gs.x += gg[r].x; gs.y += gg[r].y; gs.z += gg[r].z; gs.w += gg[r].w;
+        if (pp.mc_g != nullptr) {
+            gs = mc_ld_reduce_add(pp.mc_g + 4 * i);
+        } else
 #endif
-            }
+        {
+            float4 gg[ADM_P2P_MAX_RANKS];
+#pragma unroll
+            for (int r = 0; r < ADM_P2P_MAX_RANKS; ++r)
+                if (r < world) gg[r] = reinterpret_cast<const float4*>(pp.g[r])[i];      // all peer loads in flight together
+            gs = gg[0];
+#pragma unroll
+            for (int r = 1; r < ADM_P2P_MAX_RANKS; ++r)
+                if (r < world) {
+#ifndef ADM_HOST_EMU
+                    gs.x = __fadd_rn(gs.x, gg[r].x); gs.y = __fadd_rn(gs.y, gg[r].y);
+                    gs.z = __fadd_rn(gs.z, gg[r].z); gs.w = __fadd_rn(gs.w, gg[r].w);
+#else
+                    gs.x += gg[r].x; gs.y += gg[r].y; gs.z += gg[r].z; gs.w += gg[r].w;
+#endif
+                }
+        }
         float4 xx = reinterpret_cast<const float4*>(x_self)[i];
         float4 mm = reinterpret_cast<const float4*>(m)[i];
         float4 vv = reinterpret_cast<const float4*>(v)[i];
@@ -156,15 +180,21 @@ __global__ void __launch_bounds__(256) k_p2p_reduce_adam(P2PPtrs pp, int world, 
         }
         reinterpret_cast<float4*>(m)[i] = mm;
         reinterpret_cast<float4*>(v)[i] = vv;
+#ifndef ADM_HOST_EMU
+        if (pp.mc_x != nullptr) {
+            mc_st(pp.mc_x + 4 * i, xx);
+            continue;
+        }
+#endif
 #pragma unroll
         for (int r = 0; r < ADM_P2P_MAX_RANKS; ++r)
             if (r < world) reinterpret_cast<float4*>(pp.x[r])[i] = xx;
     }
 }
 
-extern "C" int adm_p2p_reduce_adam(float* const* x_ptrs, const float* const* g_ptrs, int world, int rank, float* m, float* v,
-                                   long long n, double step_size, double b1, double b2, double eps, int step, int flags,
-                                   const float* mask, void* stream) {
+extern "C" int adm_p2p_reduce_adam(float* const* x_ptrs, const float* const* g_ptrs, float* x_multicast, const float* g_multicast,
+                                   int world, int rank, float* m, float* v, long long n, double step_size, double b1,
+                                   double b2, double eps, int step, int flags, const float* mask, void* stream) {
     if (!x_ptrs || !g_ptrs || !m || !v || n < 4 || (n & 3) || step < 0) return ADM_ERR_ARG;
     if (world < 1 || world > ADM_P2P_MAX_RANKS || rank < 0 || rank >= world) return ADM_ERR_ARG;
     P2PPtrs pp;
@@ -173,6 +203,9 @@ extern "C" int adm_p2p_reduce_adam(float* const* x_ptrs, const float* const* g_p
         pp.g[r] = r < world ? g_ptrs[r] : nullptr;
         if (r < world && (!pp.x[r] || !pp.g[r] || ((((uintptr_t)pp.x[r]) | ((uintptr_t)pp.g[r])) & 15))) return ADM_ERR_ARG;
     }
+    if ((x_multicast == nullptr) != (g_multicast == nullptr)) return ADM_ERR_ARG;
+    if (((((uintptr_t)x_multicast) | ((uintptr_t)g_multicast)) & 15)) return ADM_ERR_ARG;
+    pp.mc_x = x_multicast; pp.mc_g = g_multicast;
     if (((((uintptr_t)m) | ((uintptr_t)v)) & 15) || (mask && (((uintptr_t)mask) & 7))) return ADM_ERR_ARG;
     AdamArgs a;
     a.step_size = (float)step_size; a.b1 = (float)b1; a.b2 = (float)b2; a.eps = (float)eps; a.flags = flags;

@@ -68,33 +68,47 @@ ADM_DEV void oc_xz(int& x, int& z) {
     z = blockIdx.y * OC_TZ + ((w >> 1) << 2) + (l >> 3);
 }
 
+// `bin` > 1 (propagate.py:207-254, `binning`): output slice zb is the transmission of the SUM of (delta, beta) over the
+// object slices zb*bin .. zb*bin + bin - 1 (delta_beta objects); z counts OUTPUT slices, Zo = ceil(Z / bin).
 __global__ void __launch_bounds__(128) k_object_to_transmission(int Y, int X, int Z, int Xp, const cpx* obj, const float* grid,
-                                                                int unknown_type, float k1, float sgn, cpx* tvol) {
-    int x, z;
-    oc_xz(x, z);
-    if (x >= X || z >= Z) return;
-    const OTaps t = oc_make_taps(grid, x, z, X, Z);
+                                                                int unknown_type, float k1, float sgn, cpx* tvol, int bin) {
+    int x, zb;
+    oc_xz(x, zb);
+    const int Zo = (Z + bin - 1) / bin;
+    if (x >= X || zb >= Zo) return;
     const int y0 = blockIdx.z * OC_YCHUNK;
-    cpx a[OC_YCHUNK], b[OC_YCHUNK], c[OC_YCHUNK], d[OC_YCHUNK];
     const bool one_tap = (grid == nullptr);
+    cpx acc[OC_YCHUNK];
 #pragma unroll
-    for (int k = 0; k < OC_YCHUNK; ++k) {
-        const int y = (y0 + k < Y) ? y0 + k : Y - 1;
-        const cpx* pl = obj + (size_t)y * X * Z;
-        a[k] = pl[t.i00];
-        if (!one_tap) { b[k] = pl[t.i01]; c[k] = pl[t.i10]; d[k] = pl[t.i11]; }
-    }
+    for (int k = 0; k < OC_YCHUNK; ++k) acc[k] = mk(0.f, 0.f);
+    const int z_end = (zb * bin + bin < Z) ? zb * bin + bin : Z;
+    for (int z = zb * bin; z < z_end; ++z) {
+        const OTaps t = oc_make_taps(grid, x, z, X, Z);
+        cpx a[OC_YCHUNK], b[OC_YCHUNK], c[OC_YCHUNK], d[OC_YCHUNK];
 #pragma unroll
-    for (int k = 0; k < OC_YCHUNK; ++k) {
-        const int y = y0 + k;
-        if (y < Y) {
+        for (int k = 0; k < OC_YCHUNK; ++k) {
+            const int y = (y0 + k < Y) ? y0 + k : Y - 1;
+            const cpx* pl = obj + (size_t)y * X * Z;
+            a[k] = pl[t.i00];
+            if (!one_tap) { b[k] = pl[t.i01]; c[k] = pl[t.i10]; d[k] = pl[t.i11]; }
+        }
+#pragma unroll
+        for (int k = 0; k < OC_YCHUNK; ++k) {
             cpx r = a[k];
             if (!one_tap) {
                 r.x = a[k].x * t.w00 + b[k].x * t.w01 + c[k].x * t.w10 + d[k].x * t.w11;
                 r.y = a[k].y * t.w00 + b[k].y * t.w01 + c[k].y * t.w10 + d[k].y * t.w11;
             }
-            cpx* row = tvol + ((size_t)z * Y + y) * Xp;
-            row[x] = oc_transmission_m1(r, unknown_type, k1, sgn);
+            if (bin == 1) acc[k] = r;
+            else { acc[k].x += r.x; acc[k].y += r.y; }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < OC_YCHUNK; ++k) {
+        const int y = y0 + k;
+        if (y < Y) {
+            cpx* row = tvol + ((size_t)zb * Y + y) * Xp;
+            row[x] = oc_transmission_m1(acc[k], unknown_type, k1, sgn);
             if (x == X - 1 && Xp > X) row[X] = mk(0.f, 0.f);      // pad column of the TMA row pitch
         }
     }
@@ -109,37 +123,46 @@ ADM_DEV void oc_red2(cpx* addr, float a, float b) {
 #endif
 }
 
-// g_tvol: margined gradient volume [Z][Y + mg][Xg][2]; grid.z covers the y range [y0, y1) in chunks of OC_YCHUNK
+// g_tvol: margined gradient volume [Zo][Y + mg][Xg][2]; grid.z covers the y range [y0, y1) in chunks of OC_YCHUNK.
+// bin > 1: every object slice of the bin receives the gradient of the summed (delta, beta).
 __global__ void __launch_bounds__(128) k_transmission_to_object_adj(int Y, int X, int Z, int Xp, int mg, int Xg, const cpx* g_tvol,
                                                                     const cpx* tvol, const float* grid, int unknown_type,
-                                                                    float k1, float sgn, cpx* g_obj, int y_begin, int y_end) {
-    int x, z;
-    oc_xz(x, z);
-    if (x >= X || z >= Z) return;
-    const OTaps t = oc_make_taps(grid, x, z, X, Z);
+                                                                    float k1, float sgn, cpx* g_obj, int y_begin, int y_end,
+                                                                    int bin) {
+    int x, zb;
+    oc_xz(x, zb);
+    const int Zo = (Z + bin - 1) / bin;
+    if (x >= X || zb >= Zo) return;
     const int y0 = y_begin + blockIdx.z * OC_YCHUNK;
     cpx gv[OC_YCHUNK], tv[OC_YCHUNK];
 #pragma unroll
     for (int k = 0; k < OC_YCHUNK; ++k) {
         const int y = (y0 + k < y_end) ? y0 + k : y_end - 1;
-        gv[k] = g_tvol[((size_t)z * (Y + mg) + y + mg) * Xg + x + mg];
-        if (unknown_type == ADM_DELTA_BETA) tv[k] = tvol[((size_t)z * Y + y) * Xp + x];
+        gv[k] = g_tvol[((size_t)zb * (Y + mg) + y + mg) * Xg + x + mg];
+        if (unknown_type == ADM_DELTA_BETA) tv[k] = tvol[((size_t)zb * Y + y) * Xp + x];
     }
 #pragma unroll
     for (int k = 0; k < OC_YCHUNK; ++k) {
-        const int y = y0 + k;
-        if (y >= y_end) break;
-        cpx v = gv[k];
         if (unknown_type == ADM_DELTA_BETA) {
             // dL/ddelta = -s k1 Im(g_T conj(T)), dL/dbeta = -k1 Re(g_T conj(T))   (transmission.cu)
-            cpx u = cmulc(v, mk(tv[k].x + 1.f, tv[k].y));
-            v = mk(-sgn * k1 * u.y, -k1 * u.x);
+            cpx u = cmulc(gv[k], mk(tv[k].x + 1.f, tv[k].y));
+            gv[k] = mk(-sgn * k1 * u.y, -k1 * u.x);
         }
-        cpx* pl = g_obj + (size_t)y * X * Z;
-        if (t.w00 != 0.f) oc_red2(pl + t.i00, v.x * t.w00, v.y * t.w00);
-        if (t.w01 != 0.f) oc_red2(pl + t.i01, v.x * t.w01, v.y * t.w01);
-        if (t.w10 != 0.f) oc_red2(pl + t.i10, v.x * t.w10, v.y * t.w10);
-        if (t.w11 != 0.f) oc_red2(pl + t.i11, v.x * t.w11, v.y * t.w11);
+    }
+    const int z_end = (zb * bin + bin < Z) ? zb * bin + bin : Z;
+    for (int z = zb * bin; z < z_end; ++z) {
+        const OTaps t = oc_make_taps(grid, x, z, X, Z);
+#pragma unroll
+        for (int k = 0; k < OC_YCHUNK; ++k) {
+            const int y = y0 + k;
+            if (y >= y_end) break;
+            const cpx v = gv[k];
+            cpx* pl = g_obj + (size_t)y * X * Z;
+            if (t.w00 != 0.f) oc_red2(pl + t.i00, v.x * t.w00, v.y * t.w00);
+            if (t.w01 != 0.f) oc_red2(pl + t.i01, v.x * t.w01, v.y * t.w01);
+            if (t.w10 != 0.f) oc_red2(pl + t.i10, v.x * t.w10, v.y * t.w10);
+            if (t.w11 != 0.f) oc_red2(pl + t.i11, v.x * t.w11, v.y * t.w11);
+        }
     }
 }
 
@@ -150,29 +173,33 @@ static int oc_check(int Y, int X, int Z) {
 }
 
 extern "C" int adm_object_to_transmission(int Y, int X, int Z, const float* obj, const float* grid, int unknown_type, float k1,
-                                          int sign_convention, float* tvol, void* stream) {
-    if (!obj || !tvol) return ADM_ERR_ARG;
+                                          int sign_convention, int binning, float* tvol, void* stream) {
+    if (!obj || !tvol || binning < 1) return ADM_ERR_ARG;
     if (unknown_type != ADM_DELTA_BETA && unknown_type != ADM_REAL_IMAG) return ADM_ERR_ARG;
+    if (binning > 1 && unknown_type != ADM_DELTA_BETA) return ADM_ERR_UNSUPPORTED;
     int rc = oc_check(Y, X, Z);
     if (rc) return rc;
-    dim3 gr((X + OC_TX - 1) / OC_TX, (Z + OC_TZ - 1) / OC_TZ, (Y + OC_YCHUNK - 1) / OC_YCHUNK);
+    const int Zo = (Z + binning - 1) / binning;
+    dim3 gr((X + OC_TX - 1) / OC_TX, (Zo + OC_TZ - 1) / OC_TZ, (Y + OC_YCHUNK - 1) / OC_YCHUNK);
     ADM_LAUNCH(k_object_to_transmission, gr, 128, 0, stream, Y, X, Z, ADM_TVOL_PITCH(X), (const cpx*)obj, grid, unknown_type,
-               k1, (float)sign_convention, (cpx*)tvol);
+               k1, (float)sign_convention, (cpx*)tvol, binning);
     return ADM_OK;
 }
 
 extern "C" int adm_transmission_to_object_adj(int Y, int X, int Z, int P, const float* g_tvol, const float* tvol,
                                               const float* grid, int unknown_type, float k1, int sign_convention,
-                                              float* g_obj, int y_begin, int y_end, void* stream) {
-    if (!g_tvol || !g_obj || P < 1) return ADM_ERR_ARG;
+                                              int binning, float* g_obj, int y_begin, int y_end, void* stream) {
+    if (!g_tvol || !g_obj || P < 1 || binning < 1) return ADM_ERR_ARG;
+    if (binning > 1 && unknown_type != ADM_DELTA_BETA) return ADM_ERR_UNSUPPORTED;
     if (unknown_type != ADM_DELTA_BETA && unknown_type != ADM_REAL_IMAG) return ADM_ERR_ARG;
     if (unknown_type == ADM_DELTA_BETA && !tvol) return ADM_ERR_ARG;
     if (y_begin < 0 || y_end > Y || y_begin >= y_end) return ADM_ERR_ARG;
     int rc = oc_check(Y, X, Z);
     if (rc) return rc;
-    dim3 gr((X + OC_TX - 1) / OC_TX, (Z + OC_TZ - 1) / OC_TZ, (y_end - y_begin + OC_YCHUNK - 1) / OC_YCHUNK);
+    const int Zo = (Z + binning - 1) / binning;
+    dim3 gr((X + OC_TX - 1) / OC_TX, (Zo + OC_TZ - 1) / OC_TZ, (y_end - y_begin + OC_YCHUNK - 1) / OC_YCHUNK);
     ADM_LAUNCH(k_transmission_to_object_adj, gr, 128, 0, stream, Y, X, Z, ADM_TVOL_PITCH(X), ADM_GVOL_MARGIN(P),
                ADM_GVOL_PITCH(X, P), (const cpx*)g_tvol, (const cpx*)tvol, grid, unknown_type, k1, (float)sign_convention,
-               (cpx*)g_obj, y_begin, y_end);
+               (cpx*)g_obj, y_begin, y_end, binning);
     return ADM_OK;
 }

@@ -128,6 +128,16 @@ class PeerUpdate(object):
             raise NotImplementedError('PeerUpdate: at most 8 ranks (one NVSwitch node)')
         self._xp = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hx.buffer_ptrs])
         self._gp = (ctypes.c_void_p * self.world)(*[int(p) for p in self.hg.buffer_ptrs])
+        # NVLS multicast mappings (in-switch reduction / replication) when the fabric offers them; ADM_P2P_MULTICAST=0
+        # selects plain peer loads / stores
+        self.mc_x = self.mc_g = None
+        try:
+            if os.environ.get('ADM_P2P_MULTICAST', '1') != '0' and self.hx.has_multicast_support:
+                mx, mg = int(self.hx.multicast_ptr), int(self.hg.multicast_ptr)
+                if mx and mg:
+                    self.mc_x, self.mc_g = ctypes.c_void_p(mx), ctypes.c_void_p(mg)
+        except Exception:
+            self.mc_x = self.mc_g = None
         self.x.zero_()
         self.g.zero_()
 
@@ -151,7 +161,7 @@ class PeerUpdate(object):
         flags = (1 if clip_nonneg else 0) | (2 if zero_channel == 0 else 0) | (4 if zero_channel == 1 else 0)
         self.hg.barrier(channel=0)          # every rank's gradient is complete (and its reads of x are done)
         ops.call('adm_p2p_reduce_adam', ctypes.cast(self._xp, ctypes.c_void_p), ctypes.cast(self._gp, ctypes.c_void_p),
-                 self.world, self.rank, ops.ptr(m), ops.ptr(v), self.n, float(step_size), float(b1), float(b2), float(eps),
+                 self.mc_x, self.mc_g, self.world, self.rank, ops.ptr(m), ops.ptr(v), self.n, float(step_size), float(b1), float(b2), float(eps),
                  int(i_batch), flags, ops.ptr(mask), ops.stream_ptr())
         self.hx.barrier(channel=1)          # every rank's shard has landed in every copy of x
         opt.i_batch += 1

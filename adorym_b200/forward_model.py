@@ -126,10 +126,11 @@ class ForwardModel(object):
                 raise NotImplementedError('adorym_b200: option %s is not on the accelerated path yet' % n)
         if cv.get('initial_tilt', None) is not None:
             raise NotImplementedError('adorym_b200: initial_tilt is not on the accelerated path yet')
-        if cv.get('pure_projection', False):
-            raise NotImplementedError('adorym_b200: pure_projection is not on the accelerated path')
-        if self.binning != 1:
-            raise NotImplementedError('adorym_b200: binning > 1 is not on the accelerated path')
+        if cv.get('pure_projection', False) and (self.is_minus_logged or self.unknown_type != 'delta_beta'):
+            raise NotImplementedError('adorym_b200: pure_projection is accelerated for delta_beta objects that are not '
+                                      'minus-logged')
+        if self.binning != 1 and self.unknown_type != 'delta_beta':
+            raise NotImplementedError('adorym_b200: binning > 1 is accelerated for delta_beta objects only')
         if self.forward_algorithm != 'fresnel':
             raise NotImplementedError('adorym_b200: forward_algorithm=%r' % (self.forward_algorithm,))
 
@@ -212,7 +213,12 @@ class ForwardModel(object):
     def _plan(self, dev, P, Nz, Y, X, free_prop_cm):
         cv = self.common_vars
         mode = _free_prop_mode(free_prop_cm)
-        key = (P, Nz, Y, X, mode, float(free_prop_cm) if mode == 'near' else 0., str(dev))
+        # binning (propagate.py:207-254): Nz object slices -> ceil(Nz / binning) propagation steps; pure_projection
+        # (propagate.py:158-186) is the single step that sums all slices, without any in-object propagation
+        obj_slices = Nz
+        binning = obj_slices if cv.get('pure_projection', False) else int(self.binning)
+        Nz = -(-obj_slices // binning)
+        key = (P, Nz, obj_slices, Y, X, mode, float(free_prop_cm) if mode == 'near' else 0., str(dev))
         plan = self._plans.get(key)
         if plan is None:
             ds_level = cv.get('ds_level', 1)
@@ -225,7 +231,8 @@ class ForwardModel(object):
             plan = ops.MultislicePlan(P, Nz, Y, X, ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k),
                                       cv['h'] if Nz > 1 else None, dev, sign_convention=self.sign_convention,
                                       unknown_type=self.unknown_type, free_prop=mode,
-                                      normalize_fft=self.normalize_fft, h_free=h_free)
+                                      normalize_fft=self.normalize_fft, h_free=h_free, binning=binning,
+                                      obj_slices=obj_slices)
             self._plans[key] = plan
         return plan
 

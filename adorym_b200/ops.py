@@ -70,12 +70,20 @@ class MultislicePlan(object):
     """Static description of one multislice configuration + prepared transfer functions (cached per model)."""
 
     def __init__(self, P, n_slices, Y, X, k1, h, device, sign_convention=1, unknown_type='delta_beta', free_prop='none',
-                 normalize_fft=False, h_free=None, allow_separable=True, h_gaps=None):
+                 normalize_fft=False, h_free=None, allow_separable=True, h_gaps=None, binning=1, obj_slices=None):
         """h: the in-object transfer function [P,P] (all gaps equal), or h_gaps: a list of n_slices-1 separable transfer
         functions, one per gap between consecutive slices (sparse multislice, propagate.py:479-534)."""
         if P not in SUPPORTED_P:
             raise NotImplementedError('adorym_b200: probe size %d is not supported yet (supported: %s)' % (P, SUPPORTED_P))
         self.P, self.n_slices, self.Y, self.X = int(P), int(n_slices), int(Y), int(X)
+        # binning (propagate.py:207-254): n_slices counts PROPAGATION steps = ceil(obj_slices / binning); each step's
+        # transmission is that of (delta, beta) summed over `binning` object slices (layout 'yxz' only)
+        self.binning = int(binning)
+        self.obj_slices = int(obj_slices) if obj_slices is not None else int(n_slices)
+        if self.binning < 1 or -(-self.obj_slices // self.binning) != self.n_slices:
+            raise ValueError('n_slices must equal ceil(obj_slices / binning)')
+        if self.binning > 1 and unknown_type != 'delta_beta':
+            raise NotImplementedError('adorym_b200: binning > 1 is accelerated for delta_beta objects only')
         self.k1 = float(k1)
         self.sign_convention = int(sign_convention)
         self.unknown_type = UNKNOWN_TYPES[unknown_type]
@@ -189,7 +197,10 @@ class MultisliceFn(torch.autograd.Function):
             raise RuntimeError('pos must be an int32 CUDA tensor [B, 2]')
         pos = pos.contiguous()
         P, Nz, Y, X = plan.P, plan.n_slices, plan.Y, plan.X
-        want = (Y, X, Nz, 2) if layout == 'yxz' else (Nz, Y, X, 2)
+        Zo = plan.obj_slices
+        want = (Y, X, Zo, 2) if layout == 'yxz' else (Nz, Y, X, 2)
+        if layout != 'yxz' and plan.binning != 1:
+            raise RuntimeError('binning needs the reference layout [Y,X,Z,2]')
         if tuple(obj.shape) != want:
             raise RuntimeError('object must be %s for layout %s, got %s' % (want, layout, tuple(obj.shape)))
         if layout != 'yxz' and (reg is not None or grid is not None):
@@ -203,8 +214,8 @@ class MultisliceFn(torch.autograd.Function):
         cfg = plan.cfg(B, M, per_pattern)
         tvol = torch.empty((Nz, Y, tvol_pitch(X), 2), dtype=torch.float32, device=dev)
         if layout == 'yxz':
-            call('adm_object_to_transmission', Y, X, Nz, ptr(obj), ptr(grid), plan.unknown_type, plan.k1,
-                 plan.sign_convention, ptr(tvol), stream_ptr())
+            call('adm_object_to_transmission', Y, X, Zo, ptr(obj), ptr(grid), plan.unknown_type, plan.k1,
+                 plan.sign_convention, plan.binning, ptr(tvol), stream_ptr())
         else:
             call('adm_transmission_fwd', plan.unknown_type, plan.k1, plan.sign_convention, Nz * Y, X, ptr(obj), ptr(tvol),
                  stream_ptr())
@@ -214,7 +225,7 @@ class MultisliceFn(torch.autograd.Function):
             w = _f32c(w) if w is not None else None
             reg = (w, float(ad or 0.), float(ab or 0.), float(gm or 0.))
             val = torch.zeros((1,), dtype=torch.float32, device=dev)
-            call('adm_regularizer_l1tv_scaled', Y, X, Nz, ptr(obj), ptr(w), reg[1], reg[2], reg[3], ptr(val), None, None, 0,
+            call('adm_regularizer_l1tv_scaled', Y, X, Zo, ptr(obj), ptr(w), reg[1], reg[2], reg[3], ptr(val), None, None, 0,
                  stream_ptr())
             reg_val = val[0]
         ckpt = torch.empty((B, M, Nz, P, P + 2, 2), dtype=torch.float32, device=dev)
@@ -247,6 +258,7 @@ class MultisliceFn(torch.autograd.Function):
         w = rest.pop(0) if (ctx.reg is not None and ctx.reg[0] is not None) else None
         plan = ctx.plan
         P, Nz, Y, X = plan.P, plan.n_slices, plan.Y, plan.X
+        Zo = plan.obj_slices
         dev = tvol.device
         g_det = _f32c(g_det)
         # margined gradient volume (ADM_GVOL_MARGIN in include/adorym_b200.h); the adjoint kernel reduce-adds into it
@@ -259,21 +271,21 @@ class MultisliceFn(torch.autograd.Function):
         g_obj = None
         if ctx.needs_input_grad[0]:
             if ctx.layout == 'yxz':
-                if OBJ_GRAD_OUT is not None and tuple(OBJ_GRAD_OUT.shape) == (Y, X, Nz, 2) and OBJ_GRAD_OUT.device == dev:
+                if OBJ_GRAD_OUT is not None and tuple(OBJ_GRAD_OUT.shape) == (Y, X, Zo, 2) and OBJ_GRAD_OUT.device == dev:
                     g_obj = OBJ_GRAD_OUT
                 else:
-                    g_obj = torch.empty((Y, X, Nz, 2), dtype=torch.float32, device=dev)
+                    g_obj = torch.empty((Y, X, Zo, 2), dtype=torch.float32, device=dev)
                 use_reg = ctx.reg is not None and g_reg is not None
                 gs = _f32c(g_reg.reshape(1)) if use_reg else None
                 slabs = []
                 for (y0, y1) in slab_ranges(Y, GRAD_SLABS):
                     if use_reg:
-                        call('adm_regularizer_l1tv_range', Y, X, Nz, ptr(obj), ptr(w), ctx.reg[1], ctx.reg[2], ctx.reg[3], None,
+                        call('adm_regularizer_l1tv_range', Y, X, Zo, ptr(obj), ptr(w), ctx.reg[1], ctx.reg[2], ctx.reg[3], None,
                              ptr(g_obj), ptr(gs), 0, y0, y1, stream_ptr())
                     else:
                         g_obj[y0:y1].zero_()
-                    call('adm_transmission_to_object_adj', Y, X, Nz, P, ptr(g_tvol), ptr(tvol), ptr(grid), plan.unknown_type,
-                         plan.k1, plan.sign_convention, ptr(g_obj), y0, y1, stream_ptr())
+                    call('adm_transmission_to_object_adj', Y, X, Zo, P, ptr(g_tvol), ptr(tvol), ptr(grid), plan.unknown_type,
+                         plan.k1, plan.sign_convention, plan.binning, ptr(g_obj), y0, y1, stream_ptr())
                     if GRAD_SLABS > 1:
                         ev = torch.cuda.Event()
                         ev.record()

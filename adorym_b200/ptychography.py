@@ -111,13 +111,13 @@ def reconstruct_ptychography(
         raise NotImplementedError('adorym_b200 has no CPU path (cpu_only=True); use the reference for CPU runs')
     if distribution_mode is not None:
         raise NotImplementedError('adorym_b200: distribution_mode=%r is replaced by NCCL data parallelism' % (distribution_mode,))
-    for name, val in (('use_epie', use_epie), ('pure_projection', pure_projection), ('xpu', xpu),
+    for name, val in (('use_epie', use_epie), ('xpu', xpu),
                       ('run_bfloat16', run_bfloat16), ('run_float64', run_float64),
                       ('fourier_disparity', fourier_disparity), ('dynamic_dropping', dynamic_dropping)):
         if val:
             raise NotImplementedError('adorym_b200: %s is not on the accelerated path' % name)
-    if multiscale_level != 1 or binning != 1 or forward_algorithm != 'fresnel' or interpolation != 'bilinear':
-        raise NotImplementedError('adorym_b200: multiscale_level / binning / forward_algorithm / interpolation option')
+    if multiscale_level != 1 or forward_algorithm != 'fresnel' or interpolation != 'bilinear':
+        raise NotImplementedError('adorym_b200: multiscale_level / forward_algorithm / interpolation option')
     if backend not in ('pytorch', 'autograd'):
         raise ValueError('backend')
     if not shared_probe_among_angles or not common_probe_pos:

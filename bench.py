@@ -443,7 +443,9 @@ def run_gpu_arm(args):
         sum_err, p2p_err = dp_check(torch, ab, runner, dev, rank, world)
         dp = {'max_abs_replica_difference': float(d.item()), 'allreduced_vs_summed_single_rank_gradient_rel': sum_err,
               'p2p_update_vs_allgather_sum_adam_max_abs': p2p_err,
-              'grad_slabs': _ops.GRAD_SLABS, 'update': 'p2p fused pull-reduce + Adam + push (adm_p2p_reduce_adam)'
+              'grad_slabs': _ops.GRAD_SLABS, 'update': 'p2p fused pull-reduce + Adam + push (adm_p2p_reduce_adam, %s)'
+              % ('NVLS multimem.ld_reduce / multimem.st' if runner.peer is not None and runner.peer.mc_x is not None
+                 else 'peer loads / stores')
               if runner.peer is not None else 'NCCL all-reduce (slab pipelined) + Adam'}
 
     # ---- secondary figure: the reference demo's own schedule (minibatch_size = 2, update after every minibatch,

@@ -159,15 +159,17 @@ int adm_rotate_adj(int Y, int X, int Z, const float* g_rot, const float* grid, f
 /* Object -> transmission volume in one pass (adm_rotate_fwd + adm_transmission_fwd without the intermediate rotated
  * volume): tvol [Z][Y][Xp][2] = T'( R_grid obj [Y][X][Z][2] ).  grid == NULL: no rotation, a pure
  * [Y][X][Z] -> [Z][Y][X] transposition (the object is already in the beam frame: rotate_out_of_loop,
- * ptychography.py:1011, or a single angle).                                                                    */
+ * ptychography.py:1011, or a single angle).  binning > 1 (propagate.py:207-254; delta_beta only): tvol has
+ * ceil(Z / binning) slices, each the transmission of the SUM of (delta, beta) over `binning` rotated object slices;
+ * binning == Z is the pure-projection model (propagate.py:158-186).                                              */
 int adm_object_to_transmission(int Y, int X, int Z, const float* obj, const float* grid, int unknown_type, float k1,
-                               int sign_convention, float* tvol, void* stream);
+                               int sign_convention, int binning, float* tvol, void* stream);
 /* Its transpose on the planes y in [y_begin, y_end) (adm_transmission_adj + adm_rotate_adj without the intermediate):
  * g_obj [Y][X][Z][2] += R^T chain(g_tvol, tvol).  g_obj is NOT cleared: initialise it with zeros or with the
  * regulariser gradient (adm_regularizer_l1tv_range, accumulate = 0).  tvol may be NULL for ADM_REAL_IMAG.        */
 int adm_transmission_to_object_adj(int Y, int X, int Z, int P, const float* g_tvol, const float* tvol, const float* grid,
-                                   int unknown_type, float k1, int sign_convention, float* g_obj, int y_begin, int y_end,
-                                   void* stream);
+                                   int unknown_type, float k1, int sign_convention, int binning, float* g_obj, int y_begin,
+                                   int y_end, void* stream);
 
 /* Fused Adam (optimizers.py:309-318) with optional epilogue.  In place on x, m, v (n floats each).
  *   step = i_batch of the reference (bias correction uses step+1); hyper-parameters are doubles (python floats):
@@ -184,10 +186,13 @@ int adm_adam_step(float* x, float* m, float* v, const float* g, long long n, dou
  * pointers -- every rank's object x [n] and gradient g [n] buffers, peer-mapped into this process (symmetric memory /
  * CUDA IPC); m, v: this rank's Adam moments [n] (only its shard is touched).  Rank r pulls its shard of every g (summed in
  * rank order), applies adm_adam_step's update to its shard of x and pushes the result into every rank's x.  The caller
- * must place a cross-GPU barrier before the call (all g complete) and after it (all pushes complete).  n % 4 == 0.   */
-int adm_p2p_reduce_adam(float* const* x_ptrs, const float* const* g_ptrs, int world, int rank, float* m, float* v,
-                        long long n, double step_size, double b1, double b2, double eps, int step, int flags,
-                        const float* mask, void* stream);
+ * must place a cross-GPU barrier before the call (all g complete) and after it (all pushes complete).  n % 4 == 0.
+ * x_multicast / g_multicast: NVLS multicast mappings of the same two symmetric buffers (both or neither; NULL = peer
+ * loads / stores): the pull then is ONE multimem.ld_reduce per 16 bytes (the switch adds the G copies, fp32) and the push
+ * ONE multimem.st (the switch replicates it), which halves the bytes on every link.                                  */
+int adm_p2p_reduce_adam(float* const* x_ptrs, const float* const* g_ptrs, float* x_multicast, const float* g_multicast,
+                        int world, int rank, float* m, float* v, long long n, double step_size, double b1, double b2,
+                        double eps, int step, int flags, const float* mask, void* stream);
 
 /* Gradient descent (optimizers.py:432-464: x <- x - step g) and momentum (optimizers.py:366-411: v <- gamma v + step g,
  * x <- x - v; v == NULL selects plain GD), in place, with the flags / mask epilogue of adm_adam_step.  The dynamic

@@ -211,7 +211,7 @@ def realign_image_fourier(a, shift, axes=(-2, -1)):
 def multislice_propagate_batch(grid_batch, probe, energy_ev, psize_cm, free_prop_cm=None, kernel=None,
                                fresnel_approx=True, binning=1, type='delta_beta', normalize_fft=False,
                                sign_convention=1, scale_ri_by_k=True, shift_exit_wave=None,
-                               return_intermediate=False, slice_pos_cm_ls=None):
+                               return_intermediate=False, slice_pos_cm_ls=None, pure_projection=False):
     """adorym/propagate.py:131-288 for pure_projection=False, kappa=None, repeating_slice=None.
 
     slice_pos_cm_ls given: sparse_multislice_propagate_batch (propagate.py:479-534) -- the propagation after slice i
@@ -239,6 +239,9 @@ def multislice_propagate_batch(grid_batch, probe, energy_ev, psize_cm, free_prop
     if psi.dim() == 2:
         psi = psi.unsqueeze(0).expand(grid_batch.shape[0], -1, -1)
     inter = []
+    if pure_projection:
+        # propagate.py:158-186 (delta_beta, not minus-logged, kappa None): one modulation by the line sums, no propagation
+        binning = n_slices
     n_steps = int(np.ceil(n_slices / binning))
     for i_step in range(n_steps):
         if return_intermediate:
@@ -327,7 +330,8 @@ def predict_ptycho(obj, probe_real, probe_imag, pos_batch, coord_old, cfg, probe
                                          normalize_fft=cfg.get('normalize_fft', False),
                                          sign_convention=cfg.get('sign_convention', 1),
                                          scale_ri_by_k=cfg.get('scale_ri_by_k', True),
-                                         slice_pos_cm_ls=cfg.get('slice_pos_cm_ls'))
+                                         slice_pos_cm_ls=cfg.get('slice_pos_cm_ls'),
+                                         pure_projection=cfg.get('pure_projection', False))
         if M == 1:
             # w.norm -> torch.norm(stack) (wrappers.py:1062-1067): zero subgradient at 0
             return torch.norm(torch.stack([psi.real, psi.imag], dim=0), dim=0)

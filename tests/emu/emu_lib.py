@@ -32,11 +32,12 @@ def ck(rc):
 def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *, unknown_type='delta_beta',
                        free_prop='inf', sign_convention=1, normalize_fft=False, loss='lsq', raw_data_type='magnitude',
                        poisson_multiplier=1.0, shift=None, reg=None, Hfree=None, separable=False, fused_chain=True,
-                       grad_slabs=1, weight_l1=None, beamstop=None, h_gaps=None):
+                       grad_slabs=1, weight_l1=None, beamstop=None, h_gaps=None, binning=1):
     """fused_chain: object -> transmission volume and back through the fused kernels (object_chain.cu), as
     ops.MultisliceFn layout 'yxz' does; False: the separate rotate / transmission kernels (rotate.cu, transmission.cu)."""
     L = emu()
-    Y, X, Z, _ = obj.shape
+    Y, X, Zfull, _ = obj.shape
+    Z = -(-Zfull // binning)          # propagation steps
     M, Pp, _ = probe_real.shape
     B = len(pos)
     obj = np.ascontiguousarray(obj, dtype='float32')
@@ -101,7 +102,8 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
     utype = 0 if unknown_type == 'delta_beta' else 1
     tvol = np.full((Z, Y, Xp, 2), np.nan, 'float32')
     if fused_chain:
-        ck(L.adm_object_to_transmission(Y, X, Z, P(obj), P(grid), utype, float(np.float32(k1)), sign_convention, P(tvol), None))
+        ck(L.adm_object_to_transmission(Y, X, Zfull, P(obj), P(grid), utype, float(np.float32(k1)), sign_convention, binning,
+                                        P(tvol), None))
     else:
         ck(L.adm_transmission_fwd(utype, float(np.float32(k1)), sign_convention, Z * Y, X, P(rot), P(tvol), None))
     ws = np.zeros(int(L.adm_multislice_workspace_bytes(Pp)), 'uint8')
@@ -148,16 +150,16 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
             if y1 <= y0:
                 continue
             if reg:
-                ck(L.adm_regularizer_l1tv_range(Y, X, Z, P(obj), P(wl1), float(reg.get('alpha_d') or 0.),
+                ck(L.adm_regularizer_l1tv_range(Y, X, Zfull, P(obj), P(wl1), float(reg.get('alpha_d') or 0.),
                                                 float(reg.get('alpha_b') or 0.), float(reg.get('gamma') or 0.), None, P(g_obj),
                                                 P(one), 0, y0, y1, None))
             else:
                 g_obj[y0:y1] = 0
-            ck(L.adm_transmission_to_object_adj(Y, X, Z, Pp, P(g_tvol), P(tvol), P(grid), utype, float(np.float32(k1)),
-                                                sign_convention, P(g_obj), y0, y1, None))
+            ck(L.adm_transmission_to_object_adj(Y, X, Zfull, Pp, P(g_tvol), P(tvol), P(grid), utype, float(np.float32(k1)),
+                                                sign_convention, binning, P(g_obj), y0, y1, None))
         if reg:
             val = np.zeros((1,), 'float32')
-            ck(L.adm_regularizer_l1tv_scaled(Y, X, Z, P(obj), P(wl1), float(reg.get('alpha_d') or 0.),
+            ck(L.adm_regularizer_l1tv_scaled(Y, X, Zfull, P(obj), P(wl1), float(reg.get('alpha_d') or 0.),
                                              float(reg.get('alpha_b') or 0.), float(reg.get('gamma') or 0.), P(val), None, None,
                                              0, None))
             out['loss'] += float(val[0])

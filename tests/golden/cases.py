@@ -83,6 +83,16 @@ CASES = {
                               psize_cm=0.67e-7, theta=0.0, n_theta=3, i_theta=0, pos=[(0, 0)], n_modes=1,
                               free_prop_cm=2e-5, unknown_type='real_imag', delta_scale=0.2, beta_scale=0.2, seed=25,
                               loss='lsq', raw_data_type='intensity', rotate_out_of_loop=True),
+    # binning = 3 over 50 slices (propagate.py:207-254: 17 propagation steps, the last bin holds two slices), rotation
+    'ptycho3d_p72_bin3': dict(kind='ptycho', obj_size=(48, 50, 50), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                              theta=0.9, n_theta=4, i_theta=2, pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=1,
+                              free_prop_cm='inf', unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=26,
+                              loss='lsq', raw_data_type='magnitude', binning=3),
+    # pure projection (propagate.py:158-186): one modulation by the line integrals, no in-object propagation
+    'ptycho3d_p72_pureproj': dict(kind='ptycho', obj_size=(48, 48, 48), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                                  theta=-0.6, n_theta=4, i_theta=1, pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=2,
+                                  free_prop_cm='inf', unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=27,
+                                  loss='lsq', raw_data_type='magnitude', optimize_probe=True, pure_projection=True),
     # sparse multislice (SparseMultisliceModel, forward_model.py:589-806): three thin slices at unequal positions, one
     # paraxial transfer function per gap; the object is handed over in the beam frame (rotate_out_of_loop)
     'sparse3_p72': dict(kind='sparse', obj_size=(90, 84, 3), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,

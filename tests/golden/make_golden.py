@@ -52,7 +52,7 @@ def run_reference(name):
     sign = c.get('sign_convention', 1)
     voxel_nm = np.array([c['psize_cm']] * 3) * 1e7
     lmbda_nm = 1240. / c['energy_ev']
-    h = get_kernel(voxel_nm[-1], lmbda_nm, voxel_nm, P, fresnel_approx=True, sign_convention=sign)
+    h = get_kernel(voxel_nm[-1] * c.get('binning', 1), lmbda_nm, voxel_nm, P, fresnel_approx=True, sign_convention=sign)
     B = len(inp['pos'])
     prj_full = np.zeros([n_theta, 16, P[0], P[1]], dtype='float32')
     prj_full[c['i_theta'], inp['this_ind_batch']] = inp['prj']
@@ -66,10 +66,11 @@ def run_reference(name):
         cv = dict(unknown_type=c['unknown_type'], normalize_fft=c.get('normalize_fft', False), sign_convention=sign,
                   rotate_out_of_loop=c.get('rotate_out_of_loop', False), scale_ri_by_k=True, is_minus_logged=False, forward_algorithm='fresnel',
                   stdout_options={'save_stdout': False, 'output_folder': tmp, 'timestamp': ''},
-                  poisson_multiplier=c.get('poisson_multiplier', 1.), common_probe_pos=True, binning=1, prj=prj_full,
+                  poisson_multiplier=c.get('poisson_multiplier', 1.), common_probe_pos=True, binning=c.get('binning', 1),
+                  prj=prj_full,
                   device_obj=None, lmbda_nm=lmbda_nm, voxel_nm=voxel_nm, probe_size=P, fresnel_approx=True,
                   two_d_mode=two_d, minibatch_size=B, ds_level=1, this_obj_size=[Y, X, Z], energy_ev=c['energy_ev'],
-                  psize_cm=c['psize_cm'], h=h, pure_projection=False, n_dp_batch=20, free_prop_cm=c['free_prop_cm'],
+                  psize_cm=c['psize_cm'], h=h, pure_projection=c.get('pure_projection', False), n_dp_batch=20, free_prop_cm=c['free_prop_cm'],
                   optimize_probe_defocusing=False, optimize_probe_pos_offset=False, optimize_prj_pos_offset=False,
                   optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=False, initial_tilt=None,
                   debug=False, output_folder=tmp, n_probe_modes=c['n_modes'], n_theta=n_theta,

@@ -29,9 +29,11 @@ def case_cfg(name):
     sign = c.get('sign_convention', 1)
     voxel_nm = np.array([c['psize_cm']] * 3) * 1e7
     lmbda_nm = 1240. / c['energy_ev']
-    h = orc.get_kernel(voxel_nm[-1], lmbda_nm, voxel_nm, c['probe_size'], fresnel_approx=True, sign_convention=sign)
+    h = orc.get_kernel(voxel_nm[-1] * c.get('binning', 1), lmbda_nm, voxel_nm, c['probe_size'], fresnel_approx=True,
+                       sign_convention=sign)
     cfg = dict(this_obj_size=[Y, X, Z], probe_size=list(c['probe_size']), energy_ev=c['energy_ev'], psize_cm=c['psize_cm'],
-               h=h, free_prop_cm=c['free_prop_cm'], unknown_type=c['unknown_type'], binning=1,
+               h=h, free_prop_cm=c['free_prop_cm'], unknown_type=c['unknown_type'], binning=c.get('binning', 1),
+               pure_projection=c.get('pure_projection', False),
                normalize_fft=c.get('normalize_fft', False), sign_convention=sign, scale_ri_by_k=True,
                fresnel_approx=True, optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), two_d_mode=(Z == 1),
                loss_function_type=c['loss'], raw_data_type=c['raw_data_type'],

@@ -24,10 +24,12 @@ def _common_vars(inp, cfg, dev, prj_full, theta_ls, n_theta):
                 sign_convention=c.get('sign_convention', 1), rotate_out_of_loop=c.get('rotate_out_of_loop', False),
                 scale_ri_by_k=True,
                 is_minus_logged=False, forward_algorithm='fresnel', stdout_options={},
-                poisson_multiplier=c.get('poisson_multiplier', 1.), common_probe_pos=True, binning=1, prj=prj_full,
+                poisson_multiplier=c.get('poisson_multiplier', 1.), common_probe_pos=True, binning=c.get('binning', 1),
+                prj=prj_full,
                 device_obj=dev, probe_size=list(c['probe_size']), fresnel_approx=True, two_d_mode=(Z == 1),
                 minibatch_size=len(inp['pos']), ds_level=1, this_obj_size=[Y, X, Z], energy_ev=c['energy_ev'],
-                psize_cm=c['psize_cm'], h=cfg['h'], pure_projection=False, n_dp_batch=20, free_prop_cm=c['free_prop_cm'],
+                psize_cm=c['psize_cm'], h=cfg['h'], pure_projection=c.get('pure_projection', False), n_dp_batch=20,
+                free_prop_cm=c['free_prop_cm'],
                 optimize_probe_defocusing=False, optimize_probe_pos_offset=False, optimize_prj_pos_offset=False,
                 optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=False, initial_tilt=None,
                 n_probe_modes=c['n_modes'], n_theta=n_theta, precalculate_rotation_coords=False, theta_ls=theta_ls,

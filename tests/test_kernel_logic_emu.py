@@ -28,6 +28,10 @@ def run_emu_case(name, separable=False, **kw):
     if inp['probe_pos_correction'] is not None:
         shift = inp['probe_pos_correction'][c['i_theta'], inp['this_ind_batch']]
     fp = 'inf' if c['free_prop_cm'] == 'inf' else ('none' if c['free_prop_cm'] in (0, None) else 'near')
+    if c.get('pure_projection', False):
+        kw = dict(kw, binning=Z)
+    elif c.get('binning', 1) > 1:
+        kw = dict(kw, binning=c['binning'])
     if c.get('slice_pos_cm') is not None:
         gaps = np.diff(np.array(c['slice_pos_cm'])) * 1e7
         kw = dict(kw, h_gaps=[orc.get_kernel(float(g), 1240. / c['energy_ev'], np.array([voxel_nm] * 3), c['probe_size'])
@@ -43,7 +47,7 @@ def run_emu_case(name, separable=False, **kw):
 @pytest.mark.parametrize('name', ['ptycho2d_modes', 'ptycho2d_realimag_p64', 'fullfield64', 'ptycho3d_p72',
                                   'ptycho3d_p72_poisson', 'ptycho3d_p72_edge', 'ptycho3d_p72_exitwave',
                                   'ptycho3d_p72_strongreg', 'ptycho3d_p72_rwl1', 'ptycho3d_p72_beamstop',
-                                  'sparse3_p72'])
+                                  'sparse3_p72', 'ptycho3d_p72_bin3', 'ptycho3d_p72_pureproj'])
 def test_emulated_kernels_match_oracle_and_golden(name):
     # the separable-H path (Fresnel kernel in two shared-memory tables) on the 3-D P=72 cases, the general-H path elsewhere
     inp, out = run_emu_case(name, separable=name.startswith('ptycho3d'))
@@ -146,3 +150,36 @@ def test_emulated_adam_matches_reference_golden_bitwise():
         assert np.array_equal(m, gold['m%d' % i])
         assert np.array_equal(v, gold['v%d' % i])
         np.testing.assert_allclose(x, gold['x%d' % i], rtol=2e-7, atol=0)
+
+
+def test_emulated_peer_memory_update_equals_allreduce_plus_adam():
+    """adm_p2p_reduce_adam (the data-parallel object update over NVLink peer memory): three emulated ranks, each pulling
+    its shard of every rank's gradient, applying Adam and pushing the shard into every rank's object, must leave every
+    copy of the object equal -- bit for bit -- to rank-ordered sum + adm_adam_step on the whole volume."""
+    import ctypes
+    L = emu_lib.emu()
+    P = emu_lib.P
+    rs = np.random.RandomState(8)
+    world, n = 3, 4 * 1234
+    x0 = (rs.normal(size=n) * 1e-3).astype('float32')
+    gs = [(rs.normal(size=n) * 10.0 ** rs.uniform(-6, 0, size=n)).astype('float32') for _ in range(world)]
+    mask = (rs.uniform(size=n // 2) > 0.3).astype('float32')
+    # reference: sum in rank order, one Adam step with the epilogue (clip + mask)
+    gsum = gs[0].copy()
+    for g in gs[1:]:
+        gsum = gsum + g
+    xr, mr, vr = x0.copy(), np.zeros(n, 'float32'), np.zeros(n, 'float32')
+    assert L.adm_adam_step(P(xr), P(mr), P(vr), P(gsum), n, 1e-3, 0.9, 0.999, 1e-7, 2, 1, P(mask), None) == 0
+    xs = [x0.copy() for _ in range(world)]
+    ms = [np.zeros(n, 'float32') for _ in range(world)]
+    vs = [np.zeros(n, 'float32') for _ in range(world)]
+    xp = (ctypes.c_void_p * world)(*[a.ctypes.data for a in xs])
+    gp = (ctypes.c_void_p * world)(*[a.ctypes.data for a in gs])
+    for r in range(world):
+        rc = L.adm_p2p_reduce_adam(ctypes.cast(xp, ctypes.c_void_p), ctypes.cast(gp, ctypes.c_void_p), None, None, world, r,
+                                   P(ms[r]), P(vs[r]), n, 1e-3, 0.9, 0.999, 1e-7, 2, 1, P(mask), None)
+        assert rc == 0
+    for r in range(world):
+        assert np.array_equal(xs[r], xr), r
+        i0, i1 = 4 * ((n // 4) * r // world), 4 * ((n // 4) * (r + 1) // world)
+        assert np.array_equal(ms[r][i0:i1], mr[i0:i1]) and np.array_equal(vs[r][i0:i1], vr[i0:i1])

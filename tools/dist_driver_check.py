@@ -25,7 +25,6 @@ for mode in ('p2p', 'nccl', 'nccl1'):
     os.environ['ADM_DP'] = mode[:4]
     os.environ['ADM_GRAD_SLABS'] = '1' if mode == 'nccl1' else '4'
     params = driver_params('driver_immediate')
-    params['minibatch_size'] = 1 if world > 2 else 2
     r = ab.reconstruct_ptychography(data, **params, finite_support_mask_path=driver_mask(), verbose=False, save_outputs=False,
                                     output_folder='/tmp/adm_dist_check_%s_%d' % (mode, rank))
     res[mode] = r
