@@ -70,8 +70,10 @@ ADM_DEV void oc_xz(int& x, int& z) {
 
 // `bin` > 1 (propagate.py:207-254, `binning`): output slice zb is the transmission of the SUM of (delta, beta) over the
 // object slices zb*bin .. zb*bin + bin - 1 (delta_beta objects); z counts OUTPUT slices, Zo = ceil(Z / bin).
-__global__ void __launch_bounds__(128) k_object_to_transmission(int Y, int X, int Z, int Xp, const cpx* obj, const float* grid,
-                                                                int unknown_type, float k1, float sgn, cpx* tvol, int bin) {
+template <bool BIN1> __global__ void __launch_bounds__(128) k_object_to_transmission(int Y, int X, int Z, int Xp, const cpx* obj,
+                                                                                     const float* grid, int unknown_type, float k1,
+                                                                                     float sgn, cpx* tvol, int bin_) {
+    const int bin = BIN1 ? 1 : bin_;
     int x, zb;
     oc_xz(x, zb);
     const int Zo = (Z + bin - 1) / bin;
@@ -99,7 +101,7 @@ __global__ void __launch_bounds__(128) k_object_to_transmission(int Y, int X, in
                 r.x = a[k].x * t.w00 + b[k].x * t.w01 + c[k].x * t.w10 + d[k].x * t.w11;
                 r.y = a[k].y * t.w00 + b[k].y * t.w01 + c[k].y * t.w10 + d[k].y * t.w11;
             }
-            if (bin == 1) acc[k] = r;
+            if (BIN1) acc[k] = r;
             else { acc[k].x += r.x; acc[k].y += r.y; }
         }
     }
@@ -181,8 +183,12 @@ extern "C" int adm_object_to_transmission(int Y, int X, int Z, const float* obj,
     if (rc) return rc;
     const int Zo = (Z + binning - 1) / binning;
     dim3 gr((X + OC_TX - 1) / OC_TX, (Zo + OC_TZ - 1) / OC_TZ, (Y + OC_YCHUNK - 1) / OC_YCHUNK);
-    ADM_LAUNCH(k_object_to_transmission, gr, 128, 0, stream, Y, X, Z, ADM_TVOL_PITCH(X), (const cpx*)obj, grid, unknown_type,
-               k1, (float)sign_convention, (cpx*)tvol, binning);
+    if (binning == 1)
+        ADM_LAUNCH(k_object_to_transmission<true>, gr, 128, 0, stream, Y, X, Z, ADM_TVOL_PITCH(X), (const cpx*)obj, grid,
+                   unknown_type, k1, (float)sign_convention, (cpx*)tvol, 1);
+    else
+        ADM_LAUNCH(k_object_to_transmission<false>, gr, 128, 0, stream, Y, X, Z, ADM_TVOL_PITCH(X), (const cpx*)obj, grid,
+                   unknown_type, k1, (float)sign_convention, (cpx*)tvol, binning);
     return ADM_OK;
 }
 
