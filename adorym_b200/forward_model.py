@@ -622,7 +622,8 @@ class MultiDistModel(ForwardModel):
     def _detector_fields(self, obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj):
         cv = self.common_vars
         self._check_unsupported(['optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
-                                 'optimize_free_prop', 'optimize_prj_affine', 'optimize_ctf_lg_kappa'])
+                                 'optimize_prj_affine', 'optimize_ctf_lg_kappa'])
+        refine_dist = bool(cv.get('optimize_free_prop', False))
         if safe_zone_width not in (0, None):
             raise NotImplementedError('adorym_b200: MultiDistModel with safe_zone_width > 0 is not accelerated yet')
         dists = [float(d) for d in np.asarray(free_prop_cm.detach().cpu() if torch.is_tensor(free_prop_cm) else free_prop_cm)]
@@ -642,8 +643,18 @@ class MultiDistModel(ForwardModel):
                 raise NotImplementedError('adorym_b200: large-frame MultiDistModel needs a single object slice (two_d_mode)')
             if any(d <= 0 for d in dists):
                 raise NotImplementedError('adorym_b200: MultiDistModel needs positive propagation distances')
+            if refine_dist:
+                # refinable distances (optimize_free_prop): in-graph paraxial transfer functions + analytic dL/d dist
+                psize_cm = cv['psize_cm'] * cv.get('ds_level', 1)
+                geom = dict(N=P, k1=ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k),
+                            sign_convention=self.sign_convention, unknown_type=self.unknown_type,
+                            lmbda_nm=1240. / cv['energy_ev'], voxel_nm=psize_cm * 1.e7)
+                fp = free_prop_cm if torch.is_tensor(free_prop_cm) else torch.tensor(dists, dtype=torch.float32, device=dev)
+                return ops.MultiDistRefineFn.apply(obj.reshape(P, P, 2), probe, fp, geom)
             plan = self._md_plan(dev, P, dists)
             return ops.MultiDistFn.apply(obj.reshape(P, P, 2), probe, plan)      # [n_dists, M, P, P, 2]
+        if refine_dist:
+            raise NotImplementedError('adorym_b200: optimize_free_prop needs large-frame sizes (128 .. 2048 pixels)')
         pos_t = torch.zeros((1, 2), dtype=torch.int32, device=dev)
         dets = []
         for d in dists:

@@ -590,6 +590,71 @@ class MultiDistFn(torch.autograd.Function):
         return g_obj, g_probe, None
 
 
+class MultiDistRefineFn(torch.autograd.Function):
+    """MultiDistFn with REFINABLE propagation distances (optimize_free_prop: propagate.py:271-276 ->
+    fresnel_propagate_wrapped :556-568 -> get_kernel_wrapped :84-103, the paraxial kernel as a differentiable function of
+    the distance): det[d] = IFFT2(H(dist_d) . FFT2(probe . T(obj))), H(dist) = exp(-i s pi lambda dist (u^2 + v^2)).
+
+    The transfer functions are rebuilt on the device from the current distances (fp32, like the reference's in-graph H);
+    dL/d dist_d = Re sum conj(g_det) . IFFT2(i phi' H_d F) = sum g_det . IFFT2(i phi' FFT2(det_d)), phi' = d phase / d dist:
+    one more fused large-frame pass per distance on the detector field itself (vacuum object, transfer function i phi')."""
+
+    @staticmethod
+    def forward(ctx, obj2d, probe, dists_cm, geom):
+        """geom: dict(N, k1, sign_convention, unknown_type, lmbda_nm, voxel_nm)"""
+        obj2d, probe = _f32c(obj2d), _f32c(probe)
+        N = int(geom['N'])
+        dev = obj2d.device
+        M, D = probe.shape[0], int(dists_cm.numel())
+        order = lf_spectrum_order(N, dev).long()
+        f = torch.fft.fftfreq(N, device=dev, dtype=torch.float32)[order] / float(geom['voxel_nm'])
+        u2v2 = (f * f)[:, None] + (f * f)[None, :]
+        dphi = (-float(geom['sign_convention']) * PI * float(geom['lmbda_nm'])) * u2v2          # phase per nm of distance
+        ph = (dists_cm.detach().to(dev, torch.float32) * 1e7)[:, None, None] * dphi[None]
+        Hp = (torch.stack([torch.cos(ph), torch.sin(ph)], -1) * (1.0 / (N * N))).contiguous()
+        cfg = _lib.MultiDistCfg(N=N, M=int(M), D=D, k1=float(geom['k1']), sign_convention=int(geom['sign_convention']),
+                                unknown_type=UNKNOWN_TYPES[geom['unknown_type']])
+        work1 = torch.empty((M, N, N, 2), dtype=torch.float32, device=dev)
+        det = torch.empty((D, M, N, N, 2), dtype=torch.float32, device=dev)
+        call('adm_multidist_fwd', ctypes.byref(cfg), ptr(obj2d), ptr(probe), ptr(Hp), ptr(work1), ptr(det), stream_ptr())
+        ctx.cfg, ctx.geom = cfg, geom
+        ctx.save_for_backward(obj2d, probe, Hp, det, dphi)
+        return det
+
+    @staticmethod
+    def backward(ctx, g_det):
+        obj2d, probe, Hp, det, dphi = ctx.saved_tensors
+        cfg, geom = ctx.cfg, ctx.geom
+        N, M, D = cfg.N, cfg.M, cfg.D
+        dev = obj2d.device
+        g_det = _f32c(g_det)
+        g_obj = g_probe = g_dist = None
+        if ctx.needs_input_grad[0] or ctx.needs_input_grad[1]:
+            Hc = (Hp * torch.tensor([1.0, -1.0], device=dev)).contiguous()
+            work1 = torch.empty((M, N, N, 2), dtype=torch.float32, device=dev)
+            work2 = torch.empty((D, M, N, N, 2), dtype=torch.float32, device=dev)
+            g_obj = torch.empty_like(obj2d) if ctx.needs_input_grad[0] else None
+            g_probe = torch.empty_like(probe) if ctx.needs_input_grad[1] else None
+            call('adm_multidist_bwd', ctypes.byref(cfg), ptr(obj2d), ptr(probe), ptr(Hc), ptr(g_det), ptr(work1), ptr(work2),
+                 ptr(g_obj), ptr(g_probe), stream_ptr())
+        if ctx.needs_input_grad[2]:
+            # d det_d / d dist = IFFT2(i phi' FFT2(det_d)): the large-frame pass with a vacuum object and H = i phi'
+            Hd = torch.stack([torch.zeros_like(dphi), dphi], -1).unsqueeze(0).mul(1.0 / (N * N)).contiguous()
+            vac = torch.zeros((N, N, 2), dtype=torch.float32, device=dev)
+            if geom['unknown_type'] == 'real_imag':
+                vac[..., 0] = 1.0
+            cfg1 = _lib.MultiDistCfg(N=N, M=M, D=1, k1=cfg.k1, sign_convention=cfg.sign_convention, unknown_type=cfg.unknown_type)
+            work1 = torch.empty((M, N, N, 2), dtype=torch.float32, device=dev)
+            dd = torch.empty((1, M, N, N, 2), dtype=torch.float32, device=dev)
+            gd = []
+            for d in range(D):
+                call('adm_multidist_fwd', ctypes.byref(cfg1), ptr(vac), ptr(det[d].contiguous()), ptr(Hd), ptr(work1), ptr(dd),
+                     stream_ptr())
+                gd.append((g_det[d].double() * dd[0].double()).sum())
+            g_dist = (torch.stack(gd) * 1e7).to(torch.float32)              # per cm
+        return g_obj, g_probe, g_dist, None
+
+
 class FrameShiftFn(torch.autograd.Function):
     """out[F,N,N] = Re realign_image_fourier(data[F,N,N], shift[F,2]) (util.py:380-397; forward_model.py:1079-1088)."""
 

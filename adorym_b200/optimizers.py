@@ -137,9 +137,9 @@ class MomentumOptimizer(Optimizer):
 # ------------------------------------------------------------------------------------------------------
 # parameter plumbing                                                     adorym/optimizers.py:793-1089
 # ------------------------------------------------------------------------------------------------------
-_SUPPORTED_PARAM_SWITCHES = ('optimize_probe', 'optimize_all_probe_pos')
+_SUPPORTED_PARAM_SWITCHES = ('optimize_probe', 'optimize_all_probe_pos', 'optimize_free_prop')
 _UNSUPPORTED_PARAM_SWITCHES = ('optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
-                               'optimize_slice_pos', 'optimize_free_prop', 'optimize_tilt', 'optimize_prj_affine',
+                               'optimize_slice_pos', 'optimize_tilt', 'optimize_prj_affine',
                                'optimize_ctf_lg_kappa')
 
 
@@ -178,6 +178,18 @@ def create_and_initialize_parameter_optimizers(optimizable_params, kwargs):
         opt_pos.set_index_in_grad_return(len(opt_args_ls))
         opt_args_ls.append(forward_model.get_argument_index('probe_pos_correction'))
         opt_ls.append(opt_pos)
+    if kwargs.get('optimize_free_prop', False):
+        # adorym/optimizers.py:906-917
+        if kwargs.get('optimizer_free_prop') is not None:
+            opt_fp = kwargs['optimizer_free_prop']
+            opt_fp.name = 'free_prop_cm'
+        else:
+            opt_fp = AdamOptimizer('free_prop_cm', output_folder=output_folder,
+                                   options_dict={'step_size': kwargs['free_prop_learning_rate']}, forward_model=forward_model)
+        opt_fp.create_param_arrays(list(optimizable_params['free_prop_cm'].shape), device=device_obj)
+        opt_fp.set_index_in_grad_return(len(opt_args_ls))
+        opt_args_ls.append(forward_model.get_argument_index('free_prop_cm'))
+        opt_ls.append(opt_fp)
     return opt_ls, opt_args_ls
 
 
@@ -233,5 +245,10 @@ def update_parameters(opt_ls, optimizable_params, kwargs):
                     ppc = ppc - ppc.mean(dim=dims)
                     optimizable_params['probe_pos_correction'] = ppc.requires_grad_(True)
             else:
-                raise NotImplementedError('adorym_b200: parameter %s' % opt.name)
+                # adorym/optimizers.py:1077-1083: plain Adam on any other refinable parameter (free_prop_cm, ...)
+                with torch.no_grad():
+                    opt.grads = comm.allreduce(opt.grads)
+                    var = optimizable_params[opt.name].detach().clone().contiguous()
+                    var = opt.apply_gradient(var, opt.grads, i_full_angle, **opt.options_dict)
+                    optimizable_params[opt.name] = var.requires_grad_(True)
     return optimizable_params

@@ -347,6 +347,10 @@ def reconstruct_ptychography(
     optimizable_params['probe_pos_correction'] = torch.tensor(ppc0, dtype=torch.float32, device=device_obj,
                                                               requires_grad=bool(optimize_all_probe_pos))
     optimizable_params['prj_affine_ls'] = torch.tensor(prj_affine_ls, dtype=torch.float32, device=device_obj)
+    if is_multi_dist and optimize_free_prop:
+        # ptychography.py:709-710: the propagation distances become a refinable tensor
+        optimizable_params['free_prop_cm'] = torch.tensor(np.asarray(free_prop_cm, dtype='float64'), dtype=torch.float32,
+                                                          device=device_obj, requires_grad=True)
     opt_ls, opt_args_ls = create_and_initialize_parameter_optimizers(optimizable_params, locals())
 
     diff = Differentiator()

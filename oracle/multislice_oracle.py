@@ -359,9 +359,26 @@ def predict_multidist(obj, probe_real, probe_imag, free_prop_cm_ls, cfg):
     probe = torch.complex(probe_real, probe_imag)
     M = probe.shape[0]
     out = []
+    refine = cfg.get('optimize_free_prop', False)
+    if refine:
+        # in-graph paraxial kernel (propagate.py:84-103 get_kernel_wrapped with u_free, v_free of ptychography.py:320-323)
+        voxel_nm = np.array([cfg['psize_cm']] * 3) * 1.e7
+        uu, vv = gen_freq_mesh(voxel_nm, obj.shape[0:2])
+        u2v2 = torch.tensor(uu ** 2 + vv ** 2).to(obj.dtype)
+        lmbda_nm = 1240. / cfg['energy_ev']
     for dist in free_prop_cm_ls:
         ex_int = None
         for m in range(M):
+            if refine:
+                psi = multislice_propagate_batch(obj.unsqueeze(0), probe[m].unsqueeze(0), cfg['energy_ev'], cfg['psize_cm'],
+                                                 free_prop_cm=None, kernel=cfg.get('h'), type=cfg.get('unknown_type', 'delta_beta'),
+                                                 sign_convention=cfg.get('sign_convention', 1),
+                                                 scale_ri_by_k=cfg.get('scale_ri_by_k', True))
+                ph = -cfg.get('sign_convention', 1) * PI * lmbda_nm * (dist * 1e7) * u2v2
+                psi = torch.fft.ifft2(torch.fft.fft2(psi) * torch.complex(torch.cos(ph), torch.sin(ph)))
+                i2 = psi.real ** 2 + psi.imag ** 2
+                ex_int = i2 if ex_int is None else ex_int + i2
+                continue
             psi = multislice_propagate_batch(obj.unsqueeze(0), probe[m].unsqueeze(0), cfg['energy_ev'], cfg['psize_cm'],
                                              free_prop_cm=float(dist), kernel=cfg.get('h'),
                                              fresnel_approx=cfg.get('fresnel_approx', True), binning=cfg.get('binning', 1),
@@ -422,6 +439,10 @@ def multidist_loss_and_grads(obj, probe_real, probe_imag, free_prop_cm_ls, prj_a
     leaves = {'obj': obj.clone().requires_grad_('obj' in want),
               'probe_real': probe_real.clone().requires_grad_('probe_real' in want),
               'probe_imag': probe_imag.clone().requires_grad_('probe_imag' in want)}
+    if 'free_prop_cm' in want:
+        leaves['free_prop_cm'] = torch.as_tensor(np.asarray(free_prop_cm_ls, dtype='float64')).to(obj.dtype).requires_grad_(True)
+        free_prop_cm_ls = leaves['free_prop_cm']
+        cfg = dict(cfg, optimize_free_prop=True)
     pred = predict_multidist(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], free_prop_cm_ls, cfg)
     prj = prj_abs
     if probe_pos_correction is not None:

@@ -192,6 +192,10 @@ MD_CASES = {
     'multidist128_probe': dict(N=128, energy_ev=17500., psize_cm=1e-4, dists=[30., 70.], n_modes=1,
                                unknown_type='delta_beta', delta_scale=2e-7, beta_scale=2e-8, seed=32, loss='lsq',
                                raw_data_type='magnitude', shift=False, optimize_probe=True),
+    # refinable propagation distances (optimize_free_prop: in-graph transfer function, propagate.py:84-103,271-276)
+    'multidist128_dist': dict(N=128, energy_ev=17500., psize_cm=1e-4, dists=[35., 62.], n_modes=1,
+                              unknown_type='real_imag', delta_scale=0.4, beta_scale=0.3, seed=33, loss='lsq',
+                              raw_data_type='intensity', shift=False, optimize_probe=False, free_prop=True),
 }
 
 

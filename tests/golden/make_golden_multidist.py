@@ -40,10 +40,14 @@ def run_reference(name):
                   ds_level=1, this_obj_size=[N, N, 1], energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=None,
                   pure_projection=False, n_dp_batch=1, free_prop_cm=c['dists'], optimize_probe_defocusing=False,
                   optimize_probe_pos_offset=False, optimize_prj_pos_offset=False, optimize_all_probe_pos=c['shift'],
-                  optimize_free_prop=False, optimize_prj_affine=False, optimize_ctf_lg_kappa=False, optimize_tilt=False,
+                  optimize_free_prop=c.get('free_prop', False), optimize_prj_affine=False, optimize_ctf_lg_kappa=False, optimize_tilt=False,
                   initial_tilt=None, debug=False, output_folder=tmp, n_probe_modes=M, n_theta=1,
                   precalculate_rotation_coords=False, theta_ls=np.zeros(1, 'float32'), theta_downsample=None,
                   beamstop=None, u_free=None, v_free=None)
+        if c.get('free_prop', False):
+            from adorym.propagate import gen_freq_mesh
+            uf, vf = gen_freq_mesh(voxel_nm, [N, N])              # ptychography.py:320-323
+            cv['u_free'], cv['v_free'] = w.create_variable(uf, requires_grad=False), w.create_variable(vf, requires_grad=False)
         fm = MultiDistModel(loss_function_type=c['loss'], distribution_mode=None, device=None, common_vars_dict=cv,
                             raw_data_type=c['raw_data_type'])
         obj = w.create_variable(inp['obj'], requires_grad=True)
@@ -55,7 +59,12 @@ def run_reference(name):
                     this_pos_batch=np.array([[0, 0]]), prj=prj_full, probe_pos_correction=ppc, this_ind_batch=np.array([0]),
                     free_prop_cm=c['dists'], safe_zone_width=0, prj_affine_ls=None, ctf_lg_kappa=None,
                     prj_pos_offset=w.zeros([1, 2], requires_grad=True))
+        if c.get('free_prop', False):
+            args['free_prop_cm'] = w.create_variable(np.array(c['dists']), requires_grad=True)
         opt_args, names = [0], ['obj']
+        if c.get('free_prop', False):
+            opt_args += [fm.get_argument_index('free_prop_cm')]
+            names += ['free_prop_cm']
         if c['optimize_probe']:
             opt_args += [fm.get_argument_index('probe_real'), fm.get_argument_index('probe_imag')]
             names += ['probe_real', 'probe_imag']
@@ -73,7 +82,7 @@ def run_reference(name):
             if n == 'obj':
                 for k, v in compact_grad(g).items():
                     out['gobj_' + k] = v
-            elif n == 'probe_pos_correction':
+            elif n in ('probe_pos_correction', 'free_prop_cm'):
                 out['g_' + n] = g.astype('float32')
             else:
                 out['g_' + n + '_sub'] = g[:, ::4, ::4].astype('float32')

@@ -93,6 +93,8 @@ def run_md_oracle_case(name, dtype=torch.float32):
     if inp['probe_pos_correction'] is not None:
         ppc = torch.tensor(inp['probe_pos_correction']).to(dtype)
         want += ['probe_pos_correction']
+    if c.get('free_prop', False):
+        want += ['free_prop_cm']
     loss, pred, grads = orc.multidist_loss_and_grads(
         torch.tensor(inp['obj']).to(dtype), torch.tensor(inp['probe_real']).to(dtype),
         torch.tensor(inp['probe_imag']).to(dtype), c['dists'], torch.tensor(inp['prj']).to(dtype), cfg,
@@ -113,3 +115,5 @@ def check_md_against_golden(gold, loss, pred, grads, tol=1e-4, gtol=1e-4):
             assert rel_err(grads[k][:, ::4, ::4], gold['g_' + k + '_sub']) < gtol, k
     if 'g_probe_pos_correction' in gold.files:
         assert rel_err(grads['probe_pos_correction'], gold['g_probe_pos_correction']) < gtol
+    if 'g_free_prop_cm' in gold.files:
+        assert rel_err(grads['free_prop_cm'], gold['g_free_prop_cm']) < gtol

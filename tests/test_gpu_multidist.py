@@ -24,7 +24,7 @@ def md_common_vars(c, dev, prj_full, shift):
                 subprobe_size=[N, N], fresnel_approx=True, two_d_mode=True, minibatch_size=1, ds_level=1,
                 this_obj_size=[N, N, 1], energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=None, pure_projection=False,
                 n_dp_batch=1, free_prop_cm=c['dists'], optimize_probe_defocusing=False, optimize_probe_pos_offset=False,
-                optimize_prj_pos_offset=False, optimize_all_probe_pos=shift, optimize_free_prop=False,
+                optimize_prj_pos_offset=False, optimize_all_probe_pos=shift, optimize_free_prop=c.get('free_prop', False),
                 optimize_prj_affine=False, optimize_ctf_lg_kappa=False, optimize_tilt=False, initial_tilt=None,
                 n_probe_modes=c['n_modes'], n_theta=1, precalculate_rotation_coords=False,
                 theta_ls=np.zeros(1, 'float32'), theta_downsample=None, beamstop=None, u_free=None, v_free=None)
@@ -54,6 +54,10 @@ def run_gpu_md(inp, want_probe, prj_on_device=False):
     if shift:
         opt += [fm.get_argument_index('probe_pos_correction')]
         names += ['probe_pos_correction']
+    if c.get('free_prop', False):
+        args['free_prop_cm'] = torch.tensor(c['dists'], dtype=torch.float32, device=dev, requires_grad=True)
+        opt += [fm.get_argument_index('free_prop_cm')]
+        names += ['free_prop_cm']
     diff = ab.Differentiator()
     diff.create_loss_node(fm.get_loss_function(), opt)
     grads = diff.get_gradients(**args)
