@@ -269,6 +269,9 @@ ADM_DEV float sgnf(float a) { return (a > 0.f) ? 1.f : ((a < 0.f) ? -1.f : 0.f);
 // One warp per (y, x) row, lanes along z (the contiguous axis of obj [Y][X][Z][2]): no per-element index division; the
 // six TV neighbours are the same lane of four other rows and the two neighbouring lanes.  g_scale (device scalar or
 // null) multiplies the gradient (the upstream gradient of the loss node); accumulate = 0 writes g_obj, 1 adds to it.
+// WANT_V / WANT_G: compile-time "value wanted" / "gradient wanted" (the two launches of a step want one each; the kernel
+// is issue-bound -- ncu: 70 % issue slots on the gradient pass -- so the unused half of the arithmetic is compiled out).
+template <bool WANT_V, bool WANT_G>
 __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx* __restrict__ obj, const cpx* __restrict__ wl1,
                                                   float ad, float ab, float gm, float* value, cpx* g_obj,
                                                   const float* g_scale, int accumulate, long long row_begin,
@@ -280,7 +283,7 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
 #endif
     const long long N = (long long)Y * X * Z;
     const float invN = 1.0f / (float)N;
-    const float gs = (g_scale != nullptr) ? *g_scale : 1.0f;
+    const float gs = (WANT_G && g_scale != nullptr) ? *g_scale : 1.0f;
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, wpb = blockDim.x >> 5;
     const size_t sx = (size_t)Z, sy = (size_t)X * Z;
     float acc = 0.f;
@@ -295,25 +298,35 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
             const cpx c = r0[z];
             float w0 = 1.f, w1 = 1.f;
             if (wl1 != nullptr) { cpx w = wl1[(size_t)row * sx + z]; w0 = w.x; w1 = w.y; }
-            float gd = ad * w0 * sgnf(c.x) * invN;
-            float gb = ab * w1 * sgnf(c.y) * invN;
-            acc += (ad * w0 * fabsf(c.x) + ab * w1 * fabsf(c.y)) * invN;
+            // the arithmetic keeps the operation order of the single-kernel version (bit-identical results)
+            float gd = 0.f, gb = 0.f;
+            if (WANT_G) { gd = ad * w0 * sgnf(c.x) * invN; gb = ab * w1 * sgnf(c.y) * invN; }
+            if (WANT_V) acc += (ad * w0 * fabsf(c.x) + ab * w1 * fabsf(c.y)) * invN;
             if (gm != 0.f) {
                 // TV: sum over the three axes of |roll(a, 1) - a| / N (periodic), per channel
-                cpx a = rym[z], b = ryp[z];
-                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-                a = rxm[z]; b = rxp[z];
-                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
-                a = r0[(z + Z - 1) % Z]; b = r0[(z + 1) % Z];
-                acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
-                gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
-                gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                cpx a = rym[z], b;
+                if (WANT_V) acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                if (WANT_G) {
+                    b = ryp[z];
+                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                }
+                a = rxm[z];
+                if (WANT_V) acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                if (WANT_G) {
+                    b = rxp[z];
+                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                }
+                a = r0[(z + Z - 1) % Z];
+                if (WANT_V) acc += gm * (fabsf(a.x - c.x) + fabsf(a.y - c.y)) * invN;
+                if (WANT_G) {
+                    b = r0[(z + 1) % Z];
+                    gd += gm * (sgnf(c.x - a.x) + sgnf(c.x - b.x)) * invN;
+                    gb += gm * (sgnf(c.y - a.y) + sgnf(c.y - b.y)) * invN;
+                }
             }
-            if (g_obj != nullptr) {
+            if (WANT_G) {
                 cpx* o = g_obj + (size_t)row * sx + z;
                 cpx r = mk(gd * gs, gb * gs);
                 if (accumulate) { cpx t = *o; r.x += t.x; r.y += t.y; }
@@ -321,13 +334,15 @@ __global__ void __launch_bounds__(256) k_reg_l1tv(int Y, int X, int Z, const cpx
             }
         }
     }
-    red[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
-        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    if (WANT_V) {
+        red[threadIdx.x] = acc;
         __syncthreads();
+        for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+            if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) atomicAdd(value, red[0]);
     }
-    if (threadIdx.x == 0 && value != nullptr) atomicAdd(value, red[0]);
 }
 
 extern "C" int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj, const float* weight_l1, float alpha_d,
@@ -338,8 +353,13 @@ extern "C" int adm_regularizer_l1tv_range(int Y, int X, int Z, const float* obj,
     long long rows = (long long)(y_end - y_begin) * X;
     long long blocks = (rows + 7) / 8;
     if (blocks > 148LL * 16) blocks = 148LL * 16;
-    ADM_LAUNCH(k_reg_l1tv, (unsigned)blocks, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj, (const cpx*)weight_l1,
-               alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate, (long long)y_begin * X, (long long)y_end * X);
+#define ADM_REG_LAUNCH(V, G)                                                                                              \
+    ADM_LAUNCH((k_reg_l1tv<V, G>), (unsigned)blocks, 256, 256 * sizeof(float), stream, Y, X, Z, (const cpx*)obj,             \
+               (const cpx*)weight_l1, alpha_d, alpha_b, gamma, value, (cpx*)g_obj, g_scale, accumulate,                      \
+               (long long)y_begin * X, (long long)y_end * X)
+    if (value != nullptr && g_obj != nullptr) ADM_REG_LAUNCH(true, true);
+    else if (value != nullptr) ADM_REG_LAUNCH(true, false);
+    else if (g_obj != nullptr) ADM_REG_LAUNCH(false, true);
     return ADM_OK;
 }
 
