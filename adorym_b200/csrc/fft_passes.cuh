@@ -154,12 +154,33 @@ template <class C, class T> ADM_DEV void pass_BHB_x(T* psi, const T* tw, const T
     }
 }
 
-// ---- separable transfer function H(ky, kx) = hy(ky) hx(kx) (Fresnel kernel, propagate.py:72) -----------------------
-// hys / hxs are P-entry shared-memory tables indexed by spectrum position (hxs carries the 1/P^2 scale); the lanes of a
-// warp read the same few entries (broadcast), so H costs no global / L1 traffic in the slice loop.
-// hyl = hy at this thread's row (spectrum position l along y): the y factor of the separable transfer function is
-// constant along the row, so it is applied here from a register instead of through 24 table reads in the y pass
-template <class C, class T> ADM_DEV void pass_BHB_x_sep(T* psi, const T* tw, const T* hxs, T hyl, int q, int l) {
+// ---- separable transfer function, FIVE passes per slice ------------------------------------------------------------
+// With H(ky, kx) = hy(ky) hx(kx) (the paraxial Fresnel kernel, propagate.py:72; hys / hxs are P-entry shared-memory
+// tables indexed by spectrum position, hxs carries the 1/P^2 scale) the propagation is a 1-D convolution along y followed by one along x, and the two
+// commute with each other's transforms.  After P1 (which ends with the radix-8 stage Ay) the y convolution therefore
+// completes in ONE pass [By . hy . By^-1] (the closing Ay^-1 is the head of the next slice's P1), and the x convolution
+// is [Ax] [Bx . hx . Bx^-1] [Ax^-1]: five shared-memory round trips and five barriers per slice instead of six.
+// P2': y direction, lanes along x; hys indexed by the spectrum position along y (9 broadcast table reads per group).
+template <class C, class T> ADM_DEV void pass_BHB_y_sep(T* psi, const T* tw, const T* hys, int q, int l) {
+    const Idx<C> I(q);
+    ADM_FOR_GROUPS_B(gi) {
+        T v[C::R2];
+#pragma unroll
+        for (int n = 0; n < C::R2; ++n) v[n] = psi[I.b(n, gi) * C::S + l];
+        dftr<C::R2, false>(v);
+#pragma unroll
+        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], hys[I.b(k, gi)]);
+        dftr<C::R2, true>(v);
+        if constexpr (!C::PFA) {
+#pragma unroll
+            for (int n = 1; n < C::R2; ++n) v[n] = cmulc(v[n], tw[I.group(gi) * n]);
+        }
+#pragma unroll
+        for (int n = 0; n < C::R2; ++n) psi[I.b(n, gi) * C::S + l] = v[n];
+    }
+}
+// P4': x direction, lanes along y; only the x factor (hxs carries the 1/P^2 scale)
+template <class C, class T> ADM_DEV void pass_BHB_x_sep1(T* psi, const T* tw, const T* hxs, int q, int l) {
     const Idx<C> I(q);
     ADM_FOR_GROUPS_B(gi) {
         T v[C::R2];
@@ -167,7 +188,7 @@ template <class C, class T> ADM_DEV void pass_BHB_x_sep(T* psi, const T* tw, con
         for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + I.b(n, gi)];
         dftr<C::R2, false>(v);
 #pragma unroll
-        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], cmul(hxs[I.b(k, gi)], hyl));
+        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], hxs[I.b(k, gi)]);
         dftr<C::R2, true>(v);
         if constexpr (!C::PFA) {
 #pragma unroll
@@ -176,6 +197,18 @@ template <class C, class T> ADM_DEV void pass_BHB_x_sep(T* psi, const T* tw, con
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) psi[l * C::S + I.b(n, gi)] = v[n];
     }
+}
+// P2' .. P5 : psi <- IFFT2(H . FFT2(psi)) for separable H, given that pass A along y has already been applied and leaving
+// the final pass A^-1 along y to the caller.  hs = [hy(P) | hx(P)] in shared memory.
+template <class C, class T> ADM_DEV void propagate_core_sep5(T* psi, const T* tw, const T* hs, int q, int l, bool active) {
+    if (active) pass_BHB_y_sep<C>(psi, tw, hs, q, l);
+    __syncthreads();
+    if (active) pass_A_fwd<C, true>(psi, tw, q, l);
+    __syncthreads();
+    if (active) pass_BHB_x_sep1<C>(psi, tw, hs + C::P, q, l);
+    __syncthreads();
+    if (active) pass_A_inv<C, true>(psi, q, l);
+    __syncthreads();
 }
 
 template <class C, class T> ADM_DEV void init_twiddles(T* tw, int t) {
@@ -206,20 +239,6 @@ template <class C, class T> ADM_DEV void propagate_core(T* psi, const T* tw, con
     __syncthreads();
 }
 
-
-// same with a separable transfer function: hs = [hy(P) | hx(P)] in shared memory
-template <class C, class T> ADM_DEV void propagate_core_sep(T* psi, const T* tw, const T* hs, int q, int l, bool active) {
-    if (active) pass_B_fwd<C, false>(psi, q, l);
-    __syncthreads();
-    if (active) pass_A_fwd<C, true>(psi, tw, q, l);
-    __syncthreads();
-    if (active) pass_BHB_x_sep<C>(psi, tw, hs + C::P, hs[l], q, l);
-    __syncthreads();
-    if (active) pass_A_inv<C, true>(psi, q, l);
-    __syncthreads();
-    if (active) pass_B_inv<C, false>(psi, tw, q, l);
-    __syncthreads();
-}
 
 typedef MsCfg<72, 9, 3, true> Cfg72;     // prime-factor indexing, no twiddles
 typedef MsCfg<72, 9, 3, false> Cfg72ct;  // Cooley-Tukey variant of the same shape (tuning / cross-check)

@@ -160,6 +160,9 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
         for (int z = sg.zb; z < sg.ze; ++z) {
             const bool last = (z == p.Nz - 1);
             const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
+            // per-gap transfer functions (sparse multislice): tables of the gap z -> z+1; the previous slice's last reader
+            // (its x pass) is two barriers back, the first reader (P2') comes after the barrier that closes P1
+            if (!last && p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)z * 2 * P + t];
             // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
             if (active) {
                 mbar_wait(bar, ph);
@@ -228,9 +231,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                 }
                 break;
             }
-            if (!last && p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)z * 2 * P + t];   // gap z -> z+1 (read
-                                                                          // by P4, two barriers further down)
-            if (!last && p.h_separable) propagate_core_sep<C>(psi, tw, hs, q, l, active);
+            if (!last && p.h_separable) propagate_core_sep5<C>(psi, tw, hs, q, l, active);      // five passes per slice
             else propagate_core<C>(psi, tw, (const T*)(last ? p.Hf : p.Hp), q, l, active);
             if (last) {
                 // near field: final Ay^-1, natural order store
@@ -358,6 +359,8 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
         for (int z = sg.ze - 1; z >= sg.zb; --z, phase ^= 1) {
             const bool last = (z == p.Nz - 1);
             const T* tz = tcol + (size_t)z * slice_stride;
+            // per-gap transfer functions: tables of the gap z-1 -> z (read after the barrier that closes P1')
+            if (z > 0 && p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)(z - 1) * 2 * P + t];
             // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] --------------------------
             if (active) {
                 ADM_FOR_GROUPS_A(gi) {
@@ -422,10 +425,14 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                 bulk_commit();
             }
             if (z == 0) { phase ^= 1; break; }
-            if (p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)(z - 1) * 2 * P + t];     // gap z-1 -> z
-            if (active) pass_B_fwd<C, false>(psi, q, l);
+            // adjoint propagation to slice z-1.  Separable H: five passes [By conj(hy) By^-1] [Ax] [Bx conj(hx) Bx^-1] [Ax^-1]
+            // (+ the Ay^-1 at the head of the next P1'); general H: six.
+            if (active) {
+                if (p.h_separable) pass_BHB_y_sep<C>(psi, tw, hs, q, l);
+                else pass_B_fwd<C, false>(psi, q, l);
+            }
             __syncthreads();
-            if (t == 0 && z > sg.zb) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind P3..P6
+            if (t == 0 && z > sg.zb) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind the x passes
                 bulk_wait_read_all();
                 mbar_expect_tx(bar, TILE_BYTES);
                 bulk_load(ckb, ckpt + (size_t)(z - 1) * P * TP, TILE_BYTES, bar);
@@ -433,14 +440,16 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
             if (active) pass_A_fwd<C, true>(psi, tw, q, l);
             __syncthreads();
             if (active) {
-                if (p.h_separable) pass_BHB_x_sep<C>(psi, tw, hs + P, hs[l], q, l);
+                if (p.h_separable) pass_BHB_x_sep1<C>(psi, tw, hs + P, q, l);
                 else pass_BHB_x<C>(psi, tw, (const T*)p.Hp, q, l);
             }
             __syncthreads();
             if (active) pass_A_inv<C, true>(psi, q, l);
             __syncthreads();
-            if (active) pass_B_inv<C, false>(psi, tw, q, l);
-            __syncthreads();
+            if (!p.h_separable) {
+                if (active) pass_B_inv<C, false>(psi, tw, q, l);
+                __syncthreads();
+            }
         }
         if (sg.zb > 0) {                    // early part of a cut chain: hand the adjoint wavefield to CTA c - 1
             handoff_store<C>(p, c, psi);

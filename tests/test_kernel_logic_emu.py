@@ -50,7 +50,8 @@ def run_emu_case(name, separable=False, **kw):
                                   'sparse3_p72', 'ptycho3d_p72_bin3', 'ptycho3d_p72_pureproj'])
 def test_emulated_kernels_match_oracle_and_golden(name):
     # the separable-H path (Fresnel kernel in two shared-memory tables) on the 3-D P=72 cases, the general-H path elsewhere
-    inp, out = run_emu_case(name, separable=name.startswith('ptycho3d'))
+    # (fullfield64: the Cooley-Tukey 64-point transform on the separable five-pass path)
+    inp, out = run_emu_case(name, separable=name.startswith('ptycho3d') or name == 'fullfield64')
     _, loss, pred, grads = run_oracle_case(name, torch.float64)
     gold = np.load(os.path.join(GOLD, name + '.npz'))
     gtol = 1e-3 if 'poisson' in name else 1e-4
