@@ -60,25 +60,29 @@ def test_reconstruct_ptychography_matches_reference_driver_golden(name):
 @pytest.mark.gpu
 def test_reference_ci_config_matches_reference_driver():
     """BASELINE configs[0] = the reference's own CI test (tests/test_multislice_tomography_64.py): 64^3 full-field
-    multislice tomography of the shipped adhesin data, 50 of 500 angles (theta_downsample = 10), SingleBatchFullfieldModel,
-    L1 regulariser passed as an instance (quirk 15: that switches the TV default off and overrides reweighted_l1),
-    finite-support mask, Adam 1e-7, one epoch of 50 single-projection minibatches -- adorym_b200.reconstruct_ptychography
-    against the UNMODIFIED reference's run of the same parameters (tests/golden/make_golden_ci.py)."""
+    multislice tomography of the shipped adhesin data, SingleBatchFullfieldModel, L1 regulariser passed as an instance
+    (quirk 15: that switches the TV default off and overrides reweighted_l1), finite-support mask, Adam 1e-7, one epoch of
+    single-projection minibatches (10 of the 500 angles: theta_downsample = 50, so the fp32 frames fit a fixture) --
+    adorym_b200.reconstruct_ptychography against the UNMODIFIED reference's run of the same parameters
+    (tests/golden/make_golden_ci.py).  Tolerance: 5x the reference's own sensitivity to a 1e-7 perturbation of its initial
+    guess (stored in the golden: 2.1e-3 on the loss history, 1.8e-3 on the object; the measured magnitudes are 1 - O(1e-5),
+    so the fp32 data term is a difference of nearly equal numbers)."""
     import adorym_b200 as ab
-    from make_golden_ci import ci_params
+    from make_golden_ci import ci_params, DS
     gold = np.load(os.path.join(GOLD, 'driver_ci64.npz'))
     data = np.zeros((500, 1, 64, 64), dtype='float32')
-    data[0:500:10] = gold['frames'].astype('float32')
+    data[0:500:DS] = gold['frames']
     mask = np.unpackbits(gold['mask_bits'])[:64 ** 3].reshape(64, 64, 64).astype('float32')
     out = ab.reconstruct_ptychography(data, **ci_params(), verbose=False, save_outputs=False,
                                       regularizers=[ab.L1Regularizer(alpha_d=1.e-9 * 64 ** 3, alpha_b=1.e-10 * 64 ** 3)],
                                       finite_support_mask_path=mask, output_folder='/tmp/adm_test_ci64')
     gh = gold['loss_history']
     hist = np.array([(e, b, l) for (e, b, l, t) in out['loss_history']])
-    assert len(hist) == len(gh) == 50
+    assert len(hist) == len(gh) == 500 // DS
     assert np.array_equal(hist[:, :2].astype(int), gh[:, :2].astype(int))
-    assert abs(hist[0, 2] - gh[0, 2]) <= 1e-4 * gh[0, 2]
     rel = np.abs(hist[:, 2] - gh[:, 2]) / gh[:, 2]
-    print('CI config: max rel. loss-history difference %.3e, object %.3e' % (rel.max(), rel_err(out['obj'].cpu().numpy(), gold['obj'])))
-    np.testing.assert_allclose(hist[:, 2], gh[:, 2], rtol=1.5e-2)
-    assert rel_err(out['obj'].cpu().numpy(), gold['obj']) < 3e-2
+    oerr = rel_err(out['obj'].cpu().numpy(), gold['obj'])
+    print('CI config: rel. loss-history difference first %.3e max %.3e, object %.3e' % (rel[0], rel.max(), oerr))
+    assert rel[0] < 5 * float(gold['sensitivity_loss_history'])
+    assert rel.max() < 5 * float(gold['sensitivity_loss_history'])
+    assert oerr < 5 * float(gold['sensitivity_obj'])
