@@ -38,6 +38,7 @@ template <class C> struct MsSmem {
     static constexpr size_t TW = sizeof(cpx) * C::P;
     static constexpr size_t HS = sizeof(cpx) * 2 * C::P;     // separable transfer function tables hy | hx
     static constexpr size_t BYTES = TILE + PSI + TW + HS + 16;
+    static constexpr size_t BYTES_NOTILE = PSI + TW + HS + 16;     // forward variant that reads T' with plain loads
     static constexpr int PSI_F4 = (int)(PSI / 16);           // the psi buffer as float4 (hand-off copies)
     static_assert(PSI % 16 == 0 && TILE % 16 == 0, "16-byte granularity");
 };
@@ -110,14 +111,16 @@ template <class C> ADM_DEV void handoff_load(const MsParams& p, int slot, void* 
 // ================================================================================================
 // Forward
 // ================================================================================================
-// T' tile by TMA into shared memory, prefetched one slice ahead (86 KB of shared memory, 2 CTAs per SM).
-template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+// TILE = true : T' tile by TMA into shared memory, prefetched one slice ahead (86 KB of shared memory, 2 CTAs per SM).
+// TILE = false: T' by plain coalesced loads at the top of P1 (the volume is L2 resident), 44 KB of shared memory: with
+//               <= 96 registers THREE CTAs are resident per SM (21 warps instead of 14 to hide barrier / dependency stalls).
+template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
     constexpr int TP = MsSmem<C>::TP;
     T* tile = (T*)smem_raw;
-    T* psi = tile + P * TP;
+    T* psi = TILE ? tile + P * TP : (T*)smem_raw;
     T* tw = psi + P * S;
     T* hs = tw + P;
     adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
@@ -129,7 +132,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
 
     init_twiddles<C>(tw, t);
     if (p.h_separable && t < 2 * P) hs[t] = ((const T*)p.Hp)[t];
-    if (t == 0) mbar_init(bar, 1);
+    if (TILE && t == 0) mbar_init(bar, 1);
     unsigned ph = 0;                        // parity of the next tile completion
 
     int wf_first, wf_last;
@@ -146,10 +149,15 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
         T* det = (T*)p.det + (size_t)wf * P * P;
 
         __syncthreads();                    // the previous segment is done with the tile and the wavefield
-        if (t == 0) {                       // prefetch the T' tile of the first slice of the segment
+        if (TILE && t == 0) {               // prefetch the T' tile of the first slice of the segment
             mbar_expect_tx(bar, TILE_BYTES);
             tma_load_tile(tile, &tmap, 2 * pxa, py, sg.zb, bar);
         }
+        // TILE = false: this thread's column of the transmission volume
+        const int gx = px + l;
+        const bool x_in = (gx >= 0) && (gx < p.X);
+        const T* tcol = (const T*)p.tvol + (x_in ? gx : 0);
+        const size_t slice_stride = (size_t)p.Y * p.Xp;
         if (sg.zb > 0) {                    // late part of a cut chain: the wavefield comes from CTA c - 1
             if (t == 0) flag_wait_and_clear(p.flags + c);
             __syncthreads();
@@ -164,11 +172,20 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
             // (its x pass) is two barriers back, the first reader (P2') comes after the barrier that closes P1
             if (!last && p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)z * 2 * P + t];
             // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
+            const T* tz = tcol + (size_t)z * slice_stride;
             if (active) {
-                mbar_wait(bar, ph);
+                if (TILE) mbar_wait(bar, ph);
                 ADM_FOR_GROUPS_A(gi) {
                     const int g = I.group(gi);
-                    T v[8];
+                    T v[8], tp[8];
+                    if (!TILE) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int gy = py + I.a(j, gi);
+                            const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
+                            tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : tmk<T>(0.f, 0.f);
+                        }
+                    }
                     if (z == 0) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = probe[I.a(j, gi) * P + l];
@@ -181,7 +198,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                     for (int j = 0; j < 8; ++j) {
                         const int y = I.a(j, gi);
                         ckpt[(size_t)z * P * TP + y * TP + lt] = v[j];
-                        v[j] = modulate(v[j], tile[y * TP + lt]);
+                        v[j] = modulate(v[j], TILE ? tile[y * TP + lt] : tp[j]);
                     }
                     if (go_on) {
                         if (last && p.ff_conj) {
@@ -203,7 +220,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
             }
             ph ^= 1;
             __syncthreads();
-            if (t == 0 && z + 1 < sg.ze) {   // every thread has consumed tile(z): prefetch tile(z+1) behind P2..P6
+            if (TILE && t == 0 && z + 1 < sg.ze) {   // every thread has consumed tile(z): prefetch tile(z+1) behind P2..P5
                 mbar_expect_tx(bar, TILE_BYTES);
                 tma_load_tile(tile, &tmap, 2 * pxa, py, z + 1, bar);
             }
@@ -586,22 +603,24 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     AdmTileMap map;
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int var = adm_variant("ADM_FWD_VARIANT");
-#define ADM_FWD(CFG, MINB, CT)                                                                                        \
+#define ADM_FWD(CFG, MINB, TILE, CT)                                                                                  \
     do {                                                                                                           \
-        const size_t sm_ = MsSmem<CFG>::BYTES;                                                                     \
-        if (set_smem(k_multislice_fwd<CFG, MINB, CT>, sm_)) return ADM_ERR_CUDA;                                   \
+        const size_t sm_ = TILE ? MsSmem<CFG>::BYTES : MsSmem<CFG>::BYTES_NOTILE;                                  \
+        if (set_smem(k_multislice_fwd<CFG, MINB, TILE, CT>, sm_)) return ADM_ERR_CUDA;                             \
         int grid_;                                                                                                 \
-        if (ms_schedule(p, ms_resident_ctas(k_multislice_fwd<CFG, MINB, CT>, CFG::NTHREADS, sm_), workspace,       \
+        if (ms_schedule(p, ms_resident_ctas(k_multislice_fwd<CFG, MINB, TILE, CT>, CFG::NTHREADS, sm_), workspace, \
                         CFG::P, grid_))                                                                            \
             return ADM_ERR_CUDA;                                                                                   \
-        ADM_LAUNCH((k_multislice_fwd<CFG, MINB, CT>), grid_, CFG::NTHREADS, sm_, stream, map, p);                  \
+        ADM_LAUNCH((k_multislice_fwd<CFG, MINB, TILE, CT>), grid_, CFG::NTHREADS, sm_, stream, map, p);            \
     } while (0)
     if (cfg->P == 72) {
-        if (var == 4) ADM_FWD(Cfg72, 2, cpx);      // scalar butterflies (one FADD / FFMA per component)
-        else ADM_FWD(Cfg72, 2, cpk);               // packed complex arithmetic (cpk.cuh)
+        if (var == 4) ADM_FWD(Cfg72, 2, true, cpx);      // scalar butterflies (one FADD / FFMA per component)
+        else if (var == 3) ADM_FWD(Cfg72, 3, false, cpk);   // no T' tile, three CTAs per SM
+        else if (var == 2) ADM_FWD(Cfg72, 2, false, cpk);   // no T' tile, two CTAs per SM
+        else ADM_FWD(Cfg72, 2, true, cpk);               // packed complex arithmetic (cpk.cuh)
     } else {
-        if (var == 4) ADM_FWD(Cfg64, 2, cpx);
-        else ADM_FWD(Cfg64, 2, cpk);
+        if (var == 4) ADM_FWD(Cfg64, 2, true, cpx);
+        else ADM_FWD(Cfg64, 2, true, cpk);
     }
     return ADM_OK;
 }
