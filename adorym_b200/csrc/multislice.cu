@@ -312,6 +312,22 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
         const T* gdet = (const T*)p.det + (size_t)wf * P * P;
         const size_t slice_stride = (size_t)p.Y * p.Xp;
         const T* tcol = (const T*)p.tvol + (x_in ? gx : 0);     // this thread's column of the transmission volume
+        // T' of one slice for this thread's P1' groups (L2-resident volume, plain loads with 32-bit offsets from the
+        // per-slice column pointer).  The loads are ISSUED one barrier early -- behind the last pass of the previous
+        // slice -- so that their L2 latency (~700 cycles, the adjoint's former top stall) overlaps the barrier wait.
+        T tpa[C::NGA][8];
+        auto load_tp = [&](int zz) {
+            const T* tzz = tcol + (size_t)zz * slice_stride;
+            ADM_FOR_GROUPS_A(gi) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int gy = py + I.a(j, gi);
+                    const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
+                    tpa[gi][j] = inb ? tzz[(unsigned)(gy * p.Xp)] : tmk<T>(0.f, 0.f);
+                }
+            }
+        };
+        if (active) load_tp(sg.ze - 1);
 
         __syncthreads();                    // the previous segment is done with the wavefield
         if (t == 0) {   // prefetch the checkpoint of the first (highest) slice of the segment
@@ -375,22 +391,13 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
 
         for (int z = sg.ze - 1; z >= sg.zb; --z, phase ^= 1) {
             const bool last = (z == p.Nz - 1);
-            const T* tz = tcol + (size_t)z * slice_stride;
             // per-gap transfer functions: tables of the gap z-1 -> z (read after the barrier that closes P1')
             if (z > 0 && p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)(z - 1) * 2 * P + t];
             // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] --------------------------
             if (active) {
                 ADM_FOR_GROUPS_A(gi) {
                     const int g = I.group(gi);
-                    T v[8], tp[8];
-                    // T' of this slice (L2-resident volume; issued first so the butterfly hides the latency); 32-bit
-                    // offsets from the per-slice column pointer, one unsigned compare per row
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const int gy = py + I.a(j, gi);
-                        const bool inb = x_in && (unsigned)gy < (unsigned)p.Y;
-                        tp[j] = inb ? tz[(unsigned)(gy * p.Xp)] : tmk<T>(0.f, 0.f);
-                    }
+                    T v[8];
                     if (last && p.free_prop == ADM_PROP_NONE) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) v[j] = gdet[I.a(j, gi) * P + l];
@@ -413,7 +420,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                         const int y = I.a(j, gi);
                         const T w = ckb[y * TP + lt];               // psi_z (wave entering the slice)
                         ckb[y * TP + lt] = cmulc(v[j], w);            // dL/dT = g' conj(psi_z)
-                        v[j] = modulate_conj(v[j], tp[j]);            // g_psi = g' conj(T)
+                        v[j] = modulate_conj(v[j], tpa[gi][j]);       // g_psi = g' conj(T)
                     }
                     if (z > 0) {
                         dft8<false>(v);
@@ -462,9 +469,11 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
             }
             __syncthreads();
             if (active) pass_A_inv<C, true>(psi, q, l);
+            if (p.h_separable && active && z > sg.zb) load_tp(z - 1);      // T' of the next slice, one barrier early
             __syncthreads();
             if (!p.h_separable) {
                 if (active) pass_B_inv<C, false>(psi, tw, q, l);
+                if (active && z > sg.zb) load_tp(z - 1);
                 __syncthreads();
             }
         }
