@@ -30,12 +30,6 @@
 #include "../../include/adorym_b200.h"
 #include "ms_params.cuh"
 
-// two CTAs of 224 threads per SM leave 146 registers per thread; ptxas stops at 128 under __launch_bounds__(224, 2)
-#ifndef ADM_HOST_EMU
-#define ADM_MAXNREG(n) __maxnreg__(n)
-#else
-#define ADM_MAXNREG(n)
-#endif
 
 // shared-memory carve-up (tile first: TMA destinations / sources need 128-byte alignment)
 template <class C> struct MsSmem {
@@ -282,7 +276,7 @@ template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds
 // ================================================================================================
 // Adjoint
 // ================================================================================================
-template <class C, int MINB, class T> __global__ void ADM_MAXNREG((C::NTHREADS <= 224) ? 144 : 128) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
+template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
