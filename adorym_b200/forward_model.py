@@ -401,7 +401,15 @@ class PtychographyModel(ForwardModel):
             shift = probe_pos_correction[int(this_i_theta)].index_select(0, idx).to(torch.float32)
             probe = ops.ProbeShiftFn.apply(probe, shift)
         plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
-        pos_t = torch.from_numpy(np.ascontiguousarray(pos, dtype='int32')).to(dev)
+        # device copy of the integer positions, cached by content (the driver revisits the same minibatches every epoch)
+        pos32 = np.ascontiguousarray(pos, dtype='int32')
+        key = (pos32.tobytes(), str(dev))
+        cache = self.__dict__.setdefault('_pos_cache', {})
+        pos_t = cache.get(key)
+        if pos_t is None:
+            if len(cache) > 4096:
+                cache.clear()
+            pos_t = cache[key] = torch.from_numpy(pos32).to(dev)
         out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg)
         return out if with_reg else out[0]
 
