@@ -72,6 +72,10 @@ SIGNATURES = {
     'adm_frame_shift_bwd': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_detector_loss_large': [c_int, c_int, c_longlong, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_affine_resample_fwd': [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    'adm_affine_resample_adj': [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
+    'adm_affine_resample_dmat': [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                                 c_void_p],
 }
 
 RETURNS_LONGLONG = ('adm_multislice_workspace_bytes',)
@@ -100,7 +104,7 @@ def get_lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('adorym_b200: CUDA library %s is missing; run `python -m adorym_b200.build`' % LIB_PATH)
         _lib = bind(ctypes.CDLL(LIB_PATH))
-        if _lib.adm_abi_version() != 4:
+        if _lib.adm_abi_version() != 5:
             raise RuntimeError('adorym_b200: ABI version mismatch')
     return _lib
 

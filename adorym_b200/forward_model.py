@@ -124,8 +124,6 @@ class ForwardModel(object):
         for n in names:
             if cv.get(n, False):
                 raise NotImplementedError('adorym_b200: option %s is not on the accelerated path yet' % n)
-        if cv.get('initial_tilt', None) is not None:
-            raise NotImplementedError('adorym_b200: initial_tilt is not on the accelerated path yet')
         if cv.get('pure_projection', False) and (self.is_minus_logged or self.unknown_type != 'delta_beta'):
             raise NotImplementedError('adorym_b200: pure_projection is accelerated for delta_beta objects that are not '
                                       'minus-logged')
@@ -200,11 +198,12 @@ class ForwardModel(object):
         out = torch.stack([psi[..., 0] * tr - psi[..., 1] * ti, psi[..., 0] * ti + psi[..., 1] * tr], -1)
         return out.unsqueeze(0)
 
-    def _multislice(self, obj, this_i_theta, probe, pos_t, plan, with_reg):
+    def _multislice(self, obj, this_i_theta, probe, pos_t, plan, with_reg, in_beam_frame=False):
         """fused rotate + transmission + gather + multislice; with_reg: also the fused regulariser value (None when the
-        regulariser list is not fusable) -> (det, reg_value | None, reg_was_fused)."""
-        reg = self._fusable_regularizers() if with_reg else None
-        grid = self._object_grid(obj, this_i_theta)
+        regulariser list is not fusable) -> (det, reg_value | None, reg_was_fused).  in_beam_frame: the object has
+        already been rotated (tilt refinement); the regulariser then acts on the UN-rotated object and is not fused."""
+        reg = self._fusable_regularizers() if (with_reg and not in_beam_frame) else None
+        grid = None if in_beam_frame else self._object_grid(obj, this_i_theta)
         if reg is not None:
             det, reg_val = ops.MultisliceFn.apply(obj, grid, probe, pos_t, plan, reg, 'yxz')
             return det, reg_val, True
@@ -379,12 +378,13 @@ class PtychographyModel(ForwardModel):
         self.run_float64 = run_float64
 
     def _detector_field(self, obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                        this_ind_batch, with_reg=False):
+                        this_ind_batch, with_reg=False, tilt_ls=None, probe_pos_offset=None):
         """(shift probe) -> fused rotate + transmission + gather + multislice -> complex detector field [B, M, P, P, 2]
         (, regulariser value, fused flag)."""
         cv = self.common_vars
-        self._check_unsupported(['optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
-                                 'optimize_tilt'])
+        # optimize_probe_defocusing: get_kernel() (numpy) on a tensor that requires grad fails in the reference's own
+        # PyTorch backend (forward_model.py:247-251), so there is no behaviour to reproduce
+        self._check_unsupported(['optimize_probe_defocusing', 'optimize_prj_pos_offset'])
         dev = self._device(obj)
         probe_size = cv['probe_size']
         if probe_size[0] != probe_size[1]:
@@ -394,6 +394,19 @@ class PtychographyModel(ForwardModel):
         probe = torch.stack([probe_real, probe_imag], dim=-1)
         if probe.dim() == 3:
             probe = probe.unsqueeze(0)
+        # (callers hand over tilt_ls / probe_pos_offset only where the reference's class of the same name uses them)
+        if cv.get('optimize_probe_pos_offset', False) and probe_pos_offset is not None:
+            # forward_model.py:258-260: every mode shifted by this angle's refinable offset (one Fourier shift)
+            probe = ops.ProbeShiftFn.apply(probe, probe_pos_offset[int(this_i_theta)].reshape(1, 2).to(torch.float32))[0]
+        tilted = tilt_ls is not None and (cv.get('optimize_tilt', False) or cv.get('initial_tilt', None) is not None)
+        if tilted:
+            # forward_model.py:262-276: three differentiable rotations (wrappers.py:1177-1217) replace the lookup table
+            if cv['two_d_mode']:
+                raise NotImplementedError('Tilt optimization is not impemented for distributed mode or when two_d_mode is on.')
+            t = tilt_ls if torch.is_tensor(tilt_ls) else torch.as_tensor(np.asarray(tilt_ls), dtype=torch.float32, device=dev)
+            t = t.to(dev)
+            for axis in range(3):
+                obj = ops.rotate_with_grad(obj, t[axis, int(this_i_theta)], axis)
         # per-position probe shift: quirk 8, positive corrections only trigger it (forward_model.py:297,304)
         if probe_pos_correction is not None and (cv['optimize_all_probe_pos']
                                                  or self._any_positive_correction(probe_pos_correction)):
@@ -410,7 +423,7 @@ class PtychographyModel(ForwardModel):
             if len(cache) > 4096:
                 cache.clear()
             pos_t = cache[key] = torch.from_numpy(pos32).to(dev)
-        out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg)
+        out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg, in_beam_frame=tilted)
         return out if with_reg else out[0]
 
     def _any_positive_correction(self, ppc):
@@ -428,7 +441,7 @@ class PtychographyModel(ForwardModel):
                 probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
         """Detected magnitudes [minibatch_size, len_probe_y, len_probe_x] (adorym/forward_model.py:179-387)."""
         det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                                   this_ind_batch)
+                                   this_ind_batch, tilt_ls=tilt_ls, probe_pos_offset=probe_pos_offset)
         self.i_call += 1
         return ops.DetectorMagnitudeFn.apply(det)
 
@@ -439,7 +452,8 @@ class PtychographyModel(ForwardModel):
             theta_downsample = self.common_vars['theta_downsample']
             ds_level = self.common_vars['ds_level']
             det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch,
-                                                          probe_pos_correction, this_ind_batch, with_reg=True)
+                                                          probe_pos_correction, this_ind_batch, with_reg=True,
+                                                          tilt_ls=tilt_ls, probe_pos_offset=probe_pos_offset)
             self.i_call += 1
             this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
             return self._fused_loss(det, this_prj_batch, obj, reg_val, reg_done)
@@ -533,7 +547,7 @@ class SparseMultisliceModel(PtychographyModel):
                 prj_pos_offset):
         self._slice_pos = slice_pos_cm_ls
         det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                                   this_ind_batch)
+                                   this_ind_batch, probe_pos_offset=probe_pos_offset)
         self.i_call += 1
         return ops.DetectorMagnitudeFn.apply(det)
 
@@ -545,7 +559,8 @@ class SparseMultisliceModel(PtychographyModel):
             ds_level = self.common_vars['ds_level']
             self._slice_pos = slice_pos_cm_ls
             det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch,
-                                                          probe_pos_correction, this_ind_batch, with_reg=True)
+                                                          probe_pos_correction, this_ind_batch, with_reg=True,
+                                                          probe_pos_offset=probe_pos_offset)
             self.i_call += 1
             this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
             return self._fused_loss(det, this_prj_batch, obj, reg_val, reg_done)
@@ -561,7 +576,8 @@ class SingleBatchFullfieldModel(PtychographyModel):
                                                         raw_data_type, simulation_mode=simulation_mode, *args, **kwargs)
 
     def _detector_field(self, obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                        this_ind_batch, with_reg=False):
+                        this_ind_batch, with_reg=False, tilt_ls=None, probe_pos_offset=None):
+        # (forward_model.py:412-490 uses neither the tilt table nor the probe position offset)
         cv = self.common_vars
         self._check_unsupported(['optimize_prj_pos_offset'])
         dev = self._device(obj)
@@ -630,7 +646,7 @@ class MultiDistModel(ForwardModel):
     def _detector_fields(self, obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj):
         cv = self.common_vars
         self._check_unsupported(['optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
-                                 'optimize_prj_affine', 'optimize_ctf_lg_kappa'])
+                                 'optimize_ctf_lg_kappa'])
         refine_dist = bool(cv.get('optimize_free_prop', False))
         if safe_zone_width not in (0, None):
             raise NotImplementedError('adorym_b200: MultiDistModel with safe_zone_width > 0 is not accelerated yet')
@@ -694,6 +710,15 @@ class MultiDistModel(ForwardModel):
             full = np.concatenate([ind + i * n_blocks for i in range(n_dists)])       # forward_model.py:1058-1061
             this_prj_batch = self.get_data(this_i_theta, full, theta_downsample=theta_downsample, ds_level=1)
             large = ops.lf_supported(det.shape[2])
+            if self.common_vars.get('optimize_prj_affine', False):
+                # refinable affine alignment of every distance's hologram (forward_model.py:1066-1072,
+                # wrappers.py:1158-1174): one resampling kernel, a 2x3 matrix per frame, d/d matrix by a reduction kernel
+                if not large or self.common_vars.get('beamstop', None) is not None:
+                    raise NotImplementedError('adorym_b200: affine refinement of the data needs large-frame sizes, no beamstop')
+                nb = len(ind)
+                aff = prj_affine_ls[:n_dists].to(torch.float32)
+                mats = aff.repeat_interleave(nb, dim=0) if nb > 1 else aff
+                this_prj_batch = ops.AffineResampleFn.apply(this_prj_batch, mats, (0, 1, 2))
             if self.common_vars.get('optimize_all_probe_pos', False):
                 # per-distance sub-pixel shift of the measured frames, real part kept (forward_model.py:1079-1088)
                 if not large:

@@ -671,19 +671,29 @@ class FrameShiftFn(torch.autograd.Function):
         spec = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
         out = torch.empty((F, N, N), dtype=torch.float32, device=dev)
         call('adm_frame_shift_fwd', N, F, ptr(data), ptr(shift), ptr(order), ptr(work), ptr(spec), ptr(out), stream_ptr())
-        ctx.save_for_backward(spec, order)
+        ctx.save_for_backward(spec, order, shift)
         ctx.dims = (F, N)
         return out
 
     @staticmethod
     def backward(ctx, g_out):
-        spec, order = ctx.saved_tensors
+        spec, order, shift = ctx.saved_tensors
         F, N = ctx.dims
         g_out = _f32c(g_out)
         work = torch.empty((F, N, N, 2), dtype=torch.float32, device=g_out.device)
-        g_shift = torch.zeros((F, 2), dtype=torch.float32, device=g_out.device)
-        call('adm_frame_shift_bwd', N, F, ptr(g_out), ptr(spec), ptr(order), ptr(work), ptr(g_shift), stream_ptr())
-        return None, g_shift
+        g_shift = None
+        if ctx.needs_input_grad[1]:
+            g_shift = torch.zeros((F, 2), dtype=torch.float32, device=g_out.device)
+            call('adm_frame_shift_bwd', N, F, ptr(g_out), ptr(spec), ptr(order), ptr(work), ptr(g_shift), stream_ptr())
+        g_data = None
+        if ctx.needs_input_grad[0]:
+            # the shift of real frames with the real part kept is a real-linear map whose transpose is the shift by -s
+            # (the data carry a gradient when an upstream refinable transformation -- the affine alignment -- made them)
+            spec2 = torch.empty((F, N, N, 2), dtype=torch.float32, device=g_out.device)
+            g_data = torch.empty((F, N, N), dtype=torch.float32, device=g_out.device)
+            call('adm_frame_shift_fwd', N, F, ptr(g_out), ptr((-shift).contiguous()), ptr(order), ptr(work), ptr(spec2),
+                 ptr(g_data), stream_ptr())
+        return g_data, g_shift
 
 
 class DetectorLossLargeFn(torch.autograd.Function):
@@ -715,3 +725,71 @@ class DetectorLossLargeFn(torch.autograd.Function):
     def backward(ctx, g_loss, g_pred, g_lpp):
         g_det, g_meas = ctx.saved_tensors
         return g_det * g_loss, (g_meas * g_loss if g_meas is not None else None), None, None, None
+
+
+# ------------------------------------------------------------------------------------------------------
+# affine resampling: tilt refinement (wrappers.py:1177-1217) and affine alignment of the data (wrappers.py:1158-1174)
+# ------------------------------------------------------------------------------------------------------
+class AffineResampleFn(torch.autograd.Function):
+    """out = grid_sample(arr, affine_grid(mats), bilinear, border, align_corners=False) on the planes of a dense
+    [D0, D1, D2(, 2)] array.  roles = (dim_n, dim_h, dim_w): which memory dimension is the plane index, the rows and the
+    columns.  mats: [6] / [2, 3] (shared by all planes) or [N, 2, 3].  Differentiable with respect to arr and mats."""
+
+    @staticmethod
+    def forward(ctx, arr, mats, roles):
+        arr = _f32c(arr)
+        mats = _f32c(mats)
+        if arr.dim() == 4 and arr.shape[-1] == 2:
+            C = 2
+        elif arr.dim() == 3:
+            C = 1
+        else:
+            raise RuntimeError('AffineResampleFn: array must be [D0,D1,D2] or [D0,D1,D2,2], got %s' % (tuple(arr.shape),))
+        D = tuple(arr.shape[:3])
+        N = D[roles[0]]
+        per_plane = int(mats.numel() == 6 * N and mats.dim() == 3)
+        if not per_plane and mats.numel() != 6:
+            raise RuntimeError('AffineResampleFn: mats must hold one 2x3 matrix, or one per plane')
+        out = torch.empty_like(arr)
+        call('adm_affine_resample_fwd', D[0], D[1], D[2], C, roles[0], roles[1], roles[2], ptr(arr), ptr(mats), per_plane,
+             ptr(out), stream_ptr())
+        ctx.geom = (D, C, tuple(roles), per_plane, N, tuple(mats.shape))
+        ctx.save_for_backward(arr, mats)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        arr, mats = ctx.saved_tensors
+        D, C, roles, per_plane, N, mshape = ctx.geom
+        g_out = _f32c(g_out)
+        g_arr = g_mats = None
+        if ctx.needs_input_grad[0]:
+            g_arr = torch.zeros_like(arr)
+            call('adm_affine_resample_adj', D[0], D[1], D[2], C, roles[0], roles[1], roles[2], ptr(g_out), ptr(mats),
+                 per_plane, ptr(g_arr), stream_ptr())
+        if ctx.needs_input_grad[1]:
+            gm = torch.zeros((N, 6), dtype=torch.float32, device=arr.device)
+            call('adm_affine_resample_dmat', D[0], D[1], D[2], C, roles[0], roles[1], roles[2], ptr(arr), ptr(g_out),
+                 ptr(mats), per_plane, ptr(gm), stream_ptr())
+            g_mats = (gm if per_plane else gm.sum(0)).reshape(mshape)
+        return g_arr, g_mats, None
+
+
+# (plane index, rows, columns) of wrappers.rotate's permutation for an object [Y, X, Z, C], and the sign it gives theta
+_TILT_ROLES = {0: ((0, 2, 1), 1.0), 1: ((1, 2, 0), 1.0), 2: ((2, 0, 1), -1.0)}
+
+
+def rotate_with_grad(obj, theta, axis):
+    """adorym/wrappers.py:1177-1217 `rotate` (PyTorch backend): rotation of obj[Y,X,Z,2] about `axis` by the 0-d tensor
+    theta in NORMALISED grid coordinates, differentiable with respect to theta (optimize_tilt)."""
+    roles, sign = _TILT_ROLES[int(axis)]
+    th = theta.reshape(1).to(torch.float32) * sign
+    zero = torch.zeros_like(th)
+    c, s = torch.cos(th), torch.sin(th)
+    mats = torch.cat([c, -s, zero, s, c, zero])
+    return AffineResampleFn.apply(obj, mats, roles)
+
+
+def affine_transform_frames(frames, transform):
+    """adorym/wrappers.py:1158-1174 `affine_transform` of a stack of frames [N, H, W] by one [2, 3] matrix."""
+    return AffineResampleFn.apply(frames, transform.reshape(6), (0, 1, 2))

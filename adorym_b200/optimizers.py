@@ -137,18 +137,26 @@ class MomentumOptimizer(Optimizer):
 # ------------------------------------------------------------------------------------------------------
 # parameter plumbing                                                     adorym/optimizers.py:793-1089
 # ------------------------------------------------------------------------------------------------------
-_SUPPORTED_PARAM_SWITCHES = ('optimize_probe', 'optimize_all_probe_pos', 'optimize_free_prop')
-_UNSUPPORTED_PARAM_SWITCHES = ('optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
-                               'optimize_slice_pos', 'optimize_tilt', 'optimize_prj_affine',
+# (switch, optimizer kwarg, learning-rate kwarg, parameter name) in the order of adorym/optimizers.py:793-958: the
+# gradient tuple of the Differentiator follows this order (quirk 17)
+_PARAM_TABLE = (('optimize_probe_pos_offset', 'optimizer_probe_pos_offset', 'probe_pos_offset_learning_rate', 'probe_pos_offset'),
+                ('optimize_all_probe_pos', 'optimizer_all_probe_pos', 'all_probe_pos_learning_rate', 'probe_pos_correction'),
+                ('optimize_free_prop', 'optimizer_free_prop', 'free_prop_learning_rate', 'free_prop_cm'),
+                ('optimize_tilt', 'optimizer_tilt', 'tilt_learning_rate', 'tilt_ls'),
+                ('optimize_prj_affine', 'optimizer_prj_affine', 'prj_affine_learning_rate', 'prj_affine_ls'))
+# optimize_probe_defocusing: the reference's PyTorch backend itself fails on it (numpy get_kernel on a tensor that
+# requires grad, forward_model.py:247-251); the others have no accelerated forward path
+_UNSUPPORTED_PARAM_SWITCHES = ('optimize_probe_defocusing', 'optimize_prj_pos_offset', 'optimize_slice_pos',
                                'optimize_ctf_lg_kappa')
 
 
 def create_and_initialize_parameter_optimizers(optimizable_params, kwargs):
-    """adorym/optimizers.py:793-958 for the refinable parameters on the accelerated path (probe, probe positions);
-    the gradient tuple is ordered (obj, probe_real, probe_imag, probe_pos_correction) (quirk 17)."""
+    """adorym/optimizers.py:793-958 for the refinable parameters on the accelerated path: probe, per-angle probe position
+    offset, probe positions (MultiDist: per-distance data shift), propagation distances, tilt angles, affine alignment of
+    the data.  The gradient tuple is ordered (obj, probe_real, probe_imag, <the rest in the order above>) (quirk 17)."""
     for sw in _UNSUPPORTED_PARAM_SWITCHES:
         if kwargs.get(sw, False):
-            raise NotImplementedError('adorym_b200: %s is not on the accelerated path yet' % sw)
+            raise NotImplementedError('adorym_b200: %s is not on the accelerated path' % sw)
     opt_ls = kwargs['opt_ls']
     forward_model = kwargs['forward_model']
     output_folder = kwargs['output_folder']
@@ -166,30 +174,27 @@ def create_and_initialize_parameter_optimizers(optimizable_params, kwargs):
         opt_args_ls = opt_args_ls + [forward_model.get_argument_index('probe_real'),
                                      forward_model.get_argument_index('probe_imag')]
         opt_ls.append(opt_probe)
-    if kwargs['optimize_all_probe_pos']:
-        if kwargs['optimizer_all_probe_pos'] is not None:
-            opt_pos = kwargs['optimizer_all_probe_pos']
-            opt_pos.name = 'probe_pos_correction'
+    for switch, opt_kw, lr_kw, name in _PARAM_TABLE:
+        if not kwargs.get(switch, False):
+            continue
+        if name == 'free_prop_cm' and not kwargs.get('is_multi_dist', False):      # optimizers.py:905
+            continue
+        if name == 'probe_pos_offset':
+            assert kwargs['optimize_all_probe_pos'] == False                       # optimizers.py:846
+        if kwargs.get(opt_kw) is not None:
+            o = kwargs[opt_kw]
+            o.name = name
+        elif name == 'probe_pos_offset':
+            # optimizers.py:851-857: plain gradient descent without the step-halving schedule
+            o = GDOptimizer(name, output_folder=output_folder,
+                            options_dict={'step_size': kwargs[lr_kw], 'dynamic_rate': False})
         else:
-            opt_pos = AdamOptimizer('probe_pos_correction', output_folder=output_folder,
-                                    options_dict={'step_size': kwargs['all_probe_pos_learning_rate']},
-                                    forward_model=forward_model)
-        opt_pos.create_param_arrays(list(optimizable_params['probe_pos_correction'].shape), device=device_obj)
-        opt_pos.set_index_in_grad_return(len(opt_args_ls))
-        opt_args_ls.append(forward_model.get_argument_index('probe_pos_correction'))
-        opt_ls.append(opt_pos)
-    if kwargs.get('optimize_free_prop', False):
-        # adorym/optimizers.py:906-917
-        if kwargs.get('optimizer_free_prop') is not None:
-            opt_fp = kwargs['optimizer_free_prop']
-            opt_fp.name = 'free_prop_cm'
-        else:
-            opt_fp = AdamOptimizer('free_prop_cm', output_folder=output_folder,
-                                   options_dict={'step_size': kwargs['free_prop_learning_rate']}, forward_model=forward_model)
-        opt_fp.create_param_arrays(list(optimizable_params['free_prop_cm'].shape), device=device_obj)
-        opt_fp.set_index_in_grad_return(len(opt_args_ls))
-        opt_args_ls.append(forward_model.get_argument_index('free_prop_cm'))
-        opt_ls.append(opt_fp)
+            o = AdamOptimizer(name, output_folder=output_folder, options_dict={'step_size': kwargs[lr_kw]},
+                              forward_model=forward_model)
+        o.create_param_arrays(list(optimizable_params[name].shape), device=device_obj)
+        o.set_index_in_grad_return(len(opt_args_ls))
+        opt_args_ls.append(forward_model.get_argument_index(name))
+        opt_ls.append(o)
     return opt_ls, opt_args_ls
 
 
@@ -244,6 +249,14 @@ def update_parameters(opt_ls, optimizable_params, kwargs):
                     dims = tuple(range(ppc.dim() - 1))
                     ppc = ppc - ppc.mean(dim=dims)
                     optimizable_params['probe_pos_correction'] = ppc.requires_grad_(True)
+            elif opt.name == 'prj_affine_ls':
+                # adorym/optimizers.py:1062-1075: Adam, then the transformation of the first frame is pinned to identity
+                with torch.no_grad():
+                    opt.grads = comm.allreduce(opt.grads)
+                    aff = optimizable_params['prj_affine_ls'].detach().clone().contiguous()
+                    aff = opt.apply_gradient(aff, opt.grads, i_full_angle, **opt.options_dict)
+                    aff[0] = torch.tensor([[1., 0., 0.], [0., 1., 0.]], dtype=aff.dtype, device=aff.device)
+                    optimizable_params['prj_affine_ls'] = aff.requires_grad_(True)
             else:
                 # adorym/optimizers.py:1077-1083: plain Adam on any other refinable parameter (free_prop_cm, ...)
                 with torch.no_grad():

@@ -4,7 +4,8 @@ schedule of the reference (ptychography.py:786-850,901-909), SUM all-reduce of t
 over NCCL (replacing mpi4py, :1113-1114), identical Adam update on every rank.
 
 Out of scope (raise NotImplementedError when requested): shared_file / distributed_object modes, ePIE, multiscale,
-CTF forward algorithm, optimizers other than adam / gd, sparse multislice, tilt / defocus / affine refinement.
+CTF forward algorithm, optimizers other than adam / gd / momentum, probe-defocus / exit-wave-offset / slice-position
+refinement.
 """
 import datetime
 import os
@@ -332,21 +333,31 @@ def reconstruct_ptychography(
 
     # ---- refinable parameters (ptychography.py:673-735) ------------------------------------------------------------
     probe_pos_int = np.round(probe_pos).astype(int)
-    tilt_ls = np.zeros([3, n_theta])
-    tilt_ls[0] = theta_ls
+    if initial_tilt is None:                       # ptychography.py:680-684
+        tilt_ls = np.zeros([3, n_theta])
+        tilt_ls[0] = theta_ls
+    else:
+        tilt_ls = np.asarray(initial_tilt, dtype='float64')
     n_dists = len(free_prop_cm) if is_multi_dist else 1
     prj_affine_ls = np.tile(np.array([[1., 0, 0], [0, 1., 0]]).reshape([1, 2, 3]), [n_dists, 1, 1])
     optimizable_params = {'probe_real': probe_real, 'probe_imag': probe_imag,
                           'probe_defocus_mm': torch.tensor(0.0, device=device_obj),
-                          'probe_pos_offset': torch.zeros([n_theta, 2], device=device_obj),
+                          'probe_pos_offset': torch.zeros([n_theta, 2], device=device_obj,
+                                                          requires_grad=bool(optimize_probe_pos_offset)),
                           'prj_pos_offset': torch.zeros([n_theta, 2], device=device_obj)}
+    if optimize_tilt:
+        # ptychography.py:725-726: the tilt table [3, n_theta] becomes a refinable tensor (row 0 = the rotation angles)
+        optimizable_params['tilt_ls'] = torch.tensor(tilt_ls, dtype=torch.float32, device=device_obj, requires_grad=True)
+    elif initial_tilt is not None:
+        tilt_ls = torch.tensor(tilt_ls, dtype=torch.float32, device=device_obj)
     if is_multi_dist:
         ppc0 = np.zeros([n_dists, 2])
     else:
         ppc0 = np.tile(probe_pos - probe_pos_int, [n_theta, 1, 1])
     optimizable_params['probe_pos_correction'] = torch.tensor(ppc0, dtype=torch.float32, device=device_obj,
                                                               requires_grad=bool(optimize_all_probe_pos))
-    optimizable_params['prj_affine_ls'] = torch.tensor(prj_affine_ls, dtype=torch.float32, device=device_obj)
+    optimizable_params['prj_affine_ls'] = torch.tensor(prj_affine_ls, dtype=torch.float32, device=device_obj,
+                                                       requires_grad=bool(optimize_prj_affine))
     if is_multi_dist and optimize_free_prop:
         # ptychography.py:709-710: the propagation distances become a refinable tensor
         optimizable_params['free_prop_cm'] = torch.tensor(np.asarray(free_prop_cm, dtype='float64'), dtype=torch.float32,
@@ -523,7 +534,9 @@ def reconstruct_ptychography(
                     torch.stack([optimizable_params['probe_real'], optimizable_params['probe_imag']], -1).detach().cpu().numpy())
     comm.Barrier()
     ops.OBJ_GRAD_OUT = None
+    extras = {k: optimizable_params[k].detach() for k in ('tilt_ls', 'prj_affine_ls', 'probe_pos_offset', 'free_prop_cm')
+              if k in optimizable_params}
     return {'obj': obj.arr.detach(), 'probe_real': optimizable_params['probe_real'].detach(),
             'probe_imag': optimizable_params['probe_imag'].detach(),
-            'probe_pos_correction': optimizable_params['probe_pos_correction'].detach(),
+            'probe_pos_correction': optimizable_params['probe_pos_correction'].detach(), **extras,
             'loss_history': loss_history, 'output_folder': output_folder}

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ADM_ABI_VERSION 4
+#define ADM_ABI_VERSION 5
 
 /* unknown_type */
 #define ADM_DELTA_BETA 0
@@ -269,6 +269,22 @@ int adm_frame_shift_bwd(int N, int frames, const float* g_out, const float* spec
 int adm_detector_loss_large(int B, int M, long long npix, int loss_type, int raw_data_type, float poisson_multiplier,
                             float inv_n, const float* det, const float* meas, float* pred, float* g_det, float* g_meas,
                             float* partial, float* loss_per_pattern, void* stream);
+
+/* ---- affine resampling of a stack of planes (tilt refinement, affine alignment of the measured frames) -------------
+ * Replaces adorym/wrappers.py:1158-1174 `affine_transform` (forward_model.py:1066-1072, optimize_prj_affine) and
+ * wrappers.py:1177-1217 `rotate` (forward_model.py:274-276, optimize_tilt): F.affine_grid(m, align_corners=False) +
+ * F.grid_sample(bilinear, padding_mode='border', align_corners=False), and what autograd derives from them.
+ *   The array is dense [D0][D1][D2][C] fp32 (C = 1 or 2); dim_n / dim_h / dim_w in {0,1,2} say which memory dimension is
+ *   the plane index N, the rows H and the columns W.  mats: row-major 2x3 matrices, [N][6] (mat_per_plane = 1) or [6].
+ *   _fwd : out = resampled array (same layout as in).
+ *   _adj : g_in += transpose applied to g_out (caller zero-fills g_in).
+ *   _dmat: g_mats [N][6] += d/d(mats) of sum(g_out . out) per plane (caller zero-fills; sum over N for a shared matrix). */
+int adm_affine_resample_fwd(int D0, int D1, int D2, int C, int dim_n, int dim_h, int dim_w, const float* in,
+                            const float* mats, int mat_per_plane, float* out, void* stream);
+int adm_affine_resample_adj(int D0, int D1, int D2, int C, int dim_n, int dim_h, int dim_w, const float* g_out,
+                            const float* mats, int mat_per_plane, float* g_in, void* stream);
+int adm_affine_resample_dmat(int D0, int D1, int D2, int C, int dim_n, int dim_h, int dim_w, const float* in,
+                             const float* g_out, const float* mats, int mat_per_plane, float* g_mats, void* stream);
 
 #ifdef __cplusplus
 }

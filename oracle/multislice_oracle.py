@@ -144,6 +144,70 @@ def apply_rotation(obj, coord_old):
 
 
 # ----------------------------------------------------------------------------------------------
+# Affine resampling: tilt refinement and affine alignment of the data   adorym/wrappers.py:1158-1217
+# ----------------------------------------------------------------------------------------------
+def _linspace_base(n, dtype):
+    """F.affine_grid(align_corners=False) base coordinates: torch.linspace(-1, 1, n) * (n - 1) / n
+    (ATen AffineGridGenerator.cpp linspace_from_neg_one)."""
+    return torch.linspace(-1, 1, n, dtype=dtype) * (n - 1) / n
+
+
+def affine_resample(planes, mats):
+    """grid_sample(planes, affine_grid(mats, align_corners=False), bilinear, padding_mode='border',
+    align_corners=False) restated as an explicit 4-tap gather.  planes [N, H, W, C]; mats [N, 2, 3] or [2, 3].
+    Differentiable w.r.t. planes and mats; as in ATen's clip_coordinates_set_grad the derivative with respect to the
+    sampling position is ZERO where the position lies at or beyond the border."""
+    N, H, W, C = planes.shape
+    dt = planes.dtype
+    mats = mats.reshape(-1, 2, 3).to(dt)
+    if mats.shape[0] == 1:
+        mats = mats.expand(N, 2, 3)
+    bx = _linspace_base(W, dt).reshape(1, 1, W)
+    by = _linspace_base(H, dt).reshape(1, H, 1)
+    m = mats.reshape(N, 6, 1, 1)
+    xs = bx * m[:, 0] + by * m[:, 1] + m[:, 2]
+    ys = bx * m[:, 3] + by * m[:, 4] + m[:, 5]
+    ix = (xs + 1) * (W / 2.) - 0.5           # ATen GridSamplerKernel.cpp (CPU): (in + 1) * (size / 2) - 0.5
+    iy = (ys + 1) * (H / 2.) - 0.5
+
+    def clip(v, hi):
+        inside = ((v > 0) & (v < hi)).to(dt)
+        vc = torch.clamp(v, 0, hi)
+        return vc.detach() + (v - v.detach()) * inside
+
+    ix, iy = clip(ix, W - 1), clip(iy, H - 1)
+    x0, y0 = torch.floor(ix).detach(), torch.floor(iy).detach()
+    x1, y1 = x0 + 1, y0 + 1
+    flat = planes.reshape(N, H * W, C)
+
+    def tap(yi, xi, wgt):
+        valid = ((xi <= W - 1) & (yi <= H - 1)).to(dt)
+        idx = (torch.clamp(yi, 0, H - 1) * W + torch.clamp(xi, 0, W - 1)).long().reshape(N, H * W, 1).expand(N, H * W, C)
+        return torch.gather(flat, 1, idx).reshape(N, H, W, C) * (wgt * valid).unsqueeze(-1)
+
+    return (tap(y0, x0, (x1 - ix) * (y1 - iy)) + tap(y0, x1, (ix - x0) * (y1 - iy))
+            + tap(y1, x0, (x1 - ix) * (iy - y0)) + tap(y1, x1, (ix - x0) * (iy - y0)))
+
+
+def rotate_tilt(obj, theta, axis):
+    """adorym/wrappers.py:1177-1217 `rotate` (PyTorch backend) on obj[Y, X, Z, C]: the permutation that brings `axis` to
+    the front, the sign flip of theta for axis 2 (:1203-1204), m = [[cos, -sin, 0], [sin, cos, 0]] in normalised
+    coordinates, affine_grid + bilinear / border grid_sample."""
+    perm, sign = {0: ((0, 2, 1, 3), 1.), 1: ((1, 2, 0, 3), 1.), 2: ((2, 0, 1, 3), -1.)}[int(axis)]
+    th = torch.as_tensor(theta, dtype=obj.dtype).reshape(()) * sign
+    zero = torch.zeros((), dtype=obj.dtype)
+    m = torch.stack([torch.stack([torch.cos(th), -torch.sin(th), zero]), torch.stack([torch.sin(th), torch.cos(th), zero])])
+    out = affine_resample(obj.permute(*perm), m)
+    inv = [perm.index(i) for i in range(4)]
+    return out.permute(*inv)
+
+
+def affine_transform(frames, transform):
+    """adorym/wrappers.py:1158-1174 `affine_transform`: frames [N, H, W], one [2, 3] matrix."""
+    return affine_resample(frames.unsqueeze(-1), transform)[..., 0]
+
+
+# ----------------------------------------------------------------------------------------------
 # Padding / patch gather                          adorym/util.py:1327-1406, forward_model.py:313-331
 # ----------------------------------------------------------------------------------------------
 def calculate_pad_len(this_obj_size, probe_pos, probe_size):
@@ -293,7 +357,7 @@ def multislice_propagate_batch(grid_batch, probe, energy_ev, psize_cm, free_prop
 # Forward models                                              adorym/forward_model.py:179-490,819-1037
 # ----------------------------------------------------------------------------------------------
 def predict_ptycho(obj, probe_real, probe_imag, pos_batch, coord_old, cfg, probe_pos_correction=None,
-                   this_i_theta=0, this_ind_batch=None):
+                   this_i_theta=0, this_ind_batch=None, tilt=None, probe_pos_offset=None):
     """PtychographyModel.predict (adorym/forward_model.py:179-387), DP mode, no tilt/defocus refinement.
 
     cfg keys: this_obj_size, probe_size, energy_ev, psize_cm, h (kernel or None), free_prop_cm,
@@ -304,12 +368,18 @@ def predict_ptycho(obj, probe_real, probe_imag, pos_batch, coord_old, cfg, probe
     probe_size = cfg['probe_size']
     unknown_type = cfg.get('unknown_type', 'delta_beta')
     pos_batch = np.round(np.asarray(pos_batch)).astype(int)
-    if coord_old is not None and not cfg.get('two_d_mode', False):
+    if tilt is not None and not cfg.get('two_d_mode', False):
+        # optimize_tilt / initial_tilt (forward_model.py:274-276): three w.rotate calls, tilt = tilt_ls[:, this_i_theta]
+        obj_rot = rotate_tilt(rotate_tilt(rotate_tilt(obj, tilt[0], 0), tilt[1], 1), tilt[2], 2)
+    elif coord_old is not None and not cfg.get('two_d_mode', False):
         obj_rot = apply_rotation(obj, coord_old)
     else:
         obj_rot = obj
     sub = gather_patches(obj_rot, cfg['this_obj_size'], pos_batch, probe_size, unknown_type)
     probe = torch.complex(probe_real, probe_imag)  # [M, P0, P1]
+    if probe_pos_offset is not None:
+        # optimize_probe_pos_offset (forward_model.py:258-260): one Fourier shift of all modes by the angle's offset
+        probe = realign_image_fourier(probe, probe_pos_offset, axes=(1, 2))
     M = probe.shape[0]
     shifted = False
     if probe_pos_correction is not None:
@@ -431,7 +501,7 @@ def regularization_value(obj, alpha_d=None, alpha_b=None, gamma=None, weight_l1=
 
 
 def multidist_loss_and_grads(obj, probe_real, probe_imag, free_prop_cm_ls, prj_abs, cfg, probe_pos_correction=None,
-                             want=('obj',)):
+                             want=('obj',), prj_affine_ls=None):
     """MultiDistModel.get_loss_function (adorym/forward_model.py:1039-1092) for n_blocks == 1, no affine / offset
     refinement: predict (:819-1037), optional per-distance Fourier shift of the measured frames with the real part
     kept (:1079-1088, optimize_all_probe_pos; probe_pos_correction is [n_dists, 2]), mismatch loss (:88-103 applies
@@ -445,11 +515,15 @@ def multidist_loss_and_grads(obj, probe_real, probe_imag, free_prop_cm_ls, prj_a
         cfg = dict(cfg, optimize_free_prop=True)
     pred = predict_multidist(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], free_prop_cm_ls, cfg)
     prj = prj_abs
+    if prj_affine_ls is not None:
+        # optimize_prj_affine (forward_model.py:1066-1072): every distance's frame resampled by its own 2x3 matrix
+        leaves['prj_affine_ls'] = prj_affine_ls.clone().requires_grad_('prj_affine_ls' in want)
+        prj = torch.cat([affine_transform(prj[i:i + 1], leaves['prj_affine_ls'][i]) for i in range(len(free_prop_cm_ls))])
     if probe_pos_correction is not None:
         leaves['probe_pos_correction'] = probe_pos_correction.clone().requires_grad_('probe_pos_correction' in want)
         out = []
         for i in range(len(free_prop_cm_ls)):
-            fr = prj_abs[i:i + 1]
+            fr = prj[i:i + 1]
             sh = realign_image_fourier(torch.complex(fr, torch.zeros_like(fr)), leaves['probe_pos_correction'][i],
                                        axes=(1, 2))
             out.append(sh.real)
@@ -480,8 +554,9 @@ def adam_step(x, g, m, v, i_batch, step_size=0.001, b1=0.9, b2=0.999, eps=1e-7):
 # ----------------------------------------------------------------------------------------------
 def ptycho_loss_and_grads(obj, probe_real, probe_imag, pos_batch, prj_abs, coord_old, cfg, reg=None,
                           probe_pos_correction=None, this_i_theta=0, this_ind_batch=None,
-                          want=('obj', 'probe_real', 'probe_imag')):
-    """Loss of calculate_loss (forward_model.py:389-401) and its gradient w.r.t. `want`."""
+                          want=('obj', 'probe_real', 'probe_imag'), tilt=None, probe_pos_offset=None):
+    """Loss of calculate_loss (forward_model.py:389-401) and its gradient w.r.t. `want`.  tilt: [3] angles of this
+    rotation angle (tilt_ls[:, i_theta]); probe_pos_offset: [2] offset of this angle (probe_pos_offset[i_theta])."""
     leaves = {'obj': obj.clone().requires_grad_('obj' in want),
               'probe_real': probe_real.clone().requires_grad_('probe_real' in want),
               'probe_imag': probe_imag.clone().requires_grad_('probe_imag' in want)}
@@ -489,8 +564,14 @@ def ptycho_loss_and_grads(obj, probe_real, probe_imag, pos_batch, prj_abs, coord
     if probe_pos_correction is not None:
         ppc = probe_pos_correction.clone().requires_grad_('probe_pos_correction' in want)
         leaves['probe_pos_correction'] = ppc
+    if tilt is not None:
+        tilt = leaves['tilt'] = torch.as_tensor(tilt).to(obj.dtype).clone().requires_grad_('tilt' in want)
+    if probe_pos_offset is not None:
+        probe_pos_offset = leaves['probe_pos_offset'] = torch.as_tensor(probe_pos_offset).to(obj.dtype).clone().requires_grad_(
+            'probe_pos_offset' in want)
     pred = predict_ptycho(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], pos_batch, coord_old, cfg,
-                          probe_pos_correction=ppc, this_i_theta=this_i_theta, this_ind_batch=this_ind_batch)
+                          probe_pos_correction=ppc, this_i_theta=this_i_theta, this_ind_batch=this_ind_batch, tilt=tilt,
+                          probe_pos_offset=probe_pos_offset)
     pred_l, prj_l = pred, prj_abs
     if cfg.get('beamstop', None) is not None:
         # forward_model.py:128-136: pixels with beamstop < 1e-5 are dropped from the mean

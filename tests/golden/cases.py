@@ -100,6 +100,13 @@ CASES = {
                         free_prop_cm='inf', unknown_type='delta_beta', delta_scale=3e-2, beta_scale=3e-3, seed=23,
                         loss='lsq', raw_data_type='magnitude', optimize_probe=True, optimize_all_probe_pos=True,
                         slice_pos_cm=[0., 2.0e-6, 7.5e-6], rotate_out_of_loop=True),
+    # tilt refinement (optimize_tilt, forward_model.py:274-276: three differentiable rotations instead of the lookup
+    # table) + per-angle probe position offset (optimize_probe_pos_offset, forward_model.py:258-260)
+    'ptycho3d_p72_tilt': dict(kind='ptycho', obj_size=(48, 48, 48), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                              theta=0.7, n_theta=4, i_theta=1, pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=1,
+                              free_prop_cm='inf', unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=28,
+                              loss='lsq', raw_data_type='magnitude', optimize_tilt=True, tilt=(0.7, 0.06, -0.05),
+                              optimize_probe_pos_offset=True, probe_pos_offset=(0.4, -0.3)),
     # 2-D ptychography with probe modes + probe and position refinement (BASELINE config B shape, small)
     'ptycho2d_modes': dict(kind='ptycho', obj_size=(128, 128, 1), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
                            theta=0.0, n_theta=1, i_theta=0,
@@ -196,6 +203,11 @@ MD_CASES = {
     'multidist128_dist': dict(N=128, energy_ev=17500., psize_cm=1e-4, dists=[35., 62.], n_modes=1,
                               unknown_type='real_imag', delta_scale=0.4, beta_scale=0.3, seed=33, loss='lsq',
                               raw_data_type='intensity', shift=False, optimize_probe=False, free_prop=True),
+    # refinable affine alignment of the measured holograms (optimize_prj_affine, forward_model.py:1066-1072;
+    # demos/2d_multidist_holography_w_affine.py)
+    'multidist128_affine': dict(N=128, energy_ev=17500., psize_cm=1e-4, dists=[35., 62., 90.], n_modes=1,
+                                unknown_type='real_imag', delta_scale=0.4, beta_scale=0.3, seed=34, loss='lsq',
+                                raw_data_type='intensity', shift=False, optimize_probe=False, affine=True),
 }
 
 
@@ -222,4 +234,9 @@ def make_md_inputs(name):
     if c['raw_data_type'] == 'intensity':
         prj = (prj ** 2).astype('float32')
     ppc = rs.uniform(-0.8, 0.8, size=(D, 2)).astype('float32') if c['shift'] else None
-    return dict(cfg=c, obj=obj, probe_real=pr, probe_imag=pi, prj=prj, probe_pos_correction=ppc)
+    aff = None
+    if c.get('affine', False):
+        ident = np.array([[1., 0, 0], [0, 1., 0]])
+        aff = (ident[None] + rs.uniform(-0.03, 0.03, size=(D, 2, 3))).astype('float32')
+        aff[0] = ident               # the driver pins the first frame's transformation (optimizers.py:1069-1074)
+    return dict(cfg=c, obj=obj, probe_real=pr, probe_imag=pi, prj=prj, probe_pos_correction=ppc, prj_affine_ls=aff)

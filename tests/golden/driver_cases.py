@@ -11,6 +11,12 @@ DRIVER_CASES = {
     # rotate_out_of_loop (ptychography.py:918-943,1011,1067-1078): the object is rotated once per angle, the minibatches work
     # on obj.arr_rot, the gradient is rotated back with the inverse-angle table after every minibatch
     'driver_rot_out_of_loop': dict(update_scheme='immediate', n_epochs=1, rotate_out_of_loop=True),
+    # tilt refinement (three differentiable rotations per angle, ptychography.py:725-726,919-930, forward_model.py:274-276)
+    # + per-angle probe position offset (optimizers.py:845-861); checked against the reference golden on the GPU only
+    # (the oracle driver does not restate the parameter plumbing of these two)
+    'driver_tilt': dict(update_scheme='immediate', n_epochs=1, gpu_only=True,
+                        extra=dict(optimize_tilt=True, tilt_learning_rate=2e-3, optimize_probe_pos_offset=True,
+                                   probe_pos_offset_learning_rate=1e-2, optimize_all_probe_pos=False)),
 }
 OBJ_SIZE = (32, 40, 40)
 P = 72
@@ -22,7 +28,7 @@ def driver_params(name):
     c = DRIVER_CASES[name]
     rs = np.random.RandomState(77)
     init = [_smooth_noise(rs, OBJ_SIZE, 3e-4), _smooth_noise(rs, OBJ_SIZE, 3e-5)]
-    return dict(obj_size=OBJ_SIZE, probe_pos=POS, theta_st=0, theta_end=2 * np.pi, n_theta=N_THETA, energy_ev=5000.,
+    p = dict(obj_size=OBJ_SIZE, probe_pos=POS, theta_st=0, theta_end=2 * np.pi, n_theta=N_THETA, energy_ev=5000.,
                 psize_cm=1e-7, free_prop_cm='inf', minibatch_size=2, n_epochs=c['n_epochs'], alpha_d=2e-2, alpha_b=2e-3,
                 gamma=5e-2, reweighted_l1=True, learning_rate=2e-5, optimizer='adam', update_scheme=c['update_scheme'],
                 probe_type='gaussian', probe_mag_sigma=6, probe_phase_sigma=6, probe_phase_max=0.5,
@@ -30,6 +36,8 @@ def driver_params(name):
                 non_negativity=True, initial_guess=init, unknown_type='delta_beta', loss_function_type='lsq',
                 raw_data_type='magnitude', randomize_probe_pos=False, shared_probe_among_angles=True,
                 rotate_out_of_loop=c.get('rotate_out_of_loop', False))
+    p.update(c.get('extra', {}))
+    return p
 
 
 def driver_truth():

@@ -71,8 +71,10 @@ def run_reference(name):
                   device_obj=None, lmbda_nm=lmbda_nm, voxel_nm=voxel_nm, probe_size=P, fresnel_approx=True,
                   two_d_mode=two_d, minibatch_size=B, ds_level=1, this_obj_size=[Y, X, Z], energy_ev=c['energy_ev'],
                   psize_cm=c['psize_cm'], h=h, pure_projection=c.get('pure_projection', False), n_dp_batch=20, free_prop_cm=c['free_prop_cm'],
-                  optimize_probe_defocusing=False, optimize_probe_pos_offset=False, optimize_prj_pos_offset=False,
-                  optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=False, initial_tilt=None,
+                  optimize_probe_defocusing=False, optimize_probe_pos_offset=c.get('optimize_probe_pos_offset', False),
+                  optimize_prj_pos_offset=False,
+                  optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=c.get('optimize_tilt', False),
+                  initial_tilt=None,
                   debug=False, output_folder=tmp, n_probe_modes=c['n_modes'], n_theta=n_theta,
                   precalculate_rotation_coords=True, theta_ls=theta_ls, theta_downsample=None,
                   beamstop=None if inp['beamstop'] is None else torch.tensor(inp['beamstop'].copy()))
@@ -104,6 +106,15 @@ def run_reference(name):
                     this_pos_batch=inp['pos'], prj=prj_full, probe_pos_correction=ppc,
                     this_ind_batch=inp['this_ind_batch'], tilt_ls=np.zeros([3, n_theta]),
                     prj_pos_offset=w.zeros([n_theta, 2], requires_grad=True))
+        if c.get('optimize_tilt', False):
+            tilt_full = np.zeros([3, n_theta])
+            tilt_full[0] = theta_ls                                   # ptychography.py:680-682
+            tilt_full[:, c['i_theta']] = c['tilt']
+            args['tilt_ls'] = w.create_variable(tilt_full, requires_grad=True)
+        if c.get('optimize_probe_pos_offset', False):
+            off = np.zeros([n_theta, 2])
+            off[c['i_theta']] = c['probe_pos_offset']
+            args['probe_pos_offset'] = w.create_variable(off, requires_grad=True)
         if c['kind'] == 'sparse':
             del args['tilt_ls']
             args['slice_pos_cm_ls'] = w.create_variable(np.array(c['slice_pos_cm']), requires_grad=False)
@@ -112,9 +123,15 @@ def run_reference(name):
         if c.get('optimize_probe', False):
             opt_args += [fm.get_argument_index('probe_real'), fm.get_argument_index('probe_imag')]
             names += ['probe_real', 'probe_imag']
+        if c.get('optimize_probe_pos_offset', False):
+            opt_args += [fm.get_argument_index('probe_pos_offset')]
+            names += ['probe_pos_offset']
         if c.get('optimize_all_probe_pos', False):
             opt_args += [fm.get_argument_index('probe_pos_correction')]
             names += ['probe_pos_correction']
+        if c.get('optimize_tilt', False):
+            opt_args += [fm.get_argument_index('tilt_ls')]
+            names += ['tilt_ls']
         loss_fn = fm.get_loss_function()
         grads = w.get_gradients(loss_fn, opt_args_ls=opt_args, **args)
         loss = float(fm.current_loss)

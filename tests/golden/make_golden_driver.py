@@ -48,6 +48,9 @@ def run(name, data):
                'probe_real': last['probe_real'].detach().numpy().astype('float32'),
                'probe_imag': last['probe_imag'].detach().numpy().astype('float32'),
                'probe_pos_correction': last['probe_pos_correction'].detach().numpy().astype('float32')}
+        for k in ('tilt_ls', 'probe_pos_offset'):
+            if k in last and last[k].requires_grad:
+                out[k] = last[k].detach().numpy().astype('float32')
         return out
     finally:
         ptych.update_parameters = orig
@@ -56,7 +59,8 @@ def run(name, data):
 
 def main():
     data = driver_data()
-    np.savez_compressed(os.path.join(HERE, 'driver_data.npz'), data=np.abs(data).astype('float16'))
+    if not sys.argv[1:]:
+        np.savez_compressed(os.path.join(HERE, 'driver_data.npz'), data=np.abs(data).astype('float16'))
     # the data are stored as fp16 magnitudes (compact); every consumer (reference run included) uses the fp16-rounded values
     data = np.abs(data).astype('float16').astype('float32').astype('complex64')
     for name in (sys.argv[1:] or DRIVER_CASES):

@@ -40,7 +40,7 @@ def run_reference(name):
                   ds_level=1, this_obj_size=[N, N, 1], energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=None,
                   pure_projection=False, n_dp_batch=1, free_prop_cm=c['dists'], optimize_probe_defocusing=False,
                   optimize_probe_pos_offset=False, optimize_prj_pos_offset=False, optimize_all_probe_pos=c['shift'],
-                  optimize_free_prop=c.get('free_prop', False), optimize_prj_affine=False, optimize_ctf_lg_kappa=False, optimize_tilt=False,
+                  optimize_free_prop=c.get('free_prop', False), optimize_prj_affine=c.get('affine', False), optimize_ctf_lg_kappa=False, optimize_tilt=False,
                   initial_tilt=None, debug=False, output_folder=tmp, n_probe_modes=M, n_theta=1,
                   precalculate_rotation_coords=False, theta_ls=np.zeros(1, 'float32'), theta_downsample=None,
                   beamstop=None, u_free=None, v_free=None)
@@ -61,6 +61,8 @@ def run_reference(name):
                     prj_pos_offset=w.zeros([1, 2], requires_grad=True))
         if c.get('free_prop', False):
             args['free_prop_cm'] = w.create_variable(np.array(c['dists']), requires_grad=True)
+        if c.get('affine', False):
+            args['prj_affine_ls'] = w.create_variable(inp['prj_affine_ls'], requires_grad=True)
         opt_args, names = [0], ['obj']
         if c.get('free_prop', False):
             opt_args += [fm.get_argument_index('free_prop_cm')]
@@ -71,6 +73,9 @@ def run_reference(name):
         if c['shift']:
             opt_args += [fm.get_argument_index('probe_pos_correction')]
             names += ['probe_pos_correction']
+        if c.get('affine', False):
+            opt_args += [fm.get_argument_index('prj_affine_ls')]
+            names += ['prj_affine_ls']
         grads = w.get_gradients(fm.get_loss_function(), opt_args_ls=opt_args, **args)
         loss = float(fm.current_loss)
         with torch.no_grad():
@@ -82,7 +87,7 @@ def run_reference(name):
             if n == 'obj':
                 for k, v in compact_grad(g).items():
                     out['gobj_' + k] = v
-            elif n in ('probe_pos_correction', 'free_prop_cm'):
+            elif n in ('probe_pos_correction', 'free_prop_cm', 'prj_affine_ls'):
                 out['g_' + n] = g.astype('float32')
             else:
                 out['g_' + n + '_sub'] = g[:, ::4, ::4].astype('float32')

@@ -64,10 +64,17 @@ def run_oracle_case(name, dtype=torch.float32):
         want += ['probe_pos_correction']
     if reg is not None and reg.get('weight_l1') is not None:
         reg = dict(reg, weight_l1=torch.tensor(reg['weight_l1']).to(dtype))
+    extra = {}
+    if c.get('optimize_probe_pos_offset', False):
+        extra['probe_pos_offset'] = torch.tensor(np.asarray(c['probe_pos_offset'], dtype='float32'))
+        want += ['probe_pos_offset']
+    if c.get('optimize_tilt', False):
+        extra['tilt'] = torch.tensor(np.asarray(c['tilt'], dtype='float32'))       # tilt_ls[:, i_theta], fp32 like the driver
+        want += ['tilt']
     loss, data_loss, pred, grads = orc.ptycho_loss_and_grads(
         torch.tensor(inp['obj']).to(dtype), torch.tensor(inp['probe_real']).to(dtype),
         torch.tensor(inp['probe_imag']).to(dtype), inp['pos'], torch.tensor(inp['prj']).to(dtype), coord, cfg, reg=reg,
-        probe_pos_correction=ppc, this_i_theta=c['i_theta'], this_ind_batch=inp['this_ind_batch'], want=tuple(want))
+        probe_pos_correction=ppc, this_i_theta=c['i_theta'], this_ind_batch=inp['this_ind_batch'], want=tuple(want), **extra)
     return inp, float(loss), pred.numpy(), {k: v.numpy() for k, v in grads.items()}
 
 
@@ -95,10 +102,14 @@ def run_md_oracle_case(name, dtype=torch.float32):
         want += ['probe_pos_correction']
     if c.get('free_prop', False):
         want += ['free_prop_cm']
+    aff = None
+    if c.get('affine', False):
+        aff = torch.tensor(inp['prj_affine_ls']).to(dtype)
+        want += ['prj_affine_ls']
     loss, pred, grads = orc.multidist_loss_and_grads(
         torch.tensor(inp['obj']).to(dtype), torch.tensor(inp['probe_real']).to(dtype),
         torch.tensor(inp['probe_imag']).to(dtype), c['dists'], torch.tensor(inp['prj']).to(dtype), cfg,
-        probe_pos_correction=ppc, want=tuple(want))
+        probe_pos_correction=ppc, want=tuple(want), prj_affine_ls=aff)
     return inp, float(loss), pred.numpy(), {k: v.numpy() for k, v in grads.items()}
 
 
@@ -117,3 +128,14 @@ def check_md_against_golden(gold, loss, pred, grads, tol=1e-4, gtol=1e-4):
         assert rel_err(grads['probe_pos_correction'], gold['g_probe_pos_correction']) < gtol
     if 'g_free_prop_cm' in gold.files:
         assert rel_err(grads['free_prop_cm'], gold['g_free_prop_cm']) < gtol
+    if 'g_prj_affine_ls' in gold.files:
+        assert rel_err(grads['prj_affine_ls'], gold['g_prj_affine_ls']) < 5 * gtol
+
+
+def check_param_grads_against_golden(gold, grads, i_theta, tol=1e-4):
+    """Refinable-parameter gradients the goldens hold as full per-angle tables: tilt_ls [3, n_theta] and
+    probe_pos_offset [n_theta, 2]; `grads` holds this angle's entries ('tilt' [3], 'probe_pos_offset' [2])."""
+    if 'g_tilt_ls' in gold.files:
+        assert rel_err(grads['tilt'], gold['g_tilt_ls'][:, i_theta]) < tol, 'tilt'
+    if 'g_probe_pos_offset' in gold.files:
+        assert rel_err(grads['probe_pos_offset'], gold['g_probe_pos_offset'][i_theta]) < tol, 'probe_pos_offset'

@@ -25,7 +25,7 @@ def md_common_vars(c, dev, prj_full, shift):
                 this_obj_size=[N, N, 1], energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=None, pure_projection=False,
                 n_dp_batch=1, free_prop_cm=c['dists'], optimize_probe_defocusing=False, optimize_probe_pos_offset=False,
                 optimize_prj_pos_offset=False, optimize_all_probe_pos=shift, optimize_free_prop=c.get('free_prop', False),
-                optimize_prj_affine=False, optimize_ctf_lg_kappa=False, optimize_tilt=False, initial_tilt=None,
+                optimize_prj_affine=c.get('affine', False), optimize_ctf_lg_kappa=False, optimize_tilt=False, initial_tilt=None,
                 n_probe_modes=c['n_modes'], n_theta=1, precalculate_rotation_coords=False,
                 theta_ls=np.zeros(1, 'float32'), theta_downsample=None, beamstop=None, u_free=None, v_free=None)
 
@@ -58,6 +58,10 @@ def run_gpu_md(inp, want_probe, prj_on_device=False):
         args['free_prop_cm'] = torch.tensor(c['dists'], dtype=torch.float32, device=dev, requires_grad=True)
         opt += [fm.get_argument_index('free_prop_cm')]
         names += ['free_prop_cm']
+    if c.get('affine', False):
+        args['prj_affine_ls'] = t(inp['prj_affine_ls'])
+        opt += [fm.get_argument_index('prj_affine_ls')]
+        names += ['prj_affine_ls']
     diff = ab.Differentiator()
     diff.create_loss_node(fm.get_loss_function(), opt)
     grads = diff.get_gradients(**args)
@@ -76,6 +80,12 @@ def test_multidist_loss_and_gradients_match_oracle_and_reference(name):
     assert abs(loss - loss64) <= TOL * abs(loss64)
     assert rel_err(pred, pred64) < TOL
     for k in grads64:
+        if k == 'prj_affine_ls':
+            # frame 0 carries the identity matrix: its border pixels sit EXACTLY on the clamp, where ATen's derivative is
+            # defined as zero in fp32 and rounding decides in fp64 -- compared with the fp32 reference golden below only;
+            # scalar sums with cancellation: 5e-4 (see test_oracle_golden.py)
+            assert rel_err(grads[k][1:], grads64[k][1:]) < 5e-4, k
+            continue
         assert rel_err(grads[k], grads64[k]) < TOL, k
     gold = np.load(os.path.join(GOLD, name + '.npz'))
     check_md_against_golden(gold, loss, pred, grads)

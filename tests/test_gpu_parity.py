@@ -30,8 +30,10 @@ def _common_vars(inp, cfg, dev, prj_full, theta_ls, n_theta):
                 minibatch_size=len(inp['pos']), ds_level=1, this_obj_size=[Y, X, Z], energy_ev=c['energy_ev'],
                 psize_cm=c['psize_cm'], h=cfg['h'], pure_projection=c.get('pure_projection', False), n_dp_batch=20,
                 free_prop_cm=c['free_prop_cm'],
-                optimize_probe_defocusing=False, optimize_probe_pos_offset=False, optimize_prj_pos_offset=False,
-                optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=False, initial_tilt=None,
+                optimize_probe_defocusing=False, optimize_probe_pos_offset=c.get('optimize_probe_pos_offset', False),
+                optimize_prj_pos_offset=False,
+                optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=c.get('optimize_tilt', False),
+                initial_tilt=None,
                 n_probe_modes=c['n_modes'], n_theta=n_theta, precalculate_rotation_coords=False, theta_ls=theta_ls,
                 theta_downsample=None, beamstop=inp.get('beamstop'))
 
@@ -77,9 +79,22 @@ def run_gpu_case(name):
     if c.get('optimize_probe', False):
         opt_args += [fm.get_argument_index('probe_real'), fm.get_argument_index('probe_imag')]
         names += ['probe_real', 'probe_imag']
+    if c.get('optimize_probe_pos_offset', False):
+        off = np.zeros([n_theta, 2], 'float32')
+        off[c['i_theta']] = c['probe_pos_offset']
+        args['probe_pos_offset'] = t(off)
+        opt_args += [fm.get_argument_index('probe_pos_offset')]
+        names += ['probe_pos_offset']
     if has_ppc:
         opt_args += [fm.get_argument_index('probe_pos_correction')]
         names += ['probe_pos_correction']
+    if c.get('optimize_tilt', False):
+        tilt = np.zeros([3, n_theta], 'float32')
+        tilt[0] = theta_ls
+        tilt[:, c['i_theta']] = c['tilt']
+        args['tilt_ls'] = t(tilt)
+        opt_args += [fm.get_argument_index('tilt_ls')]
+        names += ['tilt_ls']
     diff = ab.Differentiator()
     diff.create_loss_node(fm.get_loss_function(), opt_args)
     grads = diff.get_gradients(**args)
@@ -114,6 +129,16 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
         if k in grads:
             assert rel_err(grads[k], grads64[k]) < TOL, k
             assert rel_err(grads[k], gold['g_' + k]) < TOL, k
+    # refinable tilt angles / per-angle probe offset: full tables [3, n_theta] / [n_theta, 2], only this angle's entries are
+    # non-zero.  Scalar sums with heavy cancellation: the reference's own fp32 values sit 1.4e-4 from fp64 (5e-4, see
+    # test_oracle_golden.py)
+    it = inp['cfg']['i_theta']
+    if 'tilt_ls' in grads:
+        assert rel_err(grads['tilt_ls'][:, it], grads64['tilt']) < 5e-4
+        assert rel_err(grads['tilt_ls'], gold['g_tilt_ls']) < 5e-4
+    if 'probe_pos_offset' in grads:
+        assert rel_err(grads['probe_pos_offset'][it], grads64['probe_pos_offset']) < 5e-4
+        assert rel_err(grads['probe_pos_offset'], gold['g_probe_pos_offset']) < 5e-4
 
 
 def test_single_batch_ptychography_model_matches_oracle():

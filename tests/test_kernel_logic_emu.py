@@ -184,3 +184,43 @@ def test_emulated_peer_memory_update_equals_allreduce_plus_adam():
         assert np.array_equal(xs[r], xr), r
         i0, i1 = 4 * ((n // 4) * r // world), 4 * ((n // 4) * (r + 1) // world)
         assert np.array_equal(ms[r][i0:i1], mr[i0:i1]) and np.array_equal(vs[r][i0:i1], vr[i0:i1])
+
+
+@pytest.mark.parametrize('shape,C,roles', [((3, 16, 20), 1, (0, 1, 2)), ((6, 10, 12), 2, (0, 2, 1)),
+                                            ((6, 10, 12), 2, (1, 2, 0)), ((6, 10, 12), 2, (2, 0, 1))])
+def test_emulated_affine_resample_matches_oracle(shape, C, roles):
+    """affine.cu (tilt rotation / affine alignment of the data: wrappers.py:1158-1217) against the oracle's restatement
+    of affine_grid + grid_sample: value, transpose and matrix gradient, per-plane and shared matrices, all three axis
+    roles of wrappers.rotate."""
+    import ctypes
+    L = emu_lib.emu()
+    P = emu_lib.P
+    rs = np.random.RandomState(5)
+    full = shape + ((2,) if C == 2 else ())
+    arr = rs.normal(size=full).astype('float32')
+    w = rs.normal(size=full).astype('float32')
+    N = shape[roles[0]]
+    perm = list(roles) + ([3] if C == 2 else [])
+    inv = [perm.index(i) for i in range(len(perm))]
+    for per_plane in (1, 0):
+        nm = N if per_plane else 1
+        mats = (np.array([[1., 0, 0], [0, 1., 0]]) + 0.15 * rs.normal(size=(nm, 2, 3))).astype('float32')
+        out = np.full(full, np.nan, 'float32')
+        emu_lib.ck(L.adm_affine_resample_fwd(shape[0], shape[1], shape[2], C, roles[0], roles[1], roles[2], P(arr), P(mats),
+                                             per_plane, P(out), None))
+        g_in = np.zeros(full, 'float32')
+        emu_lib.ck(L.adm_affine_resample_adj(shape[0], shape[1], shape[2], C, roles[0], roles[1], roles[2], P(w), P(mats),
+                                             per_plane, P(g_in), None))
+        g_m = np.zeros((N, 6), 'float32')
+        emu_lib.ck(L.adm_affine_resample_dmat(shape[0], shape[1], shape[2], C, roles[0], roles[1], roles[2], P(arr), P(w),
+                                              P(mats), per_plane, P(g_m), None))
+        a = torch.tensor(arr, dtype=torch.float64, requires_grad=True)
+        m = torch.tensor(mats, dtype=torch.float64, requires_grad=True)
+        planes = a.permute(*perm) if C == 2 else a.permute(*perm).unsqueeze(-1)
+        ref = orc.affine_resample(planes, m)
+        ref = ref.permute(*inv) if C == 2 else ref[..., 0].permute(*inv)
+        ga, gm = torch.autograd.grad((ref * torch.tensor(w, dtype=torch.float64)).sum(), [a, m])
+        assert rel_err(out, ref.detach().numpy()) < 1e-5
+        assert rel_err(g_in, ga.numpy()) < 1e-5
+        got = g_m.reshape(N, 2, 3) if per_plane else g_m.sum(0).reshape(1, 2, 3)
+        assert rel_err(got, gm.numpy()) < 1e-4

@@ -6,7 +6,8 @@ import numpy as np
 import pytest
 import torch
 from cases import CASES, MD_CASES
-from oracle_util import run_oracle_case, compact_grad, rel_err, run_md_oracle_case, check_md_against_golden
+from oracle_util import (run_oracle_case, compact_grad, rel_err, run_md_oracle_case, check_md_against_golden,
+                         check_param_grads_against_golden)
 from oracle import multislice_oracle as orc
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
@@ -30,6 +31,9 @@ def test_oracle_matches_reference_golden(name):
     for k in ('probe_real', 'probe_imag', 'probe_pos_correction'):
         if 'g_' + k in gold.files:
             assert rel_err(grads[k], gold['g_' + k]) < TOL, k
+    # scalar parameter gradients (tilt angles, per-angle offset) are sums with heavy cancellation: the reference's own fp32
+    # values sit 1.4e-4 from an fp64 evaluation of the same chain, so they are compared at 5e-4
+    check_param_grads_against_golden(gold, grads, inp['cfg']['i_theta'], 5e-4)
 
 
 @pytest.mark.parametrize('name', sorted(MD_CASES.keys()))
