@@ -94,3 +94,33 @@ def test_reference_ci_config_matches_reference_driver():
     assert rel[0] < 5 * float(gold['sensitivity_loss_history'])
     assert rel.max() < 5 * float(gold['sensitivity_loss_history'])
     assert oerr < 5 * float(gold['sensitivity_obj'])
+
+
+@pytest.mark.gpu
+def test_multidist_driver_with_distance_and_affine_refinement_matches_reference_driver():
+    """Multi-distance holography through the driver with the option set of demos/2d_multidist_holography_w_affine.py
+    (refinable propagation distances + refinable affine alignment of the holograms; 128^2 frames, 3 distances, 5 updates)
+    against the unmodified reference's reconstruct_ptychography (tests/golden/make_golden_driver_md.py).  Same stated
+    tolerances as above; the refined parameters are compared as updates (final - initial)."""
+    import adorym_b200 as ab
+    from make_golden_driver_md import md_driver_params, START_DISTS
+    gold = np.load(os.path.join(GOLD, 'driver_md_affine.npz'))
+    data = gold['data'].astype('float32')
+    out = ab.reconstruct_ptychography(data, **md_driver_params(), verbose=False, save_outputs=False,
+                                      output_folder='/tmp/adm_test_driver_md')
+    gh = gold['loss_history']
+    lh = np.array([l for (e, b, l, t) in out['loss_history']])
+    assert len(lh) == len(gh)
+    assert abs(lh[0] - gh[0, 2]) <= 1e-4 * gh[0, 2]
+    np.testing.assert_allclose(lh, gh[:, 2], rtol=1.5e-2)
+    obj = out['obj'].cpu().numpy()
+    mag = np.sqrt(obj[..., 0] ** 2 + obj[..., 1] ** 2)
+    phase = np.arctan2(obj[..., 1], obj[..., 0])
+    assert rel_err(mag, gold['out_obj_mag_ds_1']) < 3e-2
+    assert rel_err(phase, gold['out_obj_phase_ds_1']) < 3e-2
+    d0 = np.array(START_DISTS, dtype='float32')
+    assert rel_err(out['free_prop_cm'].cpu().numpy() - d0, gold['free_prop_cm'] - d0) < 5e-2
+    ident = np.tile(np.array([[1., 0, 0], [0, 1., 0]], dtype='float32'), (3, 1, 1))
+    got = out['prj_affine_ls'].cpu().numpy()
+    assert np.array_equal(got[0], ident[0])                       # the first frame's transformation stays pinned
+    assert rel_err(got - ident, gold['prj_affine_ls'] - ident) < 5e-2
