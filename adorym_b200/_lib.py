@@ -72,6 +72,14 @@ SIGNATURES = {
     'adm_frame_shift_bwd': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_detector_loss_large': [c_int, c_int, c_longlong, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_lf_patch_step_fwd': [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p],
+    'adm_lf_patch_step_bwd': [c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_void_p, c_void_p, c_void_p, c_int, c_void_p],
+    'adm_lf_farfield_fwd': [c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p],
+    'adm_lf_farfield_bwd': [c_int, c_int, c_void_p, c_void_p, c_float, c_void_p, c_void_p, c_void_p],
+    'adm_frame_shift_complex_fwd': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
+    'adm_frame_shift_complex_bwd': [c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p],
     'adm_affine_resample_fwd': [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     'adm_affine_resample_adj': [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p],
     'adm_affine_resample_dmat': [c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
@@ -104,7 +112,7 @@ def get_lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('adorym_b200: CUDA library %s is missing; run `python -m adorym_b200.build`' % LIB_PATH)
         _lib = bind(ctypes.CDLL(LIB_PATH))
-        if _lib.adm_abi_version() != 5:
+        if _lib.adm_abi_version() != 6:
             raise RuntimeError('adorym_b200: ABI version mismatch')
     return _lib
 

@@ -32,6 +32,22 @@
 ADM_HD int lf_pad(int n) { return n + (n >> 3); }
 ADM_HD int lf_ld(int N) { int l = N + (N >> 3); return l + ((18 - (l & 15)) & 15); }
 
+ADM_DEV void lf_red2(cpx* addr, float a, float b) {
+#ifndef ADM_HOST_EMU
+    asm volatile("red.global.add.v2.f32 [%0], {%1, %2};\n" ::"l"(addr), "f"(a), "f"(b) : "memory");
+#else
+    atomicAdd(&addr->x, a);
+    atomicAdd(&addr->y, b);
+#endif
+}
+// psi (1 + T') and g conj(1 + T') (T' = T - 1 is what the transmission volume stores)
+ADM_DEV cpx modulate(cpx v, cpx tp) {
+    return mk(fmaf(-v.y, tp.y, fmaf(v.x, tp.x, v.x)), fmaf(v.y, tp.x, fmaf(v.x, tp.y, v.y)));
+}
+ADM_DEV cpx modulate_conj(cpx v, cpx tp) {
+    return mk(fmaf(v.y, tp.y, fmaf(v.x, tp.x, v.x)), fmaf(v.y, tp.x, fmaf(-v.x, tp.y, v.y)));
+}
+
 template <int R, bool INV> ADM_DEV void lf_dft(cpx* v) {
     if constexpr (R == 8) dft8<INV>(v);
     else if constexpr (R == 4) dft4<INV>(v[0], v[1], v[2], v[3]);
@@ -447,6 +463,139 @@ template <int N, bool GRAD> __global__ void __launch_bounds__(LF_NT) k_lf_cols_s
     }
 }
 
+// ---- ptychography with probes the shared-memory FFT cannot hold (128 .. 2048 pixels): batched patch steps -------------------
+// One slice step of propagate.py:208-258 for B*M wavefields at once, every pattern b reading ITS patch of the slice-major
+// transmission volume T' (origin pos[b], vacuum outside the object: util.py:1327-1351, forward_model.py:313-331):
+//   psi <- IFFT2(H . FFT2(psi (1 + T'_patch)))      (H == NULL: modulation only -- the last slice, propagate.py:253)
+// as   P1 [modulation + row FFT]  ->  k_lf_cols (column FFT . H . column IFFT)  ->  k_lf_rows (row IFFT),
+// and the adjoint in the reverse order; dL/dT = g conj(psi_in) is scatter-added into the gradient volume (red.add, the
+// patches of a scan overlap).
+struct LfPatch {
+    const cpx* tvol;     // [Nz][Y][Xp]
+    const int* pos;      // [B][2] (y, x)
+    const cpx* psi_in;   // [B*M][N][N]
+    const cpx* g_in;     // adjoint: incoming gradient (row-transformed when FFT)
+    cpx* out;            // forward: [B*M][N][N]
+    cpx* g_psi;          // adjoint: dL/d psi_in [B*M][N][N]
+    cpx* g_tvol;         // adjoint: [Nz][Y + gm][gP], accumulated
+    int Y, X, Xp, z, M, gm, gP;
+};
+
+ADM_DEV cpx lf_patch_tp(const LfPatch& p, int gy, int gx) {
+    const bool inb = (unsigned)gy < (unsigned)p.Y && (unsigned)gx < (unsigned)p.X;
+    return inb ? p.tvol[((size_t)p.z * p.Y + gy) * p.Xp + gx] : mk(0.f, 0.f);
+}
+
+template <int N, bool FFT> __global__ void __launch_bounds__(LF_NT) k_lf_patch_mod(LfPatch p) {
+    ADM_SMEM_DECL
+    constexpr int RPC = LF_ROW_ELEMS / N, EPT = LF_ROW_ELEMS / LF_NT;
+    const int ld = lf_ld(N), tid = threadIdx.x;
+    cpx* s = (cpx*)smem_raw;
+    cpx* tw = s + RPC * ld;
+    if (FFT) lf_init_twiddles<N>(tw, tid);
+    const int y0 = blockIdx.x * RPC, fr = blockIdx.y, b = fr / p.M;
+    const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
+    const cpx* in = p.psi_in + (size_t)fr * N * N;
+    cpx* o = p.out + (size_t)fr * N * N;
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int idx = tid + k * LF_NT, f = idx / N, x = idx % N;
+        const cpx v = modulate(in[(size_t)(y0 + f) * N + x], lf_patch_tp(p, py + y0 + f, px + x));
+        if (FFT) s[f * ld + lf_pad(x)] = v;
+        else o[(size_t)(y0 + f) * N + x] = v;
+    }
+    if (FFT) {
+        __syncthreads();
+        lf_fwd_from<N, N>(s, ld, RPC, tw, tid);
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int idx = tid + k * LF_NT, f = idx / N, x = idx % N;
+            o[(size_t)(y0 + f) * N + x] = s[f * ld + lf_pad(x)];
+        }
+    }
+}
+
+template <int N, bool FFT> __global__ void __launch_bounds__(LF_NT) k_lf_patch_mod_adj(LfPatch p) {
+    ADM_SMEM_DECL
+    constexpr int RPC = LF_ROW_ELEMS / N, EPT = LF_ROW_ELEMS / LF_NT;
+    const int ld = lf_ld(N), tid = threadIdx.x;
+    cpx* s = (cpx*)smem_raw;
+    cpx* tw = s + RPC * ld;
+    if (FFT) lf_init_twiddles<N>(tw, tid);
+    const int y0 = blockIdx.x * RPC, fr = blockIdx.y, b = fr / p.M;
+    const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
+    const cpx* gi = p.g_in + (size_t)fr * N * N;
+    const cpx* in = p.psi_in + (size_t)fr * N * N;
+    if (FFT) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int idx = tid + k * LF_NT, f = idx / N, x = idx % N;
+            s[f * ld + lf_pad(x)] = gi[(size_t)(y0 + f) * N + x];
+        }
+        __syncthreads();
+        lf_inv_from<N, N>(s, ld, RPC, tw, tid);
+    }
+#pragma unroll
+    for (int k = 0; k < EPT; ++k) {
+        const int idx = tid + k * LF_NT, f = idx / N, x = idx % N;
+        const size_t e = (size_t)(y0 + f) * N + x;
+        const cpx g = FFT ? s[f * ld + lf_pad(x)] : gi[e];
+        const int gy = py + y0 + f, gx = px + x;
+        if (p.g_psi != nullptr) p.g_psi[(size_t)fr * N * N + e] = modulate_conj(g, lf_patch_tp(p, gy, gx));
+        if (p.g_tvol != nullptr && (unsigned)gy < (unsigned)p.Y && (unsigned)gx < (unsigned)p.X) {
+            const cpx c = cmulc(g, in[e]);                     // dL/dT = g conj(psi_in)
+            lf_red2(p.g_tvol + ((size_t)p.z * (p.Y + p.gm) + gy + p.gm) * p.gP + gx + p.gm, c.x, c.y);
+        }
+    }
+}
+
+// far field (propagate.py:263-270, sign_convention = +1): det = fftshift(FFT2(psi)) . scale, natural order.
+//   ADJ = false: in = row-transformed frames (k_lf_rows<N, false>), column DIF FFT, scatter to the shifted natural position
+//   ADJ = true : in = dL/d det (natural, shifted), gather into the permuted order, column inverse (= conjugate transpose)
+// grid (N / C, frames); order [N] = frequency index at each spectrum position.
+template <int N, bool ADJ> __global__ void __launch_bounds__(LF_NT) k_lf_cols_far(const cpx* in, const int* order, float scale,
+                                                                                   cpx* out) {
+    ADM_SMEM_DECL
+    constexpr int C = LF_COL_ELEMS / N, EPT = LF_COL_ELEMS / LF_NT;
+    const int ld = lf_ld(N), tid = threadIdx.x;
+    cpx* a = (cpx*)smem_raw;
+    cpx* tw = a + C * ld;
+    lf_init_twiddles<N>(tw, tid);
+    const int x0 = blockIdx.x * C, fr = blockIdx.y;
+    const size_t frame = (size_t)N * N;
+    const cpx* src = in + (size_t)fr * frame;
+    cpx* dst = out + (size_t)fr * frame;
+    if constexpr (!ADJ) {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int idx = tid + k * LF_NT, c = idx % C, y = idx / C;
+            a[c * ld + lf_pad(y)] = src[(size_t)y * N + x0 + c];
+        }
+        __syncthreads();
+        lf_fwd_from<N, N>(a, ld, C, tw, tid);
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int idx = tid + k * LF_NT, c = idx % C, y = idx / C;
+            const int fy = (order[y] + N / 2) % N, fx = (order[x0 + c] + N / 2) % N;
+            dst[(size_t)fy * N + fx] = cscale(a[c * ld + lf_pad(y)], scale);
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int idx = tid + k * LF_NT, c = idx % C, y = idx / C;
+            const int fy = (order[y] + N / 2) % N, fx = (order[x0 + c] + N / 2) % N;
+            a[c * ld + lf_pad(y)] = cscale(src[(size_t)fy * N + fx], scale);
+        }
+        __syncthreads();
+        lf_inv_from<N, N>(a, ld, C, tw, tid);
+#pragma unroll
+        for (int k = 0; k < EPT; ++k) {
+            const int idx = tid + k * LF_NT, c = idx % C, y = idx / C;
+            dst[(size_t)y * N + x0 + c] = a[c * ld + lf_pad(y)];
+        }
+    }
+}
+
 // ---- detector magnitude + mismatch + residuals for large frames: grid (chunks, frames), deterministic 2-stage sum ------
 #define LF_LOSS_CHUNKS 64
 __global__ void __launch_bounds__(LF_NT) k_lf_detector_loss(int M, int npix, int loss_type, int raw_type, float pm, float inv_n,
@@ -603,6 +752,102 @@ extern "C" int adm_multidist_bwd(const adm_multidist_cfg* cfg, const float* obj,
     return ADM_OK;
 }
 
+static int lf_patch_fill(LfPatch& q, int B, int M, int Y, int X, int z, const float* tvol, const int* pos) {
+    if (B < 1 || M < 1 || Y < 1 || X < 1 || z < 0 || !tvol || !pos) return ADM_ERR_ARG;
+    if ((long long)B * M > 65535) return ADM_ERR_UNSUPPORTED;
+    q.tvol = (const cpx*)tvol; q.pos = pos; q.psi_in = nullptr; q.g_in = nullptr; q.out = nullptr; q.g_psi = nullptr;
+    q.g_tvol = nullptr; q.Y = Y; q.X = X; q.Xp = ADM_TVOL_PITCH(X); q.z = z; q.M = M; q.gm = 0; q.gP = 0;
+    return ADM_OK;
+}
+
+extern "C" int adm_lf_patch_step_fwd(int N, int B, int M, int Y, int X, int z, const float* tvol, const int* pos,
+                                     const float* psi_in, const float* Hprep, float* work, float* psi_out, void* stream) {
+    LfPatch q;
+    int rc = lf_patch_fill(q, B, M, Y, X, z, tvol, pos);
+    if (rc) return rc;
+    if (!psi_in || !psi_out || (Hprep && !work)) return ADM_ERR_ARG;
+    const int F = B * M;
+    q.psi_in = (const cpx*)psi_in;
+    LF_DISPATCH(N, {
+        if (!Hprep) {
+            q.out = (cpx*)psi_out;
+            ADM_LAUNCH((k_lf_patch_mod<LN, false>), dim3(LN / LfSizes<LN>::RPC, F), LF_NT, 16, stream, q);
+        } else {
+            if (set_smem(k_lf_patch_mod<LN, true>, LfSizes<LN>::rows()) || set_smem(k_lf_cols<LN, false>, LfSizes<LN>::cols2()) ||
+                set_smem(k_lf_rows<LN, true>, LfSizes<LN>::rows()))
+                return ADM_ERR_CUDA;
+            q.out = (cpx*)work;
+            ADM_LAUNCH((k_lf_patch_mod<LN, true>), dim3(LN / LfSizes<LN>::RPC, F), LF_NT, LfSizes<LN>::rows(), stream, q);
+            LfParams b;
+            b.obj = nullptr; b.probe = nullptr; b.g_obj = nullptr; b.g_probe = nullptr; b.unknown_type = 0; b.k1 = 0.f; b.sgn = 1.f;
+            b.M = F; b.D = 1; b.in = (const cpx*)work; b.H = (const cpx*)Hprep; b.out = (cpx*)psi_out;
+            ADM_LAUNCH((k_lf_cols<LN, false>), dim3(LN / LfSizes<LN>::C, F), LF_NT, LfSizes<LN>::cols2(), stream, b);
+            ADM_LAUNCH((k_lf_rows<LN, true>), F * (LN / LfSizes<LN>::RPC), LF_NT, LfSizes<LN>::rows(), stream,
+                       (const cpx*)psi_out, (cpx*)psi_out);
+        }
+    })
+    return ADM_OK;
+}
+
+extern "C" int adm_lf_patch_step_bwd(int N, int B, int M, int Y, int X, int z, const float* tvol, const int* pos,
+                                     const float* psi_in, const float* HprepC, const float* g_out, float* work1, float* work2,
+                                     float* g_psi, float* g_tvol, int g_margin, void* stream) {
+    LfPatch q;
+    int rc = lf_patch_fill(q, B, M, Y, X, z, tvol, pos);
+    if (rc) return rc;
+    if (!psi_in || !g_out || g_margin < 0 || (HprepC && (!work1 || !work2))) return ADM_ERR_ARG;
+    const int F = B * M;
+    q.psi_in = (const cpx*)psi_in; q.g_psi = (cpx*)g_psi; q.g_tvol = (cpx*)g_tvol;
+    q.gm = g_margin; q.gP = ADM_GVOL_PITCH(X, g_margin);
+    LF_DISPATCH(N, {
+        if (!HprepC) {
+            q.g_in = (const cpx*)g_out;
+            ADM_LAUNCH((k_lf_patch_mod_adj<LN, false>), dim3(LN / LfSizes<LN>::RPC, F), LF_NT, 16, stream, q);
+        } else {
+            if (set_smem(k_lf_patch_mod_adj<LN, true>, LfSizes<LN>::rows()) || set_smem(k_lf_cols<LN, true>, LfSizes<LN>::cols2()) ||
+                set_smem(k_lf_rows<LN, false>, LfSizes<LN>::rows()))
+                return ADM_ERR_CUDA;
+            ADM_LAUNCH((k_lf_rows<LN, false>), F * (LN / LfSizes<LN>::RPC), LF_NT, LfSizes<LN>::rows(), stream,
+                       (const cpx*)g_out, (cpx*)work2);
+            LfParams b;
+            b.obj = nullptr; b.probe = nullptr; b.g_obj = nullptr; b.g_probe = nullptr; b.unknown_type = 0; b.k1 = 0.f; b.sgn = 1.f;
+            b.M = F; b.D = 1; b.in = (const cpx*)work2; b.H = (const cpx*)HprepC; b.out = (cpx*)work1;
+            ADM_LAUNCH((k_lf_cols<LN, true>), dim3(LN / LfSizes<LN>::C, F), LF_NT, LfSizes<LN>::cols2(), stream, b);
+            q.g_in = (const cpx*)work1;
+            ADM_LAUNCH((k_lf_patch_mod_adj<LN, true>), dim3(LN / LfSizes<LN>::RPC, F), LF_NT, LfSizes<LN>::rows(), stream, q);
+        }
+    })
+    return ADM_OK;
+}
+
+extern "C" int adm_lf_farfield_fwd(int N, int frames, const float* in, const int* order, float scale, float* work, float* out,
+                                   void* stream) {
+    if (!in || !order || !work || !out || frames < 1 || frames > 65535) return ADM_ERR_ARG;
+    LF_DISPATCH(N, {
+        if (set_smem(k_lf_rows<LN, false>, LfSizes<LN>::rows()) || set_smem(k_lf_cols_far<LN, false>, LfSizes<LN>::cols1()))
+            return ADM_ERR_CUDA;
+        ADM_LAUNCH((k_lf_rows<LN, false>), frames * (LN / LfSizes<LN>::RPC), LF_NT, LfSizes<LN>::rows(), stream, (const cpx*)in,
+                   (cpx*)work);
+        ADM_LAUNCH((k_lf_cols_far<LN, false>), dim3(LN / LfSizes<LN>::C, frames), LF_NT, LfSizes<LN>::cols1(), stream,
+                   (const cpx*)work, order, scale, (cpx*)out);
+    })
+    return ADM_OK;
+}
+
+extern "C" int adm_lf_farfield_bwd(int N, int frames, const float* g_out, const int* order, float scale, float* work,
+                                   float* g_in, void* stream) {
+    if (!g_out || !order || !work || !g_in || frames < 1 || frames > 65535) return ADM_ERR_ARG;
+    LF_DISPATCH(N, {
+        if (set_smem(k_lf_rows<LN, true>, LfSizes<LN>::rows()) || set_smem(k_lf_cols_far<LN, true>, LfSizes<LN>::cols1()))
+            return ADM_ERR_CUDA;
+        ADM_LAUNCH((k_lf_cols_far<LN, true>), dim3(LN / LfSizes<LN>::C, frames), LF_NT, LfSizes<LN>::cols1(), stream,
+                   (const cpx*)g_out, order, scale, (cpx*)work);
+        ADM_LAUNCH((k_lf_rows<LN, true>), frames * (LN / LfSizes<LN>::RPC), LF_NT, LfSizes<LN>::rows(), stream, (const cpx*)work,
+                   (cpx*)g_in);
+    })
+    return ADM_OK;
+}
+
 extern "C" int adm_frame_shift_fwd(int N, int frames, const float* data, const float* shift, const int* order, float* work,
                                    float* spec, float* out, void* stream) {
     if (!data || !shift || !order || !work || !spec || !out || frames < 1) return ADM_ERR_ARG;
@@ -627,6 +872,44 @@ extern "C" int adm_frame_shift_bwd(int N, int frames, const float* g_out, const 
             return ADM_ERR_CUDA;
         const int rg = frames * (LN / LfSizes<LN>::RPC);
         ADM_LAUNCH(k_lf_rows_real_fwd<LN>, rg, LF_NT, LfSizes<LN>::rows(), stream, g_out, (cpx*)work);
+        ADM_LAUNCH((k_lf_cols_shift<LN, true>), dim3(LN / LfSizes<LN>::C, frames), LF_NT, LfSizes<LN>::cols1(), stream,
+                   (const cpx*)work, (const float*)nullptr, order, (cpx*)spec, (cpx*)nullptr, g_shift);
+    })
+    return ADM_OK;
+}
+
+// complex frames: the same column kernels behind plain complex row transforms; the inverse is scaled by 1 / N^2 in place
+__global__ void k_lf_scale(cpx* a, float sc, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) a[i] = cscale(a[i], sc);
+}
+
+extern "C" int adm_frame_shift_complex_fwd(int N, int frames, const float* in, const float* shift, const int* order,
+                                           float* work, float* spec, float* out, void* stream) {
+    if (!in || !shift || !order || !work || !spec || !out || frames < 1 || frames > 65535) return ADM_ERR_ARG;
+    LF_DISPATCH(N, {
+        if (set_smem(k_lf_rows<LN, false>, LfSizes<LN>::rows()) || set_smem(k_lf_cols_shift<LN, false>, LfSizes<LN>::cols1()) ||
+            set_smem(k_lf_rows<LN, true>, LfSizes<LN>::rows()))
+            return ADM_ERR_CUDA;
+        const int rg = frames * (LN / LfSizes<LN>::RPC);
+        ADM_LAUNCH((k_lf_rows<LN, false>), rg, LF_NT, LfSizes<LN>::rows(), stream, (const cpx*)in, (cpx*)work);
+        ADM_LAUNCH((k_lf_cols_shift<LN, false>), dim3(LN / LfSizes<LN>::C, frames), LF_NT, LfSizes<LN>::cols1(), stream,
+                   (const cpx*)work, shift, order, (cpx*)spec, (cpx*)work, (float*)nullptr);
+        ADM_LAUNCH((k_lf_rows<LN, true>), rg, LF_NT, LfSizes<LN>::rows(), stream, (const cpx*)work, (cpx*)out);
+        const long long n = (long long)frames * LN * LN;
+        ADM_LAUNCH(k_lf_scale, (unsigned)((n + 255) / 256), 256, 0, stream, (cpx*)out, 1.0f / ((float)LN * (float)LN), n);
+    })
+    return ADM_OK;
+}
+
+extern "C" int adm_frame_shift_complex_bwd(int N, int frames, const float* g_out, const float* spec, const int* order,
+                                           float* work, float* g_shift, void* stream) {
+    if (!g_out || !spec || !order || !work || !g_shift || frames < 1 || frames > 65535) return ADM_ERR_ARG;
+    LF_DISPATCH(N, {
+        if (set_smem(k_lf_rows<LN, false>, LfSizes<LN>::rows()) || set_smem(k_lf_cols_shift<LN, true>, LfSizes<LN>::cols1()))
+            return ADM_ERR_CUDA;
+        const int rg = frames * (LN / LfSizes<LN>::RPC);
+        ADM_LAUNCH((k_lf_rows<LN, false>), rg, LF_NT, LfSizes<LN>::rows(), stream, (const cpx*)g_out, (cpx*)work);
         ADM_LAUNCH((k_lf_cols_shift<LN, true>), dim3(LN / LfSizes<LN>::C, frames), LF_NT, LfSizes<LN>::cols1(), stream,
                    (const cpx*)work, (const float*)nullptr, order, (cpx*)spec, (cpx*)nullptr, g_shift);
     })

@@ -195,7 +195,7 @@ extern "C" int adm_object_to_transmission(int Y, int X, int Z, const float* obj,
 extern "C" int adm_transmission_to_object_adj(int Y, int X, int Z, int P, const float* g_tvol, const float* tvol,
                                               const float* grid, int unknown_type, float k1, int sign_convention,
                                               int binning, float* g_obj, int y_begin, int y_end, void* stream) {
-    if (!g_tvol || !g_obj || P < 1 || binning < 1) return ADM_ERR_ARG;
+    if (!g_tvol || !g_obj || P < 0 || binning < 1) return ADM_ERR_ARG;      // P = 0: un-margined gradient volume
     if (binning > 1 && unknown_type != ADM_DELTA_BETA) return ADM_ERR_UNSUPPORTED;
     if (unknown_type != ADM_DELTA_BETA && unknown_type != ADM_REAL_IMAG) return ADM_ERR_ARG;
     if (unknown_type == ADM_DELTA_BETA && !tvol) return ADM_ERR_ARG;

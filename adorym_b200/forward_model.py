@@ -202,8 +202,12 @@ class ForwardModel(object):
         """fused rotate + transmission + gather + multislice; with_reg: also the fused regulariser value (None when the
         regulariser list is not fusable) -> (det, reg_value | None, reg_was_fused).  in_beam_frame: the object has
         already been rotated (tilt refinement); the regulariser then acts on the UN-rotated object and is not fused."""
-        reg = self._fusable_regularizers() if (with_reg and not in_beam_frame) else None
         grid = None if in_beam_frame else self._object_grid(obj, this_i_theta)
+        if getattr(plan, 'large', False):
+            # probes of 128 .. 2048 pixels: slice loop on the batched large-frame kernels; the regulariser is evaluated on
+            # its own (ops.RegL1TVFn through get_regularization_value)
+            return ops.MultisliceLargeFn.apply(obj, grid, probe, pos_t, plan), None, False
+        reg = self._fusable_regularizers() if (with_reg and not in_beam_frame) else None
         if reg is not None:
             det, reg_val = ops.MultisliceFn.apply(obj, grid, probe, pos_t, plan, reg, 'yxz')
             return det, reg_val, True
@@ -227,11 +231,18 @@ class ForwardModel(object):
                 voxel_nm = np.array([psize_cm] * 3) * 1.e7
                 h_free = get_kernel(float(free_prop_cm) * 1e7, 1240. / cv['energy_ev'], voxel_nm, [P, P],
                                     sign_convention=self.sign_convention)   # quirk 10: always paraxial
-            plan = ops.MultislicePlan(P, Nz, Y, X, ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k),
-                                      cv['h'] if Nz > 1 else None, dev, sign_convention=self.sign_convention,
-                                      unknown_type=self.unknown_type, free_prop=mode,
-                                      normalize_fft=self.normalize_fft, h_free=h_free, binning=binning,
-                                      obj_slices=obj_slices)
+            if P in ops.SUPPORTED_P:
+                plan = ops.MultislicePlan(P, Nz, Y, X, ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k),
+                                          cv['h'] if Nz > 1 else None, dev, sign_convention=self.sign_convention,
+                                          unknown_type=self.unknown_type, free_prop=mode,
+                                          normalize_fft=self.normalize_fft, h_free=h_free, binning=binning,
+                                          obj_slices=obj_slices)
+            else:
+                plan = ops.LargeMultislicePlan(P, Nz, Y, X, ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k),
+                                               cv['h'] if Nz > 1 else None, dev, sign_convention=self.sign_convention,
+                                               unknown_type=self.unknown_type, free_prop=mode,
+                                               normalize_fft=self.normalize_fft, h_free=h_free, binning=binning,
+                                               obj_slices=obj_slices)
             self._plans[key] = plan
         return plan
 
@@ -397,7 +408,7 @@ class PtychographyModel(ForwardModel):
         # (callers hand over tilt_ls / probe_pos_offset only where the reference's class of the same name uses them)
         if cv.get('optimize_probe_pos_offset', False) and probe_pos_offset is not None:
             # forward_model.py:258-260: every mode shifted by this angle's refinable offset (one Fourier shift)
-            probe = ops.ProbeShiftFn.apply(probe, probe_pos_offset[int(this_i_theta)].reshape(1, 2).to(torch.float32))[0]
+            probe = ops.probe_shift(probe, probe_pos_offset[int(this_i_theta)].reshape(1, 2).to(torch.float32))[0]
         tilted = tilt_ls is not None and (cv.get('optimize_tilt', False) or cv.get('initial_tilt', None) is not None)
         if tilted:
             # forward_model.py:262-276: three differentiable rotations (wrappers.py:1177-1217) replace the lookup table
@@ -412,7 +423,7 @@ class PtychographyModel(ForwardModel):
                                                  or self._any_positive_correction(probe_pos_correction)):
             idx = torch.as_tensor(np.asarray(this_ind_batch), device=dev, dtype=torch.long)
             shift = probe_pos_correction[int(this_i_theta)].index_select(0, idx).to(torch.float32)
-            probe = ops.ProbeShiftFn.apply(probe, shift)
+            probe = ops.probe_shift(probe, shift)
         plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
         # device copy of the integer positions, cached by content (the driver revisits the same minibatches every epoch)
         pos32 = np.ascontiguousarray(pos, dtype='int32')
@@ -588,7 +599,8 @@ class SingleBatchFullfieldModel(PtychographyModel):
         probe = torch.stack([probe_real, probe_imag], dim=-1)
         if probe.dim() == 3:
             probe = probe.unsqueeze(0)
-        if probe_size[0] not in ops.SUPPORTED_P and probe_size[0] == probe_size[1] and ops.lf_supported(probe_size[0]):
+        if (probe_size[0] not in ops.SUPPORTED_P and probe_size[0] == probe_size[1] and ops.lf_supported(probe_size[0])
+                and _free_prop_mode(cv['free_prop_cm']) != 'inf'):
             self._check_unsupported([])
             det = self._large_frame_multislice(obj, this_i_theta, probe.contiguous())
             return (det, None, False) if with_reg else det

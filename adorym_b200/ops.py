@@ -793,3 +793,204 @@ def rotate_with_grad(obj, theta, axis):
 def affine_transform_frames(frames, transform):
     """adorym/wrappers.py:1158-1174 `affine_transform` of a stack of frames [N, H, W] by one [2, 3] matrix."""
     return AffineResampleFn.apply(frames, transform.reshape(6), (0, 1, 2))
+
+
+# ------------------------------------------------------------------------------------------------------
+# ptychography with probes of 128 .. 2048 pixels: slice loop on the batched large-frame kernels
+# ------------------------------------------------------------------------------------------------------
+def _lf_prepare(h, N, device):
+    """[N, N] complex transfer function (natural fftfreq order) -> (Hprep, conj) in the permuted spectrum order, / N^2."""
+    order = lf_spectrum_order(N)
+    h = np.asarray(h)
+    if h.shape != (N, N):
+        raise ValueError('transfer function shape %s != (%d, %d)' % (h.shape, N, N))
+    hh = h[np.ix_(order, order)]
+    hp = torch.from_numpy(np.stack([hh.real, hh.imag], -1).astype('float32')).to(device) * (1.0 / (N * N))
+    return hp.contiguous(), (hp * torch.tensor([1.0, -1.0], device=device)).contiguous()
+
+
+class LargeMultislicePlan(object):
+    """MultislicePlan for probe sizes the shared-memory FFT cannot hold (power of two, 128 .. 2048): same attributes, the
+    transfer functions prepared for the large-frame kernels."""
+    large = True
+
+    def __init__(self, P, n_slices, Y, X, k1, h, device, sign_convention=1, unknown_type='delta_beta', free_prop='none',
+                 normalize_fft=False, h_free=None, binning=1, obj_slices=None):
+        if not lf_supported(P):
+            raise NotImplementedError('adorym_b200: probe size %d is not supported (64, 72, or a power of two from 128 to '
+                                      '2048)' % P)
+        self.P, self.n_slices, self.Y, self.X = int(P), int(n_slices), int(Y), int(X)
+        self.binning = int(binning)
+        self.obj_slices = int(obj_slices) if obj_slices is not None else int(n_slices)
+        if self.binning < 1 or -(-self.obj_slices // self.binning) != self.n_slices:
+            raise ValueError('n_slices must equal ceil(obj_slices / binning)')
+        if self.binning > 1 and unknown_type != 'delta_beta':
+            raise NotImplementedError('adorym_b200: binning > 1 is accelerated for delta_beta objects only')
+        self.k1, self.sign_convention = float(k1), int(sign_convention)
+        self.unknown_type = UNKNOWN_TYPES[unknown_type]
+        self.free_prop = {'none': 0, 'inf': 1, 'near': 2}[free_prop]
+        if self.free_prop == 1 and self.sign_convention != 1:
+            raise NotImplementedError('adorym_b200: far-field detection of large probes with sign_convention = -1')
+        self.normalize_fft = int(bool(normalize_fft))
+        self.device = device
+        self.Hp = self.Hc = self.Hfp = self.Hfc = None
+        if self.n_slices > 1:
+            if h is None:
+                raise ValueError('a transfer function is required when n_slices > 1')
+            self.Hp, self.Hc = _lf_prepare(h, self.P, device)
+        if self.free_prop == 2:
+            self.Hfp, self.Hfc = _lf_prepare(h_free, self.P, device)
+        self.ff_scale = (1.0 / self.P) if self.normalize_fft else 1.0        # propagate.py:267 (sign +1: fft2, unnormalised)
+
+
+class MultisliceLargeFn(torch.autograd.Function):
+    """det[B,M,N,N,2] = multislice(obj[Y,X,Z,2], probe[M,N,N,2] | [B,M,N,N,2], pos[B,2] int32) for N = 128 .. 2048: the
+    fused object -> transmission volume kernel, then one batched large-frame step per slice (adm_lf_patch_step_fwd), the
+    detector transform (adm_lf_farfield_fwd | one vacuum step with the free-space kernel | none).  The wavefield entering
+    every slice is kept for the adjoint (adm_lf_patch_step_bwd), whose dL/dT is scatter-added into an un-margined
+    gradient volume and taken back to the object by adm_transmission_to_object_adj."""
+
+    @staticmethod
+    def forward(ctx, obj, grid, probe, pos, plan):
+        obj, probe = _f32c(obj), _f32c(probe)
+        if pos.dtype != torch.int32 or not pos.is_cuda:
+            raise RuntimeError('pos must be an int32 CUDA tensor [B, 2]')
+        pos = pos.contiguous()
+        N, Nz, Y, X, Zo = plan.P, plan.n_slices, plan.Y, plan.X, plan.obj_slices
+        if tuple(obj.shape) != (Y, X, Zo, 2):
+            raise RuntimeError('object must be %s, got %s' % ((Y, X, Zo, 2), tuple(obj.shape)))
+        dev = obj.device
+        B = pos.shape[0]
+        per_pattern = probe.dim() == 5
+        M = probe.shape[1] if per_pattern else probe.shape[0]
+        if tuple(probe.shape[-3:]) != (N, N, 2) or (per_pattern and probe.shape[0] != B):
+            raise RuntimeError('probe must be [M,N,N,2] or [B,M,N,N,2]')
+        F = B * M
+        tvol = torch.empty((Nz, Y, tvol_pitch(X), 2), dtype=torch.float32, device=dev)
+        call('adm_object_to_transmission', Y, X, Zo, ptr(obj), ptr(grid), plan.unknown_type, plan.k1, plan.sign_convention,
+             plan.binning, ptr(tvol), stream_ptr())
+        psi = (probe if per_pattern else probe.unsqueeze(0).expand(B, M, N, N, 2)).reshape(F, N, N, 2).contiguous()
+        work = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        ckpt = []
+        for z in range(Nz):
+            ckpt.append(psi)
+            nxt = torch.empty_like(psi)
+            call('adm_lf_patch_step_fwd', N, B, M, Y, X, z, ptr(tvol), ptr(pos), ptr(psi), ptr(plan.Hp) if z < Nz - 1 else None,
+                 ptr(work), ptr(nxt), stream_ptr())
+            psi = nxt
+        vac = None
+        if plan.free_prop == 1:
+            det = torch.empty_like(psi)
+            call('adm_lf_farfield_fwd', N, F, ptr(psi), ptr(lf_spectrum_order(N, dev)), plan.ff_scale, ptr(work), ptr(det),
+                 stream_ptr())
+        elif plan.free_prop == 2:
+            # free-space propagation of the exit wave (propagate.py:271-280): one step through vacuum (every patch placed
+            # outside the object) with the free-space kernel
+            vac = torch.full((B, 2), -4 * N - 4 * max(Y, X), dtype=torch.int32, device=dev)
+            det = torch.empty_like(psi)
+            call('adm_lf_patch_step_fwd', N, B, M, Y, X, 0, ptr(tvol), ptr(vac), ptr(psi), ptr(plan.Hfp), ptr(work), ptr(det),
+                 stream_ptr())
+        else:
+            det = psi
+        ctx.plan, ctx.dims, ctx.per_pattern, ctx.has_grid = plan, (B, M), per_pattern, grid is not None
+        ctx.probe_shape = tuple(probe.shape)
+        saved = [tvol, pos] + ckpt + ([grid] if grid is not None else []) + ([vac] if vac is not None else [])
+        ctx.save_for_backward(*saved)
+        return det.reshape(B, M, N, N, 2)
+
+    @staticmethod
+    def backward(ctx, g_det):
+        plan = ctx.plan
+        N, Nz, Y, X, Zo = plan.P, plan.n_slices, plan.Y, plan.X, plan.obj_slices
+        B, M = ctx.dims
+        F = B * M
+        saved = list(ctx.saved_tensors)
+        tvol, pos = saved[0], saved[1]
+        ckpt = saved[2:2 + Nz]
+        rest = saved[2 + Nz:]
+        grid = rest.pop(0) if ctx.has_grid else None
+        vac = rest.pop(0) if plan.free_prop == 2 else None
+        dev = tvol.device
+        g = _f32c(g_det).reshape(F, N, N, 2)
+        work1 = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        work2 = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        if plan.free_prop == 1:
+            g2 = torch.empty_like(g)
+            call('adm_lf_farfield_bwd', N, F, ptr(g), ptr(lf_spectrum_order(N, dev)), plan.ff_scale, ptr(work1), ptr(g2),
+                 stream_ptr())
+            g = g2
+        elif plan.free_prop == 2:
+            g2 = torch.empty_like(g)
+            call('adm_lf_patch_step_bwd', N, B, M, Y, X, 0, ptr(tvol), ptr(vac), ptr(ckpt[0]), ptr(plan.Hfc), ptr(g), ptr(work1),
+                 ptr(work2), ptr(g2), None, 0, stream_ptr())
+            g = g2
+        need_obj = ctx.needs_input_grad[0]
+        g_tvol = torch.zeros((Nz, Y, gvol_pitch(X, 0), 2), dtype=torch.float32, device=dev) if need_obj else None
+        for z in range(Nz - 1, -1, -1):
+            g2 = torch.empty_like(g)
+            call('adm_lf_patch_step_bwd', N, B, M, Y, X, z, ptr(tvol), ptr(pos), ptr(ckpt[z]),
+                 ptr(plan.Hc) if z < Nz - 1 else None, ptr(g), ptr(work1), ptr(work2), ptr(g2), ptr(g_tvol), 0, stream_ptr())
+            g = g2
+        g_probe = None
+        if ctx.needs_input_grad[2]:
+            g_probe = g.reshape(B, M, N, N, 2)
+            if not ctx.per_pattern:
+                g_probe = g_probe.sum(0)
+        g_obj = None
+        if need_obj:
+            g_obj = torch.zeros((Y, X, Zo, 2), dtype=torch.float32, device=dev)
+            call('adm_transmission_to_object_adj', Y, X, Zo, 0, ptr(g_tvol), ptr(tvol), ptr(grid), plan.unknown_type, plan.k1,
+                 plan.sign_convention, plan.binning, ptr(g_obj), 0, Y, stream_ptr())
+        return g_obj, None, g_probe, None, None
+
+
+class ProbeShiftLargeFn(torch.autograd.Function):
+    """ProbeShiftFn for probes of 128 .. 2048 pixels: out[B,M,N,N,2] = Fourier shift of probe[M,N,N,2] by shift[B,2]
+    (util.py:380-397) on the large-frame row / column kernels (adm_frame_shift_complex_fwd)."""
+
+    @staticmethod
+    def forward(ctx, probe, shift):
+        probe, shift = _f32c(probe), _f32c(shift)
+        M, N = probe.shape[0], probe.shape[1]
+        B = shift.shape[0]
+        dev = probe.device
+        F = B * M
+        frames = probe.unsqueeze(0).expand(B, M, N, N, 2).reshape(F, N, N, 2).contiguous()
+        sh = shift.repeat_interleave(M, dim=0).contiguous()
+        order = lf_spectrum_order(N, dev)
+        work = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        spec = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        out = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        call('adm_frame_shift_complex_fwd', N, F, ptr(frames), ptr(sh), ptr(order), ptr(work), ptr(spec), ptr(out), stream_ptr())
+        ctx.save_for_backward(spec, order, sh)
+        ctx.dims = (B, M, N)
+        return out.reshape(B, M, N, N, 2)
+
+    @staticmethod
+    def backward(ctx, g_out):
+        spec, order, sh = ctx.saved_tensors
+        B, M, N = ctx.dims
+        F = B * M
+        dev = spec.device
+        g = _f32c(g_out).reshape(F, N, N, 2)
+        work = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+        g_probe = g_shift = None
+        if ctx.needs_input_grad[1]:
+            gs = torch.zeros((F, 2), dtype=torch.float32, device=dev)
+            call('adm_frame_shift_complex_bwd', N, F, ptr(g), ptr(spec), ptr(order), ptr(work), ptr(gs), stream_ptr())
+            g_shift = gs.reshape(B, M, 2).sum(1)
+        if ctx.needs_input_grad[0]:
+            # the shift is unitary up to its 1/N^2: its adjoint is the shift by -s
+            spec2 = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+            gp = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
+            call('adm_frame_shift_complex_fwd', N, F, ptr(g), ptr((-sh).contiguous()), ptr(order), ptr(work), ptr(spec2), ptr(gp),
+                 stream_ptr())
+            g_probe = gp.reshape(B, M, N, N, 2).sum(0)
+        return g_probe, g_shift
+
+
+def probe_shift(probe, shift):
+    """Per-pattern Fourier shift of the probe modes, dispatching on the probe size."""
+    if probe.shape[1] in SUPPORTED_P:
+        return ProbeShiftFn.apply(probe, shift)
+    return ProbeShiftLargeFn.apply(probe, shift)

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ADM_ABI_VERSION 5
+#define ADM_ABI_VERSION 6
 
 /* unknown_type */
 #define ADM_DELTA_BETA 0
@@ -285,6 +285,34 @@ int adm_affine_resample_adj(int D0, int D1, int D2, int C, int dim_n, int dim_h,
                             const float* mats, int mat_per_plane, float* g_in, void* stream);
 int adm_affine_resample_dmat(int D0, int D1, int D2, int C, int dim_n, int dim_h, int dim_w, const float* in,
                              const float* g_out, const float* mats, int mat_per_plane, float* g_mats, void* stream);
+
+/* ---- ptychography with probes of 128 .. 2048 pixels (power of two): batched slice steps on the large-frame kernels ----
+ * One step of the slice loop (propagate.py:208-258) for B*M wavefields, pattern b reading its patch (origin pos[b], vacuum
+ * outside the object: util.py:1327-1351, forward_model.py:313-331) of slice z of the transmission volume
+ * tvol [Nz][Y][ADM_TVOL_PITCH(X)][2]:   psi_out = IFFT2(Hprep . FFT2(psi_in (1 + T'_patch))).
+ *   Hprep == NULL: modulation only (the last slice is not propagated, propagate.py:253); work is then unused.
+ *   psi_in / psi_out / work [B*M][N][N][2]; Hprep [N][N][2] prepared as for adm_multidist_fwd (permuted, / N^2).        */
+int adm_lf_patch_step_fwd(int N, int B, int M, int Y, int X, int z, const float* tvol, const int* pos, const float* psi_in,
+                          const float* Hprep, float* work, float* psi_out, void* stream);
+/* Adjoint of the step: g_psi [B*M][N][N][2] WRITTEN (may be NULL); g_tvol [Nz][Y + g_margin][ADM_GVOL_PITCH(X, g_margin)][2]
+ * ACCUMULATED at slice z (dL/dT = g conj(psi_in), red.add: patches overlap; may be NULL).  HprepC = conj of Hprep.       */
+int adm_lf_patch_step_bwd(int N, int B, int M, int Y, int X, int z, const float* tvol, const int* pos, const float* psi_in,
+                          const float* HprepC, const float* g_out, float* work1, float* work2, float* g_psi, float* g_tvol,
+                          int g_margin, void* stream);
+/* Far-field detection of large frames (propagate.py:263-270, sign_convention +1): out = scale . fftshift(FFT2(in)), natural
+ * order; in / work / out [frames][N][N][2]; order = DEVICE copy of adm_lf_spectrum_order.  _bwd: its adjoint.           */
+int adm_lf_farfield_fwd(int N, int frames, const float* in, const int* order, float scale, float* work, float* out,
+                        void* stream);
+int adm_lf_farfield_bwd(int N, int frames, const float* g_out, const int* order, float scale, float* work, float* g_in,
+                        void* stream);
+/* Sub-pixel Fourier shift of COMPLEX frames (the per-position probe shift of forward_model.py:296-303 for large probes):
+ * out[f] = IFFT2(FFT2(in[f]) exp(-2 pi i (fx sx + fy sy))); shift [frames][2] = (sy, sx); spec = shifted spectrum kept
+ * for adm_frame_shift_complex_bwd, which ACCUMULATES g_shift [frames][2] (the gradient with respect to `in` is the same
+ * call with -shift applied to g_out).                                                                                   */
+int adm_frame_shift_complex_fwd(int N, int frames, const float* in, const float* shift, const int* order, float* work,
+                                float* spec, float* out, void* stream);
+int adm_frame_shift_complex_bwd(int N, int frames, const float* g_out, const float* spec, const int* order, float* work,
+                                float* g_shift, void* stream);
 
 #ifdef __cplusplus
 }

@@ -107,6 +107,17 @@ CASES = {
                               free_prop_cm='inf', unknown_type='delta_beta', delta_scale=8e-4, beta_scale=8e-5, seed=28,
                               loss='lsq', raw_data_type='magnitude', optimize_tilt=True, tilt=(0.7, 0.06, -0.05),
                               optimize_probe_pos_offset=True, probe_pos_offset=(0.4, -0.3)),
+    # probes the shared-memory FFT cannot hold (128 pixels): the batched large-frame slice steps.  2-D ptychography with two
+    # modes, probe + position refinement, patches overhanging the object on every side, far field
+    'ptycho2d_p128': dict(kind='ptycho', obj_size=(160, 150, 1), probe_size=(128, 128), energy_ev=5000., psize_cm=1e-7,
+                          theta=0.0, n_theta=1, i_theta=0, pos=[(-20, -30), (40, 31), (5, -3)], n_modes=2,
+                          free_prop_cm='inf', unknown_type='delta_beta', delta_scale=3e-2, beta_scale=3e-3, seed=29,
+                          loss='lsq', raw_data_type='magnitude', optimize_probe=True, optimize_all_probe_pos=True),
+    # 3-D (rotation, 5 slices), 128-pixel probe, near-field detection, intensity data
+    'ptycho3d_p128_near': dict(kind='ptycho', obj_size=(140, 132, 5), probe_size=(128, 128), energy_ev=5000., psize_cm=1e-7,
+                               theta=0.6, n_theta=3, i_theta=1, pos=[(-10, 9), (20, -14)], n_modes=1,
+                               free_prop_cm=2e-6, unknown_type='delta_beta', delta_scale=3e-3, beta_scale=3e-4, seed=30,
+                               loss='lsq', raw_data_type='intensity', optimize_probe=True, probe_background=0.4),
     # 2-D ptychography with probe modes + probe and position refinement (BASELINE config B shape, small)
     'ptycho2d_modes': dict(kind='ptycho', obj_size=(128, 128, 1), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
                            theta=0.0, n_theta=1, i_theta=0,
@@ -150,6 +161,10 @@ def make_inputs(name):
         r0, i0 = _gaussian_probe(P, 6.0, 0.5, 6.0)
         pr = np.stack([r0 * (1 + 0.3 * m) + 0.05 * rs.normal(size=P) * np.abs(r0) for m in range(M)]).astype('float32')
         pi = np.stack([i0 * (1 - 0.2 * m) + 0.05 * rs.normal(size=P) * np.abs(r0) for m in range(M)]).astype('float32')
+        if c.get('probe_background'):
+            # a plane-wave pedestal: without it the near-field magnitude is ~0 away from the beam and the phase of a
+            # vanishing field -- hence the gradient there -- is rounding noise in fp32 (reference included)
+            pr = (pr + np.float32(c['probe_background'])).astype('float32')
     pos = np.array(c['pos'], dtype='int64')
     B = len(pos)
     # synthetic "measured" data: positive, smooth-ish, same order of magnitude as a plausible prediction

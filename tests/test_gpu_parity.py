@@ -141,6 +141,22 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
         assert rel_err(grads['probe_pos_offset'], gold['g_probe_pos_offset']) < 5e-4
 
 
+@pytest.mark.parametrize('P', [256, 512])
+def test_large_probe_sizes_match_oracle(P):
+    """Probe sizes 256 / 512 (2-D ptychography, two modes, probe + position refinement, far field) on the batched
+    large-frame slice steps against the fp64 oracle (the 128-pixel cases also carry reference goldens)."""
+    CASES['_tmp_large'] = dict(CASES['ptycho2d_p128'], probe_size=(P, P), obj_size=(P + 40, P + 30, 1), seed=40 + P)
+    try:
+        inp, loss, pred, grads, fm = run_gpu_case('_tmp_large')
+        _, loss64, pred64, grads64 = run_oracle_case('_tmp_large', torch.float64)
+    finally:
+        del CASES['_tmp_large']
+    assert abs(loss - loss64) <= TOL * abs(loss64)
+    assert rel_err(pred, pred64) < TOL
+    for k in ('obj', 'probe_real', 'probe_imag', 'probe_pos_correction'):
+        assert rel_err(grads[k], grads64[k]) < TOL, k
+
+
 def test_single_batch_ptychography_model_matches_oracle():
     """SingleBatchPtychographyModel (forward_model.py:493-586: one probe position per call, no probe shift) on the fused
     kernels vs the oracle for single positions of the 3-D P = 72 case."""
