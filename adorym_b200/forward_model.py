@@ -655,17 +655,63 @@ class MultiDistModel(ForwardModel):
             self._md_plans[key] = plan
         return plan
 
-    def _detector_fields(self, obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj):
+    def _tiled_detector_fields(self, obj, probe_real, probe_imag, dists, szw, this_pos_batch):
+        """Frames sub-divided into tiles (n_blocks > 1) and / or a safe zone (forward_model.py:917-1026): every tile of the
+        minibatch reads the region [pos - szw, pos + subprobe + szw) of the object (vacuum outside) and of the probe ((1, 0)
+        outside), is propagated on its own by the patch kernels (tile size 64 / 72: shared-memory multislice kernels, 128 ..
+        2048: batched large-frame steps), and the safe zone is cropped from the detector field.  One probe mode: the
+        reference indexes the imaginary probe patches by mode on the BATCH axis (:1005, quirk 9), i.e. every tile of a
+        sub-batch of n_dp_batch tiles gets the imaginary patch of the sub-batch's first tile -- reproduced."""
+        cv = self.common_vars
+        dev = self._device(obj)
+        Y, X, Z = cv['this_obj_size']
+        sub = list(cv['subprobe_size'])
+        if sub[0] != sub[1]:
+            raise NotImplementedError('adorym_b200: only square tiles are supported')
+        if Z != 1:
+            # the in-object kernel `h` of the driver has the size of the whole frame (ptychography.py:389-392): the reference
+            # cannot propagate a tile through more than one slice either
+            raise NotImplementedError('adorym_b200: sub-divided MultiDistModel frames need a single object slice')
+        if probe_real.dim() != 3 or probe_real.shape[0] != 1:
+            raise NotImplementedError('adorym_b200: sub-divided MultiDistModel frames run with one probe mode (quirk 9)')
+        tile = sub[0] + 2 * szw
+        pos = _np_int_positions(this_pos_batch) - szw
+        B = len(pos)
+        # (1, 0)-padded probe, one [tile, tile] patch per tile
+        lo_y, lo_x = max(0, -int(pos[:, 0].min())), max(0, -int(pos[:, 1].min()))
+        hi_y, hi_x = max(0, int(pos[:, 0].max()) + tile - Y), max(0, int(pos[:, 1].max()) + tile - X)
+        pad = [lo_x, hi_x, lo_y, hi_y]
+        pr = torch.nn.functional.pad(probe_real, pad, value=1.)
+        pi = torch.nn.functional.pad(probe_imag, pad, value=0.)
+        n_dp = int(cv.get('n_dp_batch', 20))
+        pr_ls, pi_ls = [], []
+        for j in range(B):
+            y0, x0 = int(pos[j, 0]) + lo_y, int(pos[j, 1]) + lo_x
+            j0 = (j // n_dp) * n_dp                                      # first tile of this sub-batch (quirk 9)
+            yq, xq = int(pos[j0, 0]) + lo_y, int(pos[j0, 1]) + lo_x
+            pr_ls.append(pr[:, y0:y0 + tile, x0:x0 + tile])
+            pi_ls.append(pi[:, yq:yq + tile, xq:xq + tile])
+        probe = torch.stack([torch.stack(pr_ls), torch.stack(pi_ls)], dim=-1).contiguous()      # [B, 1, tile, tile, 2]
+        pos_t = torch.from_numpy(np.ascontiguousarray(pos, dtype='int32')).to(dev)
+        dets = []
+        for d in dists:
+            plan = self._plan(dev, tile, Z, Y, X, d)
+            det = self._multislice(obj, 0, probe, pos_t, plan, False)[0]                         # [B, 1, tile, tile, 2]
+            dets.append(det[:, :, szw:szw + sub[0], szw:szw + sub[1]] if szw > 0 else det)
+        return torch.cat(dets, 0).contiguous()
+
+    def _detector_fields(self, obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj, this_pos_batch=None):
         cv = self.common_vars
         self._check_unsupported(['optimize_probe_defocusing', 'optimize_probe_pos_offset', 'optimize_prj_pos_offset',
                                  'optimize_ctf_lg_kappa'])
         refine_dist = bool(cv.get('optimize_free_prop', False))
-        if safe_zone_width not in (0, None):
-            raise NotImplementedError('adorym_b200: MultiDistModel with safe_zone_width > 0 is not accelerated yet')
         dists = [float(d) for d in np.asarray(free_prop_cm.detach().cpu() if torch.is_tensor(free_prop_cm) else free_prop_cm)]
         n_dists = len(dists)
-        if prj.shape[1] // n_dists != 1:
-            raise NotImplementedError('adorym_b200: MultiDistModel with sub-divided frames (n_blocks > 1)')
+        szw = int(safe_zone_width or 0)
+        if szw > 0 or prj.shape[1] // n_dists != 1:
+            if refine_dist:
+                raise NotImplementedError('adorym_b200: optimize_free_prop with sub-divided frames / a safe zone')
+            return self._tiled_detector_fields(obj, probe_real, probe_imag, dists, szw, this_pos_batch)
         dev = self._device(obj)
         this_obj_size = cv['this_obj_size']
         P = this_obj_size[0]
@@ -702,7 +748,7 @@ class MultiDistModel(ForwardModel):
                 probe_pos_offset, this_i_theta, this_pos_batch, prj,
                 probe_pos_correction, this_ind_batch, free_prop_cm, safe_zone_width, prj_affine_ls, ctf_lg_kappa,
                 prj_pos_offset):
-        det = self._detector_fields(obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj)
+        det = self._detector_fields(obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj, this_pos_batch)
         self.i_call += 1
         return ops.DetectorMagnitudeFn.apply(det)
 
@@ -714,9 +760,9 @@ class MultiDistModel(ForwardModel):
             theta_downsample = self.common_vars['theta_downsample']
             if theta_downsample is None:
                 theta_downsample = 1
-            det = self._detector_fields(obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj)
+            det = self._detector_fields(obj, probe_real, probe_imag, free_prop_cm, safe_zone_width, prj, this_pos_batch)
             self.i_call += 1
-            n_dists = det.shape[0]
+            n_dists = len(free_prop_cm)
             n_blocks = prj.shape[1] // n_dists
             ind = np.asarray(this_ind_batch)
             full = np.concatenate([ind + i * n_blocks for i in range(n_dists)])       # forward_model.py:1058-1061

@@ -461,6 +461,51 @@ def predict_multidist(obj, probe_real, probe_imag, free_prop_cm_ls, cfg):
     return torch.cat(out, 0)
 
 
+def predict_multidist_tiled(obj, probe_real, probe_imag, free_prop_cm_ls, cfg, pos_batch, subprobe_size, safe_zone_width=0,
+                            n_dp_batch=20):
+    """MultiDistModel.predict (adorym/forward_model.py:884-1030) for frames sub-divided into tiles (n_blocks > 1) and / or
+    a safe zone: the object is padded with vacuum and the probe with (1, 0) (:917-927), every tile reads the region
+    [pos - szw, pos + subprobe + szw) of both (:951-963), is propagated on its own, and the safe zone is cropped from the
+    magnitudes (:1024-1026).  The reference indexes the real probe patches as [:, i_mode] but the imaginary ones as
+    [i_mode] (:1005, quirk 9): with one mode every tile of a sub-batch gets the imaginary patch of the sub-batch's FIRST
+    tile -- reproduced here.  One probe mode, sub-batches of at least two tiles (the reference's single-tile branch
+    :937-948 cuts an object region of the full probe size and fails on the shape mismatch).
+    Returns [n_dists * B, sub_y, sub_x] magnitudes, distance-major."""
+    szw = int(safe_zone_width)
+    sub = list(subprobe_size)
+    tile = [sub[0] + 2 * szw, sub[1] + 2 * szw]
+    pos = np.round(np.asarray(pos_batch)).astype(int) - szw
+    unknown_type = cfg.get('unknown_type', 'delta_beta')
+    Y, X = obj.shape[0], obj.shape[1]
+    pad = calculate_pad_len([Y, X], pos, tile)
+    obj_p, _ = pad_object(obj, [Y, X, obj.shape[2]], pos, tile, unknown_type)
+    pw = [int(pad[1][0]), int(pad[1][1]), int(pad[0][0]), int(pad[0][1])]
+    pr_p = torch.nn.functional.pad(probe_real, pw, value=1.)
+    pi_p = torch.nn.functional.pad(probe_imag, pw, value=0.)
+    assert probe_real.shape[0] == 1, 'quirk 9: the reference only runs with one probe mode here'
+    chunks = [list(range(i, min(i + n_dp_batch, len(pos)))) for i in range(0, len(pos), n_dp_batch)]
+    out = []
+    for dist in free_prop_cm_ls:
+        for ch in chunks:
+            so, sr, si = [], [], []
+            for j in ch:
+                y0, x0 = pos[j][0] + int(pad[0][0]), pos[j][1] + int(pad[1][0])
+                so.append(obj_p[y0:y0 + tile[0], x0:x0 + tile[1]])
+                sr.append(pr_p[0, y0:y0 + tile[0], x0:x0 + tile[1]])
+                si.append(pi_p[0, y0:y0 + tile[0], x0:x0 + tile[1]])
+            so, sr = torch.stack(so), torch.stack(sr)
+            si = si[0].unsqueeze(0).expand_as(sr)            # quirk 9
+            psi = multislice_propagate_batch(so, torch.complex(sr, si), cfg['energy_ev'], cfg['psize_cm'],
+                                             free_prop_cm=float(dist), kernel=cfg.get('h'),
+                                             type=unknown_type, sign_convention=cfg.get('sign_convention', 1),
+                                             scale_ri_by_k=cfg.get('scale_ri_by_k', True))
+            out.append(torch.sqrt(psi.real ** 2 + psi.imag ** 2))
+    out = torch.cat(out, 0)
+    if szw > 0:
+        out = out[:, szw:szw + sub[0], szw:szw + sub[1]]
+    return out
+
+
 # ----------------------------------------------------------------------------------------------
 # Loss and regularisers               adorym/forward_model.py:88-147, regularizers.py:30-110
 # ----------------------------------------------------------------------------------------------
@@ -501,7 +546,7 @@ def regularization_value(obj, alpha_d=None, alpha_b=None, gamma=None, weight_l1=
 
 
 def multidist_loss_and_grads(obj, probe_real, probe_imag, free_prop_cm_ls, prj_abs, cfg, probe_pos_correction=None,
-                             want=('obj',), prj_affine_ls=None):
+                             want=('obj',), prj_affine_ls=None, tiles=None):
     """MultiDistModel.get_loss_function (adorym/forward_model.py:1039-1092) for n_blocks == 1, no affine / offset
     refinement: predict (:819-1037), optional per-distance Fourier shift of the measured frames with the real part
     kept (:1079-1088, optimize_all_probe_pos; probe_pos_correction is [n_dists, 2]), mismatch loss (:88-103 applies
@@ -513,7 +558,11 @@ def multidist_loss_and_grads(obj, probe_real, probe_imag, free_prop_cm_ls, prj_a
         leaves['free_prop_cm'] = torch.as_tensor(np.asarray(free_prop_cm_ls, dtype='float64')).to(obj.dtype).requires_grad_(True)
         free_prop_cm_ls = leaves['free_prop_cm']
         cfg = dict(cfg, optimize_free_prop=True)
-    pred = predict_multidist(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], free_prop_cm_ls, cfg)
+    if tiles is not None:
+        # tiles = dict(pos_batch, subprobe_size, safe_zone_width, n_dp_batch): sub-divided frames / safe zone
+        pred = predict_multidist_tiled(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], free_prop_cm_ls, cfg, **tiles)
+    else:
+        pred = predict_multidist(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], free_prop_cm_ls, cfg)
     prj = prj_abs
     if prj_affine_ls is not None:
         # optimize_prj_affine (forward_model.py:1066-1072): every distance's frame resampled by its own 2x3 matrix

@@ -223,7 +223,19 @@ MD_CASES = {
     'multidist128_affine': dict(N=128, energy_ev=17500., psize_cm=1e-4, dists=[35., 62., 90.], n_modes=1,
                                 unknown_type='real_imag', delta_scale=0.4, beta_scale=0.3, seed=34, loss='lsq',
                                 raw_data_type='intensity', shift=False, optimize_probe=False, affine=True),
+    # frames sub-divided into 3 x 3 tiles of 48 pixels, propagated with a safe zone of 8 pixels (64-pixel wavefields), a
+    # minibatch of 4 tiles in sub-batches of 2 (forward_model.py:917-1026); structured probe so that the reference's
+    # imaginary-patch indexing (quirk 9) is visible
+    'multidist144_tiled': dict(N=144, energy_ev=17500., psize_cm=1e-4, dists=[30., 70.], n_modes=1,
+                               unknown_type='real_imag', delta_scale=0.4, beta_scale=0.3, seed=35, loss='lsq',
+                               raw_data_type='intensity', shift=False, optimize_probe=True,
+                               tiles=dict(sub=48, szw=8, ind=[1, 3, 4, 8], n_dp_batch=2)),
 }
+
+
+def md_tile_positions(N, sub):
+    n = N // sub
+    return np.array([(sub * (i // n), sub * (i % n)) for i in range(n * n)], dtype='int64')
 
 
 def make_md_inputs(name):
@@ -248,6 +260,11 @@ def make_md_inputs(name):
     prj = (amp * (0.5 + 0.5 * np.stack([_smooth_noise(rs, (N, N), 1.0) for _ in range(D)]))).astype('float32')
     if c['raw_data_type'] == 'intensity':
         prj = (prj ** 2).astype('float32')
+    if c.get('tiles'):
+        # exchange/data of a tiled acquisition: [n_dists * n_blocks, sub, sub], distance-major, blocks in raster order
+        sub = c['tiles']['sub']
+        tp = md_tile_positions(N, sub)
+        prj = np.stack([prj[d, y:y + sub, x:x + sub] for d in range(D) for (y, x) in tp]).astype('float32')
     ppc = rs.uniform(-0.8, 0.8, size=(D, 2)).astype('float32') if c['shift'] else None
     aff = None
     if c.get('affine', False):

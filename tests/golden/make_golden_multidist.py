@@ -11,7 +11,7 @@ import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
-from cases import MD_CASES, make_md_inputs  # noqa: E402
+from cases import MD_CASES, make_md_inputs, md_tile_positions  # noqa: E402
 from make_golden import compact_grad  # noqa: E402
 
 
@@ -28,6 +28,11 @@ def run_reference(name):
     voxel_nm = np.array([c['psize_cm']] * 3) * 1e7
     lmbda_nm = 1240. / c['energy_ev']
     prj_full = inp['prj'][None]                  # [n_theta = 1, n_dists, N, N]
+    tiles = c.get('tiles')
+    sub = tiles['sub'] if tiles else N
+    szw = tiles['szw'] if tiles else 0
+    ind = np.array(tiles['ind']) if tiles else np.array([0])
+    pos = md_tile_positions(N, sub)[ind] if tiles else np.array([[0, 0]])
     tmp = tempfile.mkdtemp()
     cwd = os.getcwd()
     os.chdir(tmp)
@@ -36,9 +41,9 @@ def run_reference(name):
                   scale_ri_by_k=True, is_minus_logged=False, forward_algorithm='fresnel',
                   stdout_options={'save_stdout': False, 'output_folder': tmp, 'timestamp': ''}, poisson_multiplier=1.,
                   common_probe_pos=True, binning=1, prj=prj_full, device_obj=None, lmbda_nm=lmbda_nm, voxel_nm=voxel_nm,
-                  probe_size=[N, N], subprobe_size=[N, N], fresnel_approx=True, two_d_mode=True, minibatch_size=1,
+                  probe_size=[N, N], subprobe_size=[sub, sub], fresnel_approx=True, two_d_mode=True, minibatch_size=len(ind),
                   ds_level=1, this_obj_size=[N, N, 1], energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=None,
-                  pure_projection=False, n_dp_batch=1, free_prop_cm=c['dists'], optimize_probe_defocusing=False,
+                  pure_projection=False, n_dp_batch=tiles['n_dp_batch'] if tiles else 1, free_prop_cm=c['dists'], optimize_probe_defocusing=False,
                   optimize_probe_pos_offset=False, optimize_prj_pos_offset=False, optimize_all_probe_pos=c['shift'],
                   optimize_free_prop=c.get('free_prop', False), optimize_prj_affine=c.get('affine', False), optimize_ctf_lg_kappa=False, optimize_tilt=False,
                   initial_tilt=None, debug=False, output_folder=tmp, n_probe_modes=M, n_theta=1,
@@ -56,8 +61,8 @@ def run_reference(name):
         ppc = w.create_variable(inp['probe_pos_correction'] if c['shift'] else np.zeros([D, 2]), requires_grad=c['shift'])
         args = dict(obj=obj, probe_real=pr, probe_imag=pi, probe_defocus_mm=w.create_variable(0.0),
                     probe_pos_offset=w.zeros([1, 2], requires_grad=True), this_i_theta=0,
-                    this_pos_batch=np.array([[0, 0]]), prj=prj_full, probe_pos_correction=ppc, this_ind_batch=np.array([0]),
-                    free_prop_cm=c['dists'], safe_zone_width=0, prj_affine_ls=None, ctf_lg_kappa=None,
+                    this_pos_batch=pos, prj=prj_full, probe_pos_correction=ppc, this_ind_batch=ind,
+                    free_prop_cm=c['dists'], safe_zone_width=szw, prj_affine_ls=None, ctf_lg_kappa=None,
                     prj_pos_offset=w.zeros([1, 2], requires_grad=True))
         if c.get('free_prop', False):
             args['free_prop_cm'] = w.create_variable(np.array(c['dists']), requires_grad=True)
@@ -80,6 +85,9 @@ def run_reference(name):
         loss = float(fm.current_loss)
         with torch.no_grad():
             pred = fm.predict(**args)
+        if tiles:
+            # the reference's single-mode magnitude is torch.sqrt(ex_int) (forward_model.py:1017): not finite-gradient at 0
+            assert np.isfinite(loss)
         out = {'loss': np.float64(loss), 'pred_sub': pred.numpy()[:, ::4, ::4].astype('float32'),
                'pred_norm': np.float64(np.sqrt((pred.numpy().astype('float64') ** 2).sum()))}
         for n, g in zip(names, grads):

@@ -102,6 +102,15 @@ def run_md_oracle_case(name, dtype=torch.float32):
         want += ['probe_pos_correction']
     if c.get('free_prop', False):
         want += ['free_prop_cm']
+    tiles = None
+    if c.get('tiles'):
+        from cases import md_tile_positions
+        t = c['tiles']
+        tiles = dict(pos_batch=md_tile_positions(c['N'], t['sub'])[np.array(t['ind'])], subprobe_size=[t['sub'], t['sub']],
+                     safe_zone_width=t['szw'], n_dp_batch=t['n_dp_batch'])
+        nb = (c['N'] // t['sub']) ** 2
+        sel = np.concatenate([np.array(t['ind']) + d * nb for d in range(len(c['dists']))])
+        inp = dict(inp, prj=inp['prj'][sel])
     aff = None
     if c.get('affine', False):
         aff = torch.tensor(inp['prj_affine_ls']).to(dtype)
@@ -109,7 +118,7 @@ def run_md_oracle_case(name, dtype=torch.float32):
     loss, pred, grads = orc.multidist_loss_and_grads(
         torch.tensor(inp['obj']).to(dtype), torch.tensor(inp['probe_real']).to(dtype),
         torch.tensor(inp['probe_imag']).to(dtype), c['dists'], torch.tensor(inp['prj']).to(dtype), cfg,
-        probe_pos_correction=ppc, want=tuple(want), prj_affine_ls=aff)
+        probe_pos_correction=ppc, want=tuple(want), prj_affine_ls=aff, tiles=tiles)
     return inp, float(loss), pred.numpy(), {k: v.numpy() for k, v in grads.items()}
 
 

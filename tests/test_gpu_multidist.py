@@ -18,12 +18,14 @@ TOL = 1e-4
 
 def md_common_vars(c, dev, prj_full, shift):
     N = c['N']
+    t = c.get('tiles')
+    sub = t['sub'] if t else N
     return dict(unknown_type=c['unknown_type'], normalize_fft=False, sign_convention=1, rotate_out_of_loop=False,
                 scale_ri_by_k=True, is_minus_logged=False, forward_algorithm='fresnel', stdout_options={},
                 poisson_multiplier=1., common_probe_pos=True, binning=1, prj=prj_full, device_obj=dev, probe_size=[N, N],
-                subprobe_size=[N, N], fresnel_approx=True, two_d_mode=True, minibatch_size=1, ds_level=1,
+                subprobe_size=[sub, sub], fresnel_approx=True, two_d_mode=True, minibatch_size=len(t['ind']) if t else 1, ds_level=1,
                 this_obj_size=[N, N, 1], energy_ev=c['energy_ev'], psize_cm=c['psize_cm'], h=None, pure_projection=False,
-                n_dp_batch=1, free_prop_cm=c['dists'], optimize_probe_defocusing=False, optimize_probe_pos_offset=False,
+                n_dp_batch=t['n_dp_batch'] if t else 1, free_prop_cm=c['dists'], optimize_probe_defocusing=False, optimize_probe_pos_offset=False,
                 optimize_prj_pos_offset=False, optimize_all_probe_pos=shift, optimize_free_prop=c.get('free_prop', False),
                 optimize_prj_affine=c.get('affine', False), optimize_ctf_lg_kappa=False, optimize_tilt=False, initial_tilt=None,
                 n_probe_modes=c['n_modes'], n_theta=1, precalculate_rotation_coords=False,
@@ -44,9 +46,16 @@ def run_gpu_md(inp, want_probe, prj_on_device=False):
     t = lambda a, rg=True: torch.tensor(a, dtype=torch.float32, device=dev, requires_grad=rg)
     obj, pr, pi = t(inp['obj']), t(inp['probe_real'], want_probe), t(inp['probe_imag'], want_probe)
     ppc = t(inp['probe_pos_correction']) if shift else torch.zeros((D, 2), device=dev)
+    tl = c.get('tiles')
+    if tl:
+        from cases import md_tile_positions
+        ind = np.array(tl['ind'])
+        pos = md_tile_positions(c['N'], tl['sub'])[ind]
+    else:
+        ind, pos = np.array([0]), np.array([[0, 0]])
     args = dict(obj=obj, probe_real=pr, probe_imag=pi, probe_defocus_mm=None, probe_pos_offset=None, this_i_theta=0,
-                this_pos_batch=np.array([[0, 0]]), prj=prj_full, probe_pos_correction=ppc, this_ind_batch=np.array([0]),
-                free_prop_cm=c['dists'], safe_zone_width=0, prj_affine_ls=None, ctf_lg_kappa=None, prj_pos_offset=None)
+                this_pos_batch=pos, prj=prj_full, probe_pos_correction=ppc, this_ind_batch=ind,
+                free_prop_cm=c['dists'], safe_zone_width=tl['szw'] if tl else 0, prj_affine_ls=None, ctf_lg_kappa=None, prj_pos_offset=None)
     opt, names = [0], ['obj']
     if want_probe:
         opt += [fm.get_argument_index('probe_real'), fm.get_argument_index('probe_imag')]
