@@ -154,6 +154,51 @@ template <class C, class T> ADM_DEV void pass_BHB_x(T* psi, const T* tw, const T
     }
 }
 
+// ---- shared-memory layout of the separable transfer-function tables ------------------------------------------------
+// A thread multiplies the R2 outputs of its gi-th B-type group by h[I.b(k, gi)], k = 0 .. R2-1: positions that depend on
+// the thread row q only.  The tables are therefore stored per (thread row, group): hsq[(q NGB + gi) RP + k] = h[I.b(k, gi)],
+// RP = R2 rounded up to even, so that one 16-byte broadcast load (LDS.128) brings two factors: 5 instead of 9 shared-memory
+// wavefronts per group for R2 = 9 (the table reads were 8 % of the wavefronts of a slice).
+template <class C> struct HsLayout {
+    static constexpr int RP = (C::R2 + 1) & ~1;
+    static constexpr int N = C::Q * C::NGB * RP;      // entries per direction
+};
+// position along the axis whose factor sits at table entry i (-1: padding)
+template <class C> ADM_DEV int hs_source(int i) {
+    constexpr int RP = HsLayout<C>::RP;
+    const int q = i / (C::NGB * RP), gi = (i / RP) % C::NGB, k = i % RP;
+    if (k >= C::R2 || q + C::Q * gi >= C::R1) return -1;
+    return Idx<C>(q).b(k, gi);
+}
+// fill both tables (hy | hx) from the prepared [2][P] vectors in global memory; threads t < 2 N
+template <class C, class T> ADM_DEV void hs_fill(T* hs, const T* Hsep, int t) {
+    constexpr int N = HsLayout<C>::N;
+    if (t < 2 * N) {
+        const int src = hs_source<C>(t % N);
+        hs[t] = src >= 0 ? Hsep[(t / N) * C::P + src] : tmk<T>(0.f, 0.f);
+    }
+}
+template <class T> ADM_DEV void lds_pair(const T* p, T& a, T& b) {
+#ifndef ADM_HOST_EMU
+    const float4 f = *reinterpret_cast<const float4*>(p);
+    a = tmk<T>(f.x, f.y); b = tmk<T>(f.z, f.w);
+#else
+    a = p[0]; b = p[1];
+#endif
+}
+// v[k] *= h[I.b(k, gi)] for the R2 outputs of the gi-th B-type group of thread row q
+template <class C, class T> ADM_DEV void hs_apply_group(const T* hsq, int q, int gi, T* v) {
+    constexpr int RP = HsLayout<C>::RP;
+    const T* hq = hsq + (q * C::NGB + gi) * RP;
+#pragma unroll
+    for (int k = 0; k < RP; k += 2) {
+        T ha, hb;
+        lds_pair(hq + k, ha, hb);
+        v[k] = cmul(v[k], ha);
+        if (k + 1 < C::R2) v[k + 1] = cmul(v[k + 1], hb);
+    }
+}
+
 // ---- separable transfer function, FIVE passes per slice ------------------------------------------------------------
 // With H(ky, kx) = hy(ky) hx(kx) (the paraxial Fresnel kernel, propagate.py:72; hys / hxs are P-entry shared-memory
 // tables indexed by spectrum position, hxs carries the 1/P^2 scale) the propagation is a 1-D convolution along y followed by one along x, and the two
@@ -168,8 +213,7 @@ template <class C, class T> ADM_DEV void pass_BHB_y_sep(T* psi, const T* tw, con
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) v[n] = psi[I.b(n, gi) * C::S + l];
         dftr<C::R2, false>(v);
-#pragma unroll
-        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], hys[I.b(k, gi)]);
+        hs_apply_group<C>(hys, q, gi, v);
         dftr<C::R2, true>(v);
         if constexpr (!C::PFA) {
 #pragma unroll
@@ -187,8 +231,7 @@ template <class C, class T> ADM_DEV void pass_BHB_x_sep1(T* psi, const T* tw, co
 #pragma unroll
         for (int n = 0; n < C::R2; ++n) v[n] = psi[l * C::S + I.b(n, gi)];
         dftr<C::R2, false>(v);
-#pragma unroll
-        for (int k = 0; k < C::R2; ++k) v[k] = cmul(v[k], hxs[I.b(k, gi)]);
+        hs_apply_group<C>(hxs, q, gi, v);
         dftr<C::R2, true>(v);
         if constexpr (!C::PFA) {
 #pragma unroll
@@ -205,7 +248,7 @@ template <class C, class T> ADM_DEV void propagate_core_sep5(T* psi, const T* tw
     __syncthreads();
     if (active) pass_A_fwd<C, true>(psi, tw, q, l);
     __syncthreads();
-    if (active) pass_BHB_x_sep1<C>(psi, tw, hs + C::P, q, l);
+    if (active) pass_BHB_x_sep1<C>(psi, tw, hs + HsLayout<C>::N, q, l);
     __syncthreads();
     if (active) pass_A_inv<C, true>(psi, q, l);
     __syncthreads();

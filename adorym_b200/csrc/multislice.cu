@@ -37,7 +37,7 @@ template <class C> struct MsSmem {
     static constexpr size_t TILE = sizeof(cpx) * C::P * TP;
     static constexpr size_t PSI = sizeof(cpx) * C::P * C::S;
     static constexpr size_t TW = sizeof(cpx) * C::P;
-    static constexpr size_t HS = sizeof(cpx) * 2 * C::P;     // separable transfer function tables hy | hx
+    static constexpr size_t HS = sizeof(cpx) * 2 * HsLayout<C>::N;     // separable transfer function tables hy | hx (per thread row)
     static constexpr size_t BYTES = TILE + PSI + TW + HS + 16;
     static constexpr size_t BYTES_NOTILE = PSI + TW + HS + 16;     // forward variant that reads T' with plain loads
     static constexpr int PSI_F4 = (int)(PSI / 16);           // the psi buffer as float4 (hand-off copies)
@@ -124,7 +124,7 @@ template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds
     T* psi = TILE ? tile + P * TP : (T*)smem_raw;
     T* tw = psi + P * S;
     T* hs = tw + P;
-    adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
+    adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * HsLayout<C>::N);
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
@@ -132,7 +132,7 @@ template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds
     const int c = blockIdx.x;               // logical CTA index (dependencies point to c - 1)
 
     init_twiddles<C>(tw, t);
-    if (p.h_separable && t < 2 * P) hs[t] = ((const T*)p.Hp)[t];
+    if (p.h_separable) hs_fill<C>(hs, (const T*)p.Hp, t);
     if (TILE && t == 0) mbar_init(bar, 1);
     unsigned ph = 0;                        // parity of the next tile completion
 
@@ -171,7 +171,7 @@ template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds
             const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
             // per-gap transfer functions (sparse multislice): tables of the gap z -> z+1; the previous slice's last reader
             // (its x pass) is two barriers back, the first reader (P2') comes after the barrier that closes P1
-            if (!last && p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)z * 2 * P + t];
+            if (!last && p.h_per_slice) hs_fill<C>(hs, (const T*)p.Hp + (size_t)z * 2 * P, t);
             // ---- P1: [Ay^-1] . checkpoint . modulation . [Ay] ------------------------------------------------
             const T* tz = tcol + (size_t)z * slice_stride;
             if (active) {
@@ -285,7 +285,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
     T* psi = ckb + P * TP;            // running adjoint wavefield g
     T* tw = psi + P * S;
     T* hs = tw + P;
-    adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
+    adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * HsLayout<C>::N);
     const int t = threadIdx.x;
     const bool active = t < C::NACT;
     const int q = t / P, l = t % P;
@@ -294,7 +294,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                                                 // FIRST segment of CTA c + 1 = a lower blockIdx
 
     init_twiddles<C>(tw, t);
-    if (p.h_separable && t < 2 * P) hs[t] = ((const T*)p.Hp)[t];
+    if (p.h_separable) hs_fill<C>(hs, (const T*)p.Hp, t);
     if (t == 0) mbar_init(bar, 1);
     unsigned phase = 0;
 
@@ -393,7 +393,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
         for (int z = sg.ze - 1; z >= sg.zb; --z, phase ^= 1) {
             const bool last = (z == p.Nz - 1);
             // per-gap transfer functions: tables of the gap z-1 -> z (read after the barrier that closes P1')
-            if (z > 0 && p.h_per_slice && t < 2 * P) hs[t] = ((const T*)p.Hp)[(size_t)(z - 1) * 2 * P + t];
+            if (z > 0 && p.h_per_slice) hs_fill<C>(hs, (const T*)p.Hp + (size_t)(z - 1) * 2 * P, t);
             // ---- P1': [Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay] --------------------------
             if (active) {
                 ADM_FOR_GROUPS_A(gi) {
@@ -465,7 +465,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
             if (active) pass_A_fwd<C, true>(psi, tw, q, l);
             __syncthreads();
             if (active) {
-                if (p.h_separable) pass_BHB_x_sep1<C>(psi, tw, hs + P, q, l);
+                if (p.h_separable) pass_BHB_x_sep1<C>(psi, tw, hs + HsLayout<C>::N, q, l);
                 else pass_BHB_x<C>(psi, tw, (const T*)p.Hp, q, l);
             }
             __syncthreads();
