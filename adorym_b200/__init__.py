@@ -10,6 +10,7 @@ from .optimizers import Optimizer, AdamOptimizer, GDOptimizer, MomentumOptimizer
 from .regularizers import Regularizer, L1Regularizer, ReweightedL1Regularizer, TVRegularizer
 from .array_ops import ObjectFunction, Gradient, Mask
 from .differentiator import Differentiator
+from .graph import GraphedDifferentiator
 from .ptychography import reconstruct_ptychography
 
 __all__ = ['multislice_propagate_batch', 'get_kernel', 'gen_freq_mesh', 'apply_rotation', 'pad_object',
@@ -17,4 +18,4 @@ __all__ = ['multislice_propagate_batch', 'get_kernel', 'gen_freq_mesh', 'apply_r
            'ForwardModel', 'PtychographyModel', 'SingleBatchFullfieldModel', 'SingleBatchPtychographyModel',
            'SparseMultisliceModel', 'MultiDistModel',
            'Optimizer', 'AdamOptimizer', 'GDOptimizer', 'MomentumOptimizer', 'Regularizer', 'L1Regularizer', 'ReweightedL1Regularizer',
-           'TVRegularizer', 'ObjectFunction', 'Gradient', 'Mask', 'Differentiator', 'reconstruct_ptychography']
+           'TVRegularizer', 'ObjectFunction', 'Gradient', 'Mask', 'Differentiator', 'GraphedDifferentiator', 'reconstruct_ptychography']

@@ -56,6 +56,10 @@ class ForwardModel(object):
         self._plans = {}
         self._rot_table = None
         self.last_reg_value = None
+        # CUDA-graph mode (adorym_b200.graph.GraphedDifferentiator): dict of STATIC device buffers that replace every
+        # per-minibatch host value on the device side (rotation grid, patch positions, gather indices, angle index), so
+        # that the captured launches can be replayed for any minibatch; None in eager mode
+        self._static = None
 
     # -- the reference exposes current_loss as a float; reading it synchronises (forward_model.py:140-146) --
     @property
@@ -132,14 +136,34 @@ class ForwardModel(object):
         if self.forward_algorithm != 'fresnel':
             raise NotImplementedError('adorym_b200: forward_algorithm=%r' % (self.forward_algorithm,))
 
+    def static_indices(self, this_i_theta, this_pos_batch, this_ind_batch, n_pos_ppc=0):
+        """Host side of graph mode: the int32 device-side indices one minibatch needs, as a dict of numpy arrays
+        ('pos' [B,2] patch corners, 'ppc' flat rows of the position-correction table, 'data' flat rows of exchange/data,
+        'theta' [1]).  Must mirror what predict / get_data index with in eager mode."""
+        cv = self.common_vars
+        it = int(this_i_theta)
+        ind = np.asarray(this_ind_batch).astype('int64')
+        td = cv.get('theta_downsample', None) or 1
+        n_spots = int(self.prj.shape[1])
+        return {'pos': _np_int_positions(this_pos_batch).astype('int32').reshape(-1, 2),
+                'ppc': (it * int(n_pos_ppc) + ind).astype('int32'),
+                'data': (it * td * n_spots + ind).astype('int32'),
+                'theta': np.array([it], dtype='int32')}
+
     def _rotation_grid(self, this_i_theta, device):
+        cv = self.common_vars
+        if self._static is not None and self._static.get('grid') is not None:
+            return self._static['grid']
+        return self._rot_table_for(device).grid(this_i_theta)
+
+    def _rot_table_for(self, device):
         cv = self.common_vars
         if self._rot_table is None:
             n_theta = cv['n_theta']
             folder = 'arrsize_{}_{}_{}_ntheta_{}'.format(*cv['this_obj_size'], n_theta)
             self._rot_table = RotationTable(cv['this_obj_size'], cv['theta_ls'], device,
                                             src_folder=folder if cv.get('precalculate_rotation_coords', True) else None)
-        return self._rot_table.grid(this_i_theta)
+        return self._rot_table
 
     def _object_grid(self, obj, this_i_theta):
         """Normalised rotation grid for ops.MultisliceFn (layout 'yxz'), or None when the object already is in the beam
@@ -256,14 +280,18 @@ class ForwardModel(object):
         dev = self.device
         ind = np.asarray(this_ind_batch)
         it = int(this_i_theta) * theta_downsample
-        pf = getattr(self, '_prefetched', None)
+        pf = getattr(self, '_prefetched', None) if self._static is None else None
         if pf is not None:
             self._prefetched = None
             if pf[0] == (id(prj), it, ind.tobytes(), int(ds_level)):
                 torch.cuda.current_stream(pf[1].device).wait_event(pf[2])
                 pf[1].record_stream(torch.cuda.current_stream(pf[1].device))
                 return pf[1]
-        if torch.is_tensor(prj) and prj.is_cuda:
+        if torch.is_tensor(prj) and prj.is_cuda and self._static is not None:
+            # graph mode: one gather over the flattened [n_theta * n_spots] frame table by a static device index
+            frames = prj.reshape((-1,) + tuple(prj.shape[2:])).index_select(0, self._static['data'])
+            batch = (frames.abs() if frames.is_complex() else frames).to(dev, dtype=torch.float32)
+        elif torch.is_tensor(prj) and prj.is_cuda:
             frames = prj[it]
             if not (len(ind) == frames.shape[0] and np.array_equal(ind, np.arange(len(ind)))):
                 frames = frames.index_select(0, torch.as_tensor(ind, device=prj.device, dtype=torch.long))
@@ -408,7 +436,11 @@ class PtychographyModel(ForwardModel):
         # (callers hand over tilt_ls / probe_pos_offset only where the reference's class of the same name uses them)
         if cv.get('optimize_probe_pos_offset', False) and probe_pos_offset is not None:
             # forward_model.py:258-260: every mode shifted by this angle's refinable offset (one Fourier shift)
-            probe = ops.probe_shift(probe, probe_pos_offset[int(this_i_theta)].reshape(1, 2).to(torch.float32))[0]
+            if self._static is not None:
+                off = probe_pos_offset.index_select(0, self._static['theta'])
+            else:
+                off = probe_pos_offset[int(this_i_theta)]
+            probe = ops.probe_shift(probe, off.reshape(1, 2).to(torch.float32))[0]
         tilted = tilt_ls is not None and (cv.get('optimize_tilt', False) or cv.get('initial_tilt', None) is not None)
         if tilted:
             # forward_model.py:262-276: three differentiable rotations (wrappers.py:1177-1217) replace the lookup table
@@ -416,24 +448,31 @@ class PtychographyModel(ForwardModel):
                 raise NotImplementedError('Tilt optimization is not impemented for distributed mode or when two_d_mode is on.')
             t = tilt_ls if torch.is_tensor(tilt_ls) else torch.as_tensor(np.asarray(tilt_ls), dtype=torch.float32, device=dev)
             t = t.to(dev)
+            tcol = t.index_select(1, self._static['theta'])[:, 0] if self._static is not None else t[:, int(this_i_theta)]
             for axis in range(3):
-                obj = ops.rotate_with_grad(obj, t[axis, int(this_i_theta)], axis)
+                obj = ops.rotate_with_grad(obj, tcol[axis], axis)
         # per-position probe shift: quirk 8, positive corrections only trigger it (forward_model.py:297,304)
         if probe_pos_correction is not None and (cv['optimize_all_probe_pos']
                                                  or self._any_positive_correction(probe_pos_correction)):
-            idx = torch.as_tensor(np.asarray(this_ind_batch), device=dev, dtype=torch.long)
-            shift = probe_pos_correction[int(this_i_theta)].index_select(0, idx).to(torch.float32)
+            if self._static is not None:
+                shift = probe_pos_correction.reshape(-1, 2).index_select(0, self._static['ppc']).to(torch.float32)
+            else:
+                idx = torch.as_tensor(np.asarray(this_ind_batch), device=dev, dtype=torch.long)
+                shift = probe_pos_correction[int(this_i_theta)].index_select(0, idx).to(torch.float32)
             probe = ops.probe_shift(probe, shift)
         plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
         # device copy of the integer positions, cached by content (the driver revisits the same minibatches every epoch)
         pos32 = np.ascontiguousarray(pos, dtype='int32')
-        key = (pos32.tobytes(), str(dev))
-        cache = self.__dict__.setdefault('_pos_cache', {})
-        pos_t = cache.get(key)
-        if pos_t is None:
-            if len(cache) > 4096:
-                cache.clear()
-            pos_t = cache[key] = torch.from_numpy(pos32).to(dev)
+        if self._static is not None:
+            pos_t = self._static['pos']
+        else:
+            key = (pos32.tobytes(), str(dev))
+            cache = self.__dict__.setdefault('_pos_cache', {})
+            pos_t = cache.get(key)
+            if pos_t is None:
+                if len(cache) > 4096:
+                    cache.clear()
+                pos_t = cache[key] = torch.from_numpy(pos32).to(dev)
         out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg, in_beam_frame=tilted)
         return out if with_reg else out[0]
 
@@ -639,6 +678,19 @@ class MultiDistModel(ForwardModel):
         a.pop(0)
         self.argument_ls = a
         self._md_plans = {}
+
+    def static_indices(self, this_i_theta, this_pos_batch, this_ind_batch, n_pos_ppc=0):
+        """Graph mode: exchange/data rows of every distance's frame (forward_model.py:1058-1061)."""
+        out = super(MultiDistModel, self).static_indices(this_i_theta, this_pos_batch, this_ind_batch, n_pos_ppc)
+        cv = self.common_vars
+        n_dists = len(np.asarray(cv['free_prop_cm']).reshape(-1))
+        n_spots = int(self.prj.shape[1])
+        n_blocks = n_spots // n_dists
+        ind = np.asarray(this_ind_batch).astype('int64')
+        full = np.concatenate([ind + i * n_blocks for i in range(n_dists)])
+        td = cv.get('theta_downsample', None) or 1
+        out['data'] = (int(this_i_theta) * td * n_spots + full).astype('int32')
+        return out
 
     def _md_plan(self, dev, N, dists):
         cv = self.common_vars

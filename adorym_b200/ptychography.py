@@ -139,6 +139,9 @@ def reconstruct_ptychography(
         torch.cuda.set_device(device_obj)
     verbose = kwargs.pop('verbose', True)
     max_batches = kwargs.pop('max_batches_for_test', None)    # testing hook: stop after this many minibatches
+    # use_cuda_graph=True: the loss + gradient evaluation of a minibatch is captured once in a CUDA graph and replayed
+    # (adorym_b200.graph): worth it for the launch-bound configurations (small minibatches, thin objects)
+    use_cuda_graph = bool(kwargs.pop('use_cuda_graph', False))
 
     timestr = comm.bcast(datetime.datetime.today().strftime('%Y%m%d_%H%M%S') if rank == 0 else None, root=0)
     if output_folder is None:
@@ -364,7 +367,17 @@ def reconstruct_ptychography(
                                                           device=device_obj, requires_grad=True)
     opt_ls, opt_args_ls = create_and_initialize_parameter_optimizers(optimizable_params, locals())
 
-    diff = Differentiator()
+    graphed = use_cuda_graph and n_ranks == 1
+    if graphed:
+        from .graph import GraphedDifferentiator
+        if not (torch.is_tensor(forward_model.prj) and forward_model.prj.is_cuda):
+            # graph mode gathers the measured frames on the device: upload exchange/data once (|.| as get_data applies it)
+            full = np.abs(np.asarray(prj[...])).astype('float32')
+            forward_model.prj = torch.from_numpy(full).to(device_obj)
+        prj = forward_model.prj
+        diff = GraphedDifferentiator(forward_model)
+    else:
+        diff = Differentiator()
     diff.create_loss_node(forward_model.get_loss_function(), opt_args_ls)
 
     loss_history = []
@@ -430,7 +443,7 @@ def reconstruct_ptychography(
                     grad_func_args[arg] = local_vars[arg]
             forward_model.update_loss_args(grad_func_args)
             grads = list(diff.get_gradients(**grad_func_args))
-            if i_batch + 1 < n_batch:
+            if i_batch + 1 < n_batch and not graphed:
                 # measured frames of the next minibatch: host->device copy on a side stream under this step's kernels
                 nxt_theta, nxt_ind = rank_minibatch(ind_list_rand, i_batch + 1, rank, minibatch_size, n_ranks)
                 forward_model.prefetch_data(nxt_theta, nxt_ind, theta_downsample=forward_model.common_vars['theta_downsample'],
@@ -438,7 +451,9 @@ def reconstruct_ptychography(
 
             if initialize_gradients:
                 # ptychography.py:1065-1067: zeros + grads[0] -- the buffer becomes the new gradient (no fill, no add)
-                gradient.arr = grads[0]
+                # (graph mode: grads[0] is the graph's static output; it is accumulated into below only when the update is
+                # deferred, and then it must not alias the buffer the next replay overwrites)
+                gradient.arr = grads[0].clone() if (graphed and (update_scheme != 'immediate' or rotate_out_of_loop)) else grads[0]
                 initialize_parameter_gradients(opt_ls, device_obj)
                 initialize_gradients = False
             else:

@@ -64,7 +64,18 @@ class ReweightedL1Regularizer(Regularizer):
         self.weight_l1 = None
 
     def update_l1_weight(self, weight_l1):
-        self.weight_l1 = weight_l1
+        """regularizers.py:60-61.  New weights of the same shape are copied INTO the existing tensor, so that launches
+        captured in a CUDA graph (adorym_b200.graph) keep reading the current weights."""
+        if weight_l1 is getattr(self, '_weight_src', None):
+            return
+        self._weight_src = weight_l1
+        w = self.weight_l1
+        if (torch.is_tensor(w) and torch.is_tensor(weight_l1) and w.shape == weight_l1.shape and w.dtype == weight_l1.dtype
+                and w.device == weight_l1.device and w.data_ptr() != weight_l1.data_ptr()):
+            with torch.no_grad():
+                w.copy_(weight_l1)
+        else:
+            self.weight_l1 = weight_l1.clone() if torch.is_tensor(weight_l1) else weight_l1
 
     def get_value(self, obj, device=None, **kwargs):
         if self.unknown_type == 'delta_beta':

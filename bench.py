@@ -551,7 +551,8 @@ def run_other_configs(args):
             out = {'metric': METRIC.replace('at 256^3', 'config ' + l['config']), 'value': l['value'], 'unit': UNIT, 'n_gpus': 1,
                    'steps': l['steps'], 'warmup': l['warmup'], 'ms_per_step': l['ms_per_step'], 'higher_is_better': True,
                    'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-                   'config': {'workload': l['workload'], 'patterns_per_step': l['patterns_per_step'],
+                   'config': {'workload': l['workload'] + (' [loss + gradients replayed as one CUDA graph]' if l.get('cuda_graph') else ' [eager launches]'),
+                              'cuda_graph': bool(l.get('cuda_graph')), 'patterns_per_step': l['patterns_per_step'],
                               'l2_policy': 'working set is L2 resident by construction (<= 8 MB): launch / latency bound'},
                    'roofline': {'bound': 'hbm', 'achieved': l['algorithmic_bytes_per_step'] / (l['ms_per_step'] * 1e-3) / 1e9,
                                 'peak': l['peak_gbs'], 'unit': 'GB/s', 'frac': l['hbm_roofline_frac'], 'traffic': None},

@@ -37,6 +37,7 @@ def base_cv(**kw):
     return cv
 
 
+GRAPH = False     # True: the loss + gradient evaluation replays a CUDA graph (adorym_b200.graph.GraphedDifferentiator)
 STEPS = None      # overridden by bench.py --config (steps, warmup)
 WARMUP = None
 LINES = []
@@ -60,7 +61,7 @@ def time_steps(step, n_warm=5, n=30):
 
 def report(name, workload, patterns_per_step, ms, alg_bytes):
     n, n_warm = getattr(time_steps, 'last', (None, None))
-    line = {'config': name, 'workload': workload, 'patterns_per_step': patterns_per_step, 'ms_per_step': ms,
+    line = {'config': name, 'cuda_graph': bool(GRAPH), 'workload': workload, 'patterns_per_step': patterns_per_step, 'ms_per_step': ms,
             'value': patterns_per_step / (ms * 1e-3), 'unit': 'patterns/s', 'steps': n, 'warmup': n_warm,
             'algorithmic_bytes_per_step': alg_bytes,
             'hbm_roofline_frac': alg_bytes / (ms * 1e-3) / 1e9 / PEAK, 'peak_gbs': PEAK}
@@ -107,7 +108,7 @@ def ptycho_runner(obj_size, P, pos, M, unknown_type, energy_ev, psize_cm, raw_da
     prj = torch.zeros([1, n_pos, P, P], device=DEV)
     prj[0, :n_batches * mb] = torch.cat(frames)
     fm.prj = prj
-    diff = ab.Differentiator()
+    diff = ab.GraphedDifferentiator(fm) if GRAPH else ab.Differentiator()
     opt_args = [0]
     if refine:
         opt_args += [fm.get_argument_index('probe_real'), fm.get_argument_index('probe_imag'),
@@ -162,7 +163,7 @@ def config_A():
                            for i in range(n_theta)])
     fm.prj = prj
     fm.add_regularizers([ab.L1Regularizer(1e-9 * 64 ** 3, 1e-10 * 64 ** 3)])
-    diff = ab.Differentiator()
+    diff = ab.GraphedDifferentiator(fm) if GRAPH else ab.Differentiator()
     diff.create_loss_node(fm.get_loss_function(), [0])
     state = {'obj': torch.zeros((Y, X, Z, 2), device=DEV).add_(1e-6).requires_grad_(True), 'i': 0}
     opt = ab.AdamOptimizer('obj', options_dict={'step_size': 1e-7})
@@ -226,7 +227,7 @@ def config_E():
     pi = torch.tensor(inp['probe_imag'], device=DEV)
     state = {'obj': torch.tensor(inp['obj'], device=DEV, requires_grad=True), 'i': 0,
              'ppc': torch.tensor(inp['probe_pos_correction'], device=DEV, requires_grad=True)}
-    diff = ab.Differentiator()
+    diff = ab.GraphedDifferentiator(fm) if GRAPH else ab.Differentiator()
     diff.create_loss_node(fm.get_loss_function(), [0, fm.get_argument_index('probe_pos_correction')])
     opt = ab.AdamOptimizer('obj', options_dict={'step_size': 1e-2})
     opt.create_container([N, N, 1, 2], False, DEV)
@@ -247,13 +248,17 @@ def config_E():
            D, ms, 92e6)
 
 
-def run(which, steps=None, warmup=None):
-    """-> list of result dicts (bench.py --config adds the clocks record and prints them)."""
-    global STEPS, WARMUP
+def run(which, steps=None, warmup=None, graph=(False, True)):
+    """-> list of result dicts (bench.py --config adds the clocks record and prints them); every configuration is timed
+    eagerly and with the CUDA-graph replay of the loss + gradient evaluation."""
+    global STEPS, WARMUP, GRAPH
     STEPS, WARMUP = steps, warmup
     del LINES[:]
     for w in which:
-        {'A': config_A, 'B': config_B, 'C': config_C, 'E': config_E}[w]()
+        for g in graph:
+            GRAPH = g
+            {'A': config_A, 'B': config_B, 'C': config_C, 'E': config_E}[w]()
+    GRAPH = False
     return list(LINES)
 
 
