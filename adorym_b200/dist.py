@@ -171,6 +171,53 @@ class PeerUpdate(object):
         return self.object_tensor()
 
 
+    def update_pipelined(self, opt, i_batch, slabs, step_size=0.001, b1=0.9, b2=0.999, eps=1e-7, clip_nonneg=False,
+                         zero_channel=None, mask=None, **unused):
+        """The same update, pipelined by y slabs with the kernels that still PRODUCE the gradient: `slabs` =
+        [(y0, y1, event)] as recorded by ops.MultisliceFn.backward (ops.GRAD_SLABS > 1; the rotation is about y, so the
+        transpose chain finishes the gradient plane by plane).  On a side stream, per slab: wait for the slab's event ->
+        cross-GPU barrier (every rank has finished this slab) -> the fused kernel on the slab (every rank reduces, updates
+        and pushes ITS share of the slab), so the NVLink traffic of slab k runs under the production of slab k + 1 and only
+        the last slab's exchange is exposed.  The object is last READ (regulariser gradient) before the first slab's event
+        on every rank, so a peer's push into a finished slab cannot race with a reader."""
+        import ctypes
+        from . import ops
+        shape = list(self.shape)
+        if 'm' not in opt.params_whole_array_dict or list(opt.params_whole_array_dict['m'].shape) != shape:
+            opt.create_param_arrays(shape, device=self.x.device)
+        m, v = opt.params_whole_array_dict['m'], opt.params_whole_array_dict['v']
+        if mask is not None and (mask.dtype != torch.float32 or not mask.is_contiguous() or mask.numel() * 2 != self.n):
+            raise RuntimeError('PeerUpdate.update_pipelined: mask must be a contiguous fp32 tensor with one element per voxel')
+        flags = (1 if clip_nonneg else 0) | (2 if zero_channel == 0 else 0) | (4 if zero_channel == 1 else 0)
+        row = self.n // self.shape[0]                       # elements per y plane
+        if row % 4:
+            return self.update(opt, i_batch, step_size, b1, b2, eps, clip_nonneg, zero_channel, mask)
+        dev = self.x.device
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=dev)
+        main = torch.cuda.current_stream(dev)
+        mflat, vflat = m.view(-1), v.view(-1)
+        kflat = mask.view(-1) if mask is not None else None
+        for (y0, y1, ev) in slabs:
+            off, cnt = y0 * row, (y1 - y0) * row
+            self._side.wait_event(ev)
+            with torch.cuda.stream(self._side):
+                self.hg.barrier(channel=0)
+                xp = (ctypes.c_void_p * self.world)(*[int(p) + 4 * off for p in self.hx.buffer_ptrs])
+                gp = (ctypes.c_void_p * self.world)(*[int(p) + 4 * off for p in self.hg.buffer_ptrs])
+                mcx = ctypes.c_void_p(self.mc_x.value + 4 * off) if self.mc_x is not None else None
+                mcg = ctypes.c_void_p(self.mc_g.value + 4 * off) if self.mc_g is not None else None
+                ops.call('adm_p2p_reduce_adam', ctypes.cast(xp, ctypes.c_void_p), ctypes.cast(gp, ctypes.c_void_p), mcx, mcg,
+                         self.world, self.rank, ops.ptr(mflat[off:off + cnt]), ops.ptr(vflat[off:off + cnt]), cnt,
+                         float(step_size), float(b1), float(b2), float(eps), int(i_batch), flags,
+                         ops.ptr(kflat[off // 2:(off + cnt) // 2]) if kflat is not None else None, ops.stream_ptr())
+        with torch.cuda.stream(self._side):
+            self.hx.barrier(channel=1)
+        main.wait_stream(self._side)
+        opt.i_batch += 1
+        return self.object_tensor()
+
+
 def init_from_env(backend=None):
     """Initialise torch.distributed from torchrun's environment (RANK / WORLD_SIZE / LOCAL_RANK / MASTER_*).
     Returns (rank, world_size, local_rank).  A no-op for single-process runs."""

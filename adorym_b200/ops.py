@@ -278,12 +278,16 @@ class MultisliceFn(torch.autograd.Function):
                 use_reg = ctx.reg is not None and g_reg is not None
                 gs = _f32c(g_reg.reshape(1)) if use_reg else None
                 slabs = []
-                for (y0, y1) in slab_ranges(Y, GRAD_SLABS):
-                    if use_reg:
-                        call('adm_regularizer_l1tv_range', Y, X, Zo, ptr(obj), ptr(w), ctx.reg[1], ctx.reg[2], ctx.reg[3], None,
-                             ptr(g_obj), ptr(gs), 0, y0, y1, stream_ptr())
-                    else:
-                        g_obj[y0:y1].zero_()
+                ranges = slab_ranges(Y, GRAD_SLABS)
+                # the regulariser gradient INITIALISES the buffer: for all planes first (it is the last reader of the object
+                # in a step -- with the pipelined peer-memory update a finished slab may be overwritten by the peers while
+                # later slabs are still being produced), then the transpose chain slab by slab
+                if use_reg:
+                    call('adm_regularizer_l1tv_range', Y, X, Zo, ptr(obj), ptr(w), ctx.reg[1], ctx.reg[2], ctx.reg[3], None,
+                         ptr(g_obj), ptr(gs), 0, 0, Y, stream_ptr())
+                else:
+                    g_obj.zero_()
+                for (y0, y1) in ranges:
                     call('adm_transmission_to_object_adj', Y, X, Zo, P, ptr(g_tvol), ptr(tvol), ptr(grid), plan.unknown_type,
                          plan.k1, plan.sign_convention, plan.binning, ptr(g_obj), y0, y1, stream_ptr())
                     if GRAD_SLABS > 1:

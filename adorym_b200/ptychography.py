@@ -289,7 +289,9 @@ def reconstruct_ptychography(
         obj.arr = peer.object_tensor().requires_grad_(True)
         if update_scheme == 'immediate' and not rotate_out_of_loop:
             ops.OBJ_GRAD_OUT = peer.gradient_tensor()        # the adjoint writes straight into the symmetric buffer
-    ops.GRAD_SLABS = int(os.environ.get('ADM_GRAD_SLABS', '4')) if (n_ranks > 1 and peer is None) else 1
+    # y slabs by which the gradient exchange (NCCL all-reduce, or the fused peer-memory update) is pipelined with the
+    # transpose chain that still produces the gradient
+    ops.GRAD_SLABS = int(os.environ.get('ADM_GRAD_SLABS', '4')) if n_ranks > 1 else 1
 
     mask = None
     if finite_support_mask_path is not None:
@@ -494,7 +496,11 @@ def reconstruct_ptychography(
                         # pull-reduce over NVLink + Adam + push, one kernel (dist.PeerUpdate / adm_p2p_reduce_adam)
                         if gradient.arr.data_ptr() != peer.g.data_ptr():
                             peer.gradient_tensor().copy_(gradient.arr)
-                        new = peer.update(opt, i_opt_batch, **opt.options_dict, **extra)
+                        if (slabs is not None and slabs[0].data_ptr() == peer.g.data_ptr() and len(slabs[1]) > 1
+                                and gradient.arr.data_ptr() == peer.g.data_ptr()):
+                            new = peer.update_pipelined(opt, i_opt_batch, slabs[1], **opt.options_dict, **extra)
+                        else:
+                            new = peer.update(opt, i_opt_batch, **opt.options_dict, **extra)
                     elif pipelined:
                         # the all-reduce runs slab by slab under the adjoint kernels and under Adam (dist.py)
                         from .dist import allreduce_update_pipelined

@@ -303,7 +303,10 @@ class StepRunner(object):
             if self.peer is not None:
                 if self.gradient.data_ptr() != self.peer.g.data_ptr():
                     self.peer.gradient_tensor().copy_(self.gradient)
-                new = self.peer.update(self.opt, self.i_step, **self.opt.options_dict)
+                if slabs is not None and slabs[0].data_ptr() == self.peer.g.data_ptr() and len(slabs[1]) > 1:
+                    new = self.peer.update_pipelined(self.opt, self.i_step, slabs[1], **self.opt.options_dict)
+                else:
+                    new = self.peer.update(self.opt, self.i_step, **self.opt.options_dict)
             elif self.world > 1 and slabs is not None and slabs[0].data_ptr() == self.gradient.data_ptr():
                 # gradient all-reduce pipelined by y slabs with the adjoint rotation and with Adam
                 new = _adist.allreduce_update_pipelined(self.opt, self.obj, self.gradient, self.i_step, slabs[1],
@@ -315,6 +318,11 @@ class StepRunner(object):
         self.obj = new.requires_grad_(True)
         self.i_step += 1
         return self.fm.current_loss if host_data else None
+
+
+def _ops_mod():
+    from adorym_b200 import ops
+    return ops
 
 
 def dp_check(torch, ab, runner, dev, rank, world):
@@ -365,7 +373,12 @@ def dp_check(torch, ab, runner, dev, rank, world):
         with torch.no_grad():
             if g.data_ptr() != runner.peer.g.data_ptr():
                 runner.peer.gradient_tensor().copy_(g)
-            xn = runner.peer.update(opt_p, 0, **opt_p.options_dict)
+            slabs = _ops_mod().last_obj_grad_slabs
+            if slabs is not None and slabs[0].data_ptr() == runner.peer.g.data_ptr() and len(slabs[1]) > 1:
+                # the slab-pipelined form of the update is the one the timed steps use: check THAT one
+                xn = runner.peer.update_pipelined(opt_p, 0, slabs[1], **opt_p.options_dict)
+            else:
+                xn = runner.peer.update(opt_p, 0, **opt_p.options_dict)
         if rank == 0:
             gs = gl[0].clone()
             for r in range(1, world):
@@ -392,8 +405,10 @@ def run_gpu_arm(args):
     from adorym_b200 import _lib
     mb = args.minibatch
     K, W = args.steps, max(args.warmup, 3)
+    if args.grad_slabs is None:
+        args.grad_slabs = 4 if args.dp == 'p2p' else 2
     from adorym_b200 import ops as _ops
-    _ops.GRAD_SLABS = args.grad_slabs if (world > 1 and args.dp == 'nccl') else 1
+    _ops.GRAD_SLABS = args.grad_slabs if world > 1 else 1
     runner = StepRunner(torch, ab, dev, rank, world, K + W, mb, dp_mode=args.dp)
 
     def barrier():
@@ -444,8 +459,9 @@ def run_gpu_arm(args):
         dp = {'max_abs_replica_difference': float(d.item()), 'allreduced_vs_summed_single_rank_gradient_rel': sum_err,
               'p2p_update_vs_allgather_sum_adam_max_abs': p2p_err,
               'grad_slabs': _ops.GRAD_SLABS, 'update': 'p2p fused pull-reduce + Adam + push (adm_p2p_reduce_adam, %s)'
-              % ('NVLS multimem.ld_reduce / multimem.st' if runner.peer is not None and runner.peer.mc_x is not None
-                 else 'peer loads / stores')
+              % (('NVLS multimem.ld_reduce / multimem.st' if runner.peer is not None and runner.peer.mc_x is not None
+                  else 'peer loads / stores') + ('; pipelined by %d y slabs with the transpose chain' % _ops.GRAD_SLABS
+                                                 if _ops.GRAD_SLABS > 1 else ''))
               if runner.peer is not None else 'NCCL all-reduce (slab pipelined) + Adam'}
 
     # ---- secondary figure: the reference demo's own schedule (minibatch_size = 2, update after every minibatch,
@@ -569,7 +585,9 @@ def main():
     ap.add_argument('--minibatch', type=int, default=529)
     ap.add_argument('--dp', default='p2p', choices=['p2p', 'nccl'],
                     help='N > 1: fused peer-memory update kernel (default) or NCCL all-reduce + Adam')
-    ap.add_argument('--grad-slabs', type=int, default=2, help='y slabs of the pipelined gradient all-reduce (N > 1)')
+    ap.add_argument('--grad-slabs', type=int, default=None,
+                    help='N > 1: y slabs by which the gradient exchange is pipelined with its production (default: 4 for the '
+                         'fused peer-memory update, 2 for NCCL; 1 = not pipelined)')
     ap.add_argument('--config', nargs='*', default=None, choices=['A', 'B', 'C', 'E'],
                     help='secondary lines for the other named shapes (default: the contract line on config D)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
