@@ -183,8 +183,10 @@ class PeerUpdate(object):
         import ctypes
         from . import ops
         shape = list(self.shape)
+        fresh_state = False
         if 'm' not in opt.params_whole_array_dict or list(opt.params_whole_array_dict['m'].shape) != shape:
             opt.create_param_arrays(shape, device=self.x.device)
+            fresh_state = True          # zero-filled on the CURRENT stream: the side stream must see that (first call only)
         m, v = opt.params_whole_array_dict['m'], opt.params_whole_array_dict['v']
         if mask is not None and (mask.dtype != torch.float32 or not mask.is_contiguous() or mask.numel() * 2 != self.n):
             raise RuntimeError('PeerUpdate.update_pipelined: mask must be a contiguous fp32 tensor with one element per voxel')
@@ -196,6 +198,9 @@ class PeerUpdate(object):
         if getattr(self, '_side', None) is None:
             self._side = torch.cuda.Stream(device=dev)
         main = torch.cuda.current_stream(dev)
+        if fresh_state or getattr(self, '_side_state_owner', None) is not opt:
+            self._side.wait_stream(main)
+            self._side_state_owner = opt
         mflat, vflat = m.view(-1), v.view(-1)
         kflat = mask.view(-1) if mask is not None else None
         for (y0, y1, ev) in slabs:
