@@ -291,7 +291,9 @@ def reconstruct_ptychography(
             ops.OBJ_GRAD_OUT = peer.gradient_tensor()        # the adjoint writes straight into the symmetric buffer
     # y slabs by which the gradient exchange (NCCL all-reduce, or the fused peer-memory update) is pipelined with the
     # transpose chain that still produces the gradient
-    ops.GRAD_SLABS = int(os.environ.get('ADM_GRAD_SLABS', '4')) if n_ranks > 1 else 1
+    # (default: 4 slabs for NCCL; 1 = not pipelined for the peer-memory update, which measured faster that way: the exchange
+    # kernel competes with the producers for the SMs and every slab costs a cross-GPU barrier -- DESIGN.md section 6)
+    ops.GRAD_SLABS = int(os.environ.get('ADM_GRAD_SLABS', '1' if peer is not None else '4')) if n_ranks > 1 else 1
 
     mask = None
     if finite_support_mask_path is not None:

@@ -406,7 +406,7 @@ def run_gpu_arm(args):
     mb = args.minibatch
     K, W = args.steps, max(args.warmup, 3)
     if args.grad_slabs is None:
-        args.grad_slabs = 4 if args.dp == 'p2p' else 2
+        args.grad_slabs = 1 if args.dp == 'p2p' else 2
     from adorym_b200 import ops as _ops
     _ops.GRAD_SLABS = args.grad_slabs if world > 1 else 1
     runner = StepRunner(torch, ab, dev, rank, world, K + W, mb, dp_mode=args.dp)
@@ -586,8 +586,8 @@ def main():
     ap.add_argument('--dp', default='p2p', choices=['p2p', 'nccl'],
                     help='N > 1: fused peer-memory update kernel (default) or NCCL all-reduce + Adam')
     ap.add_argument('--grad-slabs', type=int, default=None,
-                    help='N > 1: y slabs by which the gradient exchange is pipelined with its production (default: 4 for the '
-                         'fused peer-memory update, 2 for NCCL; 1 = not pipelined)')
+                    help='N > 1: y slabs by which the gradient exchange is pipelined with its production (default: 1 = not '
+                         'pipelined for the fused peer-memory update -- measured faster, DESIGN.md section 6 -- and 2 for NCCL)')
     ap.add_argument('--config', nargs='*', default=None, choices=['A', 'B', 'C', 'E'],
                     help='secondary lines for the other named shapes (default: the contract line on config D)')
     ap.add_argument('--no-cpu-baseline', action='store_true')
