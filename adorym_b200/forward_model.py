@@ -222,11 +222,56 @@ class ForwardModel(object):
         out = torch.stack([psi[..., 0] * tr - psi[..., 1] * ti, psi[..., 0] * ti + psi[..., 1] * tr], -1)
         return out.unsqueeze(0)
 
-    def _multislice(self, obj, this_i_theta, probe, pos_t, plan, with_reg, in_beam_frame=False):
+    def _exit_shift(self, prj_pos_offset, this_i_theta):
+        """optimize_prj_pos_offset: this angle's refinable shift of the exit wave [1, 2] (forward_model.py:253-256), or
+        None."""
+        if not self.common_vars.get('optimize_prj_pos_offset', False) or prj_pos_offset is None:
+            return None
+        if self._static is not None:
+            off = prj_pos_offset.index_select(0, self._static['theta'])
+        else:
+            off = prj_pos_offset[int(this_i_theta)]
+        return off.reshape(1, 2).to(torch.float32)
+
+    def _shift_exit_wave_and_detect(self, exit_wave, shift, plan, dev):
+        """propagate.py:260-280 with shift_exit_wave: the exit wave of every pattern and mode is Fourier-shifted by the same
+        refinable offset (util.py:380-397), THEN taken to the detector (far field / free-space step / nothing).  exit_wave
+        [B, M, P, P, 2] comes from the multislice kernels run with free_prop = none; the detector transform is a second call
+        of the same kernels on vacuum (one empty slice, every patch placed outside the object) with the shifted exit waves
+        as per-pattern probes."""
+        B, M, P = exit_wave.shape[0], exit_wave.shape[1], exit_wave.shape[2]
+        shifted = ops.probe_shift(exit_wave.reshape(B * M, P, P, 2), shift)[0].reshape(B, M, P, P, 2)
+        if plan.free_prop == 0:
+            return shifted
+        key = ('vac', id(plan))
+        vplan = self._plans.get(key)
+        if vplan is None:
+            vplan = ops.MultislicePlan(P, 1, 1, 1, plan.k1, None, dev, sign_convention=plan.sign_convention,
+                                       unknown_type='delta_beta', free_prop='none', normalize_fft=bool(plan.normalize_fft))
+            vplan.free_prop, vplan.Hfp, vplan.Hfc = plan.free_prop, plan.Hfp, plan.Hfc
+            self._plans[key] = vplan
+        vac_obj = torch.zeros((1, 1, 1, 2), dtype=torch.float32, device=dev)
+        vac_pos = torch.full((B, 2), -4 * P, dtype=torch.int32, device=dev)
+        return ops.MultisliceFn.apply(vac_obj, None, shifted.contiguous(), vac_pos, vplan, None, 'yxz')
+
+    def _multislice(self, obj, this_i_theta, probe, pos_t, plan, with_reg, in_beam_frame=False, exit_shift=None):
         """fused rotate + transmission + gather + multislice; with_reg: also the fused regulariser value (None when the
         regulariser list is not fusable) -> (det, reg_value | None, reg_was_fused).  in_beam_frame: the object has
         already been rotated (tilt refinement); the regulariser then acts on the UN-rotated object and is not fused."""
         grid = None if in_beam_frame else self._object_grid(obj, this_i_theta)
+        if exit_shift is not None:
+            if getattr(plan, 'large', False):
+                raise NotImplementedError('adorym_b200: optimize_prj_pos_offset with probes larger than 72 pixels')
+            # the slice loop ends at the exit wave; shift; detector transform
+            key = ('exit', id(plan))
+            eplan = self._plans.get(key)
+            if eplan is None:
+                import copy
+                eplan = copy.copy(plan)
+                eplan.free_prop = 0
+                self._plans[key] = eplan
+            out = self._multislice(obj, this_i_theta, probe, pos_t, eplan, with_reg, in_beam_frame)
+            return (self._shift_exit_wave_and_detect(out[0], exit_shift, plan, obj.device),) + tuple(out[1:])
         if getattr(plan, 'large', False):
             # probes of 128 .. 2048 pixels: slice loop on the batched large-frame kernels; the regulariser is evaluated on
             # its own (ops.RegL1TVFn through get_regularization_value)
@@ -417,13 +462,13 @@ class PtychographyModel(ForwardModel):
         self.run_float64 = run_float64
 
     def _detector_field(self, obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                        this_ind_batch, with_reg=False, tilt_ls=None, probe_pos_offset=None):
+                        this_ind_batch, with_reg=False, tilt_ls=None, probe_pos_offset=None, prj_pos_offset=None):
         """(shift probe) -> fused rotate + transmission + gather + multislice -> complex detector field [B, M, P, P, 2]
         (, regulariser value, fused flag)."""
         cv = self.common_vars
         # optimize_probe_defocusing: get_kernel() (numpy) on a tensor that requires grad fails in the reference's own
         # PyTorch backend (forward_model.py:247-251), so there is no behaviour to reproduce
-        self._check_unsupported(['optimize_probe_defocusing', 'optimize_prj_pos_offset'])
+        self._check_unsupported(['optimize_probe_defocusing'])
         dev = self._device(obj)
         probe_size = cv['probe_size']
         if probe_size[0] != probe_size[1]:
@@ -473,7 +518,8 @@ class PtychographyModel(ForwardModel):
                 if len(cache) > 4096:
                     cache.clear()
                 pos_t = cache[key] = torch.from_numpy(pos32).to(dev)
-        out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg, in_beam_frame=tilted)
+        out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg, in_beam_frame=tilted,
+                               exit_shift=self._exit_shift(prj_pos_offset, this_i_theta))
         return out if with_reg else out[0]
 
     def _any_positive_correction(self, ppc):
@@ -491,7 +537,8 @@ class PtychographyModel(ForwardModel):
                 probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
         """Detected magnitudes [minibatch_size, len_probe_y, len_probe_x] (adorym/forward_model.py:179-387)."""
         det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                                   this_ind_batch, tilt_ls=tilt_ls, probe_pos_offset=probe_pos_offset)
+                                   this_ind_batch, tilt_ls=tilt_ls, probe_pos_offset=probe_pos_offset,
+                                   prj_pos_offset=prj_pos_offset)
         self.i_call += 1
         return ops.DetectorMagnitudeFn.apply(det)
 
@@ -503,7 +550,8 @@ class PtychographyModel(ForwardModel):
             ds_level = self.common_vars['ds_level']
             det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch,
                                                           probe_pos_correction, this_ind_batch, with_reg=True,
-                                                          tilt_ls=tilt_ls, probe_pos_offset=probe_pos_offset)
+                                                          tilt_ls=tilt_ls, probe_pos_offset=probe_pos_offset,
+                                                          prj_pos_offset=prj_pos_offset)
             self.i_call += 1
             this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
             return self._fused_loss(det, this_prj_batch, obj, reg_val, reg_done)
@@ -525,7 +573,8 @@ class SingleBatchPtychographyModel(PtychographyModel):
         if len(np.asarray(this_pos_batch)) != 1:
             raise ValueError('SingleBatchPtychographyModel takes one probe position per call')
         # forward_model.py:493-586 never shifts the probe (no probe_pos_correction branch)
-        det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, None, this_ind_batch)
+        det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, None, this_ind_batch,
+                                   prj_pos_offset=prj_pos_offset)
         self.i_call += 1
         return ops.DetectorMagnitudeFn.apply(det)
 
@@ -536,7 +585,7 @@ class SingleBatchPtychographyModel(PtychographyModel):
             theta_downsample = self.common_vars['theta_downsample']
             ds_level = self.common_vars['ds_level']
             det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, None,
-                                                          this_ind_batch, with_reg=True)
+                                                          this_ind_batch, with_reg=True, prj_pos_offset=prj_pos_offset)
             self.i_call += 1
             this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
             return self._fused_loss(det, this_prj_batch, obj, reg_val, reg_done)
@@ -597,7 +646,7 @@ class SparseMultisliceModel(PtychographyModel):
                 prj_pos_offset):
         self._slice_pos = slice_pos_cm_ls
         det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                                   this_ind_batch, probe_pos_offset=probe_pos_offset)
+                                   this_ind_batch, probe_pos_offset=probe_pos_offset, prj_pos_offset=prj_pos_offset)
         self.i_call += 1
         return ops.DetectorMagnitudeFn.apply(det)
 
@@ -610,7 +659,7 @@ class SparseMultisliceModel(PtychographyModel):
             self._slice_pos = slice_pos_cm_ls
             det, reg_val, reg_done = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch,
                                                           probe_pos_correction, this_ind_batch, with_reg=True,
-                                                          probe_pos_offset=probe_pos_offset)
+                                                          probe_pos_offset=probe_pos_offset, prj_pos_offset=prj_pos_offset)
             self.i_call += 1
             this_prj_batch = self.get_data(this_i_theta, this_ind_batch, theta_downsample=theta_downsample, ds_level=ds_level)
             return self._fused_loss(det, this_prj_batch, obj, reg_val, reg_done)
@@ -626,10 +675,9 @@ class SingleBatchFullfieldModel(PtychographyModel):
                                                         raw_data_type, simulation_mode=simulation_mode, *args, **kwargs)
 
     def _detector_field(self, obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                        this_ind_batch, with_reg=False, tilt_ls=None, probe_pos_offset=None):
+                        this_ind_batch, with_reg=False, tilt_ls=None, probe_pos_offset=None, prj_pos_offset=None):
         # (forward_model.py:412-490 uses neither the tilt table nor the probe position offset)
         cv = self.common_vars
-        self._check_unsupported(['optimize_prj_pos_offset'])
         dev = self._device(obj)
         probe_size = cv['probe_size']
         this_obj_size = cv['this_obj_size']
@@ -640,12 +688,13 @@ class SingleBatchFullfieldModel(PtychographyModel):
             probe = probe.unsqueeze(0)
         if (probe_size[0] not in ops.SUPPORTED_P and probe_size[0] == probe_size[1] and ops.lf_supported(probe_size[0])
                 and _free_prop_mode(cv['free_prop_cm']) != 'inf'):
-            self._check_unsupported([])
+            self._check_unsupported(['optimize_prj_pos_offset'])
             det = self._large_frame_multislice(obj, this_i_theta, probe.contiguous())
             return (det, None, False) if with_reg else det
         plan = self._plan(dev, probe_size[0], this_obj_size[2], this_obj_size[0], this_obj_size[1], cv['free_prop_cm'])
         pos_t = torch.zeros((1, 2), dtype=torch.int32, device=dev)
-        out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg)
+        out = self._multislice(obj, this_i_theta, probe, pos_t, plan, with_reg,
+                               exit_shift=self._exit_shift(prj_pos_offset, this_i_theta))
         return out if with_reg else out[0]
 
     def predict(self, obj, probe_real, probe_imag, probe_defocus_mm,

@@ -140,13 +140,14 @@ class MomentumOptimizer(Optimizer):
 # (switch, optimizer kwarg, learning-rate kwarg, parameter name) in the order of adorym/optimizers.py:793-958: the
 # gradient tuple of the Differentiator follows this order (quirk 17)
 _PARAM_TABLE = (('optimize_probe_pos_offset', 'optimizer_probe_pos_offset', 'probe_pos_offset_learning_rate', 'probe_pos_offset'),
+                ('optimize_prj_pos_offset', 'optimizer_prj_pos_offset', 'prj_pos_offset_learning_rate', 'prj_pos_offset'),
                 ('optimize_all_probe_pos', 'optimizer_all_probe_pos', 'all_probe_pos_learning_rate', 'probe_pos_correction'),
                 ('optimize_free_prop', 'optimizer_free_prop', 'free_prop_learning_rate', 'free_prop_cm'),
                 ('optimize_tilt', 'optimizer_tilt', 'tilt_learning_rate', 'tilt_ls'),
                 ('optimize_prj_affine', 'optimizer_prj_affine', 'prj_affine_learning_rate', 'prj_affine_ls'))
 # optimize_probe_defocusing: the reference's PyTorch backend itself fails on it (numpy get_kernel on a tensor that
 # requires grad, forward_model.py:247-251); the others have no accelerated forward path
-_UNSUPPORTED_PARAM_SWITCHES = ('optimize_probe_defocusing', 'optimize_prj_pos_offset', 'optimize_slice_pos',
+_UNSUPPORTED_PARAM_SWITCHES = ('optimize_probe_defocusing', 'optimize_slice_pos',
                                'optimize_ctf_lg_kappa')
 
 
@@ -184,8 +185,8 @@ def create_and_initialize_parameter_optimizers(optimizable_params, kwargs):
         if kwargs.get(opt_kw) is not None:
             o = kwargs[opt_kw]
             o.name = name
-        elif name == 'probe_pos_offset':
-            # optimizers.py:851-857: plain gradient descent without the step-halving schedule
+        elif name in ('probe_pos_offset', 'prj_pos_offset'):
+            # optimizers.py:851-857, :868-871: plain gradient descent without the step-halving schedule
             o = GDOptimizer(name, output_folder=output_folder,
                             options_dict={'step_size': kwargs[lr_kw], 'dynamic_rate': False})
         else:

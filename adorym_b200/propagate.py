@@ -91,21 +91,27 @@ def multislice_propagate_batch(grid_batch, probe_real, probe_imag, energy_ev, ps
     key = (P0, Nz, B, float(energy_ev), float(psize_cm), mode, float(free_prop_cm) if mode == 'near' else 0., type,
            bool(normalize_fft), int(sign_convention), bool(scale_ri_by_k), bool(fresnel_approx),
            _kernel_digest(kernel), str(grid_batch.device))
+    large = P0 not in ops.SUPPORTED_P          # 128 .. 2048 (power of two): the batched large-frame slice steps
     plan = _plan_cache.get(key)
     if plan is None:
-        plan = ops.MultislicePlan(P0, Nz, B * P0, P1, ops.k1_of(energy_ev, psize_cm, scale_ri_by_k), h, grid_batch.device,
-                                  sign_convention=sign_convention, unknown_type=type, free_prop=mode,
-                                  normalize_fft=normalize_fft, h_free=h_free)
+        Plan = ops.LargeMultislicePlan if large else ops.MultislicePlan
+        plan = Plan(P0, Nz, B * P0, P1, ops.k1_of(energy_ev, psize_cm, scale_ri_by_k), h, grid_batch.device,
+                    sign_convention=sign_convention, unknown_type=type, free_prop=mode, normalize_fft=normalize_fft,
+                    h_free=h_free)
         if len(_plan_cache) >= 32:          # bounded: drop the oldest plan
             _plan_cache.pop(next(iter(_plan_cache)))
         _plan_cache[key] = plan
-    rot = grid_batch.permute(3, 0, 1, 2, 4).reshape(Nz, B * P0, P1, 2).contiguous()
     pos = torch.stack([torch.arange(B, dtype=torch.int32) * P0, torch.zeros(B, dtype=torch.int32)], 1).to(grid_batch.device)
     if probe_real.dim() == 2:
         probe = torch.stack([probe_real, probe_imag], -1).unsqueeze(0)          # [1, P, P, 2]
     else:
         probe = torch.stack([probe_real, probe_imag], -1).unsqueeze(1)          # [B, 1, P, P, 2]
-    det = ops.MultisliceFn.apply(rot, None, probe, pos, plan, None, 'zyx')
+    if large:
+        # the patch stack [B, P, P, Nz, 2] IS an object of B * P rows in the reference layout [Y][X][Z][2]
+        det = ops.MultisliceLargeFn.apply(grid_batch.reshape(B * P0, P1, Nz, 2), None, probe, pos, plan)
+    else:
+        rot = grid_batch.permute(3, 0, 1, 2, 4).reshape(Nz, B * P0, P1, 2).contiguous()
+        det = ops.MultisliceFn.apply(rot, None, probe, pos, plan, None, 'zyx')
     ret = [det[:, 0, :, :, 0], det[:, 0, :, :, 1]]
     if return_fft_time:
         ret.append(0.)

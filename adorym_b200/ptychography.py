@@ -351,7 +351,8 @@ def reconstruct_ptychography(
                           'probe_defocus_mm': torch.tensor(0.0, device=device_obj),
                           'probe_pos_offset': torch.zeros([n_theta, 2], device=device_obj,
                                                           requires_grad=bool(optimize_probe_pos_offset)),
-                          'prj_pos_offset': torch.zeros([n_theta, 2], device=device_obj)}
+                          'prj_pos_offset': torch.zeros([n_theta, 2], device=device_obj,
+                                                        requires_grad=bool(optimize_prj_pos_offset))}
     if optimize_tilt:
         # ptychography.py:725-726: the tilt table [3, n_theta] becomes a refinable tensor (row 0 = the rotation angles)
         optimizable_params['tilt_ls'] = torch.tensor(tilt_ls, dtype=torch.float32, device=device_obj, requires_grad=True)
@@ -557,7 +558,7 @@ def reconstruct_ptychography(
                     torch.stack([optimizable_params['probe_real'], optimizable_params['probe_imag']], -1).detach().cpu().numpy())
     comm.Barrier()
     ops.OBJ_GRAD_OUT = None
-    extras = {k: optimizable_params[k].detach() for k in ('tilt_ls', 'prj_affine_ls', 'probe_pos_offset', 'free_prop_cm')
+    extras = {k: optimizable_params[k].detach() for k in ('tilt_ls', 'prj_affine_ls', 'probe_pos_offset', 'prj_pos_offset', 'free_prop_cm')
               if k in optimizable_params}
     return {'obj': obj.arr.detach(), 'probe_real': optimizable_params['probe_real'].detach(),
             'probe_imag': optimizable_params['probe_imag'].detach(),

@@ -357,7 +357,7 @@ def multislice_propagate_batch(grid_batch, probe, energy_ev, psize_cm, free_prop
 # Forward models                                              adorym/forward_model.py:179-490,819-1037
 # ----------------------------------------------------------------------------------------------
 def predict_ptycho(obj, probe_real, probe_imag, pos_batch, coord_old, cfg, probe_pos_correction=None,
-                   this_i_theta=0, this_ind_batch=None, tilt=None, probe_pos_offset=None):
+                   this_i_theta=0, this_ind_batch=None, tilt=None, probe_pos_offset=None, prj_pos_offset=None):
     """PtychographyModel.predict (adorym/forward_model.py:179-387), DP mode, no tilt/defocus refinement.
 
     cfg keys: this_obj_size, probe_size, energy_ev, psize_cm, h (kernel or None), free_prop_cm,
@@ -401,7 +401,8 @@ def predict_ptycho(obj, probe_real, probe_imag, pos_batch, coord_old, cfg, probe
                                          sign_convention=cfg.get('sign_convention', 1),
                                          scale_ri_by_k=cfg.get('scale_ri_by_k', True),
                                          slice_pos_cm_ls=cfg.get('slice_pos_cm_ls'),
-                                         pure_projection=cfg.get('pure_projection', False))
+                                         pure_projection=cfg.get('pure_projection', False),
+                                         shift_exit_wave=prj_pos_offset)      # optimize_prj_pos_offset (forward_model.py:253-256)
         if M == 1:
             # w.norm -> torch.norm(stack) (wrappers.py:1062-1067): zero subgradient at 0
             return torch.norm(torch.stack([psi.real, psi.imag], dim=0), dim=0)
@@ -603,7 +604,7 @@ def adam_step(x, g, m, v, i_batch, step_size=0.001, b1=0.9, b2=0.999, eps=1e-7):
 # ----------------------------------------------------------------------------------------------
 def ptycho_loss_and_grads(obj, probe_real, probe_imag, pos_batch, prj_abs, coord_old, cfg, reg=None,
                           probe_pos_correction=None, this_i_theta=0, this_ind_batch=None,
-                          want=('obj', 'probe_real', 'probe_imag'), tilt=None, probe_pos_offset=None):
+                          want=('obj', 'probe_real', 'probe_imag'), tilt=None, probe_pos_offset=None, prj_pos_offset=None):
     """Loss of calculate_loss (forward_model.py:389-401) and its gradient w.r.t. `want`.  tilt: [3] angles of this
     rotation angle (tilt_ls[:, i_theta]); probe_pos_offset: [2] offset of this angle (probe_pos_offset[i_theta])."""
     leaves = {'obj': obj.clone().requires_grad_('obj' in want),
@@ -618,9 +619,12 @@ def ptycho_loss_and_grads(obj, probe_real, probe_imag, pos_batch, prj_abs, coord
     if probe_pos_offset is not None:
         probe_pos_offset = leaves['probe_pos_offset'] = torch.as_tensor(probe_pos_offset).to(obj.dtype).clone().requires_grad_(
             'probe_pos_offset' in want)
+    if prj_pos_offset is not None:
+        prj_pos_offset = leaves['prj_pos_offset'] = torch.as_tensor(prj_pos_offset).to(obj.dtype).clone().requires_grad_(
+            'prj_pos_offset' in want)
     pred = predict_ptycho(leaves['obj'], leaves['probe_real'], leaves['probe_imag'], pos_batch, coord_old, cfg,
                           probe_pos_correction=ppc, this_i_theta=this_i_theta, this_ind_batch=this_ind_batch, tilt=tilt,
-                          probe_pos_offset=probe_pos_offset)
+                          probe_pos_offset=probe_pos_offset, prj_pos_offset=prj_pos_offset)
     pred_l, prj_l = pred, prj_abs
     if cfg.get('beamstop', None) is not None:
         # forward_model.py:128-136: pixels with beamstop < 1e-5 are dropped from the mean

@@ -83,6 +83,13 @@ CASES = {
                               psize_cm=0.67e-7, theta=0.0, n_theta=3, i_theta=0, pos=[(0, 0)], n_modes=1,
                               free_prop_cm=2e-5, unknown_type='real_imag', delta_scale=0.2, beta_scale=0.2, seed=25,
                               loss='lsq', raw_data_type='intensity', rotate_out_of_loop=True),
+    # refinable shift of the exit wave (optimize_prj_pos_offset / shift_exit_wave, propagate.py:260-261: plane-wave
+    # tomography alignment) followed by near-field detection
+    'fullfield64_prjoffset': dict(kind='fullfield', obj_size=(64, 64, 12), probe_size=(64, 64), energy_ev=800.,
+                                  psize_cm=0.67e-7, theta=0.9, n_theta=3, i_theta=1, pos=[(0, 0)], n_modes=1,
+                                  free_prop_cm=2e-5, unknown_type='delta_beta', delta_scale=2e-3, beta_scale=3e-4, seed=36,
+                                  loss='lsq', raw_data_type='intensity', optimize_prj_pos_offset=True,
+                                  prj_pos_offset=(0.7, -0.4)),
     # binning = 3 over 50 slices (propagate.py:207-254: 17 propagation steps, the last bin holds two slices), rotation
     'ptycho3d_p72_bin3': dict(kind='ptycho', obj_size=(48, 50, 50), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
                               theta=0.9, n_theta=4, i_theta=2, pos=[(-12, -12), (-30, 5), (1, -19)], n_modes=1,

@@ -72,7 +72,7 @@ def run_reference(name):
                   two_d_mode=two_d, minibatch_size=B, ds_level=1, this_obj_size=[Y, X, Z], energy_ev=c['energy_ev'],
                   psize_cm=c['psize_cm'], h=h, pure_projection=c.get('pure_projection', False), n_dp_batch=20, free_prop_cm=c['free_prop_cm'],
                   optimize_probe_defocusing=False, optimize_probe_pos_offset=c.get('optimize_probe_pos_offset', False),
-                  optimize_prj_pos_offset=False,
+                  optimize_prj_pos_offset=c.get('optimize_prj_pos_offset', False),
                   optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=c.get('optimize_tilt', False),
                   initial_tilt=None,
                   debug=False, output_folder=tmp, n_probe_modes=c['n_modes'], n_theta=n_theta,
@@ -115,6 +115,10 @@ def run_reference(name):
             off = np.zeros([n_theta, 2])
             off[c['i_theta']] = c['probe_pos_offset']
             args['probe_pos_offset'] = w.create_variable(off, requires_grad=True)
+        if c.get('optimize_prj_pos_offset', False):
+            off = np.zeros([n_theta, 2])
+            off[c['i_theta']] = c['prj_pos_offset']
+            args['prj_pos_offset'] = w.create_variable(off, requires_grad=True)
         if c['kind'] == 'sparse':
             del args['tilt_ls']
             args['slice_pos_cm_ls'] = w.create_variable(np.array(c['slice_pos_cm']), requires_grad=False)
@@ -126,6 +130,9 @@ def run_reference(name):
         if c.get('optimize_probe_pos_offset', False):
             opt_args += [fm.get_argument_index('probe_pos_offset')]
             names += ['probe_pos_offset']
+        if c.get('optimize_prj_pos_offset', False):
+            opt_args += [fm.get_argument_index('prj_pos_offset')]
+            names += ['prj_pos_offset']
         if c.get('optimize_all_probe_pos', False):
             opt_args += [fm.get_argument_index('probe_pos_correction')]
             names += ['probe_pos_correction']

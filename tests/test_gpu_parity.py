@@ -31,7 +31,7 @@ def _common_vars(inp, cfg, dev, prj_full, theta_ls, n_theta):
                 psize_cm=c['psize_cm'], h=cfg['h'], pure_projection=c.get('pure_projection', False), n_dp_batch=20,
                 free_prop_cm=c['free_prop_cm'],
                 optimize_probe_defocusing=False, optimize_probe_pos_offset=c.get('optimize_probe_pos_offset', False),
-                optimize_prj_pos_offset=False,
+                optimize_prj_pos_offset=c.get('optimize_prj_pos_offset', False),
                 optimize_all_probe_pos=c.get('optimize_all_probe_pos', False), optimize_tilt=c.get('optimize_tilt', False),
                 initial_tilt=None,
                 n_probe_modes=c['n_modes'], n_theta=n_theta, precalculate_rotation_coords=False, theta_ls=theta_ls,
@@ -85,6 +85,12 @@ def run_gpu_case(name):
         args['probe_pos_offset'] = t(off)
         opt_args += [fm.get_argument_index('probe_pos_offset')]
         names += ['probe_pos_offset']
+    if c.get('optimize_prj_pos_offset', False):
+        off = np.zeros([n_theta, 2], 'float32')
+        off[c['i_theta']] = c['prj_pos_offset']
+        args['prj_pos_offset'] = t(off)
+        opt_args += [fm.get_argument_index('prj_pos_offset')]
+        names += ['prj_pos_offset']
     if has_ppc:
         opt_args += [fm.get_argument_index('probe_pos_correction')]
         names += ['probe_pos_correction']
@@ -139,6 +145,9 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
     if 'probe_pos_offset' in grads:
         assert rel_err(grads['probe_pos_offset'][it], grads64['probe_pos_offset']) < 5e-4
         assert rel_err(grads['probe_pos_offset'], gold['g_probe_pos_offset']) < 5e-4
+    if 'prj_pos_offset' in grads:
+        assert rel_err(grads['prj_pos_offset'][it], grads64['prj_pos_offset']) < 5e-4
+        assert rel_err(grads['prj_pos_offset'], gold['g_prj_pos_offset']) < 5e-4
 
 
 @pytest.mark.parametrize('P', [256, 512])
@@ -210,7 +219,7 @@ def test_multislice_propagate_batch_dropin():
     import adorym_b200 as ab
     dev = torch.device('cuda', 0)
     rs = np.random.RandomState(3)
-    for P, fp in ((64, 0), (72, 'inf'), (64, 3e-4), (72, None)):
+    for P, fp in ((64, 0), (72, 'inf'), (64, 3e-4), (72, None), (128, 'inf'), (256, 3e-4)):
         B, Nz = 3, 5
         grid = np.stack([rs.uniform(0, 2e-3, (B, P, P, Nz)), rs.uniform(0, 2e-4, (B, P, P, Nz))], -1).astype('float32')
         pr = rs.normal(size=(P, P)).astype('float32')
