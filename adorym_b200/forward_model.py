@@ -701,7 +701,7 @@ class SingleBatchFullfieldModel(PtychographyModel):
                 probe_pos_offset, this_i_theta, this_pos_batch, prj,
                 probe_pos_correction, this_ind_batch, tilt_ls, prj_pos_offset):
         det = self._detector_field(obj, probe_real, probe_imag, this_i_theta, this_pos_batch, probe_pos_correction,
-                                   this_ind_batch)
+                                   this_ind_batch, prj_pos_offset=prj_pos_offset)
         self.i_call += 1
         if self.simulation_mode:
             return det[:, 0, :, :, 0], det[:, 0, :, :, 1]      # (real, imag), forward_model.py:487-488
