@@ -25,6 +25,7 @@
 // :241/:246 transmission (precomputed), :255 convolution, :263-280 detector transform; forward_model.py:313-331 +
 // util.py:1327-1351 gather with vacuum padding.  The adjoint replaces the autograd tape (wrappers.py:300-331).
 #include <stdlib.h>
+#include <stdio.h>
 #include "fft_passes.cuh"
 #include "tma.cuh"
 #include "../../include/adorym_b200.h"
@@ -520,6 +521,8 @@ template <class K> static int ms_resident_ctas(K kern, int threads, size_t smem)
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) return 0;
     cached = sms * occ;
+    if (getenv("ADM_MS_VERBOSE"))
+        fprintf(stderr, "[adm] multislice kernel: %d threads, %zu B smem -> %d CTAs per SM, %d resident\n", threads, smem, occ, cached);
     return cached;
 #else
     return 8;
