@@ -43,6 +43,8 @@ SIGNATURES = {
                            c_void_p],
     'adm_multislice_bwd': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                            c_void_p, c_void_p],
+    'adm_multislice_bwd_gpsi': [P_CFG, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p, c_void_p],
     'adm_detector_loss': [c_int, c_int, c_int, c_int, c_int, c_float, c_float, c_void_p, c_void_p, c_void_p, c_void_p,
                           c_void_p, c_void_p, c_void_p],
     'adm_rotate_fwd': [c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p],
@@ -112,7 +114,7 @@ def get_lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('adorym_b200: CUDA library %s is missing; run `python -m adorym_b200.build`' % LIB_PATH)
         _lib = bind(ctypes.CDLL(LIB_PATH))
-        if _lib.adm_abi_version() != 6:
+        if _lib.adm_abi_version() != 7:
             raise RuntimeError('adorym_b200: ABI version mismatch')
     return _lib
 

@@ -12,6 +12,7 @@ struct MsParams {
     cpx* ckpt;
     cpx* det;           // fwd: out ; bwd: g_det in
     cpx* g_probe;
+    cpx* g_ckpt;        // adjoint only, optional: dL/d psi_z (gradient w.r.t. the wave entering slice z) [B][M][Nz][P][P]
     int Nz, Y, X, Xp, B, M;
     int free_prop, probe_per_pattern, h_separable, h_per_slice;
     float ff_scale;

@@ -424,6 +424,11 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                         ckb[y * TP + lt] = cmulc(v[j], w);            // dL/dT = g' conj(psi_z)
                         v[j] = modulate_conj(v[j], tpa[gi][j]);       // g_psi = g' conj(T)
                     }
+                    if (p.g_ckpt != nullptr) {     // refinable slice positions: dL/d psi_z for the host-side d/d gap
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            ((T*)p.g_ckpt)[((size_t)wf * p.Nz + z) * P * P + I.a(j, gi) * P + l] = v[j];
+                    }
                     if (z > 0) {
                         dft8<false>(v);
                         if constexpr (!C::PFA) {
@@ -612,7 +617,7 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     if (cfg->free_prop == ADM_PROP_NEAR && !Hfree) return ADM_ERR_ARG;
     p.tvol = (const cpx*)tvol; p.probe = (const cpx*)probe; p.pos = pos;
     p.Hp = (const cpx*)Hprep; p.Hf = (const cpx*)Hfree;
-    p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)det; p.g_probe = nullptr;
+    p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)det; p.g_probe = nullptr; p.g_ckpt = nullptr;
     AdmTileMap map;
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int var = adm_variant("ADM_FWD_VARIANT");
@@ -638,9 +643,26 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     return ADM_OK;
 }
 
+static int ms_bwd_impl(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
+                       const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol, float* g_probe,
+                       float* g_psi_ckpt, void* workspace, void* stream);
+
 extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
                                   const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol,
                                   float* g_probe, void* workspace, void* stream) {
+    return ms_bwd_impl(cfg, tvol, pos, HprepC, HfreeC, psi_ckpt, g_det, g_tvol, g_probe, nullptr, workspace, stream);
+}
+
+extern "C" int adm_multislice_bwd_gpsi(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
+                                       const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol,
+                                       float* g_probe, float* g_psi_ckpt, void* workspace, void* stream) {
+    if (!g_psi_ckpt) return ADM_ERR_ARG;
+    return ms_bwd_impl(cfg, tvol, pos, HprepC, HfreeC, psi_ckpt, g_det, g_tvol, g_probe, g_psi_ckpt, workspace, stream);
+}
+
+static int ms_bwd_impl(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
+                       const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol, float* g_probe,
+                       float* g_psi_ckpt, void* workspace, void* stream) {
     MsParams p;
     int rc = fill_params(cfg, p);
     if (rc) return rc;
@@ -649,7 +671,7 @@ extern "C" int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tv
     if (cfg->free_prop == ADM_PROP_NEAR && !HfreeC) return ADM_ERR_ARG;
     p.tvol = (const cpx*)tvol; p.probe = nullptr; p.pos = pos;
     p.Hp = (const cpx*)HprepC; p.Hf = (const cpx*)HfreeC;
-    p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)g_det; p.g_probe = (cpx*)g_probe;
+    p.ckpt = (cpx*)psi_ckpt; p.det = (cpx*)g_det; p.g_probe = (cpx*)g_probe; p.g_ckpt = (cpx*)g_psi_ckpt;
     AdmTileMap map;
     if (adm_make_tile_map(&map, g_tvol, p.Nz, ADM_GVOL_ROWS(p.Y, cfg->P), p.X + ADM_GVOL_MARGIN(cfg->P),
                           ADM_GVOL_PITCH(p.X, cfg->P), cfg->P, cfg->P + 2))

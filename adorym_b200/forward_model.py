@@ -277,10 +277,11 @@ class ForwardModel(object):
             # its own (ops.RegL1TVFn through get_regularization_value)
             return ops.MultisliceLargeFn.apply(obj, grid, probe, pos_t, plan), None, False
         reg = self._fusable_regularizers() if (with_reg and not in_beam_frame) else None
+        sp = getattr(self, '_slice_pos_param', None)        # refinable slice positions (SparseMultisliceModel)
         if reg is not None:
-            det, reg_val = ops.MultisliceFn.apply(obj, grid, probe, pos_t, plan, reg, 'yxz')
+            det, reg_val = ops.MultisliceFn.apply(obj, grid, probe, pos_t, plan, reg, 'yxz', sp)
             return det, reg_val, True
-        return ops.MultisliceFn.apply(obj, grid, probe, pos_t, plan, None, 'yxz'), None, False
+        return ops.MultisliceFn.apply(obj, grid, probe, pos_t, plan, None, 'yxz', sp), None, False
 
     def _plan(self, dev, P, Nz, Y, X, free_prop_cm):
         cv = self.common_vars
@@ -610,8 +611,10 @@ class SparseMultisliceModel(PtychographyModel):
 
     def _sparse_plan(self, dev, slice_pos_cm_ls):
         cv = self.common_vars
-        if cv.get('optimize_slice_pos', False):
-            raise NotImplementedError('adorym_b200: optimize_slice_pos is not on the accelerated path yet')
+        # refinable slice positions (optimize_slice_pos): the tensor rides along to ops.MultisliceFn for its gradient; the
+        # per-gap transfer functions are rebuilt from the current values (a device->host read of Nz numbers per update)
+        self._slice_pos_param = slice_pos_cm_ls if (cv.get('optimize_slice_pos', False) and torch.is_tensor(slice_pos_cm_ls)
+                                                    and slice_pos_cm_ls.requires_grad) else None
         pos = np.asarray(slice_pos_cm_ls.detach().cpu() if torch.is_tensor(slice_pos_cm_ls) else slice_pos_cm_ls, dtype='float64')
         P = cv['probe_size'][0]
         Y, X, Z = cv['this_obj_size']
@@ -633,7 +636,10 @@ class SparseMultisliceModel(PtychographyModel):
                                     sign_convention=self.sign_convention)
             plan = ops.MultislicePlan(P, Z, Y, X, ops.k1_of(cv['energy_ev'], psize_cm, self.scale_ri_by_k), None, dev,
                                       sign_convention=self.sign_convention, unknown_type=self.unknown_type, free_prop=mode,
-                                      normalize_fft=self.normalize_fft, h_free=h_free, h_gaps=h_gaps)
+                                      normalize_fft=self.normalize_fft, h_free=h_free, h_gaps=h_gaps, lmbda_nm=lmbda_nm,
+                                      voxel_nm=float(voxel_nm[0]))
+            if len(self._sparse_plans) > 8:
+                self._sparse_plans.clear()
             self._sparse_plans[key] = plan
         return plan
 

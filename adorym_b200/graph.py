@@ -48,6 +48,8 @@ class GraphedDifferentiator(Differentiator):
             return 'measured data are not a CUDA tensor'
         if fm.common_vars.get('beamstop', None) is not None:
             return 'beamstop mask'
+        if fm.common_vars.get('optimize_slice_pos', False):
+            return 'refinable slice positions (the transfer-function tables change with every update)'
         if 'safe_zone_width' in kwargs:
             n_d = len(kwargs['free_prop_cm'])
             if (kwargs.get('safe_zone_width') or 0) > 0 or prj.shape[1] // n_d != 1:

@@ -70,12 +70,14 @@ class MultislicePlan(object):
     """Static description of one multislice configuration + prepared transfer functions (cached per model)."""
 
     def __init__(self, P, n_slices, Y, X, k1, h, device, sign_convention=1, unknown_type='delta_beta', free_prop='none',
-                 normalize_fft=False, h_free=None, allow_separable=True, h_gaps=None, binning=1, obj_slices=None):
+                 normalize_fft=False, h_free=None, allow_separable=True, h_gaps=None, binning=1, obj_slices=None,
+                 lmbda_nm=None, voxel_nm=None):
         """h: the in-object transfer function [P,P] (all gaps equal), or h_gaps: a list of n_slices-1 separable transfer
         functions, one per gap between consecutive slices (sparse multislice, propagate.py:479-534)."""
         if P not in SUPPORTED_P:
             raise NotImplementedError('adorym_b200: probe size %d is not supported yet (supported: %s)' % (P, SUPPORTED_P))
         self.P, self.n_slices, self.Y, self.X = int(P), int(n_slices), int(Y), int(X)
+        self.lmbda_nm, self.voxel_nm = lmbda_nm, voxel_nm          # needed only for refinable slice positions
         # binning (propagate.py:207-254): n_slices counts PROPAGATION steps = ceil(obj_slices / binning); each step's
         # transmission is that of (delta, beta) summed over `binning` object slices (layout 'yxz' only)
         self.binning = int(binning)
@@ -190,13 +192,19 @@ class MultisliceFn(torch.autograd.Function):
     backward: adm_multislice_bwd (dL/dT scattered into the margined gradient volume by TMA reduce-adds) -> chain rule."""
 
     @staticmethod
-    def forward(ctx, obj, grid, probe, pos, plan, reg=None, layout='zyx'):
+    def forward(ctx, obj, grid, probe, pos, plan, reg=None, layout='zyx', slice_pos=None):
+        """slice_pos: optional tensor [Nz] of refinable slice positions (cm) of the sparse multislice model; the plan's
+        per-gap transfer functions must have been prepared from its current values.  It only enters the backward pass
+        (dL/d slice_pos, propagate.py:479-534 with fresnel_propagate_wrapped :556-568)."""
         obj = _f32c(obj)
         probe = _f32c(probe)
         if pos.dtype != torch.int32 or not pos.is_cuda:
             raise RuntimeError('pos must be an int32 CUDA tensor [B, 2]')
         pos = pos.contiguous()
         P, Nz, Y, X = plan.P, plan.n_slices, plan.Y, plan.X
+        ctx.want_slice_pos = slice_pos is not None and slice_pos.requires_grad
+        if ctx.want_slice_pos and not plan.h_per_slice:
+            raise RuntimeError('refinable slice positions need a plan with per-gap transfer functions (h_gaps)')
         Zo = plan.obj_slices
         want = (Y, X, Zo, 2) if layout == 'yxz' else (Nz, Y, X, 2)
         if layout != 'yxz' and plan.binning != 1:
@@ -266,8 +274,16 @@ class MultisliceFn(torch.autograd.Function):
         g_probe = None
         if ctx.needs_input_grad[2]:
             g_probe = torch.zeros(ctx.probe_shape, dtype=torch.float32, device=dev)
-        call('adm_multislice_bwd', ctypes.byref(ctx.cfg), ptr(tvol), ptr(pos), ptr(plan.Hc), ptr(plan.Hfc), ptr(ckpt),
-             ptr(g_det), ptr(g_tvol), ptr(g_probe), ptr(multislice_workspace(dev, P)), stream_ptr())
+        g_slice_pos = None
+        if ctx.want_slice_pos:
+            B, M = ckpt.shape[0], ckpt.shape[1]
+            g_psi = torch.empty((B, M, Nz, P, P, 2), dtype=torch.float32, device=dev)
+            call('adm_multislice_bwd_gpsi', ctypes.byref(ctx.cfg), ptr(tvol), ptr(pos), ptr(plan.Hc), ptr(plan.Hfc), ptr(ckpt),
+                 ptr(g_det), ptr(g_tvol), ptr(g_probe), ptr(g_psi), ptr(multislice_workspace(dev, P)), stream_ptr())
+            g_slice_pos = _slice_pos_gradient(plan, ckpt, g_psi, pos)
+        else:
+            call('adm_multislice_bwd', ctypes.byref(ctx.cfg), ptr(tvol), ptr(pos), ptr(plan.Hc), ptr(plan.Hfc), ptr(ckpt),
+                 ptr(g_det), ptr(g_tvol), ptr(g_probe), ptr(multislice_workspace(dev, P)), stream_ptr())
         g_obj = None
         if ctx.needs_input_grad[0]:
             if ctx.layout == 'yxz':
@@ -299,7 +315,31 @@ class MultisliceFn(torch.autograd.Function):
                 g_obj = torch.empty((Nz, Y, X, 2), dtype=torch.float32, device=dev)
                 call('adm_transmission_adj', plan.unknown_type, plan.k1, plan.sign_convention, Nz, Y, X, P, ptr(g_tvol),
                      ptr(tvol), ptr(g_obj), stream_ptr())
-        return g_obj, None, g_probe, None, None, None, None
+        return g_obj, None, g_probe, None, None, None, None, g_slice_pos
+
+
+def _slice_pos_gradient(plan, ckpt, g_psi, pos):
+    """dL/d slice_pos [Nz] (per cm) of the sparse multislice model from the wavefields psi_z ENTERING every slice (the
+    checkpoints) and the adjoint wavefields g_z = dL/d psi_z: the gap d_i between slices i and i+1 enters through
+    psi_{i+1} = IFFT2(H(d_i) FFT2(.)), H = exp(i phi' d_i), so d psi_{i+1} / d d_i = IFFT2(i phi' FFT2(psi_{i+1})) and, by
+    Parseval, dL/d d_i = -(1/P^2) sum_k phi'_k Im(conj(G_k) Psi_k) over all wavefields; slice_pos[j] appears in d_{j-1} with +
+    and in d_j with - .  A few slices of a few wavefields: library FFTs, not a hot path."""
+    B, M, Nz, P = ckpt.shape[0], ckpt.shape[1], ckpt.shape[2], plan.P
+    dev = ckpt.device
+    # checkpoint rows carry the tile pitch P + 2 at column offset (px & 1)
+    off = (pos[:, 1] & 1).long()
+    cols = off.view(B, 1) + torch.arange(P, device=dev).view(1, P)                      # [B, P]
+    psi = torch.gather(ckpt, 4, cols.view(B, 1, 1, 1, P, 1).expand(B, M, Nz, P, P, 2))
+    Psi = torch.fft.fft2(torch.view_as_complex(psi.contiguous())[:, :, 1:])             # psi_{i+1}, i = 0 .. Nz-2
+    G = torch.fft.fft2(torch.view_as_complex(g_psi)[:, :, 1:])
+    f = torch.fft.fftfreq(P, device=dev, dtype=torch.float32) / float(plan.voxel_nm)
+    dphi = (-float(plan.sign_convention) * PI * float(plan.lmbda_nm)) * (f[:, None] ** 2 + f[None, :] ** 2)   # per nm
+    im = (torch.conj(G) * Psi).imag.double()
+    g_gap = -(im * dphi.double()).sum(dim=(0, 1, 3, 4)) / float(P * P)                  # [Nz - 1], per nm
+    g_pos = torch.zeros((Nz,), dtype=torch.float64, device=dev)
+    g_pos[1:] += g_gap
+    g_pos[:-1] -= g_gap
+    return (g_pos * 1e7).to(torch.float32)
 
 
 # ------------------------------------------------------------------------------------------------------

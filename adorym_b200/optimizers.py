@@ -142,12 +142,13 @@ class MomentumOptimizer(Optimizer):
 _PARAM_TABLE = (('optimize_probe_pos_offset', 'optimizer_probe_pos_offset', 'probe_pos_offset_learning_rate', 'probe_pos_offset'),
                 ('optimize_prj_pos_offset', 'optimizer_prj_pos_offset', 'prj_pos_offset_learning_rate', 'prj_pos_offset'),
                 ('optimize_all_probe_pos', 'optimizer_all_probe_pos', 'all_probe_pos_learning_rate', 'probe_pos_correction'),
+                ('optimize_slice_pos', 'optimizer_slice_pos', 'slice_pos_learning_rate', 'slice_pos_cm_ls'),
                 ('optimize_free_prop', 'optimizer_free_prop', 'free_prop_learning_rate', 'free_prop_cm'),
                 ('optimize_tilt', 'optimizer_tilt', 'tilt_learning_rate', 'tilt_ls'),
                 ('optimize_prj_affine', 'optimizer_prj_affine', 'prj_affine_learning_rate', 'prj_affine_ls'))
 # optimize_probe_defocusing: the reference's PyTorch backend itself fails on it (numpy get_kernel on a tensor that
 # requires grad, forward_model.py:247-251); the others have no accelerated forward path
-_UNSUPPORTED_PARAM_SWITCHES = ('optimize_probe_defocusing', 'optimize_slice_pos',
+_UNSUPPORTED_PARAM_SWITCHES = ('optimize_probe_defocusing',
                                'optimize_ctf_lg_kappa')
 
 
@@ -179,6 +180,8 @@ def create_and_initialize_parameter_optimizers(optimizable_params, kwargs):
         if not kwargs.get(switch, False):
             continue
         if name == 'free_prop_cm' and not kwargs.get('is_multi_dist', False):      # optimizers.py:905
+            continue
+        if name == 'slice_pos_cm_ls' and not kwargs.get('is_sparse_multislice', False):      # optimizers.py:891
             continue
         if name == 'probe_pos_offset':
             assert kwargs['optimize_all_probe_pos'] == False                       # optimizers.py:846
@@ -250,6 +253,13 @@ def update_parameters(opt_ls, optimizable_params, kwargs):
                     dims = tuple(range(ppc.dim() - 1))
                     ppc = ppc - ppc.mean(dim=dims)
                     optimizable_params['probe_pos_correction'] = ppc.requires_grad_(True)
+            elif opt.name == 'slice_pos_cm_ls':
+                # adorym/optimizers.py:1050-1060: Adam, then the first slice is pinned to position 0
+                with torch.no_grad():
+                    opt.grads = comm.allreduce(opt.grads)
+                    sp = optimizable_params['slice_pos_cm_ls'].detach().clone().contiguous()
+                    sp = opt.apply_gradient(sp, opt.grads, i_full_angle, **opt.options_dict)
+                    optimizable_params['slice_pos_cm_ls'] = (sp - sp[0]).requires_grad_(True)
             elif opt.name == 'prj_affine_ls':
                 # adorym/optimizers.py:1062-1075: Adam, then the transformation of the first frame is pinned to identity
                 with torch.no_grad():

@@ -125,8 +125,6 @@ def reconstruct_ptychography(
         raise NotImplementedError('adorym_b200: per-angle probes / per-angle probe positions')
     if update_using_external_algorithm is not None:
         raise NotImplementedError('adorym_b200: external update algorithms')
-    if optimize_slice_pos:
-        raise NotImplementedError('adorym_b200: optimize_slice_pos is not on the accelerated path yet')
 
     comm = Comm()
     n_ranks, rank = comm.Get_size(), comm.Get_rank()
@@ -366,6 +364,10 @@ def reconstruct_ptychography(
                                                               requires_grad=bool(optimize_all_probe_pos))
     optimizable_params['prj_affine_ls'] = torch.tensor(prj_affine_ls, dtype=torch.float32, device=device_obj,
                                                        requires_grad=bool(optimize_prj_affine))
+    if is_sparse_multislice and optimize_slice_pos:
+        # ptychography.py:719-720
+        optimizable_params['slice_pos_cm_ls'] = torch.tensor(np.asarray(slice_pos_cm_ls, dtype='float64'), dtype=torch.float32,
+                                                             device=device_obj, requires_grad=bool(optimize_slice_pos))
     if is_multi_dist and optimize_free_prop:
         # ptychography.py:709-710: the propagation distances become a refinable tensor
         optimizable_params['free_prop_cm'] = torch.tensor(np.asarray(free_prop_cm, dtype='float64'), dtype=torch.float32,
@@ -558,7 +560,7 @@ def reconstruct_ptychography(
                     torch.stack([optimizable_params['probe_real'], optimizable_params['probe_imag']], -1).detach().cpu().numpy())
     comm.Barrier()
     ops.OBJ_GRAD_OUT = None
-    extras = {k: optimizable_params[k].detach() for k in ('tilt_ls', 'prj_affine_ls', 'probe_pos_offset', 'prj_pos_offset', 'free_prop_cm')
+    extras = {k: optimizable_params[k].detach() for k in ('tilt_ls', 'prj_affine_ls', 'probe_pos_offset', 'prj_pos_offset', 'free_prop_cm', 'slice_pos_cm_ls')
               if k in optimizable_params}
     return {'obj': obj.arr.detach(), 'probe_real': optimizable_params['probe_real'].detach(),
             'probe_imag': optimizable_params['probe_imag'].detach(),

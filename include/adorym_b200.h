@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ADM_ABI_VERSION 6
+#define ADM_ABI_VERSION 7
 
 /* unknown_type */
 #define ADM_DELTA_BETA 0
@@ -138,6 +138,13 @@ int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tvol, const f
 int adm_multislice_bwd(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
                        const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol,
                        float* g_probe, void* workspace, void* stream);
+/* The same, additionally storing dL/d psi_z -- the gradient with respect to the wavefield ENTERING every slice z -- in
+ * g_psi_ckpt [B][M][Nz][P][P][2] (natural order): with psi_ckpt it gives the derivative with respect to the gap between
+ * slices z-1 and z (refinable slice positions of the sparse multislice model, propagate.py:479-534,
+ * fresnel_propagate_wrapped :556-568):  dL/d gap = Re sum conj(g_z) IFFT2(i phi' FFT2(psi_z)), phi' = d phase / d gap.   */
+int adm_multislice_bwd_gpsi(const adm_multislice_cfg* cfg, const float* tvol, const int* pos, const float* HprepC,
+                            const float* HfreeC, const float* psi_ckpt, const float* g_det, float* g_tvol,
+                            float* g_probe, float* g_psi_ckpt, void* workspace, void* stream);
 
 /* Detector magnitude, mismatch loss and residual (forward_model.py:88-103,353,371-375).
  *   det [B][M][P][P][2]; meas [B][P][P] = |prj| as stored (magnitude or intensity, see raw_data_type);

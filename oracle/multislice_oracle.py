@@ -324,7 +324,15 @@ def multislice_propagate_batch(grid_batch, probe, energy_ev, psize_cm, free_prop
         else:
             c = torch.prod(torch.complex(d, b), dim=3) if this_step > 1 else torch.complex(d[..., 0], b[..., 0])
         psi = psi * c
-        if i_step < n_steps - 1 and slice_pos_cm_ls is not None:
+        if i_step < n_steps - 1 and slice_pos_cm_ls is not None and torch.is_tensor(slice_pos_cm_ls) \
+                and slice_pos_cm_ls.requires_grad:
+            # refinable slice positions: the gap's paraxial kernel stays in the graph (get_kernel_wrapped, propagate.py:84-103)
+            uu, vv = gen_freq_mesh(voxel_nm, grid_shape)
+            u2v2 = torch.tensor(uu ** 2 + vv ** 2).to(rdt)
+            gap_nm = (slice_pos_cm_ls[i_step + 1] - slice_pos_cm_ls[i_step]) * 1e7
+            ph = -sign_convention * PI * lmbda_nm * gap_nm * u2v2
+            psi = torch.fft.ifft2(torch.fft.fft2(psi) * torch.complex(torch.cos(ph), torch.sin(ph)))
+        elif i_step < n_steps - 1 and slice_pos_cm_ls is not None:
             gap_nm = float(slice_pos_cm_ls[i_step + 1] - slice_pos_cm_ls[i_step]) * 1e7
             hg = get_kernel(gap_nm, lmbda_nm, voxel_nm, grid_shape, sign_convention=sign_convention)
             psi = torch.fft.ifft2(torch.fft.fft2(psi) * torch.tensor(hg).to(cdt))
@@ -619,6 +627,9 @@ def ptycho_loss_and_grads(obj, probe_real, probe_imag, pos_batch, prj_abs, coord
     if probe_pos_offset is not None:
         probe_pos_offset = leaves['probe_pos_offset'] = torch.as_tensor(probe_pos_offset).to(obj.dtype).clone().requires_grad_(
             'probe_pos_offset' in want)
+    if 'slice_pos_cm_ls' in want:
+        leaves['slice_pos_cm_ls'] = torch.as_tensor(np.asarray(cfg['slice_pos_cm_ls'], dtype='float64')).to(obj.dtype).clone().requires_grad_(True)
+        cfg = dict(cfg, slice_pos_cm_ls=leaves['slice_pos_cm_ls'])
     if prj_pos_offset is not None:
         prj_pos_offset = leaves['prj_pos_offset'] = torch.as_tensor(prj_pos_offset).to(obj.dtype).clone().requires_grad_(
             'prj_pos_offset' in want)

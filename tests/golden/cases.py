@@ -125,6 +125,13 @@ CASES = {
                                theta=0.6, n_theta=3, i_theta=1, pos=[(-10, 9), (20, -14)], n_modes=1,
                                free_prop_cm=2e-6, unknown_type='delta_beta', delta_scale=3e-3, beta_scale=3e-4, seed=30,
                                loss='lsq', raw_data_type='intensity', optimize_probe=True, probe_background=0.4),
+    # sparse multislice with REFINABLE slice positions (optimize_slice_pos: the per-gap paraxial kernels stay in the graph,
+    # propagate.py:479-534, :556-568)
+    'sparse3_p72_slicepos': dict(kind='sparse', obj_size=(90, 84, 3), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
+                                 theta=0.0, n_theta=1, i_theta=0, pos=[(-10, -10), (20, 13), (9, -12)], n_modes=1,
+                                 free_prop_cm='inf', unknown_type='delta_beta', delta_scale=3e-2, beta_scale=3e-3, seed=37,
+                                 loss='lsq', raw_data_type='magnitude', optimize_probe=True,
+                                 slice_pos_cm=[0., 2.0e-6, 7.5e-6], rotate_out_of_loop=True, optimize_slice_pos=True),
     # 2-D ptychography with probe modes + probe and position refinement (BASELINE config B shape, small)
     'ptycho2d_modes': dict(kind='ptycho', obj_size=(128, 128, 1), probe_size=(72, 72), energy_ev=5000., psize_cm=1e-7,
                            theta=0.0, n_theta=1, i_theta=0,

@@ -121,7 +121,8 @@ def run_reference(name):
             args['prj_pos_offset'] = w.create_variable(off, requires_grad=True)
         if c['kind'] == 'sparse':
             del args['tilt_ls']
-            args['slice_pos_cm_ls'] = w.create_variable(np.array(c['slice_pos_cm']), requires_grad=False)
+            args['slice_pos_cm_ls'] = w.create_variable(np.array(c['slice_pos_cm']), requires_grad=c.get('optimize_slice_pos', False))
+        args = {k: args[k] for k in fm.argument_ls}            # w.get_gradients indexes the kwargs BY POSITION
         opt_args = [0]
         names = ['obj']
         if c.get('optimize_probe', False):
@@ -136,6 +137,9 @@ def run_reference(name):
         if c.get('optimize_all_probe_pos', False):
             opt_args += [fm.get_argument_index('probe_pos_correction')]
             names += ['probe_pos_correction']
+        if c.get('optimize_slice_pos', False):
+            opt_args += [fm.get_argument_index('slice_pos_cm_ls')]
+            names += ['slice_pos_cm_ls']
         if c.get('optimize_tilt', False):
             opt_args += [fm.get_argument_index('tilt_ls')]
             names += ['tilt_ls']

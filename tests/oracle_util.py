@@ -71,6 +71,8 @@ def run_oracle_case(name, dtype=torch.float32):
     if c.get('optimize_prj_pos_offset', False):
         extra['prj_pos_offset'] = torch.tensor(np.asarray(c['prj_pos_offset'], dtype='float32'))
         want += ['prj_pos_offset']
+    if c.get('optimize_slice_pos', False):
+        want += ['slice_pos_cm_ls']
     if c.get('optimize_tilt', False):
         extra['tilt'] = torch.tensor(np.asarray(c['tilt'], dtype='float32'))       # tilt_ls[:, i_theta], fp32 like the driver
         want += ['tilt']
@@ -151,5 +153,7 @@ def check_param_grads_against_golden(gold, grads, i_theta, tol=1e-4):
         assert rel_err(grads['tilt'], gold['g_tilt_ls'][:, i_theta]) < tol, 'tilt'
     if 'g_probe_pos_offset' in gold.files:
         assert rel_err(grads['probe_pos_offset'], gold['g_probe_pos_offset'][i_theta]) < tol, 'probe_pos_offset'
+    if 'g_slice_pos_cm_ls' in gold.files:
+        assert rel_err(grads['slice_pos_cm_ls'], gold['g_slice_pos_cm_ls']) < tol, 'slice_pos_cm_ls'
     if 'g_prj_pos_offset' in gold.files:
         assert rel_err(grads['prj_pos_offset'], gold['g_prj_pos_offset'][i_theta]) < tol, 'prj_pos_offset'

@@ -75,6 +75,10 @@ def run_gpu_case(name):
     if c['kind'] == 'sparse':
         del args['tilt_ls']
         args['slice_pos_cm_ls'] = np.array(c['slice_pos_cm'])
+        if c.get('optimize_slice_pos', False):
+            cv['optimize_slice_pos'] = True
+            args['slice_pos_cm_ls'] = t(np.array(c['slice_pos_cm']))
+        args = {k: args[k] for k in fm.argument_ls}          # the Differentiator indexes the kwargs BY POSITION
     opt_args, names = [0], ['obj']
     if c.get('optimize_probe', False):
         opt_args += [fm.get_argument_index('probe_real'), fm.get_argument_index('probe_imag')]
@@ -94,6 +98,9 @@ def run_gpu_case(name):
     if has_ppc:
         opt_args += [fm.get_argument_index('probe_pos_correction')]
         names += ['probe_pos_correction']
+    if c.get('optimize_slice_pos', False):
+        opt_args += [fm.get_argument_index('slice_pos_cm_ls')]
+        names += ['slice_pos_cm_ls']
     if c.get('optimize_tilt', False):
         tilt = np.zeros([3, n_theta], 'float32')
         tilt[0] = theta_ls
@@ -145,6 +152,9 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
     if 'probe_pos_offset' in grads:
         assert rel_err(grads['probe_pos_offset'][it], grads64['probe_pos_offset']) < 5e-4
         assert rel_err(grads['probe_pos_offset'], gold['g_probe_pos_offset']) < 5e-4
+    if 'slice_pos_cm_ls' in grads:
+        assert rel_err(grads['slice_pos_cm_ls'], grads64['slice_pos_cm_ls']) < 5e-4
+        assert rel_err(grads['slice_pos_cm_ls'], gold['g_slice_pos_cm_ls']) < 5e-4
     if 'prj_pos_offset' in grads:
         assert rel_err(grads['prj_pos_offset'][it], grads64['prj_pos_offset']) < 5e-4
         assert rel_err(grads['prj_pos_offset'], gold['g_prj_pos_offset']) < 5e-4
