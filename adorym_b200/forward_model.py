@@ -598,7 +598,8 @@ class SparseMultisliceModel(PtychographyModel):
     by the paraxial Fresnel kernel over each gap slice_pos[i+1] - slice_pos[i] (propagate.py:479-534,
     fresnel_propagate_wrapped :556-568), the transmission of every slice still uses the voxel size as its thickness
     (propagate.py:505).  Same fused kernels as PtychographyModel with one separable transfer function per gap
-    (adm_multislice_cfg.h_per_slice).  Refinement of the slice positions (optimize_slice_pos) is not accelerated."""
+    (adm_multislice_cfg.h_per_slice).  Refinable slice positions (optimize_slice_pos): the tables are rebuilt from the
+    current positions and dL/d slice_pos comes from the checkpointed forward / adjoint wavefields (ops._slice_pos_gradient)."""
 
     def __init__(self, loss_function_type='lsq', distribution_mode=None, device=None, common_vars_dict=None,
                  raw_data_type='magnitude', simulation_mode=False, *args, **kwargs):
