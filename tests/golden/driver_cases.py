@@ -17,6 +17,9 @@ DRIVER_CASES = {
     'driver_tilt': dict(update_scheme='immediate', n_epochs=1, gpu_only=True,
                         extra=dict(optimize_tilt=True, tilt_learning_rate=2e-3, optimize_probe_pos_offset=True,
                                    probe_pos_offset_learning_rate=1e-2, optimize_all_probe_pos=False)),
+    # 2-D ptychography, the shape of BASELINE configs B / C scaled down: real_imag object, intensity data, two supplied probe
+    # modes, probe + position refinement, minibatches of 3 of 9 positions (randomised order), 3 epochs
+    'driver_2d_realimag': dict(kind='2d', update_scheme='immediate', n_epochs=3, gpu_only=True),
 }
 OBJ_SIZE = (32, 40, 40)
 P = 72
@@ -72,3 +75,53 @@ def driver_data():
         for i in range(N_THETA):
             data[i] = orc.predict_ptycho(tr, pr, pi, pos, orc.rotation_coords([Y, X, Z], theta_ls[i]), cfg).numpy()
     return data
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# 2-D ptychography driver case
+# ---------------------------------------------------------------------------------------------------------------
+OBJ2D = (100, 92, 1)
+P2D = 64
+POS2D = [(-8.2, -7.6), (9.7, 12.1), (30.4, 20.2), (34.6, -4.9), (2.8, 27.3), (18.1, 3.3), (25.5, 28.4), (-3.1, 11.8), (12.4, -6.2)]
+
+
+def probe_modes_2d():
+    """Two probe modes as [mag, phase] stacks [M, P, P] (probe_type='supplied', ptychography.py:105,234-235)."""
+    rs = np.random.RandomState(81)
+    r0, i0 = _gaussian_probe((P2D, P2D), 7.0, 0.4, 7.0)
+    pr = np.stack([r0 * (1 - 0.5 * m) + 0.03 * rs.normal(size=(P2D, P2D)) * np.abs(r0) for m in range(2)])
+    pi = np.stack([i0 * (1 + 0.3 * m) + 0.03 * rs.normal(size=(P2D, P2D)) * np.abs(r0) for m in range(2)])
+    c = pr + 1j * pi
+    return np.abs(c).astype('float32'), np.angle(c).astype('float32')
+
+
+def driver_params_2d(name):
+    c = DRIVER_CASES[name]
+    rs = np.random.RandomState(82)
+    init = [(1.0 - _smooth_noise(rs, OBJ2D, 0.05)).astype('float32'), _smooth_noise(rs, OBJ2D, 0.05)]        # [mag, phase]
+    mag, ph = probe_modes_2d()
+    return dict(obj_size=OBJ2D, probe_pos=POS2D, theta_st=0, theta_end=0, n_theta=1, energy_ev=8801.12, psize_cm=1.3279e-6,
+                free_prop_cm='inf', minibatch_size=3, n_epochs=c['n_epochs'], alpha_d=0, alpha_b=0, gamma=0,
+                learning_rate=1e-3, optimizer='adam', update_scheme=c['update_scheme'], two_d_mode=True,
+                probe_type='supplied', probe_initial=[mag, ph], n_probe_modes=2, optimize_probe=True, probe_learning_rate=1e-3,
+                optimize_all_probe_pos=True, all_probe_pos_learning_rate=1e-2, initial_guess=init, unknown_type='real_imag',
+                loss_function_type='lsq', raw_data_type='intensity', randomize_probe_pos=True, shared_probe_among_angles=True)
+
+
+def driver_data_2d():
+    """Intensities [1, n_pos, P, P] from the oracle's forward model of a 'true' real_imag object with perturbed probe modes."""
+    import torch
+    from oracle import multislice_oracle as orc
+    rs = np.random.RandomState(83)
+    mag = 1.0 - _smooth_noise(rs, OBJ2D, 0.35)
+    ph = _smooth_noise(rs, OBJ2D, 0.8)
+    tr = torch.tensor(np.stack([mag * np.cos(ph), mag * np.sin(ph)], -1).astype('float32'))
+    pm, pp = probe_modes_2d()
+    pr = torch.tensor(pm * np.cos(pp) * 1.08)
+    pi = torch.tensor(pm * np.sin(pp) * 0.93)
+    cfg = dict(this_obj_size=list(OBJ2D), probe_size=[P2D, P2D], energy_ev=8801.12, psize_cm=1.3279e-6, h=None,
+               free_prop_cm='inf', unknown_type='real_imag', two_d_mode=True)
+    pos = np.round(np.array(POS2D)).astype(int)
+    with torch.no_grad():
+        a = orc.predict_ptycho(tr, pr, pi, pos, None, cfg).numpy()
+    return (a ** 2)[None].astype('float32')

@@ -14,7 +14,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
-from driver_cases import DRIVER_CASES, driver_params, driver_data, driver_mask  # noqa: E402
+from driver_cases import (DRIVER_CASES, driver_params, driver_data, driver_mask, driver_params_2d,  # noqa: E402
+                          driver_data_2d)
 
 
 def run(name, data):
@@ -35,15 +36,27 @@ def run(name, data):
     try:
         np.savez(os.path.join(tmp, 'data.h5'), **{'exchange|data': data})
         os.rename(os.path.join(tmp, 'data.h5.npz'), os.path.join(tmp, 'data.h5'))
-        np.save(os.path.join(tmp, 'mask.npy'), driver_mask())
-        params = driver_params(name)
-        params.update(fname='data.h5', save_path=tmp, output_folder=os.path.join(tmp, 'out'), backend='pytorch', cpu_only=True,
-                      finite_support_mask_path=os.path.join(tmp, 'mask.npy'), store_checkpoint=False, use_checkpoint=False,
-                      save_intermediate=False, n_batch_per_checkpoint=1000)
+        two_d = DRIVER_CASES[name].get('kind') == '2d'
+        if two_d:
+            params = driver_params_2d(name)
+            params.update(fname='data.h5', save_path=tmp, output_folder=os.path.join(tmp, 'out'), backend='pytorch', cpu_only=True,
+                          store_checkpoint=False, use_checkpoint=False, save_intermediate=False, n_batch_per_checkpoint=1000)
+        else:
+            np.save(os.path.join(tmp, 'mask.npy'), driver_mask())
+            params = driver_params(name)
+            params.update(fname='data.h5', save_path=tmp, output_folder=os.path.join(tmp, 'out'), backend='pytorch', cpu_only=True,
+                          finite_support_mask_path=os.path.join(tmp, 'mask.npy'), store_checkpoint=False, use_checkpoint=False,
+                          save_intermediate=False, n_batch_per_checkpoint=1000)
         ptych.reconstruct_ptychography(**params)
         hist = np.loadtxt(os.path.join(tmp, 'out', 'convergence', 'loss_rank_0.txt'), delimiter=',', ndmin=2, skiprows=1)
-        delta = np.load(os.path.join(tmp, 'out', 'delta_ds_1.npy'))
-        beta = np.load(os.path.join(tmp, 'out', 'beta_ds_1.npy'))
+        if two_d:
+            # real_imag objects are written as magnitude / phase (ptychography.py:1275-1283)
+            mag = np.load(os.path.join(tmp, 'out', 'obj_mag_ds_1.npy'))
+            phs = np.load(os.path.join(tmp, 'out', 'obj_phase_ds_1.npy'))
+            delta, beta = mag * np.cos(phs), mag * np.sin(phs)
+        else:
+            delta = np.load(os.path.join(tmp, 'out', 'delta_ds_1.npy'))
+            beta = np.load(os.path.join(tmp, 'out', 'beta_ds_1.npy'))
         out = {'loss_history': hist[:, :3].astype('float64'), 'obj': np.stack([delta, beta], -1).astype('float32'),
                'probe_real': last['probe_real'].detach().numpy().astype('float32'),
                'probe_imag': last['probe_imag'].detach().numpy().astype('float32'),
@@ -64,6 +77,14 @@ def main():
     # the data are stored as fp16 magnitudes (compact); every consumer (reference run included) uses the fp16-rounded values
     data = np.abs(data).astype('float16').astype('float32').astype('complex64')
     for name in (sys.argv[1:] or DRIVER_CASES):
+        if DRIVER_CASES[name].get('kind') == '2d':
+            d2 = driver_data_2d()                 # fp32 (far-field intensities exceed the fp16 range); stored in the golden itself
+            out = run(name, d2)
+            out['data'] = d2
+            path = os.path.join(HERE, name + '.npz')
+            np.savez_compressed(path, **out)
+            print(name, 'losses', out['loss_history'][:3, 2], '...', out['loss_history'][-1, 2], '->', os.path.getsize(path) // 1024, 'KB')
+            continue
         out = run(name, data)
         path = os.path.join(HERE, name + '.npz')
         np.savez_compressed(path, **out)

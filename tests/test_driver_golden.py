@@ -14,7 +14,7 @@ import numpy as np
 import pytest
 import torch
 
-from driver_cases import DRIVER_CASES, driver_params, driver_mask
+from driver_cases import DRIVER_CASES, driver_params, driver_mask, driver_params_2d
 from oracle_util import rel_err
 
 GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), 'golden')
@@ -49,9 +49,15 @@ def test_oracle_driver_matches_reference_driver_golden(name):
 @pytest.mark.parametrize('name', sorted(DRIVER_CASES))
 def test_reconstruct_ptychography_matches_reference_driver_golden(name):
     import adorym_b200 as ab
-    params = driver_params(name)
-    out = ab.reconstruct_ptychography(_data(), **params, finite_support_mask_path=driver_mask(), verbose=False,
-                                      save_outputs=False, output_folder='/tmp/adm_test_driver_' + name)
+    if DRIVER_CASES[name].get('kind') == '2d':
+        # 2-D ptychography (real_imag object, intensity data, two supplied probe modes, randomised position order)
+        data = np.load(os.path.join(GOLD, name + '.npz'))['data'].astype('float32')
+        out = ab.reconstruct_ptychography(data, **driver_params_2d(name), verbose=False, save_outputs=False,
+                                          output_folder='/tmp/adm_test_driver_' + name)
+    else:
+        params = driver_params(name)
+        out = ab.reconstruct_ptychography(_data(), **params, finite_support_mask_path=driver_mask(), verbose=False,
+                                          save_outputs=False, output_folder='/tmp/adm_test_driver_' + name)
     hist = [(e, b, l) for (e, b, l, t) in out['loss_history']]
     _check(name, hist, out['obj'].cpu().numpy(), out['probe_real'].cpu().numpy(), out['probe_imag'].cpu().numpy(),
            out['probe_pos_correction'].cpu().numpy())
