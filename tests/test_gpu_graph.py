@@ -83,3 +83,39 @@ def test_driver_with_cuda_graph_matches_reference_driver_golden():
         hist = [(e, b, l) for (e, b, l, t) in out['loss_history']]
         _check(name, hist, out['obj'].cpu().numpy(), out['probe_real'].cpu().numpy(), out['probe_imag'].cpu().numpy(),
                out['probe_pos_correction'].cpu().numpy())
+
+
+def test_graph_replay_equals_eager_multidist():
+    """MultiDistModel (4 distances, refinable data shift) replayed from a CUDA graph vs eager, with updates in between."""
+    import adorym_b200 as ab
+    from cases import make_md_inputs
+    from test_gpu_multidist import md_common_vars
+    dev = torch.device('cuda', 0)
+    inp = make_md_inputs('multidist256_shift')
+    c = inp['cfg']
+    prj_full = torch.tensor(inp['prj'][None], device=dev)
+    fm = ab.MultiDistModel(loss_function_type=c['loss'], distribution_mode=None, device=dev,
+                           common_vars_dict=md_common_vars(c, dev, prj_full, True), raw_data_type=c['raw_data_type'])
+    t = lambda a, rg=True: torch.tensor(a, dtype=torch.float32, device=dev, requires_grad=rg)
+    state = dict(obj=t(inp['obj']), ppc=t(inp['probe_pos_correction']))
+    pr, pi = t(inp['probe_real'], False), t(inp['probe_imag'], False)
+    opt_args = [0, fm.get_argument_index('probe_pos_correction')]
+    eager, graphed = ab.Differentiator(), ab.GraphedDifferentiator(fm)
+    eager.create_loss_node(fm.get_loss_function(), opt_args)
+    graphed.create_loss_node(fm.get_loss_function(), opt_args)
+    for step in range(3):
+        args = dict(obj=state['obj'], probe_real=pr, probe_imag=pi, probe_defocus_mm=None, probe_pos_offset=None, this_i_theta=0,
+                    this_pos_batch=np.array([[0, 0]]), prj=prj_full, probe_pos_correction=state['ppc'],
+                    this_ind_batch=np.array([0]), free_prop_cm=c['dists'], safe_zone_width=0, prj_affine_ls=None,
+                    ctf_lg_kappa=None, prj_pos_offset=None)
+        ge = [g.clone() for g in eager.get_gradients(**args)]
+        le = fm.current_loss
+        gg = graphed.get_gradients(**args)
+        assert graphed.fallback_reason is None, graphed.fallback_reason
+        assert abs(fm.current_loss - le) <= 1e-6 * abs(le)
+        for a, b in zip(gg, ge):
+            assert rel_err(a.cpu().numpy(), b.cpu().numpy()) < 1e-5
+        with torch.no_grad():
+            state['obj'] = (state['obj'].detach() - 0.01 * ge[0]).requires_grad_(True)
+            state['ppc'] = (state['ppc'].detach() - 0.05 * ge[1]).requires_grad_(True)
+    assert graphed.n_replays == 3 and len(graphed._graphs) == 1
