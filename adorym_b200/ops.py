@@ -873,8 +873,6 @@ class LargeMultislicePlan(object):
         self.k1, self.sign_convention = float(k1), int(sign_convention)
         self.unknown_type = UNKNOWN_TYPES[unknown_type]
         self.free_prop = {'none': 0, 'inf': 1, 'near': 2}[free_prop]
-        if self.free_prop == 1 and self.sign_convention != 1:
-            raise NotImplementedError('adorym_b200: far-field detection of large probes with sign_convention = -1')
         self.normalize_fft = int(bool(normalize_fft))
         self.device = device
         self.Hp = self.Hc = self.Hfp = self.Hfc = None
@@ -884,7 +882,13 @@ class LargeMultislicePlan(object):
             self.Hp, self.Hc = _lf_prepare(h, self.P, device)
         if self.free_prop == 2:
             self.Hfp, self.Hfc = _lf_prepare(h_free, self.P, device)
-        self.ff_scale = (1.0 / self.P) if self.normalize_fft else 1.0        # propagate.py:267 (sign +1: fft2, unnormalised)
+        # propagate.py:267-270: sign +1 -> fft2 (unnormalised, or 1/N with normalize_fft); sign -1 -> ifft2 (1/N^2, or 1/N),
+        # evaluated as conj(fft2(conj(psi))) with the conjugations folded around the same kernels (ff_conj)
+        self.ff_conj = self.free_prop == 1 and self.sign_convention == -1
+        if self.normalize_fft:
+            self.ff_scale = 1.0 / self.P
+        else:
+            self.ff_scale = 1.0 / (self.P * self.P) if self.sign_convention == -1 else 1.0
 
 
 class MultisliceLargeFn(torch.autograd.Function):
@@ -925,8 +929,11 @@ class MultisliceLargeFn(torch.autograd.Function):
         vac = None
         if plan.free_prop == 1:
             det = torch.empty_like(psi)
-            call('adm_lf_farfield_fwd', N, F, ptr(psi), ptr(lf_spectrum_order(N, dev)), plan.ff_scale, ptr(work), ptr(det),
+            src = (psi * torch.tensor([1.0, -1.0], device=dev)).contiguous() if plan.ff_conj else psi
+            call('adm_lf_farfield_fwd', N, F, ptr(src), ptr(lf_spectrum_order(N, dev)), plan.ff_scale, ptr(work), ptr(det),
                  stream_ptr())
+            if plan.ff_conj:
+                det = det * torch.tensor([1.0, -1.0], device=dev)
         elif plan.free_prop == 2:
             # free-space propagation of the exit wave (propagate.py:271-280): one step through vacuum (every patch placed
             # outside the object) with the free-space kernel
@@ -960,9 +967,11 @@ class MultisliceLargeFn(torch.autograd.Function):
         work2 = torch.empty((F, N, N, 2), dtype=torch.float32, device=dev)
         if plan.free_prop == 1:
             g2 = torch.empty_like(g)
-            call('adm_lf_farfield_bwd', N, F, ptr(g), ptr(lf_spectrum_order(N, dev)), plan.ff_scale, ptr(work1), ptr(g2),
+            # (re, im) -> (re, -im) is its own transpose: the conjugations of the sign -1 convention wrap the adjoint too
+            src = (g * torch.tensor([1.0, -1.0], device=dev)).contiguous() if plan.ff_conj else g
+            call('adm_lf_farfield_bwd', N, F, ptr(src), ptr(lf_spectrum_order(N, dev)), plan.ff_scale, ptr(work1), ptr(g2),
                  stream_ptr())
-            g = g2
+            g = g2 * torch.tensor([1.0, -1.0], device=dev) if plan.ff_conj else g2
         elif plan.free_prop == 2:
             g2 = torch.empty_like(g)
             call('adm_lf_patch_step_bwd', N, B, M, Y, X, 0, ptr(tvol), ptr(vac), ptr(ckpt[0]), ptr(plan.Hfc), ptr(g), ptr(work1),

@@ -160,11 +160,13 @@ def test_loss_and_gradients_match_oracle_and_reference(name):
         assert rel_err(grads['prj_pos_offset'], gold['g_prj_pos_offset']) < 5e-4
 
 
-@pytest.mark.parametrize('P', [256, 512])
-def test_large_probe_sizes_match_oracle(P):
+@pytest.mark.parametrize('P,sign,norm', [(256, 1, False), (512, 1, False), (128, -1, False), (128, -1, True)])
+def test_large_probe_sizes_match_oracle(P, sign, norm):
     """Probe sizes 256 / 512 (2-D ptychography, two modes, probe + position refinement, far field) on the batched
-    large-frame slice steps against the fp64 oracle (the 128-pixel cases also carry reference goldens)."""
-    CASES['_tmp_large'] = dict(CASES['ptycho2d_p128'], probe_size=(P, P), obj_size=(P + 40, P + 30, 1), seed=40 + P)
+    large-frame slice steps against the fp64 oracle (the 128-pixel cases also carry reference goldens); the sign -1
+    convention (ifft2 detector transform, propagate.py:269-270) with and without normalize_fft."""
+    CASES['_tmp_large'] = dict(CASES['ptycho2d_p128'], probe_size=(P, P), obj_size=(P + 40, P + 30, 1), seed=40 + P,
+                               sign_convention=sign, normalize_fft=norm)
     try:
         inp, loss, pred, grads, fm = run_gpu_case('_tmp_large')
         _, loss64, pred64, grads64 = run_oracle_case('_tmp_large', torch.float64)
