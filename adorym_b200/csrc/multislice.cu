@@ -277,7 +277,7 @@ template <class C, int MINB, bool TILE, class T> __global__ void __launch_bounds
 // ================================================================================================
 // Adjoint
 // ================================================================================================
-template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
+template <class C, int MINB, class T, bool GCK = false> __global__ void __launch_bounds__(C::NTHREADS, MINB) k_multislice_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, R2 = C::R2, S = C::S;
     constexpr unsigned TILE_BYTES = (unsigned)MsSmem<C>::TILE;
@@ -424,7 +424,7 @@ template <class C, int MINB, class T> __global__ void __launch_bounds__(C::NTHRE
                         ckb[y * TP + lt] = cmulc(v[j], w);            // dL/dT = g' conj(psi_z)
                         v[j] = modulate_conj(v[j], tpa[gi][j]);       // g_psi = g' conj(T)
                     }
-                    if (p.g_ckpt != nullptr) {     // refinable slice positions: dL/d psi_z for the host-side d/d gap
+                    if constexpr (GCK) {           // refinable slice positions: dL/d psi_z for the host-side d/d gap
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             ((T*)p.g_ckpt)[((size_t)wf * p.Nz + z) * P * P + I.a(j, gi) * P + l] = v[j];
@@ -677,22 +677,27 @@ static int ms_bwd_impl(const adm_multislice_cfg* cfg, const float* tvol, const i
                           ADM_GVOL_PITCH(p.X, cfg->P), cfg->P, cfg->P + 2))
         return ADM_ERR_CUDA;
     int var = adm_variant("ADM_BWD_VARIANT");
-#define ADM_BWD(CFG, MINB, CT)                                                                                       \
+#define ADM_BWD(CFG, MINB, CT, GCK)                                                                                  \
     do {                                                                                                           \
         const size_t sm_ = MsSmem<CFG>::BYTES;                                                                     \
-        if (set_smem(k_multislice_bwd<CFG, MINB, CT>, sm_)) return ADM_ERR_CUDA;                                   \
+        if (set_smem(k_multislice_bwd<CFG, MINB, CT, GCK>, sm_)) return ADM_ERR_CUDA;                              \
         int grid_;                                                                                                 \
-        if (ms_schedule(p, ms_resident_ctas(k_multislice_bwd<CFG, MINB, CT>, CFG::NTHREADS, sm_), workspace,       \
+        if (ms_schedule(p, ms_resident_ctas(k_multislice_bwd<CFG, MINB, CT, GCK>, CFG::NTHREADS, sm_), workspace,  \
                         CFG::P, grid_))                                                                            \
             return ADM_ERR_CUDA;                                                                                   \
-        ADM_LAUNCH((k_multislice_bwd<CFG, MINB, CT>), grid_, CFG::NTHREADS, sm_, stream, map, p);                  \
+        ADM_LAUNCH((k_multislice_bwd<CFG, MINB, CT, GCK>), grid_, CFG::NTHREADS, sm_, stream, map, p);             \
     } while (0)
+    if (p.g_ckpt != nullptr) {          // with the adjoint-wavefield checkpoints (packed arithmetic only)
+        if (cfg->P == 72) ADM_BWD(Cfg72, 2, cpk, true);
+        else ADM_BWD(Cfg64, 2, cpk, true);
+        return ADM_OK;
+    }
     if (cfg->P == 72) {
-        if (var == 4) ADM_BWD(Cfg72, 2, cpx);
-        else ADM_BWD(Cfg72, 2, cpk);
+        if (var == 4) ADM_BWD(Cfg72, 2, cpx, false);
+        else ADM_BWD(Cfg72, 2, cpk, false);
     } else {
-        if (var == 4) ADM_BWD(Cfg64, 2, cpx);
-        else ADM_BWD(Cfg64, 2, cpk);
+        if (var == 4) ADM_BWD(Cfg64, 2, cpx, false);
+        else ADM_BWD(Cfg64, 2, cpk, false);
     }
     return ADM_OK;
 }
