@@ -550,25 +550,37 @@ def run_gpu_arm(args):
 
 
 def run_other_configs(args):
-    """The other named shapes of BASELINE.json (configs A, B, C, E) on one GPU, with the same clocks sampler as the
-    headline line: one JSON line per configuration (secondary figures; `python bench.py` without --config is the
-    driver's contract line on config D)."""
+    """The other named shapes of BASELINE.json (configs A, B, C, E), with the same clocks sampler as the headline line: one
+    JSON line per configuration and execution mode (eager / CUDA graph).  Under torchrun (N > 1) the ranks run data parallel
+    as the driver does -- every rank its own minibatch (angle) of the global chunk, gradients summed with NCCL, identical
+    update; weak scaling -- except config E, which has nothing to shard.  Secondary figures: `python bench.py` without
+    --config is the driver's contract line on config D."""
     import torch
     if not torch.cuda.is_available():
         raise RuntimeError('bench.py --config: no CUDA device (there is no CPU fallback)')
+    from adorym_b200 import dist as adist
+    rank, world, local = adist.init_from_env('nccl')
+    dev = torch.device('cuda', local)
+    torch.cuda.set_device(dev)
     sys.path.insert(0, os.path.join(ROOT, 'tools'))
     import bench_configs as bc
+    bc.DEV, bc.RANK, bc.WORLD = dev, rank, world
     for cfg in args.config:
-        sampler = ClockSampler(0)
-        sampler.start()
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
         lines = bc.run([cfg], steps=args.steps, warmup=max(args.warmup, 3))
-        clocks = sampler.stop()
+        clocks = sampler.stop() if rank == 0 else None
+        if rank != 0:
+            continue
         for l in lines:
-            out = {'metric': METRIC.replace('at 256^3', 'config ' + l['config']), 'value': l['value'], 'unit': UNIT, 'n_gpus': 1,
+            out = {'metric': METRIC.replace('at 256^3', 'config ' + l['config']), 'value': l['value'], 'unit': UNIT, 'n_gpus': world,
                    'steps': l['steps'], 'warmup': l['warmup'], 'ms_per_step': l['ms_per_step'], 'higher_is_better': True,
                    'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
                    'config': {'workload': l['workload'] + (' [loss + gradients replayed as one CUDA graph]' if l.get('cuda_graph') else ' [eager launches]'),
                               'cuda_graph': bool(l.get('cuda_graph')), 'patterns_per_step': l['patterns_per_step'],
+                              'parallelism': 'dp%d: every rank its own minibatch of the global chunk, all gradients SUMMED with one '
+                                             'flat NCCL all-reduce, identical update' % world,
                               'l2_policy': 'working set is L2 resident by construction (<= 8 MB): launch / latency bound'},
                    'roofline': {'bound': 'hbm', 'achieved': l['algorithmic_bytes_per_step'] / (l['ms_per_step'] * 1e-3) / 1e9,
                                 'peak': l['peak_gbs'], 'unit': 'GB/s', 'frac': l['hbm_roofline_frac'], 'traffic': None},

@@ -18,6 +18,8 @@ sys.path.insert(0, ROOT)
 import adorym_b200 as ab  # noqa: E402
 
 DEV = torch.device('cuda', 0)
+RANK, WORLD = 0, 1          # set by bench.py --config under torchrun: data parallelism as in the driver (each rank its own
+                            # minibatch of the global chunk, gradients SUMMED over ranks with one NCCL all-reduce, identical update)
 PEAK = 6531.6
 try:
     PEAK = float(json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))['hbm_gbs'])
@@ -43,30 +45,55 @@ WARMUP = None
 LINES = []
 
 
+def sum_over_ranks(grads):
+    """ptychography.py:1113-1114 / optimizers.py:1025-1079: SUM (not mean) of every gradient over the ranks -- one flat
+    NCCL all-reduce for all of them."""
+    if WORLD == 1:
+        return list(grads)
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    torch.distributed.all_reduce(flat, op=torch.distributed.ReduceOp.SUM)
+    out, o = [], 0
+    for g in grads:
+        out.append(flat[o:o + g.numel()].view_as(g))
+        o += g.numel()
+    return out
+
+
 def time_steps(step, n_warm=5, n=30):
     n_warm = WARMUP if WARMUP is not None else n_warm
     n = STEPS if STEPS is not None else n
     for _ in range(n_warm):
         step()
+    if WORLD > 1:
+        torch.distributed.barrier()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(n):
         step()
     e1.record()
+    if WORLD > 1:
+        torch.distributed.barrier()
     torch.cuda.synchronize()
     time_steps.last = (n, n_warm)
-    return e0.elapsed_time(e1) / n
+    ms = e0.elapsed_time(e1) / n
+    if WORLD > 1:                     # the job's step time is the slowest rank's
+        t = torch.tensor([ms], device=DEV)
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
 
 
 def report(name, workload, patterns_per_step, ms, alg_bytes):
     n, n_warm = getattr(time_steps, 'last', (None, None))
-    line = {'config': name, 'cuda_graph': bool(GRAPH), 'workload': workload, 'patterns_per_step': patterns_per_step, 'ms_per_step': ms,
-            'value': patterns_per_step / (ms * 1e-3), 'unit': 'patterns/s', 'steps': n, 'warmup': n_warm,
+    # weak scaling: every rank processes `patterns_per_step` patterns per step; the roofline fraction is per GPU
+    line = {'config': name, 'cuda_graph': bool(GRAPH), 'workload': workload, 'patterns_per_step': patterns_per_step * WORLD,
+            'ms_per_step': ms, 'n_gpus': WORLD,
+            'value': patterns_per_step * WORLD / (ms * 1e-3), 'unit': 'patterns/s', 'steps': n, 'warmup': n_warm,
             'algorithmic_bytes_per_step': alg_bytes,
             'hbm_roofline_frac': alg_bytes / (ms * 1e-3) / 1e9 / PEAK, 'peak_gbs': PEAK}
     LINES.append(line)
-    if STEPS is None:
+    if STEPS is None and RANK == 0:
         print(json.dumps(line), flush=True)
 
 
@@ -121,14 +148,17 @@ def ptycho_runner(obj_size, P, pos, M, unknown_type, energy_ev, psize_cm, raw_da
     opt_p.create_container([M, P, P, 2], False, DEV)
     probe = {'t': torch.stack([probe_real.detach(), probe_imag.detach()], -1).contiguous()}
 
+    n_chunks = max(1, n_batches // WORLD)          # global chunks of WORLD minibatches; rank r takes the r-th (ptychography.py:905-907)
+
     def step():
-        i = state['i'] % n_batches
+        i = ((state['i'] % n_chunks) * WORLD + RANK) % n_batches
         ind = np.arange(i * mb, (i + 1) * mb)
         p_r = probe['t'][..., 0].contiguous().requires_grad_(refine)
         p_i = probe['t'][..., 1].contiguous().requires_grad_(refine)
         grads = diff.get_gradients(obj=state['obj'], probe_real=p_r, probe_imag=p_i, probe_defocus_mm=None,
                                    probe_pos_offset=None, this_i_theta=0, this_pos_batch=pos[ind], prj=prj,
                                    probe_pos_correction=ppc, this_ind_batch=ind, tilt_ls=None, prj_pos_offset=None)
+        grads = sum_over_ranks(grads)
         with torch.no_grad():
             new = opt.apply_gradient(state['obj'], grads[0], state['i'], **opt.options_dict)
             if refine:
@@ -170,11 +200,12 @@ def config_A():
     opt.create_container([Y, X, Z, 2], False, DEV)
 
     def step():
-        it = (7 * state['i'] + 3) % n_theta
+        it = (7 * (state['i'] * WORLD + RANK) + 3) % n_theta          # every rank its own angle of the global chunk
         grads = diff.get_gradients(obj=state['obj'], probe_real=pr, probe_imag=pi, probe_defocus_mm=None,
                                    probe_pos_offset=None, this_i_theta=it, this_pos_batch=pos, prj=prj,
                                    probe_pos_correction=ppc, this_ind_batch=np.array([0]), tilt_ls=None,
                                    prj_pos_offset=None)
+        grads = sum_over_ranks(grads)
         with torch.no_grad():
             new = opt.apply_gradient(state['obj'], grads[0], state['i'], **opt.options_dict)
         state['obj'] = new.requires_grad_(True)
@@ -255,6 +286,8 @@ def run(which, steps=None, warmup=None, graph=(False, True)):
     STEPS, WARMUP = steps, warmup
     del LINES[:]
     for w in which:
+        if w == 'E' and WORLD > 1:
+            continue          # one object, one set of holograms per iteration: nothing to shard (replicas only)
         for g in graph:
             GRAPH = g
             {'A': config_A, 'B': config_B, 'C': config_C, 'E': config_E}[w]()
