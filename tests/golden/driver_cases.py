@@ -17,6 +17,12 @@ DRIVER_CASES = {
     'driver_tilt': dict(update_scheme='immediate', n_epochs=1, gpu_only=True,
                         extra=dict(optimize_tilt=True, tilt_learning_rate=2e-3, optimize_probe_pos_offset=True,
                                    probe_pos_offset_learning_rate=1e-2, optimize_all_probe_pos=False)),
+    # plain gradient descent with the step-halving schedule (optimizers.py:432-464), phase-only object (beta pinned to 0,
+    # ptychography.py:1138-1142), finite-support mask SHRUNK every second batch (shrink_cycle, :1216-1220), TV only
+    'driver_gd_phase_only': dict(update_scheme='immediate', n_epochs=2, gpu_only=True,
+                                 extra=dict(optimizer='gd', learning_rate=3e-6, object_type='phase_only', shrink_cycle=2,
+                                            shrink_threshold=1e-4, optimize_probe=False, optimize_all_probe_pos=False,
+                                            reweighted_l1=False, alpha_d=0, alpha_b=0, non_negativity=False)),
     # 2-D ptychography, the shape of BASELINE configs B / C scaled down: real_imag object, intensity data, two supplied probe
     # modes, probe + position refinement, minibatches of 3 of 9 positions (randomised order), 3 epochs
     'driver_2d_realimag': dict(kind='2d', update_scheme='immediate', n_epochs=3, gpu_only=True),
