@@ -23,6 +23,12 @@ DRIVER_CASES = {
                                  extra=dict(optimizer='gd', learning_rate=3e-6, object_type='phase_only', shrink_cycle=2,
                                             shrink_threshold=1e-4, optimize_probe=False, optimize_all_probe_pos=False,
                                             reweighted_l1=False, alpha_d=0, alpha_b=0, non_negativity=False)),
+    # momentum optimizer (optimizers.py:366-411), Poisson loss on the magnitude data (forward_model.py:96-102), absorption-only
+    # object (delta pinned to 0), update per angle
+    'driver_momentum_poisson': dict(update_scheme='per angle', n_epochs=2, gpu_only=True,
+                                    extra=dict(optimizer='momentum', learning_rate=2e-7, object_type='absorption_only',
+                                               loss_function_type='poisson', optimize_probe=False,
+                                               optimize_all_probe_pos=False, reweighted_l1=False, non_negativity=True)),
     # 2-D ptychography, the shape of BASELINE configs B / C scaled down: real_imag object, intensity data, two supplied probe
     # modes, probe + position refinement, minibatches of 3 of 9 positions (randomised order), 3 epochs
     'driver_2d_realimag': dict(kind='2d', update_scheme='immediate', n_epochs=3, gpu_only=True),
