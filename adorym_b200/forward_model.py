@@ -136,6 +136,10 @@ class ForwardModel(object):
         if self.forward_algorithm != 'fresnel':
             raise NotImplementedError('adorym_b200: forward_algorithm=%r' % (self.forward_algorithm,))
 
+    def data_indices(self, this_ind_batch):
+        """Rows of exchange/data[i_theta] one minibatch reads (MultiDistModel: every distance's frame)."""
+        return np.asarray(this_ind_batch)
+
     def static_indices(self, this_i_theta, this_pos_batch, this_ind_batch, n_pos_ppc=0):
         """Host side of graph mode: the int32 device-side indices one minibatch needs, as a dict of numpy arrays
         ('pos' [B,2] patch corners, 'ppc' flat rows of the position-correction table, 'data' flat rows of exchange/data,
@@ -320,6 +324,9 @@ class ForwardModel(object):
     def get_data(self, this_i_theta, this_ind_batch, theta_downsample=None, ds_level=1):
         """adorym/forward_model.py:113-119.  `prj` may be an HDF5-like dataset / ndarray (host; |.| and H2D copy per
         minibatch as in the reference) or a CUDA tensor of magnitudes already resident on the device."""
+        if self._static is not None and self._static.get('frames') is not None:
+            # graph mode with host-resident data: the minibatch's frames were uploaded into a static device buffer
+            return self._static['frames']
         if theta_downsample is None:
             theta_downsample = 1
         prj = self.prj
@@ -734,6 +741,13 @@ class MultiDistModel(ForwardModel):
         a.pop(0)
         self.argument_ls = a
         self._md_plans = {}
+
+    def data_indices(self, this_ind_batch):
+        cv = self.common_vars
+        n_dists = len(np.asarray(cv['free_prop_cm']).reshape(-1))
+        n_blocks = int(self.prj.shape[1]) // n_dists
+        ind = np.asarray(this_ind_batch).astype('int64')
+        return np.concatenate([ind + i * n_blocks for i in range(n_dists)])          # forward_model.py:1058-1061
 
     def static_indices(self, this_i_theta, this_pos_batch, this_ind_batch, n_pos_ppc=0):
         """Graph mode: exchange/data rows of every distance's frame (forward_model.py:1058-1061)."""

@@ -16,8 +16,10 @@ static one.
 The returned gradients (and `forward_model.current_loss`) are the graph's static outputs: they are overwritten by the next
 call, exactly like a gradient buffer that is reused; consume (or clone) them before calling again.
 
-Falls back to the eager path (with the reason in `.fallback_reason`) when the measured data are not resident on the device,
-with a beamstop mask (its pixel count is read on the host), for sub-divided MultiDist frames, or when the capture fails.
+Measured data that live on the host (a pinned tensor, an HDF5 dataset) keep going through the model's own data path
+(`get_data` / `prefetch_data`: pinned staging, side-stream copy) and land in a static device buffer before the replay.
+
+Falls back to the eager path (with the reason in `.fallback_reason`) with a beamstop mask (its pixel count is read on the host), for sub-divided MultiDist frames, or when the capture fails.
 """
 import numpy as np
 import torch
@@ -26,7 +28,7 @@ from .differentiator import Differentiator
 
 
 class _Entry(object):
-    __slots__ = ('graph', 'static', 'S', 'stage', 'packed', 'layout', 'grads', 'has_grid', 'n_pos_ppc')
+    __slots__ = ('graph', 'static', 'S', 'stage', 'packed', 'layout', 'grads', 'has_grid', 'n_pos_ppc', 'host_frames')
 
 
 class GraphedDifferentiator(Differentiator):
@@ -44,8 +46,8 @@ class GraphedDifferentiator(Differentiator):
     def _unsupported(self, kwargs):
         fm = self.fm
         prj = getattr(fm, 'prj', None)
-        if not (torch.is_tensor(prj) and prj.is_cuda):
-            return 'measured data are not a CUDA tensor'
+        if prj is None:
+            return 'no measured data attached to the forward model'
         if fm.common_vars.get('beamstop', None) is not None:
             return 'beamstop mask'
         if fm.common_vars.get('optimize_slice_pos', False):
@@ -91,6 +93,18 @@ class GraphedDifferentiator(Differentiator):
         if e.has_grid:
             dev = e.packed.device
             e.S['grid'].copy_(fm._rot_table_for(dev).grid(int(kwargs['this_i_theta'])), non_blocking=True)
+        if e.host_frames:
+            # measured data resident on the host: this minibatch's frames through the model's own (prefetching) data path
+            # into the static device buffer the captured launches read
+            saved, fm._static = fm._static, None
+            try:
+                cv = fm.common_vars
+                batch = fm.get_data(kwargs['this_i_theta'], fm.data_indices(kwargs['this_ind_batch']),
+                                    theta_downsample=cv.get('theta_downsample', None),
+                                    ds_level=cv.get('ds_level', 1) if 'free_prop_cm' not in kwargs else 1)
+            finally:
+                fm._static = saved
+            e.S['frames'].copy_(batch, non_blocking=True)
         with torch.no_grad():
             for name, st in e.static.items():
                 v = kwargs[name]
@@ -99,8 +113,9 @@ class GraphedDifferentiator(Differentiator):
 
     def _build(self, key, kwargs):
         fm = self.fm
-        dev = fm.prj.device
+        dev = kwargs['obj'].device
         e = _Entry()
+        e.host_frames = not (torch.is_tensor(fm.prj) and fm.prj.is_cuda)
         e.static = {}
         for name, v in kwargs.items():
             if torch.is_tensor(v) and v.is_cuda:
@@ -123,6 +138,13 @@ class GraphedDifferentiator(Differentiator):
         e.has_grid = not (cv.get('two_d_mode', False) or fm.rotate_out_of_loop or cv.get('optimize_tilt', False)
                           or cv.get('initial_tilt', None) is not None)
         e.S['grid'] = torch.empty_like(fm._rot_table_for(dev).grid(int(kwargs['this_i_theta']))) if e.has_grid else None
+        e.S['frames'] = None
+        if e.host_frames:
+            cv = fm.common_vars
+            b0 = fm.get_data(kwargs['this_i_theta'], fm.data_indices(kwargs['this_ind_batch']),
+                             theta_downsample=cv.get('theta_downsample', None),
+                             ds_level=cv.get('ds_level', 1) if 'free_prop_cm' not in kwargs else 1)
+            e.S['frames'] = torch.empty_like(b0)
         if self._stream is None:
             self._stream = torch.cuda.Stream(device=dev)
         s = self._stream

@@ -378,9 +378,12 @@ def reconstruct_ptychography(
     if graphed:
         from .graph import GraphedDifferentiator
         if not (torch.is_tensor(forward_model.prj) and forward_model.prj.is_cuda):
-            # graph mode gathers the measured frames on the device: upload exchange/data once (|.| as get_data applies it)
-            full = np.abs(np.asarray(prj[...])).astype('float32')
-            forward_model.prj = torch.from_numpy(full).to(device_obj)
+            # the whole of exchange/data goes to the device when it comfortably fits (|.| as get_data applies it); otherwise
+            # it stays on the host and every minibatch's frames are uploaded into the graph's static buffer
+            nbytes = int(np.prod(prj.shape)) * 4
+            if nbytes < 0.25 * torch.cuda.mem_get_info(device_obj)[0]:
+                full = np.abs(np.asarray(prj[...])).astype('float32')
+                forward_model.prj = torch.from_numpy(full).to(device_obj)
         prj = forward_model.prj
         diff = GraphedDifferentiator(forward_model)
     else:
@@ -450,11 +453,12 @@ def reconstruct_ptychography(
                     grad_func_args[arg] = local_vars[arg]
             forward_model.update_loss_args(grad_func_args)
             grads = list(diff.get_gradients(**grad_func_args))
-            if i_batch + 1 < n_batch and not graphed:
+            if i_batch + 1 < n_batch:
                 # measured frames of the next minibatch: host->device copy on a side stream under this step's kernels
                 nxt_theta, nxt_ind = rank_minibatch(ind_list_rand, i_batch + 1, rank, minibatch_size, n_ranks)
-                forward_model.prefetch_data(nxt_theta, nxt_ind, theta_downsample=forward_model.common_vars['theta_downsample'],
-                                            ds_level=forward_model.common_vars['ds_level'])
+                forward_model.prefetch_data(nxt_theta, forward_model.data_indices(nxt_ind),
+                                            theta_downsample=forward_model.common_vars['theta_downsample'],
+                                            ds_level=1 if is_multi_dist else forward_model.common_vars['ds_level'])
 
             if initialize_gradients:
                 # ptychography.py:1065-1067: zeros + grads[0] -- the buffer becomes the new gradient (no fill, no add)

@@ -206,8 +206,9 @@ class StepRunner(object):
     """One data-parallel rank of the reference's batch loop (ptychography.py:859-1271), through the public classes
     (PtychographyModel.get_loss_function + Differentiator.get_gradients + AdamOptimizer.apply_gradient)."""
 
-    def __init__(self, torch, ab, dev, rank, world, n_steps_total, mb, dp_mode='nccl'):
+    def __init__(self, torch, ab, dev, rank, world, n_steps_total, mb, dp_mode='nccl', graph=False):
         self.torch, self.ab, self.dev, self.rank, self.world = torch, ab, dev, rank, world
+        self.graph = graph
         c = CFG_D
         Y, X, Z = c['obj_size']
         P = list(c['probe_size'])
@@ -253,8 +254,15 @@ class StepRunner(object):
         init = np.stack([rs.normal(8.7e-7, 1e-7, (Y, X, Z)), rs.normal(5.1e-8, 1e-8, (Y, X, Z))], -1).astype('float32')
         self.obj0 = torch.tensor(init, device=dev)
         self.fm.add_regularizers([ab.L1Regularizer(c['alpha_d'], c['alpha_b']), ab.TVRegularizer(c['gamma'])])
-        self.diff = ab.Differentiator()
-        self.diff.create_loss_node(self.fm.get_loss_function(), [0])
+        # eager differentiator (also the one the per-kernel CUDA-event timing pass uses) and, with --graph, the CUDA-graph
+        # replay of loss + gradients (adorym_b200.graph: reconstruct_ptychography(use_cuda_graph=True))
+        self.diff_eager = ab.Differentiator()
+        self.diff_eager.create_loss_node(self.fm.get_loss_function(), [0])
+        self.diff = self.diff_eager
+        if graph:
+            self.diff_graph = ab.GraphedDifferentiator(self.fm)
+            self.diff_graph.create_loss_node(self.fm.get_loss_function(), [0])
+            self.diff = self.diff_graph
         # N > 1 on one NVSwitch node: the object and its gradient live in symmetric (peer-mapped) memory and the update is
         # ONE fused kernel per rank (pull-reduce over NVLink + Adam + push); NCCL all-reduce is the fallback
         self.peer = None
@@ -270,6 +278,9 @@ class StepRunner(object):
             with torch.no_grad():
                 self.peer.object_tensor().copy_(self.obj0)
             self.obj = self.peer.object_tensor().requires_grad_(True)
+        elif getattr(self, 'obj', None) is not None:
+            with torch.no_grad():           # same storage across resets (a captured graph has adopted it)
+                self.obj.detach().copy_(self.obj0)
         else:
             self.obj = self.obj0.clone().requires_grad_(True)
         self.opt = ab.AdamOptimizer('obj', options_dict={'step_size': CFG_D['learning_rate']})
@@ -409,7 +420,7 @@ def run_gpu_arm(args):
         args.grad_slabs = 1 if args.dp == 'p2p' else 2
     from adorym_b200 import ops as _ops
     _ops.GRAD_SLABS = args.grad_slabs if world > 1 else 1
-    runner = StepRunner(torch, ab, dev, rank, world, K + W, mb, dp_mode=args.dp)
+    runner = StepRunner(torch, ab, dev, rank, world, K + W, mb, dp_mode=args.dp, graph=args.graph)
 
     def barrier():
         if world > 1:
@@ -417,6 +428,8 @@ def run_gpu_arm(args):
         torch.cuda.synchronize()
 
     def timed(host_data, with_kernel_timing):
+        # the per-kernel CUDA-event pass needs eager launches; everything else replays the CUDA graph when --graph is given
+        runner.diff = runner.diff_eager if (with_kernel_timing or not runner.graph) else runner.diff_graph
         runner.reset()
         for _ in range(W):
             runner.step(host_data)
@@ -444,9 +457,16 @@ def run_gpu_arm(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, launches, ksum = timed(False, True)
-    clocks = sampler.stop() if rank == 0 else None
+    ms_eager = None
+    if runner.graph:
+        ms_dev, _, _ = timed(False, False)                 # value: CUDA-graph replay of loss + gradients, Adam eager
+        clocks = sampler.stop() if rank == 0 else None
+        ms_eager, launches, ksum = timed(False, True)      # the same steps launched eagerly, a CUDA-event pair per kernel
+    else:
+        ms_dev, launches, ksum = timed(False, True)
+        clocks = sampler.stop() if rank == 0 else None
     ms_e2e, _, _ = timed(True, False)
+    runner.diff = runner.diff_eager
     frame_bytes = runner.frame_bytes
     dp = None
     if world > 1:
@@ -521,7 +541,11 @@ def run_gpu_arm(args):
                 'frac_with_checkpoints': (alg[dom] + ckpt_extra) / t_launch / 1e9 / peak,
                 'dram_frac': (traffic / t_launch / 1e9 / peak) if traffic else None,
                 'kernel_ms_per_step': {k: v[1] / K for k, v in sorted(ksum.items())},
-                'note': 'the multislice kernels are bound by the shared-memory pipe (FFT passes), not by HBM: see DESIGN.md'}
+                'note': 'the multislice kernels are bound by instruction throughput (FP32 / issue / shared-memory pipes of the '
+                        'FFT passes), not by HBM: see DESIGN.md'}
+    if ms_eager is not None:
+        roofline['kernel_timing_pass'] = ('the same %d steps launched eagerly with a CUDA-event pair around every kernel '
+                                          '(%.3f ms per step); value / e2e replay loss + gradients as one CUDA graph' % (K, ms_eager / K))
     # whole-step algorithmic bytes: B (3 p8 + d4) + 4 V8 (rotation fwd + adj) + 7 V8 (Adam)
     step_bytes = mb * (3 * p8 + d4) + 4 * V8 + 7 * V8
     roofline['step_frac'] = (step_bytes / (ms_dev / K * 1e-3) / 1e9) / peak
@@ -537,6 +561,8 @@ def run_gpu_arm(args):
             'data': 'synthetic',
             'config': {'workload': workload_name(mb), 'obj_size': [256, 256, 256], 'probe_size': [72, 72],
                        'minibatch_size': mb, 'n_slices': 256,
+                       'execution': ('loss + gradients of a step replayed as ONE CUDA graph (adorym_b200.graph), optimizer '
+                                     'update eager' if args.graph else 'eager launches'),
                        'parallelism': 'dp%d (angles sharded; object gradient summed over ranks %s)'
                                       % (world, 'by the fused NVLink peer-memory update kernel' if (world > 1 and args.dp == 'p2p')
                                          else 'with an NCCL all-reduce'),
@@ -602,6 +628,8 @@ def main():
                          'pipelined for the fused peer-memory update -- measured faster, DESIGN.md section 6 -- and 2 for NCCL)')
     ap.add_argument('--config', nargs='*', default=None, choices=['A', 'B', 'C', 'E'],
                     help='secondary lines for the other named shapes (default: the contract line on config D)')
+    ap.add_argument('--graph', action='store_true',
+                    help='replay loss + gradients of a step as one CUDA graph (adorym_b200.graph) in the value and e2e legs')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-reference-schedule', action='store_true')
     args = ap.parse_args()
