@@ -17,9 +17,10 @@ def compact_grad(g, seed=0):
 
 
 def rel_err(a, b):
-    a = np.asarray(a, dtype='float64')
-    b = np.asarray(b, dtype='float64')
-    return float(np.sqrt(((a - b) ** 2).sum()) / (np.sqrt((b ** 2).sum()) + 1e-300))
+    dt = 'complex128' if (np.iscomplexobj(a) or np.iscomplexobj(b)) else 'float64'
+    a = np.asarray(a, dtype=dt)
+    b = np.asarray(b, dtype=dt)
+    return float(np.sqrt((np.abs(a - b) ** 2).sum()) / (np.sqrt((np.abs(b) ** 2).sum()) + 1e-300))
 
 
 def case_cfg(name):

@@ -224,3 +224,85 @@ def test_emulated_affine_resample_matches_oracle(shape, C, roles):
         assert rel_err(g_in, ga.numpy()) < 1e-5
         got = g_m.reshape(N, 2, 3) if per_plane else g_m.sum(0).reshape(1, 2, 3)
         assert rel_err(got, gm.numpy()) < 1e-4
+
+
+def test_emulated_large_probe_patch_step_and_far_field():
+    """large_frame.cu patch kernels (probes of 128 pixels: adm_lf_patch_step_fwd / _bwd, adm_lf_farfield_fwd / _bwd,
+    adm_frame_shift_complex_fwd) against numpy FFTs: value of one slice step for two overhanging patches, its adjoint
+    (dL/d psi and the scatter-added dL/dT) by the definition <A x, y> = <x, A^H y>, the far-field transform and its
+    adjoint, and the complex Fourier shift (util.py:380-397)."""
+    L = emu_lib.emu()
+    P = emu_lib.P
+    ck = emu_lib.ck
+    rs = np.random.RandomState(9)
+    N, B, M, Y, X, Nz = 128, 2, 1, 150, 141, 2
+    Xp = (X + 1) & ~1
+    F = B * M
+    tvol = np.zeros((Nz, Y, Xp, 2), 'float32')
+    tvol[:, :, :X] = 0.2 * rs.normal(size=(Nz, Y, X, 2))
+    pos = np.array([[-20, 30], [40, -9]], 'int32')
+    psi = rs.normal(size=(F, N, N, 2)).astype('float32')
+    order = np.zeros(N, 'int32')
+    ck(L.adm_lf_spectrum_order(N, P(order)))
+    H = np.exp(1j * rs.uniform(0, 2 * np.pi, size=(N, N)))
+    hp = H[np.ix_(order, order)] / (N * N)
+    Hp = np.ascontiguousarray(np.stack([hp.real, hp.imag], -1), dtype='float32')
+    Hc = np.ascontiguousarray(Hp * np.array([1, -1], 'float32'))
+    z = 1
+    c = lambda a: a[..., 0].astype('float64') + 1j * a[..., 1]
+
+    def patch(b):
+        t = np.zeros((N, N), 'complex128')
+        for yy in range(N):
+            gy = pos[b, 0] + yy
+            if 0 <= gy < Y:
+                x0, x1 = max(0, -pos[b, 1]), min(N, X - pos[b, 1])
+                t[yy, x0:x1] = c(tvol[z, gy, pos[b, 1] + x0:pos[b, 1] + x1])
+        return t
+
+    work = np.full((F, N, N, 2), np.nan, 'float32')
+    out = np.full((F, N, N, 2), np.nan, 'float32')
+    ck(L.adm_lf_patch_step_fwd(N, B, M, Y, X, z, P(tvol), P(pos), P(psi), P(Hp), P(work), P(out), None))
+    ref = np.stack([np.fft.ifft2(H * np.fft.fft2(c(psi[b]) * (1 + patch(b)))) for b in range(F)])
+    assert rel_err(c(out), ref) < 1e-5
+    # modulation only (last slice)
+    out0 = np.full((F, N, N, 2), np.nan, 'float32')
+    ck(L.adm_lf_patch_step_fwd(N, B, M, Y, X, z, P(tvol), P(pos), P(psi), None, None, P(out0), None))
+    assert rel_err(c(out0), np.stack([c(psi[b]) * (1 + patch(b)) for b in range(F)])) < 1e-6
+    # adjoint: dL/d psi and dL/dT for L = Re <g, out>
+    g = rs.normal(size=(F, N, N, 2)).astype('float32')
+    w1 = np.full((F, N, N, 2), np.nan, 'float32')
+    w2 = np.full((F, N, N, 2), np.nan, 'float32')
+    g_psi = np.full((F, N, N, 2), np.nan, 'float32')
+    g_tvol = np.zeros((Nz, Y, Xp, 2), 'float32')
+    ck(L.adm_lf_patch_step_bwd(N, B, M, Y, X, z, P(tvol), P(pos), P(psi), P(Hc), P(g), P(w1), P(w2), P(g_psi), P(g_tvol), 0, None))
+    gm = np.stack([np.fft.ifft2(np.conj(H) * np.fft.fft2(c(g[b]))) for b in range(F)])          # gradient behind the modulation
+    ref_gpsi = np.stack([gm[b] * np.conj(1 + patch(b)) for b in range(F)])
+    assert rel_err(c(g_psi), ref_gpsi) < 1e-5
+    ref_gt = np.zeros((Nz, Y, Xp), 'complex128')
+    for b in range(F):
+        gt = gm[b] * np.conj(c(psi[b]))
+        for yy in range(N):
+            gy = pos[b, 0] + yy
+            if 0 <= gy < Y:
+                x0, x1 = max(0, -pos[b, 1]), min(N, X - pos[b, 1])
+                ref_gt[z, gy, pos[b, 1] + x0:pos[b, 1] + x1] += gt[yy, x0:x1]
+    assert rel_err(c(g_tvol), ref_gt) < 1e-5
+    # far field and its adjoint
+    od = np.ascontiguousarray(order)
+    ff = np.full((F, N, N, 2), np.nan, 'float32')
+    ck(L.adm_lf_farfield_fwd(N, F, P(psi), P(od), 0.5, P(work), P(ff), None))
+    assert rel_err(c(ff), 0.5 * np.fft.fftshift(np.fft.fft2(c(psi)), axes=(1, 2))) < 1e-5
+    gi = np.full((F, N, N, 2), np.nan, 'float32')
+    ck(L.adm_lf_farfield_bwd(N, F, P(g), P(od), 0.5, P(work), P(gi), None))
+    lhs = np.vdot(c(g), 0.5 * np.fft.fftshift(np.fft.fft2(c(psi)), axes=(1, 2)))         # <g, A psi>
+    rhs = np.vdot(c(gi), c(psi))                                                          # <A^H g, psi>
+    assert abs(lhs - rhs) <= 1e-5 * abs(lhs)
+    # complex Fourier shift
+    sh = np.array([[0.6, -1.3], [-2.2, 0.4]], 'float32')
+    spec = np.full((F, N, N, 2), np.nan, 'float32')
+    so = np.full((F, N, N, 2), np.nan, 'float32')
+    ck(L.adm_frame_shift_complex_fwd(N, F, P(psi), P(sh), P(od), P(work), P(spec), P(so), None))
+    fy, fx = np.meshgrid(np.fft.fftfreq(N), np.fft.fftfreq(N), indexing='ij')
+    ref_s = np.stack([np.fft.ifft2(np.fft.fft2(c(psi[b])) * np.exp(-2j * orc.PI * (fx * sh[b, 1] + fy * sh[b, 0]))) for b in range(F)])
+    assert rel_err(c(so), ref_s) < 1e-5
