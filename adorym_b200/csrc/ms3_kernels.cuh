@@ -1,0 +1,493 @@
+// Three-pass multislice kernels for 72-pixel probes and a separable (paraxial) transfer function  (sm_100a).
+// Included by multislice.cu (after MsSmem / the balanced-schedule helpers); same C ABI, same checkpoint / tile /
+// hand-off formats as the five-pass kernels there, which remain the path for P = 64, general H, near-field detection
+// and the adjoint-wavefield checkpoints.
+//
+// Why: the five-pass kernels sit on the shared-memory pipe (ncu r02y: l1tex 74 %, ~4.8 k wavefronts per slice, of which
+// 5 x 648 are the five round trips of the wavefield).  Here 72 = 3 x 24 per axis (Cooley-Tukey, twiddle W72^(r k1) between
+// the stages):  n = 24 j + r  (j = 0..2, r = 0..23);  stage A = radix 3 over j, stage B = radix 24 over r (in registers as
+// a twiddle-free 3 x 8 prime-factor transform).  The radix-3 stages of BOTH axes, their inverses and the point-wise
+// slice modulation act on the same 3 x 3 points {(24 jy + ry, 24 jx + rx)}, so a slice is THREE round trips:
+//
+//   M   [Ax^-1 Ay^-1 . checkpoint . psi (1 + T') . Ay Ax]     one thread per (ry, rx): 9 values, 576 blocks
+//   By  [By . hy . By^-1]                                      one thread per (k1y, column): 24 values, 216 groups
+//   Bx  [Bx . hx . Bx^-1]                                      one thread per (k1x, row):    24 values, 216 groups
+//
+// and three CTA barriers.  The register blocks stay small (9 / 24 values; 216 threads as before, every thread busy in
+// the B passes), the butterfly count rises by ~13 % (twiddles, radix 24 instead of 8 + 9), the shared-memory
+// wavefronts fall by ~30 %.
+//
+// Index conventions along one axis: after stage A the value (k1, r) sits at position 24 k1 + r; after the forward
+// 24-point transform register slot s of group k1 holds the frequency k1 + 3 f24(s); the transfer-function tables are
+// laid out in that order (ms3_hs_fill), and the inverse transform takes slot order back to natural order, so no reorder
+// pass exists.  Overall scale 1/72^2 is carried by the hx table (adm_prepare_transfer_function_separable).
+//
+// Reference behaviour: adorym/propagate.py:208-280 (slice loop, detector transform), as multislice.cu.
+#pragma once
+
+struct Ms3 {
+    static constexpr int P = 72, S = 73, NACT = 216, NTHREADS = 224, NB = 576, TP = 74;
+    static constexpr size_t TILE = sizeof(cpx) * P * TP;
+    static constexpr size_t PSI = sizeof(cpx) * P * S;
+    static constexpr size_t HS = sizeof(cpx) * 2 * P;
+    static constexpr size_t BYTES = TILE + PSI + HS + 16;
+};
+
+// frequency (mod 24) held by register slot s after the forward 24-point prime-factor transform
+ADM_HDM constexpr int ms3_f24(int s) { return (16 * ((2 * s) % 3) + 9 * ((3 * s) % 8)) % 24; }
+
+// 24-point DFT in registers: Good-Thomas 3 x 8, n = (8 a + 3 b) mod 24, k = (16 ka + 9 kb) mod 24, slot (8 ka + 3 kb) mod 24.
+// INV = false: natural order in, slot order out.  INV = true: slot order in, natural order out (conjugate, unnormalised).
+template <bool INV, class T> ADM_DEV void ms3_dft24(T* u) {
+    if constexpr (!INV) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) dft3<false>(u[(3 * b) % 24], u[(8 + 3 * b) % 24], u[(16 + 3 * b) % 24]);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        T v[8];
+#pragma unroll
+        for (int b = 0; b < 8; ++b) v[b] = u[(8 * a + 3 * b) % 24];
+        dft8<INV>(v);
+#pragma unroll
+        for (int b = 0; b < 8; ++b) u[(8 * a + 3 * b) % 24] = v[b];
+    }
+    if constexpr (INV) {
+#pragma unroll
+        for (int b = 0; b < 8; ++b) dft3<true>(u[(3 * b) % 24], u[(8 + 3 * b) % 24], u[(16 + 3 * b) % 24]);
+    }
+}
+
+// W72^n = exp(-2 pi i n / 72)
+template <class T> ADM_DEV T ms3_w72(int n) {
+#ifndef ADM_HOST_EMU
+    float s, c;
+    sincospif((float)n / 36.0f, &s, &c);
+    return tmk<T>(c, -s);
+#else
+    double a = 2.0 * 3.14159265358979323846 * n / 72.0;
+    return tmk<T>((float)cos(a), (float)-sin(a));
+#endif
+}
+
+// transfer-function tables in slot order: hs[dir][k1][s] = h_dir[k1 + 3 f24(s)].  Hsep = [hy | hx] in the permuted order of
+// the five-pass kernels (adm_prepare_transfer_function_separable: entry p holds frequency perm_freq<Cfg72>(p)); the
+// position of frequency f in that order is (9 (f % 8) + 64 ((9 - f % 9) % 9)) % 72.
+template <class T> ADM_DEV void ms3_hs_fill(T* hs, const T* Hsep, int t) {
+    if (t < 2 * Ms3::P) {
+        const int dir = t / Ms3::P, i = t % Ms3::P;
+        const int f = i / 24 + 3 * ms3_f24(i % 24);
+        const int p = (9 * (f % 8) + 64 * ((9 - f % 9) % 9)) % 72;
+        hs[t] = Hsep[dir * Ms3::P + p];
+    }
+}
+
+// radix-3 stages of both axes on a 3 x 3 block w[jy][jx] (+ the twiddles W72^(ry k1y) W72^(rx k1x)); wy / wx = {W^r, W^2r}
+template <bool INV, class T> ADM_DEV void ms3_A(T (&w)[3][3], const T* wy, const T* wx) {
+    if constexpr (INV) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            w[1][j] = cmulc(w[1][j], wy[0]);
+            w[2][j] = cmulc(w[2][j], wy[1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            w[j][1] = cmulc(w[j][1], wx[0]);
+            w[j][2] = cmulc(w[j][2], wx[1]);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dft3<INV>(w[j][0], w[j][1], w[j][2]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) dft3<INV>(w[0][j], w[1][j], w[2][j]);
+    if constexpr (!INV) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            w[1][j] = cmul(w[1][j], wy[0]);
+            w[2][j] = cmul(w[2][j], wy[1]);
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            w[j][1] = cmul(w[j][1], wx[0]);
+            w[j][2] = cmul(w[j][2], wx[1]);
+        }
+    }
+}
+
+// per-thread constants of the M pass: thread t owns the blocks (ry0 + 9 k, rx), k = 0..2 (k = 2 only for t < 144)
+template <class T> struct Ms3Thread {
+    int ry0, rx;
+    T wy[3][2], wx[2];
+};
+template <class T> ADM_DEV void ms3_thread_init(Ms3Thread<T>& I, int t) {
+    I.ry0 = t / 24; I.rx = t % 24;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        I.wy[k][0] = ms3_w72<T>(I.ry0 + 9 * k);
+        I.wy[k][1] = ms3_w72<T>(2 * (I.ry0 + 9 * k));
+    }
+    I.wx[0] = ms3_w72<T>(I.rx);
+    I.wx[1] = ms3_w72<T>(2 * I.rx);
+}
+
+// B pass along y (YDIR, lanes along x: l = column) or along x (lanes along y: l = row) for group q = k1.
+// MODE 0: forward . h . inverse;  1: forward only (slot order left in place);  2: inverse only (slot order in).
+template <bool YDIR, int MODE, class T> ADM_DEV void ms3_B(T* psi, const T* hsd, int q, int l) {
+    constexpr int S = Ms3::S;
+    T* base = psi + (YDIR ? 24 * q * S + l : l * S + 24 * q);
+    constexpr int st = YDIR ? S : 1;
+    T u[24];
+#pragma unroll
+    for (int r = 0; r < 24; ++r) u[r] = base[r * st];
+    if constexpr (MODE != 2) ms3_dft24<false>(u);
+    if constexpr (MODE == 0) {
+        const T* hq = hsd + 24 * q;
+#pragma unroll
+        for (int s = 0; s < 24; s += 2) {
+            T ha, hb;
+            lds_pair(hq + s, ha, hb);
+            u[s] = cmul(u[s], ha);
+            u[s + 1] = cmul(u[s + 1], hb);
+        }
+    }
+    if constexpr (MODE != 1) ms3_dft24<true>(u);
+#pragma unroll
+    for (int r = 0; r < 24; ++r) base[r * st] = u[r];
+}
+
+// ================================================================================================
+// Forward
+// ================================================================================================
+template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+    ADM_SMEM_DECL
+    constexpr int P = Ms3::P, S = Ms3::S, TP = Ms3::TP;
+    constexpr unsigned TILE_BYTES = (unsigned)Ms3::TILE;
+    T* tile = (T*)smem_raw;
+    T* psi = tile + P * TP;
+    T* hs = psi + P * S;
+    adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
+    const int t = threadIdx.x;
+    const bool active = t < Ms3::NACT;
+    const int q = t / P, l = t % P;
+    Ms3Thread<T> I;
+    ms3_thread_init(I, t);
+    const int c = blockIdx.x;
+
+    ms3_hs_fill(hs, (const T*)p.Hp, t);
+    if (t == 0) mbar_init(bar, 1);
+    unsigned ph = 0;
+
+    int wf_first, wf_last;
+    long long s0, s1;
+    ms_nseg(p, c, wf_first, wf_last, s0, s1);
+    for (int wfi = wf_last; wfi >= wf_first; --wfi) {
+        const MsSeg sg = ms_seg(p, wfi, s0, s1);
+        const int wf = sg.wf;
+        const int b = wf / p.M, m = wf % p.M;
+        const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
+        const int pxa = px & ~1, xo = I.rx + (px & 1);      // even TMA start column, this thread's first column inside the tile
+        const T* probe = (const T*)p.probe + (size_t)(p.probe_per_pattern ? wf : m) * P * P;
+        T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * P * TP;
+        T* det = (T*)p.det + (size_t)wf * P * P;
+
+        __syncthreads();                    // the previous segment is done with the tile and the wavefield
+        if (t == 0) {
+            mbar_expect_tx(bar, TILE_BYTES);
+            tma_load_tile(tile, &tmap, 2 * pxa, py, sg.zb, bar);
+        }
+        if (sg.zb > 0) {                    // late part of a cut chain: the wavefield comes from CTA c - 1
+            if (t == 0) flag_wait_and_clear(p.flags + c);
+            __syncthreads();
+            for (int i = t; i < (int)(Ms3::PSI / 16); i += Ms3::NTHREADS) {
+#ifndef ADM_HOST_EMU
+                ((float4*)psi)[i] = __ldcg(p.handoff + (size_t)c * p.slot_f4 + i);
+#else
+                ((float4*)psi)[i] = p.handoff[(size_t)c * p.slot_f4 + i];
+#endif
+            }
+            __syncthreads();
+        }
+
+        for (int z = sg.zb; z < sg.ze; ++z) {
+            const bool last = (z == p.Nz - 1);
+            const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
+            // per-gap transfer functions (sparse multislice): the previous slice's last reader (its Bx pass) is one barrier
+            // back, the first reader (By) comes after the barrier that closes M
+            if (!last && p.h_per_slice) ms3_hs_fill(hs, (const T*)p.Hp + (size_t)z * 2 * P, t);
+            // ---- M: [Ax^-1 Ay^-1] . checkpoint . modulation . [Ay Ax] ------------------------------------------
+            if (active) {
+                mbar_wait(bar, ph);
+                T* ck = ckpt + (size_t)z * P * TP;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k == 2 && t >= Ms3::NB - 2 * Ms3::NACT) break;
+                    const int ry = I.ry0 + 9 * k;
+                    T w[3][3];
+                    if (z == 0) {
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = probe[(24 * jy + ry) * P + 24 * jx + I.rx];
+                    } else {
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = psi[(24 * jy + ry) * S + 24 * jx + I.rx];
+                        ms3_A<true>(w, I.wy[k], I.wx);
+                    }
+#pragma unroll
+                    for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                        for (int jx = 0; jx < 3; ++jx) {
+                            const int o = (24 * jy + ry) * TP + 24 * jx + xo;
+                            ck[o] = w[jy][jx];
+                            w[jy][jx] = modulate(w[jy][jx], tile[o]);
+                        }
+                    if (go_on) {
+                        if (last && p.ff_conj) {
+#pragma unroll
+                            for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                                for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cconj(w[jy][jx]);
+                        }
+                        ms3_A<false>(w, I.wy[k], I.wx);
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
+                    } else {
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) det[(24 * jy + ry) * P + 24 * jx + I.rx] = w[jy][jx];   // exit wave
+                    }
+                }
+            }
+            ph ^= 1;
+            __syncthreads();
+            if (t == 0 && z + 1 < sg.ze) {   // every thread has consumed tile(z): prefetch tile(z+1) behind the B passes
+                mbar_expect_tx(bar, TILE_BYTES);
+                tma_load_tile(tile, &tmap, 2 * pxa, py, z + 1, bar);
+            }
+            if (!go_on) break;
+            if (last) {
+                // far field: finish the forward 2-D transform and store fftshift-ed, natural order
+                if (active) ms3_B<true, 1>(psi, hs, q, l);
+                __syncthreads();
+                if (active) {
+                    T u[24];
+#pragma unroll
+                    for (int r = 0; r < 24; ++r) u[r] = psi[l * S + 24 * q + r];
+                    ms3_dft24<false>(u);
+                    const int fy = (l / 24 + 3 * ms3_f24(l % 24) + P / 2) % P;
+#pragma unroll
+                    for (int s = 0; s < 24; ++s) {
+                        const int fx = (q + 3 * ms3_f24(s) + P / 2) % P;
+                        T o = cscale(u[s], p.ff_scale);
+                        det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
+                    }
+                }
+                break;
+            }
+            if (active) ms3_B<true, 0>(psi, hs, q, l);
+            __syncthreads();
+            if (active) ms3_B<false, 0>(psi, hs + P, q, l);
+            __syncthreads();
+        }
+        if (sg.ze < p.Nz) {                 // early part of a cut chain: hand the wavefield to CTA c + 1
+            float4* dst = p.handoff + (size_t)(c + 1) * p.slot_f4;
+            for (int i = t; i < (int)(Ms3::PSI / 16); i += Ms3::NTHREADS) dst[i] = ((const float4*)psi)[i];
+#ifndef ADM_HOST_EMU
+            __threadfence();
+#endif
+            __syncthreads();
+            if (t == 0) flag_set(p.flags + c + 1);
+        }
+    }
+}
+
+// ================================================================================================
+// Adjoint
+// ================================================================================================
+template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
+    ADM_SMEM_DECL
+    constexpr int P = Ms3::P, S = Ms3::S, TP = Ms3::TP;
+    constexpr unsigned TILE_BYTES = (unsigned)Ms3::TILE;
+    T* ckb = (T*)smem_raw;          // psi checkpoint of the slice (bulk copy); overwritten in place by dL/dT
+    T* psi = ckb + P * TP;          // running adjoint wavefield
+    T* hs = psi + P * S;
+    adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
+    const int t = threadIdx.x;
+    const bool active = t < Ms3::NACT;
+    const bool third = t < Ms3::NB - 2 * Ms3::NACT;      // this thread owns a third block
+    const int q = t / P, l = t % P;
+    Ms3Thread<T> I;
+    ms3_thread_init(I, t);
+    const int c = gridDim.x - 1 - blockIdx.x;
+
+    ms3_hs_fill(hs, (const T*)p.Hp, t);
+    if (t == 0) mbar_init(bar, 1);
+    unsigned phase = 0;
+
+    int wf_first, wf_last;
+    long long s0, s1;
+    ms_nseg(p, c, wf_first, wf_last, s0, s1);
+    for (int wfi = wf_first; wfi <= wf_last; ++wfi) {
+        const MsSeg sg = ms_seg(p, wfi, s0, s1);
+        const int wf = sg.wf;
+        const int b = wf / p.M, m = wf % p.M;
+        const int py = p.pos[2 * b], px = p.pos[2 * b + 1];
+        const int pxa = px & ~1, xo = I.rx + (px & 1);
+        const T* ckpt = (T*)p.ckpt + (size_t)wf * p.Nz * P * TP;
+        const T* gdet = (const T*)p.det + (size_t)wf * P * P;
+        const size_t slice_stride = (size_t)p.Y * p.Xp;
+        // T' of one slice for this thread's blocks: plain loads of the L2-resident volume, ISSUED one barrier early (behind
+        // the last pass of the previous slice) so that their latency overlaps the barrier wait
+        T tpa[3][3][3];
+        auto load_tp = [&](int zz) {
+            const T* tzz = (const T*)p.tvol + (size_t)zz * slice_stride;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (k == 2 && !third) break;
+#pragma unroll
+                for (int jy = 0; jy < 3; ++jy) {
+                    const int gy = py + 24 * jy + I.ry0 + 9 * k;
+#pragma unroll
+                    for (int jx = 0; jx < 3; ++jx) {
+                        const int gx = px + 24 * jx + I.rx;
+                        const bool inb = (unsigned)gy < (unsigned)p.Y && (unsigned)gx < (unsigned)p.X;
+                        tpa[k][jy][jx] = inb ? tzz[(unsigned)(gy * p.Xp + gx)] : tmk<T>(0.f, 0.f);
+                    }
+                }
+            }
+        };
+        if (active) load_tp(sg.ze - 1);
+
+        __syncthreads();                    // the previous segment is done with the wavefield
+        if (t == 0) {
+            bulk_wait_read_all();           // ... and its last reduce has drained the tile
+            mbar_expect_tx(bar, TILE_BYTES);
+            bulk_load(ckb, ckpt + (size_t)(sg.ze - 1) * P * TP, TILE_BYTES, bar);
+        }
+
+        if (sg.ze < p.Nz) {
+            if (t == 0) flag_wait_and_clear(p.flags + c + 1);
+            __syncthreads();
+            for (int i = t; i < (int)(Ms3::PSI / 16); i += Ms3::NTHREADS) {
+#ifndef ADM_HOST_EMU
+                ((float4*)psi)[i] = __ldcg(p.handoff + (size_t)(c + 1) * p.slot_f4 + i);
+#else
+                ((float4*)psi)[i] = p.handoff[(size_t)(c + 1) * p.slot_f4 + i];
+#endif
+            }
+            __syncthreads();
+        } else if (p.free_prop == ADM_PROP_FAR) {
+            // adjoint of the detector transform: slot order in, inverse B along x, inverse B along y
+            if (active) {
+                T u[24];
+                const int fy = (l / 24 + 3 * ms3_f24(l % 24) + P / 2) % P;
+#pragma unroll
+                for (int s = 0; s < 24; ++s) {
+                    const int fx = (q + 3 * ms3_f24(s) + P / 2) % P;
+                    T o = cscale(gdet[fy * P + fx], p.ff_scale);
+                    u[s] = p.ff_conj ? cconj(o) : o;
+                }
+                ms3_dft24<true>(u);
+#pragma unroll
+                for (int r = 0; r < 24; ++r) psi[l * S + 24 * q + r] = u[r];
+            }
+            __syncthreads();
+            if (active) ms3_B<true, 2>(psi, hs, q, l);
+            __syncthreads();
+        }
+
+        for (int z = sg.ze - 1; z >= sg.zb; --z, phase ^= 1) {
+            const bool last = (z == p.Nz - 1);
+            if (z > 0 && p.h_per_slice) ms3_hs_fill(hs, (const T*)p.Hp + (size_t)(z - 1) * 2 * P, t);
+            // ---- M': [Ax^-1 Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay Ax] ----------------------
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    if (k == 2 && !third) break;
+                    const int ry = I.ry0 + 9 * k;
+                    T w[3][3];
+                    if (last && p.free_prop == ADM_PROP_NONE) {
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = gdet[(24 * jy + ry) * P + 24 * jx + I.rx];
+                    } else {
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = psi[(24 * jy + ry) * S + 24 * jx + I.rx];
+                        ms3_A<true>(w, I.wy[k], I.wx);
+                        if (last && p.ff_conj) {
+#pragma unroll
+                            for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                                for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cconj(w[jy][jx]);
+                        }
+                    }
+                    if (k == 0) {
+                        mbar_wait(bar, phase);
+                        // the two pad columns of the tile are never written by the forward pass: add zeros there
+                        if (t < 2 * P) ckb[(t >> 1) * TP + ((t & 1) ? P + 1 : ((px & 1) ? 0 : P))] = tmk<T>(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                        for (int jx = 0; jx < 3; ++jx) {
+                            const int o = (24 * jy + ry) * TP + 24 * jx + xo;
+                            const T wz = ckb[o];                            // psi_z (wave entering the slice)
+                            ckb[o] = cmulc(w[jy][jx], wz);                  // dL/dT = g' conj(psi_z)
+                            w[jy][jx] = modulate_conj(w[jy][jx], tpa[k][jy][jx]);
+                        }
+                    if (z > 0) {
+                        ms3_A<false>(w, I.wy[k], I.wx);
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
+                    } else if (p.g_probe != nullptr) {
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) {
+                                const int o = (24 * jy + ry) * P + 24 * jx + I.rx;
+                                if (p.probe_per_pattern) ((T*)p.g_probe)[(size_t)wf * P * P + o] = w[jy][jx];
+                                else red_add2(&p.g_probe[(size_t)m * P * P + o], cx(w[jy][jx]), cy(w[jy][jx]));
+                            }
+                    }
+                }
+                fence_proxy_async();      // the dL/dT tile is about to be read by the TMA unit
+            }
+            __syncthreads();
+            if (t == 0 && pxa + P >= 0 && py + P >= 0) {
+                tma_reduce_add_tile(&gmap, 2 * (pxa + P), py + P, z, ckb);
+                bulk_commit();
+            }
+            if (z == 0) { phase ^= 1; break; }
+            if (active) ms3_B<true, 0>(psi, hs, q, l);
+            __syncthreads();
+            if (t == 0 && z > sg.zb) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind the x pass
+                bulk_wait_read_all();
+                mbar_expect_tx(bar, TILE_BYTES);
+                bulk_load(ckb, ckpt + (size_t)(z - 1) * P * TP, TILE_BYTES, bar);
+            }
+            if (active) ms3_B<false, 0>(psi, hs + P, q, l);
+            if (active && z > sg.zb) load_tp(z - 1);
+            __syncthreads();
+        }
+        if (sg.zb > 0) {                    // early part of a cut chain: hand the adjoint wavefield to CTA c - 1
+            float4* dst = p.handoff + (size_t)c * p.slot_f4;
+            for (int i = t; i < (int)(Ms3::PSI / 16); i += Ms3::NTHREADS) dst[i] = ((const float4*)psi)[i];
+#ifndef ADM_HOST_EMU
+            __threadfence();
+#endif
+            __syncthreads();
+            if (t == 0) flag_set(p.flags + c);
+        }
+    }
+    if (t == 0) bulk_wait_all();      // shared memory must stay valid until the last reduce has read it
+}

@@ -110,6 +110,8 @@ template <class C> ADM_DEV void handoff_load(const MsParams& p, int slot, void* 
     }
 }
 
+#include "ms3_kernels.cuh"
+
 // ================================================================================================
 // Forward
 // ================================================================================================
@@ -514,6 +516,13 @@ static int adm_variant(const char* name) {
     return e ? atoi(e) : 0;
 }
 
+// three-pass kernels (ms3_kernels.cuh) for P = 72 with a separable transfer function; ADM_MS3=0 selects the five-pass kernels
+static bool ms3_wanted(const adm_multislice_cfg* cfg, const MsParams& p) {
+    const char* e = getenv("ADM_MS3");
+    if (e && atoi(e) == 0) return false;
+    return cfg->P == 72 && p.h_separable && p.Nz > 1 && p.free_prop != ADM_PROP_NEAR;
+}
+
 // number of CTAs of `kern` that are co-resident on the device (SM count x occupancy); ADM_MS_GRID overrides it (tests)
 template <class K> static int ms_resident_ctas(K kern, int threads, size_t smem) {
     int forced = adm_variant("ADM_MS_GRID");
@@ -621,6 +630,13 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     AdmTileMap map;
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int var = adm_variant("ADM_FWD_VARIANT");
+    if (var == 0 && ms3_wanted(cfg, p)) {
+        if (set_smem(k_ms3_fwd<cpk>, Ms3::BYTES)) return ADM_ERR_CUDA;
+        int grid_;
+        if (ms_schedule(p, ms_resident_ctas(k_ms3_fwd<cpk>, Ms3::NTHREADS, Ms3::BYTES), workspace, 72, grid_)) return ADM_ERR_CUDA;
+        ADM_LAUNCH((k_ms3_fwd<cpk>), grid_, Ms3::NTHREADS, Ms3::BYTES, stream, map, p);
+        return ADM_OK;
+    }
 #define ADM_FWD(CFG, MINB, TILE, CT)                                                                                  \
     do {                                                                                                           \
         const size_t sm_ = TILE ? MsSmem<CFG>::BYTES : MsSmem<CFG>::BYTES_NOTILE;                                  \
@@ -677,6 +693,13 @@ static int ms_bwd_impl(const adm_multislice_cfg* cfg, const float* tvol, const i
                           ADM_GVOL_PITCH(p.X, cfg->P), cfg->P, cfg->P + 2))
         return ADM_ERR_CUDA;
     int var = adm_variant("ADM_BWD_VARIANT");
+    if (var == 0 && p.g_ckpt == nullptr && ms3_wanted(cfg, p)) {
+        if (set_smem(k_ms3_bwd<cpk>, Ms3::BYTES)) return ADM_ERR_CUDA;
+        int grid_;
+        if (ms_schedule(p, ms_resident_ctas(k_ms3_bwd<cpk>, Ms3::NTHREADS, Ms3::BYTES), workspace, 72, grid_)) return ADM_ERR_CUDA;
+        ADM_LAUNCH((k_ms3_bwd<cpk>), grid_, Ms3::NTHREADS, Ms3::BYTES, stream, map, p);
+        return ADM_OK;
+    }
 #define ADM_BWD(CFG, MINB, CT, GCK)                                                                                  \
     do {                                                                                                           \
         const size_t sm_ = MsSmem<CFG>::BYTES;                                                                     \
