@@ -24,6 +24,7 @@
 //
 // Reference behaviour: adorym/propagate.py:208-280 (slice loop, detector transform), as multislice.cu.
 #pragma once
+#include <type_traits>
 
 struct Ms3 {
     static constexpr int P = 72, S = 73, NACT = 216, NTHREADS = 224, NB = 576, TP = 74;
@@ -208,6 +209,27 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
             __syncthreads();
         }
 
+        if (sg.zb == 0 && active) {
+            // fresh wavefield: the probe enters the loop in the state every slice leaves behind (stage A applied along both
+            // axes, divided by the 9 that the unnormalised inverse stages return), so that the M pass has ONE code path.
+            // Every thread reads back exactly the positions it writes here: no barrier.
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (k == 2 && t >= Ms3::NB - 2 * Ms3::NACT) break;
+                const int ry = I.ry0 + 9 * k;
+                T w[3][3];
+#pragma unroll
+                for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                    for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cscale(probe[(24 * jy + ry) * P + 24 * jx + I.rx], 1.0f / 9.0f);
+                ms3_A<false>(w, I.wy[k], I.wx);
+#pragma unroll
+                for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                    for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
+            }
+        }
+
         for (int z = sg.zb; z < sg.ze; ++z) {
             const bool last = (z == p.Nz - 1);
             const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
@@ -215,6 +237,8 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
             // back, the first reader (By) comes after the barrier that closes M
             if (!last && p.h_per_slice) ms3_hs_fill(hs, (const T*)p.Hp + (size_t)z * 2 * P, t);
             // ---- M: [Ax^-1 Ay^-1] . checkpoint . modulation . [Ay Ax] ------------------------------------------
+            // (ONE code path for all slices: a second instantiation without the last-slice options measured 3.5 % slower --
+            // code size)
             if (active) {
                 mbar_wait(bar, ph);
                 T* ck = ckpt + (size_t)z * P * TP;
@@ -223,18 +247,11 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
                     if (k == 2 && t >= Ms3::NB - 2 * Ms3::NACT) break;
                     const int ry = I.ry0 + 9 * k;
                     T w[3][3];
-                    if (z == 0) {
 #pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
+                    for (int jy = 0; jy < 3; ++jy)
 #pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = probe[(24 * jy + ry) * P + 24 * jx + I.rx];
-                    } else {
-#pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
-#pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = psi[(24 * jy + ry) * S + 24 * jx + I.rx];
-                        ms3_A<true>(w, I.wy[k], I.wx);
-                    }
+                        for (int jx = 0; jx < 3; ++jx) w[jy][jx] = psi[(24 * jy + ry) * S + 24 * jx + I.rx];
+                    ms3_A<true>(w, I.wy[k], I.wx);
 #pragma unroll
                     for (int jy = 0; jy < 3; ++jy)
 #pragma unroll
@@ -243,24 +260,24 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
                             ck[o] = w[jy][jx];
                             w[jy][jx] = modulate(w[jy][jx], tile[o]);
                         }
-                    if (go_on) {
-                        if (last && p.ff_conj) {
-#pragma unroll
-                            for (int jy = 0; jy < 3; ++jy)
-#pragma unroll
-                                for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cconj(w[jy][jx]);
-                        }
-                        ms3_A<false>(w, I.wy[k], I.wx);
-#pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
-#pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
-                    } else {
+                    if (!go_on) {
 #pragma unroll
                         for (int jy = 0; jy < 3; ++jy)
 #pragma unroll
                             for (int jx = 0; jx < 3; ++jx) det[(24 * jy + ry) * P + 24 * jx + I.rx] = w[jy][jx];   // exit wave
+                        continue;
                     }
+                    if (last && p.ff_conj) {
+#pragma unroll
+                        for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cconj(w[jy][jx]);
+                    }
+                    ms3_A<false>(w, I.wy[k], I.wx);
+#pragma unroll
+                    for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                        for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
                 }
             }
             ph ^= 1;
@@ -399,35 +416,50 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
             __syncthreads();
             if (active) ms3_B<true, 2>(psi, hs, q, l);
             __syncthreads();
+        } else if (p.free_prop == ADM_PROP_NONE && active) {
+            // exit-wave detection: dL/d(exit wave) enters the loop in the state every slice leaves behind (as the probe does
+            // in the forward kernel); every thread reads back exactly the positions it writes here: no barrier
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                if (k == 2 && !third) break;
+                const int ry = I.ry0 + 9 * k;
+                T w[3][3];
+#pragma unroll
+                for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                    for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cscale(gdet[(24 * jy + ry) * P + 24 * jx + I.rx], 1.0f / 9.0f);
+                ms3_A<false>(w, I.wy[k], I.wx);
+#pragma unroll
+                for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                    for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
+            }
         }
 
         for (int z = sg.ze - 1; z >= sg.zb; --z, phase ^= 1) {
             const bool last = (z == p.Nz - 1);
             if (z > 0 && p.h_per_slice) ms3_hs_fill(hs, (const T*)p.Hp + (size_t)(z - 1) * 2 * P, t);
             // ---- M': [Ax^-1 Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay Ax] ----------------------
-            if (active) {
+            // (three instantiations: KIND 1 = last slice (detector options), 2 = slice 0 (probe gradient, nothing to
+            // propagate), 0 = every other slice, branch free; Nz > 1 on this path, so 1 and 2 never coincide.  Measured 0.5 %
+            // faster than one code path with run-time checks -- the opposite of the forward kernel)
+            auto m_pass = [&](auto kind_tag) {
+                constexpr int KIND = decltype(kind_tag)::value;
 #pragma unroll
                 for (int k = 0; k < 3; ++k) {
                     if (k == 2 && !third) break;
                     const int ry = I.ry0 + 9 * k;
                     T w[3][3];
-                    if (last && p.free_prop == ADM_PROP_NONE) {
+#pragma unroll
+                    for (int jy = 0; jy < 3; ++jy)
+#pragma unroll
+                        for (int jx = 0; jx < 3; ++jx) w[jy][jx] = psi[(24 * jy + ry) * S + 24 * jx + I.rx];
+                    ms3_A<true>(w, I.wy[k], I.wx);
+                    if (KIND == 1 && p.ff_conj) {
 #pragma unroll
                         for (int jy = 0; jy < 3; ++jy)
 #pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = gdet[(24 * jy + ry) * P + 24 * jx + I.rx];
-                    } else {
-#pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
-#pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = psi[(24 * jy + ry) * S + 24 * jx + I.rx];
-                        ms3_A<true>(w, I.wy[k], I.wx);
-                        if (last && p.ff_conj) {
-#pragma unroll
-                            for (int jy = 0; jy < 3; ++jy)
-#pragma unroll
-                                for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cconj(w[jy][jx]);
-                        }
+                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cconj(w[jy][jx]);
                     }
                     if (k == 0) {
                         mbar_wait(bar, phase);
@@ -443,7 +475,7 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
                             ckb[o] = cmulc(w[jy][jx], wz);                  // dL/dT = g' conj(psi_z)
                             w[jy][jx] = modulate_conj(w[jy][jx], tpa[k][jy][jx]);
                         }
-                    if (z > 0) {
+                    if constexpr (KIND != 2) {
                         ms3_A<false>(w, I.wy[k], I.wx);
 #pragma unroll
                         for (int jy = 0; jy < 3; ++jy)
@@ -461,6 +493,11 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
                     }
                 }
                 fence_proxy_async();      // the dL/dT tile is about to be read by the TMA unit
+            };
+            if (active) {
+                if (z == 0) m_pass(std::integral_constant<int, 2>());
+                else if (last) m_pass(std::integral_constant<int, 1>());
+                else m_pass(std::integral_constant<int, 0>());
             }
             __syncthreads();
             if (t == 0 && pxa + P >= 0 && py + P >= 0) {

@@ -88,6 +88,20 @@ def test_emulated_balanced_schedule_matches_one_cta_per_wavefield(name, grid, mo
     assert abs(out['loss'] - ref['loss']) <= 1e-6 * abs(ref['loss'])
 
 
+@pytest.mark.parametrize('name', ['ptycho3d_p72_edge', 'sparse3_p72'])
+def test_emulated_five_pass_kernels_match_three_pass_kernels(name, monkeypatch):
+    """72-pixel probes with a separable transfer function run on the three-pass kernels (ms3_kernels.cuh: 72 = 3 x 24) by
+    default, and every P = 72 case above exercises them; ADM_MS3=0 selects the five-pass kernels of multislice.cu
+    (72 = 8 x 9), which stay the path for near-field detection / general H / adjoint-wavefield checkpoints.  Two
+    independent factorizations of the same transform must agree to fp32 rounding."""
+    _, a = run_emu_case(name, separable=True)
+    monkeypatch.setenv('ADM_MS3', '0')
+    _, b = run_emu_case(name, separable=True)
+    for k in ('det', 'pred', 'g_obj', 'g_probe_real', 'g_probe_imag'):
+        assert 0 < rel_err(a[k], b[k]) < 5e-5, k      # 0 would mean that the switch selected nothing
+    assert abs(a['loss'] - b['loss']) <= 1e-5 * abs(b['loss'])
+
+
 @pytest.mark.parametrize('name', ['ptycho3d_p72_strongreg', 'fullfield64', 'ptycho2d_realimag_p64'])
 def test_emulated_fused_object_chain_matches_separate_kernels(name):
     """object_chain.cu (rotation + transmission in one pass, regulariser gradient as the initial value of the gradient
