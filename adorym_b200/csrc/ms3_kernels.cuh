@@ -26,13 +26,31 @@
 #pragma once
 #include <type_traits>
 
-struct Ms3 {
-    static constexpr int P = 72, S = 73, NACT = 216, NTHREADS = 224, NB = 576, TP = 74;
-    static constexpr size_t TILE = sizeof(cpx) * P * TP;
+// NT threads per CTA; the B passes use the first 216 of them (one 24-point group each), the M pass MT of them with MR blocks
+// each (thread t owns the blocks (t / 24 + (MT / 24) k, t % 24), k < MR, while t + MT k < 576).
+// TS_ (forward kernel only): rows of each of the three 24-row bands of the T' tile that are staged in shared memory by TMA.
+// 24 = the whole tile (one TMA load).  18 (needs MT = 216, MR = 3): the rows 24 jy + 0..17, which the block rounds 0 and 1
+// read, as three 18-row TMA loads; the rows 24 jy + 18..23 of round 2 (threads < 144) come by plain loads of the
+// L2-resident volume, issued at the top of the M pass.  That brings a CTA to 75.2 KB of shared memory: THREE CTAs per SM.
+template <int NT_, int MT_, int MR_, int TS_ = 24, int MINB_ = 2> struct Ms3Cfg {
+    static constexpr int P = 72, S = 73, NACT = 216, NTHREADS = NT_, MT = MT_, MR = MR_, RS = MT_ / 24, NB = 576, TP = 74;
+    static constexpr int TS = TS_, MINB = MINB_;
+    static_assert(TS_ == 24 || (TS_ == 18 && MT_ == 216 && MR_ == 3), "tile bands");
+    static constexpr size_t TILE = sizeof(cpx) * P * TP;                 // checkpoint / dL/dT tile (adjoint)
+    // band stride in the forward kernel's tile (complex values): TMA destinations are 128-byte aligned
+    static constexpr int BSTR = TS_ == 24 ? 24 * TP : (int)(((sizeof(cpx) * TS_ * TP + 127) / 128 * 128) / sizeof(cpx));
+    static constexpr size_t FTILE = sizeof(cpx) * 3 * BSTR;              // T' tile of the forward kernel
+    static constexpr size_t FBYTES = FTILE + sizeof(cpx) * P * S + sizeof(cpx) * 2 * P + 16;
     static constexpr size_t PSI = sizeof(cpx) * P * S;
     static constexpr size_t HS = sizeof(cpx) * 2 * P;
     static constexpr size_t BYTES = TILE + PSI + HS + 16;
+    static_assert(MT_ % 24 == 0 && MT_ * MR_ >= 576 && MT_ <= NT_ && NT_ >= 216, "M-pass blocks must be covered");
+    // block round k of thread t exists
+    ADM_HDM static constexpr bool full_round(int k) { return MT_ * (k + 1) <= 576; }
 };
+typedef Ms3Cfg<224, 216, 3> Ms3;      // default: 7 warps
+typedef Ms3Cfg<288, 288, 2> Ms3w;     // 9 warps, M pass in two balanced rounds (96 registers)
+typedef Ms3Cfg<224, 216, 3, 18, 3> Ms3t;   // forward: banded T' tile, three CTAs per SM (80 registers)
 
 // frequency (mod 24) held by register slot s after the forward 24-point prime-factor transform
 ADM_HDM constexpr int ms3_f24(int s) { return (16 * ((2 * s) % 3) + 9 * ((3 * s) % 8)) % 24; }
@@ -115,17 +133,17 @@ template <bool INV, class T> ADM_DEV void ms3_A(T (&w)[3][3], const T* wy, const
     }
 }
 
-// per-thread constants of the M pass: thread t owns the blocks (ry0 + 9 k, rx), k = 0..2 (k = 2 only for t < 144)
-template <class T> struct Ms3Thread {
+// per-thread constants of the M pass: thread t owns the blocks (ry0 + RS k, rx), k < MR
+template <class T, class C> struct Ms3Thread {
     int ry0, rx;
-    T wy[3][2], wx[2];
+    T wy[C::MR][2], wx[2];
 };
-template <class T> ADM_DEV void ms3_thread_init(Ms3Thread<T>& I, int t) {
-    I.ry0 = t / 24; I.rx = t % 24;
+template <class T, class C> ADM_DEV void ms3_thread_init(Ms3Thread<T, C>& I, int t) {
+    I.ry0 = (t / 24) % 24; I.rx = t % 24;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        I.wy[k][0] = ms3_w72<T>(I.ry0 + 9 * k);
-        I.wy[k][1] = ms3_w72<T>(2 * (I.ry0 + 9 * k));
+    for (int k = 0; k < C::MR; ++k) {
+        I.wy[k][0] = ms3_w72<T>((I.ry0 + C::RS * k) % 24);
+        I.wy[k][1] = ms3_w72<T>(2 * ((I.ry0 + C::RS * k) % 24));
     }
     I.wx[0] = ms3_w72<T>(I.rx);
     I.wx[1] = ms3_w72<T>(2 * I.rx);
@@ -159,19 +177,22 @@ template <bool YDIR, int MODE, class T> ADM_DEV void ms3_B(T* psi, const T* hsd,
 // ================================================================================================
 // Forward
 // ================================================================================================
-template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MINB) k_ms3_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
-    constexpr int P = Ms3::P, S = Ms3::S, TP = Ms3::TP;
-    constexpr unsigned TILE_BYTES = (unsigned)Ms3::TILE;
+    constexpr int P = C::P, S = C::S, TP = C::TP;
+    constexpr int TS = C::TS;
+    constexpr bool BANDS = TS != 24;
+    constexpr unsigned TILE_BYTES = (unsigned)(sizeof(cpx) * 3 * TS * TP);      // bytes the TMA loads of one slice deliver
     T* tile = (T*)smem_raw;
-    T* psi = tile + P * TP;
+    T* psi = tile + 3 * C::BSTR;
     T* hs = psi + P * S;
     adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
     const int t = threadIdx.x;
-    const bool active = t < Ms3::NACT;
+    const bool active = t < C::NACT;          // B passes
+    const bool mactive = t < C::MT;           // M pass
     const int q = t / P, l = t % P;
-    Ms3Thread<T> I;
-    ms3_thread_init(I, t);
+    Ms3Thread<T, C> I;
+    ms3_thread_init<T, C>(I, t);
     const int c = blockIdx.x;
 
     ms3_hs_fill(hs, (const T*)p.Hp, t);
@@ -192,14 +213,19 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
         T* det = (T*)p.det + (size_t)wf * P * P;
 
         __syncthreads();                    // the previous segment is done with the tile and the wavefield
-        if (t == 0) {
+        auto issue_tile = [&](int zz) {      // one elected thread
             mbar_expect_tx(bar, TILE_BYTES);
-            tma_load_tile(tile, &tmap, 2 * pxa, py, sg.zb, bar);
-        }
+            if constexpr (!BANDS) tma_load_tile(tile, &tmap, 2 * pxa, py, zz, bar);
+            else {
+#pragma unroll
+                for (int jy = 0; jy < 3; ++jy) tma_load_tile(tile + jy * C::BSTR, &tmap, 2 * pxa, py + 24 * jy, zz, bar, jy == 2);
+            }
+        };
+        if (t == 0) issue_tile(sg.zb);
         if (sg.zb > 0) {                    // late part of a cut chain: the wavefield comes from CTA c - 1
             if (t == 0) flag_wait_and_clear(p.flags + c);
             __syncthreads();
-            for (int i = t; i < (int)(Ms3::PSI / 16); i += Ms3::NTHREADS) {
+            for (int i = t; i < (int)(C::PSI / 16); i += C::NTHREADS) {
 #ifndef ADM_HOST_EMU
                 ((float4*)psi)[i] = __ldcg(p.handoff + (size_t)c * p.slot_f4 + i);
 #else
@@ -209,14 +235,14 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
             __syncthreads();
         }
 
-        if (sg.zb == 0 && active) {
+        if (sg.zb == 0 && mactive) {
             // fresh wavefield: the probe enters the loop in the state every slice leaves behind (stage A applied along both
             // axes, divided by the 9 that the unnormalised inverse stages return), so that the M pass has ONE code path.
             // Every thread reads back exactly the positions it writes here: no barrier.
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (k == 2 && t >= Ms3::NB - 2 * Ms3::NACT) break;
-                const int ry = I.ry0 + 9 * k;
+            for (int k = 0; k < C::MR; ++k) {
+                if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
+                const int ry = I.ry0 + C::RS * k;
                 T w[3][3];
 #pragma unroll
                 for (int jy = 0; jy < 3; ++jy)
@@ -239,13 +265,27 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
             // ---- M: [Ax^-1 Ay^-1] . checkpoint . modulation . [Ay Ax] ------------------------------------------
             // (ONE code path for all slices: a second instantiation without the last-slice options measured 3.5 % slower --
             // code size)
-            if (active) {
+            if (mactive) {
+                T tp2[3][3];           // banded tile: T' of this thread's round-2 block, by plain loads (vacuum outside the object)
+                if (BANDS && t + 2 * C::MT < C::NB) {
+                    const T* tz = (const T*)p.tvol + (size_t)z * p.Y * p.Xp;
+#pragma unroll
+                    for (int jy = 0; jy < 3; ++jy) {
+                        const int gy = py + 24 * jy + I.ry0 + 2 * C::RS;
+#pragma unroll
+                        for (int jx = 0; jx < 3; ++jx) {
+                            const int gx = px + 24 * jx + I.rx;
+                            const bool inb = (unsigned)gy < (unsigned)p.Y && (unsigned)gx < (unsigned)p.X;
+                            tp2[jy][jx] = inb ? tz[(unsigned)(gy * p.Xp + gx)] : tmk<T>(0.f, 0.f);
+                        }
+                    }
+                }
                 mbar_wait(bar, ph);
                 T* ck = ckpt + (size_t)z * P * TP;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (k == 2 && t >= Ms3::NB - 2 * Ms3::NACT) break;
-                    const int ry = I.ry0 + 9 * k;
+                for (int k = 0; k < C::MR; ++k) {
+                    if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
+                    const int ry = I.ry0 + C::RS * k;
                     T w[3][3];
 #pragma unroll
                     for (int jy = 0; jy < 3; ++jy)
@@ -258,7 +298,8 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
                         for (int jx = 0; jx < 3; ++jx) {
                             const int o = (24 * jy + ry) * TP + 24 * jx + xo;
                             ck[o] = w[jy][jx];
-                            w[jy][jx] = modulate(w[jy][jx], tile[o]);
+                            if (BANDS && k == 2) w[jy][jx] = modulate(w[jy][jx], tp2[jy][jx]);
+                            else w[jy][jx] = modulate(w[jy][jx], tile[jy * C::BSTR + ry * TP + 24 * jx + xo]);
                         }
                     if (!go_on) {
 #pragma unroll
@@ -282,10 +323,7 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
             }
             ph ^= 1;
             __syncthreads();
-            if (t == 0 && z + 1 < sg.ze) {   // every thread has consumed tile(z): prefetch tile(z+1) behind the B passes
-                mbar_expect_tx(bar, TILE_BYTES);
-                tma_load_tile(tile, &tmap, 2 * pxa, py, z + 1, bar);
-            }
+            if (t == 0 && z + 1 < sg.ze) issue_tile(z + 1);   // every thread has consumed tile(z): prefetch tile(z+1) behind the B passes
             if (!go_on) break;
             if (last) {
                 // far field: finish the forward 2-D transform and store fftshift-ed, natural order
@@ -313,7 +351,7 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
         }
         if (sg.ze < p.Nz) {                 // early part of a cut chain: hand the wavefield to CTA c + 1
             float4* dst = p.handoff + (size_t)(c + 1) * p.slot_f4;
-            for (int i = t; i < (int)(Ms3::PSI / 16); i += Ms3::NTHREADS) dst[i] = ((const float4*)psi)[i];
+            for (int i = t; i < (int)(C::PSI / 16); i += C::NTHREADS) dst[i] = ((const float4*)psi)[i];
 #ifndef ADM_HOST_EMU
             __threadfence();
 #endif
@@ -326,20 +364,20 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_fwd
 // ================================================================================================
 // Adjoint
 // ================================================================================================
-template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
+template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_ms3_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
     ADM_SMEM_DECL
-    constexpr int P = Ms3::P, S = Ms3::S, TP = Ms3::TP;
-    constexpr unsigned TILE_BYTES = (unsigned)Ms3::TILE;
+    constexpr int P = C::P, S = C::S, TP = C::TP;
+    constexpr unsigned TILE_BYTES = (unsigned)C::TILE;
     T* ckb = (T*)smem_raw;          // psi checkpoint of the slice (bulk copy); overwritten in place by dL/dT
     T* psi = ckb + P * TP;          // running adjoint wavefield
     T* hs = psi + P * S;
     adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
     const int t = threadIdx.x;
-    const bool active = t < Ms3::NACT;
-    const bool third = t < Ms3::NB - 2 * Ms3::NACT;      // this thread owns a third block
+    const bool active = t < C::NACT;          // B passes
+    const bool mactive = t < C::MT;           // M pass
     const int q = t / P, l = t % P;
-    Ms3Thread<T> I;
-    ms3_thread_init(I, t);
+    Ms3Thread<T, C> I;
+    ms3_thread_init<T, C>(I, t);
     const int c = gridDim.x - 1 - blockIdx.x;
 
     ms3_hs_fill(hs, (const T*)p.Hp, t);
@@ -360,15 +398,15 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
         const size_t slice_stride = (size_t)p.Y * p.Xp;
         // T' of one slice for this thread's blocks: plain loads of the L2-resident volume, ISSUED one barrier early (behind
         // the last pass of the previous slice) so that their latency overlaps the barrier wait
-        T tpa[3][3][3];
+        T tpa[C::MR][3][3];
         auto load_tp = [&](int zz) {
             const T* tzz = (const T*)p.tvol + (size_t)zz * slice_stride;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (k == 2 && !third) break;
+            for (int k = 0; k < C::MR; ++k) {
+                if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
 #pragma unroll
                 for (int jy = 0; jy < 3; ++jy) {
-                    const int gy = py + 24 * jy + I.ry0 + 9 * k;
+                    const int gy = py + 24 * jy + I.ry0 + C::RS * k;
 #pragma unroll
                     for (int jx = 0; jx < 3; ++jx) {
                         const int gx = px + 24 * jx + I.rx;
@@ -378,7 +416,7 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
                 }
             }
         };
-        if (active) load_tp(sg.ze - 1);
+        if (mactive) load_tp(sg.ze - 1);
 
         __syncthreads();                    // the previous segment is done with the wavefield
         if (t == 0) {
@@ -390,7 +428,7 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
         if (sg.ze < p.Nz) {
             if (t == 0) flag_wait_and_clear(p.flags + c + 1);
             __syncthreads();
-            for (int i = t; i < (int)(Ms3::PSI / 16); i += Ms3::NTHREADS) {
+            for (int i = t; i < (int)(C::PSI / 16); i += C::NTHREADS) {
 #ifndef ADM_HOST_EMU
                 ((float4*)psi)[i] = __ldcg(p.handoff + (size_t)(c + 1) * p.slot_f4 + i);
 #else
@@ -416,13 +454,13 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
             __syncthreads();
             if (active) ms3_B<true, 2>(psi, hs, q, l);
             __syncthreads();
-        } else if (p.free_prop == ADM_PROP_NONE && active) {
+        } else if (p.free_prop == ADM_PROP_NONE && mactive) {
             // exit-wave detection: dL/d(exit wave) enters the loop in the state every slice leaves behind (as the probe does
             // in the forward kernel); every thread reads back exactly the positions it writes here: no barrier
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                if (k == 2 && !third) break;
-                const int ry = I.ry0 + 9 * k;
+            for (int k = 0; k < C::MR; ++k) {
+                if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
+                const int ry = I.ry0 + C::RS * k;
                 T w[3][3];
 #pragma unroll
                 for (int jy = 0; jy < 3; ++jy)
@@ -446,9 +484,9 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
             auto m_pass = [&](auto kind_tag) {
                 constexpr int KIND = decltype(kind_tag)::value;
 #pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    if (k == 2 && !third) break;
-                    const int ry = I.ry0 + 9 * k;
+                for (int k = 0; k < C::MR; ++k) {
+                    if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
+                    const int ry = I.ry0 + C::RS * k;
                     T w[3][3];
 #pragma unroll
                     for (int jy = 0; jy < 3; ++jy)
@@ -494,7 +532,7 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
                 }
                 fence_proxy_async();      // the dL/dT tile is about to be read by the TMA unit
             };
-            if (active) {
+            if (mactive) {
                 if (z == 0) m_pass(std::integral_constant<int, 2>());
                 else if (last) m_pass(std::integral_constant<int, 1>());
                 else m_pass(std::integral_constant<int, 0>());
@@ -513,12 +551,12 @@ template <class T> __global__ void __launch_bounds__(Ms3::NTHREADS, 2) k_ms3_bwd
                 bulk_load(ckb, ckpt + (size_t)(z - 1) * P * TP, TILE_BYTES, bar);
             }
             if (active) ms3_B<false, 0>(psi, hs + P, q, l);
-            if (active && z > sg.zb) load_tp(z - 1);
+            if (mactive && z > sg.zb) load_tp(z - 1);
             __syncthreads();
         }
         if (sg.zb > 0) {                    // early part of a cut chain: hand the adjoint wavefield to CTA c - 1
             float4* dst = p.handoff + (size_t)c * p.slot_f4;
-            for (int i = t; i < (int)(Ms3::PSI / 16); i += Ms3::NTHREADS) dst[i] = ((const float4*)psi)[i];
+            for (int i = t; i < (int)(C::PSI / 16); i += C::NTHREADS) dst[i] = ((const float4*)psi)[i];
 #ifndef ADM_HOST_EMU
             __threadfence();
 #endif

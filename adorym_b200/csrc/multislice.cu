@@ -528,16 +528,21 @@ template <class K> static int ms_resident_ctas(K kern, int threads, size_t smem)
     int forced = adm_variant("ADM_MS_GRID");
     if (forced > 0) return forced;
 #ifndef ADM_HOST_EMU
-    static int cached = 0;      // per kernel instantiation (all devices of a node are the same part)
-    if (cached > 0) return cached;
+    // cache per kernel (K is the function-pointer TYPE, shared by all kernels of this signature: key on the pointer)
+    static const void* keys[16];
+    static int vals[16];
+    static int nkeys = 0;
+    for (int i = 0; i < nkeys; ++i)
+        if (keys[i] == (const void*)kern) return vals[i];
     int dev = 0, sms = 0, occ = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, threads, smem) != cudaSuccess) return 0;
-    cached = sms * occ;
+    const int res = sms * occ;
+    if (nkeys < 16) { keys[nkeys] = (const void*)kern; vals[nkeys] = res; ++nkeys; }
     if (getenv("ADM_MS_VERBOSE"))
-        fprintf(stderr, "[adm] multislice kernel: %d threads, %zu B smem -> %d CTAs per SM, %d resident\n", threads, smem, occ, cached);
-    return cached;
+        fprintf(stderr, "[adm] multislice kernel: %d threads, %zu B smem -> %d CTAs per SM, %d resident\n", threads, smem, occ, res);
+    return res;
 #else
     return 8;
 #endif
@@ -631,10 +636,20 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int var = adm_variant("ADM_FWD_VARIANT");
     if (var == 0 && ms3_wanted(cfg, p)) {
-        if (set_smem(k_ms3_fwd<cpk>, Ms3::BYTES)) return ADM_ERR_CUDA;
-        int grid_;
-        if (ms_schedule(p, ms_resident_ctas(k_ms3_fwd<cpk>, Ms3::NTHREADS, Ms3::BYTES), workspace, 72, grid_)) return ADM_ERR_CUDA;
-        ADM_LAUNCH((k_ms3_fwd<cpk>), grid_, Ms3::NTHREADS, Ms3::BYTES, stream, map, p);
+#define ADM_MS3_FWD(CFG)                                                                                               \
+    do {                                                                                                            \
+        AdmTileMap map3;      /* TMA box = one band of CFG::TS rows (24: the whole 72-row tile in one load) */          \
+        if (adm_make_tile_map(&map3, tvol, p.Nz, p.Y, p.X, p.Xp, CFG::TS == 24 ? 72 : CFG::TS, 74)) return ADM_ERR_CUDA;  \
+        if (set_smem(k_ms3_fwd<cpk, CFG>, CFG::FBYTES)) return ADM_ERR_CUDA;                                         \
+        int grid_;                                                                                                  \
+        if (ms_schedule(p, ms_resident_ctas(k_ms3_fwd<cpk, CFG>, CFG::NTHREADS, CFG::FBYTES), workspace, 72, grid_)) \
+            return ADM_ERR_CUDA;                                                                                    \
+        ADM_LAUNCH((k_ms3_fwd<cpk, CFG>), grid_, CFG::NTHREADS, CFG::FBYTES, stream, map3, p);                       \
+    } while (0)
+        { const int v3 = adm_variant("ADM_MS3_FWD");
+          if (v3 == 1) ADM_MS3_FWD(Ms3);          // 7 warps, whole tile, two CTAs per SM
+          else if (v3 == 2) ADM_MS3_FWD(Ms3w);    // 9 warps, M pass in two rounds
+          else ADM_MS3_FWD(Ms3t); }               // banded tile, three CTAs per SM
         return ADM_OK;
     }
 #define ADM_FWD(CFG, MINB, TILE, CT)                                                                                  \
@@ -694,10 +709,16 @@ static int ms_bwd_impl(const adm_multislice_cfg* cfg, const float* tvol, const i
         return ADM_ERR_CUDA;
     int var = adm_variant("ADM_BWD_VARIANT");
     if (var == 0 && p.g_ckpt == nullptr && ms3_wanted(cfg, p)) {
-        if (set_smem(k_ms3_bwd<cpk>, Ms3::BYTES)) return ADM_ERR_CUDA;
-        int grid_;
-        if (ms_schedule(p, ms_resident_ctas(k_ms3_bwd<cpk>, Ms3::NTHREADS, Ms3::BYTES), workspace, 72, grid_)) return ADM_ERR_CUDA;
-        ADM_LAUNCH((k_ms3_bwd<cpk>), grid_, Ms3::NTHREADS, Ms3::BYTES, stream, map, p);
+#define ADM_MS3_BWD(CFG)                                                                                               \
+    do {                                                                                                            \
+        if (set_smem(k_ms3_bwd<cpk, CFG>, CFG::BYTES)) return ADM_ERR_CUDA;                                          \
+        int grid_;                                                                                                  \
+        if (ms_schedule(p, ms_resident_ctas(k_ms3_bwd<cpk, CFG>, CFG::NTHREADS, CFG::BYTES), workspace, 72, grid_))  \
+            return ADM_ERR_CUDA;                                                                                    \
+        ADM_LAUNCH((k_ms3_bwd<cpk, CFG>), grid_, CFG::NTHREADS, CFG::BYTES, stream, map, p);                         \
+    } while (0)
+        if (adm_variant("ADM_MS3_BWD") == 2) ADM_MS3_BWD(Ms3w);
+        else ADM_MS3_BWD(Ms3);
         return ADM_OK;
     }
 #define ADM_BWD(CFG, MINB, CT, GCK)                                                                                  \
