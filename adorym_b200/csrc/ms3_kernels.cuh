@@ -28,19 +28,9 @@
 
 // NT threads per CTA; the B passes use the first 216 of them (one 24-point group each), the M pass MT of them with MR blocks
 // each (thread t owns the blocks (t / 24 + (MT / 24) k, t % 24), k < MR, while t + MT k < 576).
-// TS_ (forward kernel only): rows of each of the three 24-row bands of the T' tile that are staged in shared memory by TMA.
-// 24 = the whole tile (one TMA load).  18 (needs MT = 216, MR = 3): the rows 24 jy + 0..17, which the block rounds 0 and 1
-// read, as three 18-row TMA loads; the rows 24 jy + 18..23 of round 2 (threads < 144) come by plain loads of the
-// L2-resident volume, issued at the top of the M pass.  That brings a CTA to 75.2 KB of shared memory: THREE CTAs per SM.
-template <int NT_, int MT_, int MR_, int TS_ = 24, int MINB_ = 2> struct Ms3Cfg {
+template <int NT_, int MT_, int MR_> struct Ms3Cfg {
     static constexpr int P = 72, S = 73, NACT = 216, NTHREADS = NT_, MT = MT_, MR = MR_, RS = MT_ / 24, NB = 576, TP = 74;
-    static constexpr int TS = TS_, MINB = MINB_;
-    static_assert(TS_ == 24 || (TS_ == 18 && MT_ == 216 && MR_ == 3), "tile bands");
-    static constexpr size_t TILE = sizeof(cpx) * P * TP;                 // checkpoint / dL/dT tile (adjoint)
-    // band stride in the forward kernel's tile (complex values): TMA destinations are 128-byte aligned
-    static constexpr int BSTR = TS_ == 24 ? 24 * TP : (int)(((sizeof(cpx) * TS_ * TP + 127) / 128 * 128) / sizeof(cpx));
-    static constexpr size_t FTILE = sizeof(cpx) * 3 * BSTR;              // T' tile of the forward kernel
-    static constexpr size_t FBYTES = FTILE + sizeof(cpx) * P * S + sizeof(cpx) * 2 * P + 16;
+    static constexpr size_t TILE = sizeof(cpx) * P * TP;                 // T' tile (forward) / checkpoint + dL/dT tile (adjoint)
     static constexpr size_t PSI = sizeof(cpx) * P * S;
     static constexpr size_t HS = sizeof(cpx) * 2 * P;
     static constexpr size_t BYTES = TILE + PSI + HS + 16;
@@ -48,9 +38,8 @@ template <int NT_, int MT_, int MR_, int TS_ = 24, int MINB_ = 2> struct Ms3Cfg 
     // block round k of thread t exists
     ADM_HDM static constexpr bool full_round(int k) { return MT_ * (k + 1) <= 576; }
 };
-typedef Ms3Cfg<224, 216, 3> Ms3;      // default: 7 warps
-typedef Ms3Cfg<288, 288, 2> Ms3w;     // 9 warps, M pass in two balanced rounds (96 registers)
-typedef Ms3Cfg<224, 216, 3, 18, 3> Ms3t;   // forward: banded T' tile, three CTAs per SM (80 registers)
+typedef Ms3Cfg<224, 216, 3> Ms3;      // adjoint: 7 warps, 128 registers (the T' values held across a barrier need them)
+typedef Ms3Cfg<288, 288, 2> Ms3w;     // forward: 9 warps, M pass in two balanced rounds, 96 registers, no spills (2.70 vs 2.74 ms)
 
 // frequency (mod 24) held by register slot s after the forward 24-point prime-factor transform
 ADM_HDM constexpr int ms3_f24(int s) { return (16 * ((2 * s) % 3) + 9 * ((3 * s) % 8)) % 24; }
@@ -177,14 +166,12 @@ template <bool YDIR, int MODE, class T> ADM_DEV void ms3_B(T* psi, const T* hsd,
 // ================================================================================================
 // Forward
 // ================================================================================================
-template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MINB) k_ms3_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_ms3_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
     constexpr int P = C::P, S = C::S, TP = C::TP;
-    constexpr int TS = C::TS;
-    constexpr bool BANDS = TS != 24;
-    constexpr unsigned TILE_BYTES = (unsigned)(sizeof(cpx) * 3 * TS * TP);      // bytes the TMA loads of one slice deliver
+    constexpr unsigned TILE_BYTES = (unsigned)C::TILE;
     T* tile = (T*)smem_raw;
-    T* psi = tile + 3 * C::BSTR;
+    T* psi = tile + P * TP;
     T* hs = psi + P * S;
     adm_mbar_t* bar = (adm_mbar_t*)(hs + 2 * P);
     const int t = threadIdx.x;
@@ -215,11 +202,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
         __syncthreads();                    // the previous segment is done with the tile and the wavefield
         auto issue_tile = [&](int zz) {      // one elected thread
             mbar_expect_tx(bar, TILE_BYTES);
-            if constexpr (!BANDS) tma_load_tile(tile, &tmap, 2 * pxa, py, zz, bar);
-            else {
-#pragma unroll
-                for (int jy = 0; jy < 3; ++jy) tma_load_tile(tile + jy * C::BSTR, &tmap, 2 * pxa, py + 24 * jy, zz, bar, jy == 2);
-            }
+            tma_load_tile(tile, &tmap, 2 * pxa, py, zz, bar);
         };
         if (t == 0) issue_tile(sg.zb);
         if (sg.zb > 0) {                    // late part of a cut chain: the wavefield comes from CTA c - 1
@@ -266,20 +249,6 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
             // (ONE code path for all slices: a second instantiation without the last-slice options measured 3.5 % slower --
             // code size)
             if (mactive) {
-                T tp2[3][3];           // banded tile: T' of this thread's round-2 block, by plain loads (vacuum outside the object)
-                if (BANDS && t + 2 * C::MT < C::NB) {
-                    const T* tz = (const T*)p.tvol + (size_t)z * p.Y * p.Xp;
-#pragma unroll
-                    for (int jy = 0; jy < 3; ++jy) {
-                        const int gy = py + 24 * jy + I.ry0 + 2 * C::RS;
-#pragma unroll
-                        for (int jx = 0; jx < 3; ++jx) {
-                            const int gx = px + 24 * jx + I.rx;
-                            const bool inb = (unsigned)gy < (unsigned)p.Y && (unsigned)gx < (unsigned)p.X;
-                            tp2[jy][jx] = inb ? tz[(unsigned)(gy * p.Xp + gx)] : tmk<T>(0.f, 0.f);
-                        }
-                    }
-                }
                 mbar_wait(bar, ph);
                 T* ck = ckpt + (size_t)z * P * TP;
 #pragma unroll
@@ -298,8 +267,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
                         for (int jx = 0; jx < 3; ++jx) {
                             const int o = (24 * jy + ry) * TP + 24 * jx + xo;
                             ck[o] = w[jy][jx];
-                            if (BANDS && k == 2) w[jy][jx] = modulate(w[jy][jx], tp2[jy][jx]);
-                            else w[jy][jx] = modulate(w[jy][jx], tile[jy * C::BSTR + ry * TP + 24 * jx + xo]);
+                            w[jy][jx] = modulate(w[jy][jx], tile[o]);
                         }
                     if (!go_on) {
 #pragma unroll

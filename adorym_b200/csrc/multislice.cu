@@ -636,20 +636,15 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     if (adm_make_tile_map(&map, tvol, p.Nz, p.Y, p.X, p.Xp, cfg->P, cfg->P + 2)) return ADM_ERR_CUDA;
     int var = adm_variant("ADM_FWD_VARIANT");
     if (var == 0 && ms3_wanted(cfg, p)) {
-#define ADM_MS3_FWD(CFG)                                                                                               \
+#define ADM_MS3_LAUNCH(KERN, CFG)                                                                                      \
     do {                                                                                                            \
-        AdmTileMap map3;      /* TMA box = one band of CFG::TS rows (24: the whole 72-row tile in one load) */          \
-        if (adm_make_tile_map(&map3, tvol, p.Nz, p.Y, p.X, p.Xp, CFG::TS == 24 ? 72 : CFG::TS, 74)) return ADM_ERR_CUDA;  \
-        if (set_smem(k_ms3_fwd<cpk, CFG>, CFG::FBYTES)) return ADM_ERR_CUDA;                                         \
+        if (set_smem(KERN<cpk, CFG>, CFG::BYTES)) return ADM_ERR_CUDA;                                              \
         int grid_;                                                                                                  \
-        if (ms_schedule(p, ms_resident_ctas(k_ms3_fwd<cpk, CFG>, CFG::NTHREADS, CFG::FBYTES), workspace, 72, grid_)) \
+        if (ms_schedule(p, ms_resident_ctas(KERN<cpk, CFG>, CFG::NTHREADS, CFG::BYTES), workspace, 72, grid_))      \
             return ADM_ERR_CUDA;                                                                                    \
-        ADM_LAUNCH((k_ms3_fwd<cpk, CFG>), grid_, CFG::NTHREADS, CFG::FBYTES, stream, map3, p);                       \
+        ADM_LAUNCH((KERN<cpk, CFG>), grid_, CFG::NTHREADS, CFG::BYTES, stream, map, p);                             \
     } while (0)
-        { const int v3 = adm_variant("ADM_MS3_FWD");
-          if (v3 == 1) ADM_MS3_FWD(Ms3);          // 7 warps, whole tile, two CTAs per SM
-          else if (v3 == 2) ADM_MS3_FWD(Ms3w);    // 9 warps, M pass in two rounds
-          else ADM_MS3_FWD(Ms3t); }               // banded tile, three CTAs per SM
+        ADM_MS3_LAUNCH(k_ms3_fwd, Ms3w);
         return ADM_OK;
     }
 #define ADM_FWD(CFG, MINB, TILE, CT)                                                                                  \
@@ -709,16 +704,7 @@ static int ms_bwd_impl(const adm_multislice_cfg* cfg, const float* tvol, const i
         return ADM_ERR_CUDA;
     int var = adm_variant("ADM_BWD_VARIANT");
     if (var == 0 && p.g_ckpt == nullptr && ms3_wanted(cfg, p)) {
-#define ADM_MS3_BWD(CFG)                                                                                               \
-    do {                                                                                                            \
-        if (set_smem(k_ms3_bwd<cpk, CFG>, CFG::BYTES)) return ADM_ERR_CUDA;                                          \
-        int grid_;                                                                                                  \
-        if (ms_schedule(p, ms_resident_ctas(k_ms3_bwd<cpk, CFG>, CFG::NTHREADS, CFG::BYTES), workspace, 72, grid_))  \
-            return ADM_ERR_CUDA;                                                                                    \
-        ADM_LAUNCH((k_ms3_bwd<cpk, CFG>), grid_, CFG::NTHREADS, CFG::BYTES, stream, map, p);                         \
-    } while (0)
-        if (adm_variant("ADM_MS3_BWD") == 2) ADM_MS3_BWD(Ms3w);
-        else ADM_MS3_BWD(Ms3);
+        ADM_MS3_LAUNCH(k_ms3_bwd, Ms3);
         return ADM_OK;
     }
 #define ADM_BWD(CFG, MINB, CT, GCK)                                                                                  \

@@ -37,10 +37,7 @@ ADM_DEV void mbar_wait(adm_mbar_t* bar, unsigned parity) {
         "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
 }
 // tile load: box [1][P][2P floats] at (x2 = 2*px, y = py, z) -> dense smem tile, zero fill outside the tensor
-// (`last`: host emulation only -- there every signalling load completes a barrier phase, so the loads that share one
-// expect_tx signal with the last of them; the hardware counts bytes)
-ADM_DEV void tma_load_tile(void* smem_dst, const AdmTileMap* map, int x2, int y, int z, adm_mbar_t* bar, bool last = true) {
-    (void)last;
+ADM_DEV void tma_load_tile(void* smem_dst, const AdmTileMap* map, int x2, int y, int z, adm_mbar_t* bar) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];\n"
                  ::"r"(smem_u32(smem_dst)), "l"((unsigned long long)map), "r"(smem_u32(bar)), "r"(x2), "r"(y), "r"(z)
                  : "memory");
@@ -115,7 +112,7 @@ static inline void mbar_wait(adm_mbar_t* bar, unsigned parity) {
         mbar_ref(bar).wait(v);
     }
 }
-static inline void tma_load_tile(void* dst, const AdmTileMap* m, int x2, int y, int z, adm_mbar_t* bar, bool last = true) {
+static inline void tma_load_tile(void* dst, const AdmTileMap* m, int x2, int y, int z, adm_mbar_t* bar) {
     float* d = (float*)dst;
     if (x2 & 3) abort();    // the hardware raises "illegal instruction" for a start that is not 16-byte aligned
     for (int r = 0; r < m->P; ++r)
@@ -124,7 +121,6 @@ static inline void tma_load_tile(void* dst, const AdmTileMap* m, int x2, int y, 
             bool in = z >= 0 && z < m->Nz && yy >= 0 && yy < m->Y && xx >= 0 && xx < 2 * m->X;
             d[r * 2 * m->BW + c] = in ? m->base[((size_t)z * m->Y + yy) * 2 * m->Xp + xx] : 0.f;
         }
-    if (!last) return;
     mbar_ref(bar).fetch_add(1);
     mbar_ref(bar).notify_all();
 }
