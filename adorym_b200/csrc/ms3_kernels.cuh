@@ -26,23 +26,34 @@
 #pragma once
 #include <type_traits>
 
-// NT threads per CTA; the B passes use the first 216 of them (one 24-point group each), the M pass MT of them with MR blocks
-// each (thread t owns the blocks (t / 24 + (MT / 24) k, t % 24), k < MR, while t + MT k < 576).
-template <int NT_, int MT_, int MR_> struct Ms3Cfg {
-    static constexpr int P = 72, S = 73, NACT = 216, NTHREADS = NT_, MT = MT_, MR = MR_, RS = MT_ / 24, NB = 576, TP = 74;
+// P = RA * RB per axis (72 = 3 x 24, 64 = 4 x 16).  NT threads per CTA; the B passes use the first P * RA of them (one
+// RB-point group each), the M pass MT of them with MR blocks each (thread t owns the blocks (t / RB + (MT / RB) k, t % RB),
+// k < MR, while t + MT k < RB^2).  MINB: CTAs per SM the registers are capped for.
+template <int P_, int RA_, int NT_, int MT_, int MR_, int MINB_> struct Ms3Cfg {
+    static constexpr int P = P_, RA = RA_, RB = P_ / RA_, S = P_ + 1, TP = P_ + 2, NACT = P_ * RA_, NTHREADS = NT_, MT = MT_, MR = MR_;
+    static constexpr int RS = MT_ / RB, NB = RB * RB, MINB = MINB_;
     static constexpr size_t TILE = sizeof(cpx) * P * TP;                 // T' tile (forward) / checkpoint + dL/dT tile (adjoint)
     static constexpr size_t PSI = sizeof(cpx) * P * S;
     static constexpr size_t HS = sizeof(cpx) * 2 * P;
     static constexpr size_t BYTES = TILE + PSI + HS + 16;
-    static_assert(MT_ % 24 == 0 && MT_ * MR_ >= 576 && MT_ <= NT_ && NT_ >= 216, "M-pass blocks must be covered");
-    // block round k of thread t exists
-    ADM_HDM static constexpr bool full_round(int k) { return MT_ * (k + 1) <= 576; }
+    static_assert((P_ == 72 && RA_ == 3) || (P_ == 64 && RA_ == 4), "72 = 3 x 24 or 64 = 4 x 16");
+    static_assert(MT_ % RB == 0 && MT_ * MR_ >= NB && MT_ <= NT_ && NT_ >= NACT, "M-pass blocks / B-pass groups must be covered");
+    static_assert(TILE % 128 == 0 && PSI % 16 == 0, "TMA / float4 alignment of the carve-up");
+    // block round k exists for every thread
+    ADM_HDM static constexpr bool full_round(int k) { return MT_ * (k + 1) <= NB; }
+    // frequency (mod RB) held by register slot s after the forward RB-point transform
+    ADM_HDM static constexpr int fB(int s) {
+        return RB == 24 ? (16 * ((2 * s) % 3) + 9 * ((3 * s) % 8)) % 24 : s / 4 + 4 * (s % 4);
+    }
+    // position of frequency f in the permuted order of the five-pass kernels' separable tables
+    // (adm_prepare_transfer_function_separable: entry p holds frequency perm_freq<Cfg72 / Cfg64>(p))
+    ADM_HDM static constexpr int five_pass_pos(int f) {
+        return P_ == 72 ? (9 * (f % 8) + 64 * ((9 - f % 9) % 9)) % 72 : 8 * (f % 8) + f / 8;
+    }
 };
-typedef Ms3Cfg<224, 216, 3> Ms3;      // adjoint: 7 warps, 128 registers (the T' values held across a barrier need them)
-typedef Ms3Cfg<288, 288, 2> Ms3w;     // forward: 9 warps, M pass in two balanced rounds, 96 registers, no spills (2.70 vs 2.74 ms)
-
-// frequency (mod 24) held by register slot s after the forward 24-point prime-factor transform
-ADM_HDM constexpr int ms3_f24(int s) { return (16 * ((2 * s) % 3) + 9 * ((3 * s) % 8)) % 24; }
+typedef Ms3Cfg<72, 3, 224, 216, 3, 2> Ms3;      // adjoint: 7 warps, 128 registers (the T' values held across a barrier need them)
+typedef Ms3Cfg<72, 3, 288, 288, 2, 2> Ms3w;     // forward: 9 warps, M pass in two balanced rounds, 96 registers, no spills (2.70 vs 2.74 ms)
+typedef Ms3Cfg<64, 4, 256, 256, 1, 2> Ms3p64;   // 64-pixel probes: one 4 x 4 block and one 16-point group per thread
 
 // 24-point DFT in registers: Good-Thomas 3 x 8, n = (8 a + 3 b) mod 24, k = (16 ka + 9 kb) mod 24, slot (8 ka + 3 kb) mod 24.
 // INV = false: natural order in, slot order out.  INV = true: slot order in, natural order out (conjugate, unnormalised).
@@ -66,109 +77,142 @@ template <bool INV, class T> ADM_DEV void ms3_dft24(T* u) {
     }
 }
 
-// W72^n = exp(-2 pi i n / 72)
-template <class T> ADM_DEV T ms3_w72(int n) {
+// 16-point DFT in registers: Cooley-Tukey 4 x 4, n = 4 n1 + n2, k = k1 + 4 k2, slot 4 k1 + k2; twiddles W16^(n2 k1).
+// INV = false: natural order in, slot order out.  INV = true: slot order in, natural order out (conjugate, unnormalised).
+#define ADM_C16_1 0.92387953251128675613f
+#define ADM_S16_1 0.38268343236508977173f
+template <bool INV, class T> ADM_DEV void ms3_tw16(T* a) {
+    // a[4 k1 + n2] *= W16^(n2 k1) (forward) or its conjugate: exponents 1 2 3 / 2 4 6 / 3 6 9
+    a[5] = tw9<INV>(a[5], ADM_C16_1, ADM_S16_1);
+    a[6] = tw9<INV>(a[6], ADM_SQRT1_2, ADM_SQRT1_2);
+    a[7] = tw9<INV>(a[7], ADM_S16_1, ADM_C16_1);
+    a[9] = tw9<INV>(a[9], ADM_SQRT1_2, ADM_SQRT1_2);
+    a[10] = tw9<INV>(a[10], 0.0f, 1.0f);
+    a[11] = tw9<INV>(a[11], -ADM_SQRT1_2, ADM_SQRT1_2);
+    a[13] = tw9<INV>(a[13], ADM_S16_1, ADM_C16_1);
+    a[14] = tw9<INV>(a[14], -ADM_SQRT1_2, ADM_SQRT1_2);
+    a[15] = tw9<INV>(a[15], -ADM_C16_1, -ADM_S16_1);
+}
+template <bool INV, class T> ADM_DEV void ms3_dft16(T* a) {
+    if constexpr (!INV) {
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) dft4<false>(a[n2], a[4 + n2], a[8 + n2], a[12 + n2]);
+        ms3_tw16<false>(a);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) dft4<false>(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
+    } else {
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) dft4<true>(a[4 * k1], a[4 * k1 + 1], a[4 * k1 + 2], a[4 * k1 + 3]);
+        ms3_tw16<true>(a);
+#pragma unroll
+        for (int n2 = 0; n2 < 4; ++n2) dft4<true>(a[n2], a[4 + n2], a[8 + n2], a[12 + n2]);
+    }
+}
+template <int RB, bool INV, class T> ADM_DEV void ms3_dftB(T* u) {
+    if constexpr (RB == 24) ms3_dft24<INV>(u);
+    else ms3_dft16<INV>(u);
+}
+
+// W_P^n = exp(-2 pi i n / P)
+template <class T, int P> ADM_DEV T ms3_wP(int n) {
 #ifndef ADM_HOST_EMU
     float s, c;
-    sincospif((float)n / 36.0f, &s, &c);
+    sincospif(2.0f * (float)n / (float)P, &s, &c);
     return tmk<T>(c, -s);
 #else
-    double a = 2.0 * 3.14159265358979323846 * n / 72.0;
+    double a = 2.0 * 3.14159265358979323846 * n / P;
     return tmk<T>((float)cos(a), (float)-sin(a));
 #endif
 }
 
-// transfer-function tables in slot order: hs[dir][k1][s] = h_dir[k1 + 3 f24(s)].  Hsep = [hy | hx] in the permuted order of
-// the five-pass kernels (adm_prepare_transfer_function_separable: entry p holds frequency perm_freq<Cfg72>(p)); the
-// position of frequency f in that order is (9 (f % 8) + 64 ((9 - f % 9) % 9)) % 72.
-template <class T> ADM_DEV void ms3_hs_fill(T* hs, const T* Hsep, int t) {
-    if (t < 2 * Ms3::P) {
-        const int dir = t / Ms3::P, i = t % Ms3::P;
-        const int f = i / 24 + 3 * ms3_f24(i % 24);
-        const int p = (9 * (f % 8) + 64 * ((9 - f % 9) % 9)) % 72;
-        hs[t] = Hsep[dir * Ms3::P + p];
+// transfer-function tables in slot order: hs[dir][k1][s] = h_dir[k1 + RA fB(s)].  Hsep = [hy | hx] in the permuted order of
+// the five-pass kernels.
+template <class C, class T> ADM_DEV void ms3_hs_fill(T* hs, const T* Hsep, int t) {
+    if (t < 2 * C::P) {
+        const int dir = t / C::P, i = t % C::P;
+        const int f = i / C::RB + C::RA * C::fB(i % C::RB);
+        hs[t] = Hsep[dir * C::P + C::five_pass_pos(f)];
     }
 }
 
-// radix-3 stages of both axes on a 3 x 3 block w[jy][jx] (+ the twiddles W72^(ry k1y) W72^(rx k1x)); wy / wx = {W^r, W^2r}
-template <bool INV, class T> ADM_DEV void ms3_A(T (&w)[3][3], const T* wy, const T* wx) {
+// radix-RA stages of both axes on an RA x RA block w[jy][jx] (+ the twiddles W_P^(ry k1y) W_P^(rx k1x)); wy / wx = {W^r, W^2r, ..}
+template <bool INV, int RA, class T> ADM_DEV void ms3_dftA(T& a0, T& a1, T& a2, T& a3) {
+    if constexpr (RA == 3) dft3<INV>(a0, a1, a2);
+    else dft4<INV>(a0, a1, a2, a3);
+}
+template <bool INV, int RA, class T> ADM_DEV void ms3_A(T (&w)[RA][RA], const T* wy, const T* wx) {
     if constexpr (INV) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            w[1][j] = cmulc(w[1][j], wy[0]);
-            w[2][j] = cmulc(w[2][j], wy[1]);
-        }
+        for (int k = 1; k < RA; ++k)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            w[j][1] = cmulc(w[j][1], wx[0]);
-            w[j][2] = cmulc(w[j][2], wx[1]);
-        }
+            for (int j = 0; j < RA; ++j) w[k][j] = cmulc(w[k][j], wy[k - 1]);
+#pragma unroll
+        for (int k = 1; k < RA; ++k)
+#pragma unroll
+            for (int j = 0; j < RA; ++j) w[j][k] = cmulc(w[j][k], wx[k - 1]);
     }
 #pragma unroll
-    for (int j = 0; j < 3; ++j) dft3<INV>(w[j][0], w[j][1], w[j][2]);
+    for (int j = 0; j < RA; ++j) ms3_dftA<INV, RA>(w[j][0], w[j][1], w[j][2], w[j][RA - 1]);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) dft3<INV>(w[0][j], w[1][j], w[2][j]);
+    for (int j = 0; j < RA; ++j) ms3_dftA<INV, RA>(w[0][j], w[1][j], w[2][j], w[RA - 1][j]);
     if constexpr (!INV) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            w[1][j] = cmul(w[1][j], wy[0]);
-            w[2][j] = cmul(w[2][j], wy[1]);
-        }
+        for (int k = 1; k < RA; ++k)
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            w[j][1] = cmul(w[j][1], wx[0]);
-            w[j][2] = cmul(w[j][2], wx[1]);
-        }
+            for (int j = 0; j < RA; ++j) w[k][j] = cmul(w[k][j], wy[k - 1]);
+#pragma unroll
+        for (int k = 1; k < RA; ++k)
+#pragma unroll
+            for (int j = 0; j < RA; ++j) w[j][k] = cmul(w[j][k], wx[k - 1]);
     }
 }
 
 // per-thread constants of the M pass: thread t owns the blocks (ry0 + RS k, rx), k < MR
 template <class T, class C> struct Ms3Thread {
     int ry0, rx;
-    T wy[C::MR][2], wx[2];
+    T wy[C::MR][C::RA - 1], wx[C::RA - 1];
 };
 template <class T, class C> ADM_DEV void ms3_thread_init(Ms3Thread<T, C>& I, int t) {
-    I.ry0 = (t / 24) % 24; I.rx = t % 24;
+    I.ry0 = (t / C::RB) % C::RB; I.rx = t % C::RB;
 #pragma unroll
-    for (int k = 0; k < C::MR; ++k) {
-        I.wy[k][0] = ms3_w72<T>((I.ry0 + C::RS * k) % 24);
-        I.wy[k][1] = ms3_w72<T>(2 * ((I.ry0 + C::RS * k) % 24));
-    }
-    I.wx[0] = ms3_w72<T>(I.rx);
-    I.wx[1] = ms3_w72<T>(2 * I.rx);
+    for (int k = 0; k < C::MR; ++k)
+#pragma unroll
+        for (int e = 1; e < C::RA; ++e) I.wy[k][e - 1] = ms3_wP<T, C::P>(e * ((I.ry0 + C::RS * k) % C::RB));
+#pragma unroll
+    for (int e = 1; e < C::RA; ++e) I.wx[e - 1] = ms3_wP<T, C::P>(e * I.rx);
 }
 
 // B pass along y (YDIR, lanes along x: l = column) or along x (lanes along y: l = row) for group q = k1.
 // MODE 0: forward . h . inverse;  1: forward only (slot order left in place);  2: inverse only (slot order in).
-template <bool YDIR, int MODE, class T> ADM_DEV void ms3_B(T* psi, const T* hsd, int q, int l) {
-    constexpr int S = Ms3::S;
-    T* base = psi + (YDIR ? 24 * q * S + l : l * S + 24 * q);
+template <class C, bool YDIR, int MODE, class T> ADM_DEV void ms3_B(T* psi, const T* hsd, int q, int l) {
+    constexpr int S = C::S, RB = C::RB;
+    T* base = psi + (YDIR ? RB * q * S + l : l * S + RB * q);
     constexpr int st = YDIR ? S : 1;
-    T u[24];
+    T u[RB];
 #pragma unroll
-    for (int r = 0; r < 24; ++r) u[r] = base[r * st];
-    if constexpr (MODE != 2) ms3_dft24<false>(u);
+    for (int r = 0; r < RB; ++r) u[r] = base[r * st];
+    if constexpr (MODE != 2) ms3_dftB<RB, false>(u);
     if constexpr (MODE == 0) {
-        const T* hq = hsd + 24 * q;
+        const T* hq = hsd + RB * q;
 #pragma unroll
-        for (int s = 0; s < 24; s += 2) {
+        for (int s = 0; s < RB; s += 2) {
             T ha, hb;
             lds_pair(hq + s, ha, hb);
             u[s] = cmul(u[s], ha);
             u[s + 1] = cmul(u[s + 1], hb);
         }
     }
-    if constexpr (MODE != 1) ms3_dft24<true>(u);
+    if constexpr (MODE != 1) ms3_dftB<RB, true>(u);
 #pragma unroll
-    for (int r = 0; r < 24; ++r) base[r * st] = u[r];
+    for (int r = 0; r < RB; ++r) base[r * st] = u[r];
 }
 
 // ================================================================================================
 // Forward
 // ================================================================================================
-template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_ms3_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
+template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MINB) k_ms3_fwd(const ADM_GRID_CONSTANT AdmTileMap tmap, MsParams p) {
     ADM_SMEM_DECL
-    constexpr int P = C::P, S = C::S, TP = C::TP;
+    constexpr int P = C::P, S = C::S, TP = C::TP, RA = C::RA, RB = C::RB;
     constexpr unsigned TILE_BYTES = (unsigned)C::TILE;
     T* tile = (T*)smem_raw;
     T* psi = tile + P * TP;
@@ -182,7 +226,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
     ms3_thread_init<T, C>(I, t);
     const int c = blockIdx.x;
 
-    ms3_hs_fill(hs, (const T*)p.Hp, t);
+    ms3_hs_fill<C>(hs, (const T*)p.Hp, t);
     if (t == 0) mbar_init(bar, 1);
     unsigned ph = 0;
 
@@ -226,16 +270,16 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
             for (int k = 0; k < C::MR; ++k) {
                 if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
                 const int ry = I.ry0 + C::RS * k;
-                T w[3][3];
+                T w[RA][RA];
 #pragma unroll
-                for (int jy = 0; jy < 3; ++jy)
+                for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                    for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cscale(probe[(24 * jy + ry) * P + 24 * jx + I.rx], 1.0f / 9.0f);
-                ms3_A<false>(w, I.wy[k], I.wx);
+                    for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cscale(probe[(RB * jy + ry) * P + RB * jx + I.rx], 1.0f / (float)(RA * RA));
+                ms3_A<false, RA>(w, I.wy[k], I.wx);
 #pragma unroll
-                for (int jy = 0; jy < 3; ++jy)
+                for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                    for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
+                    for (int jx = 0; jx < RA; ++jx) psi[(RB * jy + ry) * S + RB * jx + I.rx] = w[jy][jx];
             }
         }
 
@@ -244,7 +288,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
             const bool go_on = !last || p.free_prop != ADM_PROP_NONE;
             // per-gap transfer functions (sparse multislice): the previous slice's last reader (its Bx pass) is one barrier
             // back, the first reader (By) comes after the barrier that closes M
-            if (!last && p.h_per_slice) ms3_hs_fill(hs, (const T*)p.Hp + (size_t)z * 2 * P, t);
+            if (!last && p.h_per_slice) ms3_hs_fill<C>(hs, (const T*)p.Hp + (size_t)z * 2 * P, t);
             // ---- M: [Ax^-1 Ay^-1] . checkpoint . modulation . [Ay Ax] ------------------------------------------
             // (ONE code path for all slices: a second instantiation without the last-slice options measured 3.5 % slower --
             // code size)
@@ -255,38 +299,38 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
                 for (int k = 0; k < C::MR; ++k) {
                     if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
                     const int ry = I.ry0 + C::RS * k;
-                    T w[3][3];
+                    T w[RA][RA];
 #pragma unroll
-                    for (int jy = 0; jy < 3; ++jy)
+                    for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                        for (int jx = 0; jx < 3; ++jx) w[jy][jx] = psi[(24 * jy + ry) * S + 24 * jx + I.rx];
-                    ms3_A<true>(w, I.wy[k], I.wx);
+                        for (int jx = 0; jx < RA; ++jx) w[jy][jx] = psi[(RB * jy + ry) * S + RB * jx + I.rx];
+                    ms3_A<true, RA>(w, I.wy[k], I.wx);
 #pragma unroll
-                    for (int jy = 0; jy < 3; ++jy)
+                    for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                        for (int jx = 0; jx < 3; ++jx) {
-                            const int o = (24 * jy + ry) * TP + 24 * jx + xo;
+                        for (int jx = 0; jx < RA; ++jx) {
+                            const int o = (RB * jy + ry) * TP + RB * jx + xo;
                             ck[o] = w[jy][jx];
                             w[jy][jx] = modulate(w[jy][jx], tile[o]);
                         }
                     if (!go_on) {
 #pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
+                        for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) det[(24 * jy + ry) * P + 24 * jx + I.rx] = w[jy][jx];   // exit wave
+                            for (int jx = 0; jx < RA; ++jx) det[(RB * jy + ry) * P + RB * jx + I.rx] = w[jy][jx];   // exit wave
                         continue;
                     }
                     if (last && p.ff_conj) {
 #pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
+                        for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cconj(w[jy][jx]);
+                            for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cconj(w[jy][jx]);
                     }
-                    ms3_A<false>(w, I.wy[k], I.wx);
+                    ms3_A<false, RA>(w, I.wy[k], I.wx);
 #pragma unroll
-                    for (int jy = 0; jy < 3; ++jy)
+                    for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                        for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
+                        for (int jx = 0; jx < RA; ++jx) psi[(RB * jy + ry) * S + RB * jx + I.rx] = w[jy][jx];
                 }
             }
             ph ^= 1;
@@ -295,26 +339,26 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
             if (!go_on) break;
             if (last) {
                 // far field: finish the forward 2-D transform and store fftshift-ed, natural order
-                if (active) ms3_B<true, 1>(psi, hs, q, l);
+                if (active) ms3_B<C, true, 1>(psi, hs, q, l);
                 __syncthreads();
                 if (active) {
-                    T u[24];
+                    T u[RB];
 #pragma unroll
-                    for (int r = 0; r < 24; ++r) u[r] = psi[l * S + 24 * q + r];
-                    ms3_dft24<false>(u);
-                    const int fy = (l / 24 + 3 * ms3_f24(l % 24) + P / 2) % P;
+                    for (int r = 0; r < RB; ++r) u[r] = psi[l * S + RB * q + r];
+                    ms3_dftB<RB, false>(u);
+                    const int fy = (l / RB + RA * C::fB(l % RB) + P / 2) % P;
 #pragma unroll
-                    for (int s = 0; s < 24; ++s) {
-                        const int fx = (q + 3 * ms3_f24(s) + P / 2) % P;
+                    for (int s = 0; s < RB; ++s) {
+                        const int fx = (q + RA * C::fB(s) + P / 2) % P;
                         T o = cscale(u[s], p.ff_scale);
                         det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
                     }
                 }
                 break;
             }
-            if (active) ms3_B<true, 0>(psi, hs, q, l);
+            if (active) ms3_B<C, true, 0>(psi, hs, q, l);
             __syncthreads();
-            if (active) ms3_B<false, 0>(psi, hs + P, q, l);
+            if (active) ms3_B<C, false, 0>(psi, hs + P, q, l);
             __syncthreads();
         }
         if (sg.ze < p.Nz) {                 // early part of a cut chain: hand the wavefield to CTA c + 1
@@ -332,9 +376,9 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
 // ================================================================================================
 // Adjoint
 // ================================================================================================
-template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_ms3_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
+template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MINB) k_ms3_bwd(const ADM_GRID_CONSTANT AdmTileMap gmap, MsParams p) {
     ADM_SMEM_DECL
-    constexpr int P = C::P, S = C::S, TP = C::TP;
+    constexpr int P = C::P, S = C::S, TP = C::TP, RA = C::RA, RB = C::RB;
     constexpr unsigned TILE_BYTES = (unsigned)C::TILE;
     T* ckb = (T*)smem_raw;          // psi checkpoint of the slice (bulk copy); overwritten in place by dL/dT
     T* psi = ckb + P * TP;          // running adjoint wavefield
@@ -348,7 +392,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
     ms3_thread_init<T, C>(I, t);
     const int c = gridDim.x - 1 - blockIdx.x;
 
-    ms3_hs_fill(hs, (const T*)p.Hp, t);
+    ms3_hs_fill<C>(hs, (const T*)p.Hp, t);
     if (t == 0) mbar_init(bar, 1);
     unsigned phase = 0;
 
@@ -366,18 +410,18 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
         const size_t slice_stride = (size_t)p.Y * p.Xp;
         // T' of one slice for this thread's blocks: plain loads of the L2-resident volume, ISSUED one barrier early (behind
         // the last pass of the previous slice) so that their latency overlaps the barrier wait
-        T tpa[C::MR][3][3];
+        T tpa[C::MR][RA][RA];
         auto load_tp = [&](int zz) {
             const T* tzz = (const T*)p.tvol + (size_t)zz * slice_stride;
 #pragma unroll
             for (int k = 0; k < C::MR; ++k) {
                 if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
 #pragma unroll
-                for (int jy = 0; jy < 3; ++jy) {
-                    const int gy = py + 24 * jy + I.ry0 + C::RS * k;
+                for (int jy = 0; jy < RA; ++jy) {
+                    const int gy = py + RB * jy + I.ry0 + C::RS * k;
 #pragma unroll
-                    for (int jx = 0; jx < 3; ++jx) {
-                        const int gx = px + 24 * jx + I.rx;
+                    for (int jx = 0; jx < RA; ++jx) {
+                        const int gx = px + RB * jx + I.rx;
                         const bool inb = (unsigned)gy < (unsigned)p.Y && (unsigned)gx < (unsigned)p.X;
                         tpa[k][jy][jx] = inb ? tzz[(unsigned)(gy * p.Xp + gx)] : tmk<T>(0.f, 0.f);
                     }
@@ -407,20 +451,20 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
         } else if (p.free_prop == ADM_PROP_FAR) {
             // adjoint of the detector transform: slot order in, inverse B along x, inverse B along y
             if (active) {
-                T u[24];
-                const int fy = (l / 24 + 3 * ms3_f24(l % 24) + P / 2) % P;
+                T u[RB];
+                const int fy = (l / RB + RA * C::fB(l % RB) + P / 2) % P;
 #pragma unroll
-                for (int s = 0; s < 24; ++s) {
-                    const int fx = (q + 3 * ms3_f24(s) + P / 2) % P;
+                for (int s = 0; s < RB; ++s) {
+                    const int fx = (q + RA * C::fB(s) + P / 2) % P;
                     T o = cscale(gdet[fy * P + fx], p.ff_scale);
                     u[s] = p.ff_conj ? cconj(o) : o;
                 }
-                ms3_dft24<true>(u);
+                ms3_dftB<RB, true>(u);
 #pragma unroll
-                for (int r = 0; r < 24; ++r) psi[l * S + 24 * q + r] = u[r];
+                for (int r = 0; r < RB; ++r) psi[l * S + RB * q + r] = u[r];
             }
             __syncthreads();
-            if (active) ms3_B<true, 2>(psi, hs, q, l);
+            if (active) ms3_B<C, true, 2>(psi, hs, q, l);
             __syncthreads();
         } else if (p.free_prop == ADM_PROP_NONE && mactive) {
             // exit-wave detection: dL/d(exit wave) enters the loop in the state every slice leaves behind (as the probe does
@@ -429,22 +473,22 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
             for (int k = 0; k < C::MR; ++k) {
                 if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
                 const int ry = I.ry0 + C::RS * k;
-                T w[3][3];
+                T w[RA][RA];
 #pragma unroll
-                for (int jy = 0; jy < 3; ++jy)
+                for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                    for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cscale(gdet[(24 * jy + ry) * P + 24 * jx + I.rx], 1.0f / 9.0f);
-                ms3_A<false>(w, I.wy[k], I.wx);
+                    for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cscale(gdet[(RB * jy + ry) * P + RB * jx + I.rx], 1.0f / (float)(RA * RA));
+                ms3_A<false, RA>(w, I.wy[k], I.wx);
 #pragma unroll
-                for (int jy = 0; jy < 3; ++jy)
+                for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                    for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
+                    for (int jx = 0; jx < RA; ++jx) psi[(RB * jy + ry) * S + RB * jx + I.rx] = w[jy][jx];
             }
         }
 
         for (int z = sg.ze - 1; z >= sg.zb; --z, phase ^= 1) {
             const bool last = (z == p.Nz - 1);
-            if (z > 0 && p.h_per_slice) ms3_hs_fill(hs, (const T*)p.Hp + (size_t)(z - 1) * 2 * P, t);
+            if (z > 0 && p.h_per_slice) ms3_hs_fill<C>(hs, (const T*)p.Hp + (size_t)(z - 1) * 2 * P, t);
             // ---- M': [Ax^-1 Ay^-1] . dL/dT = g' conj(psi_z) . g = g' conj(1 + T') . [Ay Ax] ----------------------
             // (three instantiations: KIND 1 = last slice (detector options), 2 = slice 0 (probe gradient, nothing to
             // propagate), 0 = every other slice, branch free; Nz > 1 on this path, so 1 and 2 never coincide.  Measured 0.5 %
@@ -455,17 +499,17 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
                 for (int k = 0; k < C::MR; ++k) {
                     if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
                     const int ry = I.ry0 + C::RS * k;
-                    T w[3][3];
+                    T w[RA][RA];
 #pragma unroll
-                    for (int jy = 0; jy < 3; ++jy)
+                    for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                        for (int jx = 0; jx < 3; ++jx) w[jy][jx] = psi[(24 * jy + ry) * S + 24 * jx + I.rx];
-                    ms3_A<true>(w, I.wy[k], I.wx);
+                        for (int jx = 0; jx < RA; ++jx) w[jy][jx] = psi[(RB * jy + ry) * S + RB * jx + I.rx];
+                    ms3_A<true, RA>(w, I.wy[k], I.wx);
                     if (KIND == 1 && p.ff_conj) {
 #pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
+                        for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) w[jy][jx] = cconj(w[jy][jx]);
+                            for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cconj(w[jy][jx]);
                     }
                     if (k == 0) {
                         mbar_wait(bar, phase);
@@ -473,26 +517,26 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
                         if (t < 2 * P) ckb[(t >> 1) * TP + ((t & 1) ? P + 1 : ((px & 1) ? 0 : P))] = tmk<T>(0.f, 0.f);
                     }
 #pragma unroll
-                    for (int jy = 0; jy < 3; ++jy)
+                    for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                        for (int jx = 0; jx < 3; ++jx) {
-                            const int o = (24 * jy + ry) * TP + 24 * jx + xo;
+                        for (int jx = 0; jx < RA; ++jx) {
+                            const int o = (RB * jy + ry) * TP + RB * jx + xo;
                             const T wz = ckb[o];                            // psi_z (wave entering the slice)
                             ckb[o] = cmulc(w[jy][jx], wz);                  // dL/dT = g' conj(psi_z)
                             w[jy][jx] = modulate_conj(w[jy][jx], tpa[k][jy][jx]);
                         }
                     if constexpr (KIND != 2) {
-                        ms3_A<false>(w, I.wy[k], I.wx);
+                        ms3_A<false, RA>(w, I.wy[k], I.wx);
 #pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
+                        for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) psi[(24 * jy + ry) * S + 24 * jx + I.rx] = w[jy][jx];
+                            for (int jx = 0; jx < RA; ++jx) psi[(RB * jy + ry) * S + RB * jx + I.rx] = w[jy][jx];
                     } else if (p.g_probe != nullptr) {
 #pragma unroll
-                        for (int jy = 0; jy < 3; ++jy)
+                        for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                            for (int jx = 0; jx < 3; ++jx) {
-                                const int o = (24 * jy + ry) * P + 24 * jx + I.rx;
+                            for (int jx = 0; jx < RA; ++jx) {
+                                const int o = (RB * jy + ry) * P + RB * jx + I.rx;
                                 if (p.probe_per_pattern) ((T*)p.g_probe)[(size_t)wf * P * P + o] = w[jy][jx];
                                 else red_add2(&p.g_probe[(size_t)m * P * P + o], cx(w[jy][jx]), cy(w[jy][jx]));
                             }
@@ -511,14 +555,14 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, 2) k_
                 bulk_commit();
             }
             if (z == 0) { phase ^= 1; break; }
-            if (active) ms3_B<true, 0>(psi, hs, q, l);
+            if (active) ms3_B<C, true, 0>(psi, hs, q, l);
             __syncthreads();
             if (t == 0 && z > sg.zb) {   // the reduce has drained the tile: prefetch the checkpoint of slice z-1 behind the x pass
                 bulk_wait_read_all();
                 mbar_expect_tx(bar, TILE_BYTES);
                 bulk_load(ckb, ckpt + (size_t)(z - 1) * P * TP, TILE_BYTES, bar);
             }
-            if (active) ms3_B<false, 0>(psi, hs + P, q, l);
+            if (active) ms3_B<C, false, 0>(psi, hs + P, q, l);
             if (mactive && z > sg.zb) load_tp(z - 1);
             __syncthreads();
         }

@@ -516,11 +516,11 @@ static int adm_variant(const char* name) {
     return e ? atoi(e) : 0;
 }
 
-// three-pass kernels (ms3_kernels.cuh) for P = 72 with a separable transfer function; ADM_MS3=0 selects the five-pass kernels
+// three-pass kernels (ms3_kernels.cuh) for a separable transfer function (P = 72 and 64); ADM_MS3=0 selects the five-pass kernels
 static bool ms3_wanted(const adm_multislice_cfg* cfg, const MsParams& p) {
     const char* e = getenv("ADM_MS3");
     if (e && atoi(e) == 0) return false;
-    return cfg->P == 72 && p.h_separable && p.Nz > 1 && p.free_prop != ADM_PROP_NEAR;
+    return (cfg->P == 72 || cfg->P == 64) && p.h_separable && p.Nz > 1 && p.free_prop != ADM_PROP_NEAR;
 }
 
 // number of CTAs of `kern` that are co-resident on the device (SM count x occupancy); ADM_MS_GRID overrides it (tests)
@@ -640,11 +640,12 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
     do {                                                                                                            \
         if (set_smem(KERN<cpk, CFG>, CFG::BYTES)) return ADM_ERR_CUDA;                                              \
         int grid_;                                                                                                  \
-        if (ms_schedule(p, ms_resident_ctas(KERN<cpk, CFG>, CFG::NTHREADS, CFG::BYTES), workspace, 72, grid_))      \
+        if (ms_schedule(p, ms_resident_ctas(KERN<cpk, CFG>, CFG::NTHREADS, CFG::BYTES), workspace, CFG::P, grid_))  \
             return ADM_ERR_CUDA;                                                                                    \
         ADM_LAUNCH((KERN<cpk, CFG>), grid_, CFG::NTHREADS, CFG::BYTES, stream, map, p);                             \
     } while (0)
-        ADM_MS3_LAUNCH(k_ms3_fwd, Ms3w);
+        if (cfg->P == 72) ADM_MS3_LAUNCH(k_ms3_fwd, Ms3w);
+        else ADM_MS3_LAUNCH(k_ms3_fwd, Ms3p64);
         return ADM_OK;
     }
 #define ADM_FWD(CFG, MINB, TILE, CT)                                                                                  \
@@ -704,7 +705,8 @@ static int ms_bwd_impl(const adm_multislice_cfg* cfg, const float* tvol, const i
         return ADM_ERR_CUDA;
     int var = adm_variant("ADM_BWD_VARIANT");
     if (var == 0 && p.g_ckpt == nullptr && ms3_wanted(cfg, p)) {
-        ADM_MS3_LAUNCH(k_ms3_bwd, Ms3);
+        if (cfg->P == 72) ADM_MS3_LAUNCH(k_ms3_bwd, Ms3);
+        else ADM_MS3_LAUNCH(k_ms3_bwd, Ms3p64);
         return ADM_OK;
     }
 #define ADM_BWD(CFG, MINB, CT, GCK)                                                                                  \

@@ -88,17 +88,49 @@ def test_emulated_balanced_schedule_matches_one_cta_per_wavefield(name, grid, mo
     assert abs(out['loss'] - ref['loss']) <= 1e-6 * abs(ref['loss'])
 
 
-@pytest.mark.parametrize('name', ['ptycho3d_p72_edge', 'sparse3_p72'])
+@pytest.mark.parametrize('name', ['ptycho3d_p72_edge', 'sparse3_p72', 'fullfield64'])
 def test_emulated_five_pass_kernels_match_three_pass_kernels(name, monkeypatch):
-    """72-pixel probes with a separable transfer function run on the three-pass kernels (ms3_kernels.cuh: 72 = 3 x 24) by
-    default, and every P = 72 case above exercises them; ADM_MS3=0 selects the five-pass kernels of multislice.cu
-    (72 = 8 x 9), which stay the path for near-field detection / general H / adjoint-wavefield checkpoints.  Two
-    independent factorizations of the same transform must agree to fp32 rounding."""
+    """Probes of 72 / 64 pixels with a separable transfer function run on the three-pass kernels (ms3_kernels.cuh:
+    72 = 3 x 24, 64 = 4 x 16) by default, and every such case above exercises them; ADM_MS3=0 selects the five-pass
+    kernels of multislice.cu (72 = 8 x 9, 64 = 8 x 8), which stay the path for near-field detection / general H /
+    adjoint-wavefield checkpoints.  Two independent factorizations of the same transform must agree to fp32 rounding."""
     _, a = run_emu_case(name, separable=True)
     monkeypatch.setenv('ADM_MS3', '0')
     _, b = run_emu_case(name, separable=True)
     for k in ('det', 'pred', 'g_obj', 'g_probe_real', 'g_probe_imag'):
         assert 0 < rel_err(a[k], b[k]) < 5e-5, k      # 0 would mean that the switch selected nothing
+    assert abs(a['loss'] - b['loss']) <= 1e-5 * abs(b['loss'])
+
+
+def test_emulated_three_pass_kernels_for_64_pixel_probes_with_handoff(monkeypatch):
+    """64-pixel probes on the three-pass kernels (64 = 4 x 16: 4 x 4 blocks in the M pass, 16-point transforms in the B
+    passes): several overhanging wavefields through 5 slices, far-field detection, probe gradient; (a) against the five-pass
+    kernels, (b) with the chains cut at arbitrary slices and handed from CTA to CTA (ADM_MS_GRID)."""
+    rs = np.random.RandomState(11)
+    Y, X, Z, P, B = 90, 83, 5, 64, 4
+    obj = np.zeros((Y, X, Z, 2), 'float32')
+    obj[..., 0] = 3e-3 * rs.uniform(size=(Y, X, Z))
+    obj[..., 1] = 3e-4 * rs.uniform(size=(Y, X, Z))
+    yy, xx = np.mgrid[:P, :P] - P / 2
+    amp = np.exp(-(yy ** 2 + xx ** 2) / (2 * 12. ** 2))
+    ph = 0.3 * np.sin(xx / 7.) + 0.2 * np.cos(yy / 5.)
+    pr = (amp * np.cos(ph))[None].astype('float32')
+    pi = (amp * np.sin(ph))[None].astype('float32')
+    pos = np.array([[-9, 30], [20, -5], [31, 27], [5, 3]], 'int32')
+    prj = rs.uniform(0.5, 1.5, size=(B, P, P)).astype('float32')
+    voxel, lam = 1.0, 1240. / 5000
+    h = orc.get_kernel(voxel, lam, np.array([voxel] * 3), [P, P], fresnel_approx=True, sign_convention=1)
+    k1 = 2. * orc.PI * voxel / lam
+    kw = dict(unknown_type='delta_beta', free_prop='inf', loss='lsq', raw_data_type='magnitude', separable=True)
+    a = emu_lib.loss_and_grads_emu(obj, pr, pi, pos, prj, None, h, k1, **kw)
+    monkeypatch.setenv('ADM_MS_GRID', '3')
+    c = emu_lib.loss_and_grads_emu(obj, pr, pi, pos, prj, None, h, k1, **kw)
+    monkeypatch.delenv('ADM_MS_GRID')
+    monkeypatch.setenv('ADM_MS3', '0')
+    b = emu_lib.loss_and_grads_emu(obj, pr, pi, pos, prj, None, h, k1, **kw)
+    for k in ('det', 'pred', 'g_obj', 'g_probe_real', 'g_probe_imag'):
+        assert 0 < rel_err(a[k], b[k]) < 5e-5, k
+        assert rel_err(c[k], a[k]) < 2e-6, k
     assert abs(a['loss'] - b['loss']) <= 1e-5 * abs(b['loss'])
 
 
