@@ -119,7 +119,11 @@ int adm_transmission_adj(int unknown_type, float k1, int sign_convention, int Nz
  *            the launch is persistent: the B*M*Nz slice steps are cut into equal intervals, one per CTA, and a wavefield
  *            cut by a boundary is handed from CTA to CTA through the workspace (no idle tail of a partial last wave).
  *            NULL (or few wavefields): one CTA per wavefield.
- * cfg->k1 / unknown_type are not used here (they parameterise adm_transmission_*).                          */
+ * cfg->k1 / unknown_type are not used here (they parameterise adm_transmission_*).
+ * Kernel selection (same buffers and formats either way): P = 72 / 64 with h_separable, n_slices > 1 and far-field or
+ * exit-wave detection run on the three-pass kernels (csrc/ms3_kernels.cuh); single-slice objects, a general transfer
+ * function, near-field detection and adm_multislice_bwd_gpsi on the five / six-pass kernels (csrc/multislice.cu).
+ * Environment ADM_MS3=0 selects the latter for every shape (A/B runs, tests).                                   */
 long long adm_multislice_workspace_bytes(int P);
 int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tvol, const float* probe, const int* pos,
                        const float* Hprep, const float* Hfree, float* psi_ckpt, float* det, void* workspace,
