@@ -644,7 +644,10 @@ extern "C" int adm_multislice_fwd(const adm_multislice_cfg* cfg, const float* tv
             return ADM_ERR_CUDA;                                                                                    \
         ADM_LAUNCH((KERN<cpk, CFG>), grid_, CFG::NTHREADS, CFG::BYTES, stream, map, p);                             \
     } while (0)
-        if (cfg->P == 72) ADM_MS3_LAUNCH(k_ms3_fwd, Ms3w);
+        // 9 warps (M pass in two balanced rounds) when the SMs are shared by many wavefields; 7 warps for a handful of
+        // wavefields, where the latency of one slice step counts (reference demo schedule, minibatch 2: 2.76 vs 2.88 ms per step)
+        if (cfg->P == 72 && (p.B * p.M > 148 || adm_variant("ADM_MS3_FWD") == 2)) ADM_MS3_LAUNCH(k_ms3_fwd, Ms3w);      // (2: tests)
+        else if (cfg->P == 72) ADM_MS3_LAUNCH(k_ms3_fwd, Ms3);
         else ADM_MS3_LAUNCH(k_ms3_fwd, Ms3p64);
         return ADM_OK;
     }
