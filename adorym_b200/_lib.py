@@ -17,7 +17,8 @@ class MultisliceCfg(ctypes.Structure):
     """struct adm_multislice_cfg (include/adorym_b200.h)."""
     _fields_ = [('P', c_int), ('n_slices', c_int), ('B', c_int), ('M', c_int), ('Y', c_int), ('X', c_int),
                 ('k1', c_float), ('sign_convention', c_int), ('unknown_type', c_int), ('free_prop', c_int),
-                ('normalize_fft', c_int), ('probe_per_pattern', c_int), ('h_separable', c_int), ('h_per_slice', c_int)]
+                ('normalize_fft', c_int), ('probe_per_pattern', c_int), ('h_separable', c_int), ('h_per_slice', c_int),
+                ('hfree_separable', c_int)]
 
 
 P_CFG = ctypes.POINTER(MultisliceCfg)
@@ -114,7 +115,7 @@ def get_lib():
         if not os.path.exists(LIB_PATH):
             raise RuntimeError('adorym_b200: CUDA library %s is missing; run `python -m adorym_b200.build`' % LIB_PATH)
         _lib = bind(ctypes.CDLL(LIB_PATH))
-        if _lib.adm_abi_version() != 7:
+        if _lib.adm_abi_version() != 8:
             raise RuntimeError('adorym_b200: ABI version mismatch')
     return _lib
 

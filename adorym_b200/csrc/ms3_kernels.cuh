@@ -1,7 +1,8 @@
-// Three-pass multislice kernels for 72-pixel probes and a separable (paraxial) transfer function  (sm_100a).
+// Three-pass multislice kernels for 72- and 64-pixel probes and a separable (paraxial) transfer function  (sm_100a).
 // Included by multislice.cu (after MsSmem / the balanced-schedule helpers); same C ABI, same checkpoint / tile /
-// hand-off formats as the five-pass kernels there, which remain the path for P = 64, general H, near-field detection
-// and the adjoint-wavefield checkpoints.
+// hand-off formats as the five-pass kernels there, which remain the path for single-slice objects, a general
+// (non-paraxial) transfer function and the adjoint-wavefield checkpoints (adm_multislice_bwd_gpsi).
+// Everything below is written for P = RA x RB per axis: 72 = 3 x 24 (described here) and 64 = 4 x 16.
 //
 // Why: the five-pass kernels sit on the shared-memory pipe (ncu r02y: l1tex 74 %, ~4.8 k wavefronts per slice, of which
 // 5 x 648 are the five round trips of the wavefield).  Here 72 = 3 x 24 per axis (Cooley-Tukey, twiddle W72^(r k1) between
@@ -132,6 +133,23 @@ template <class C, class T> ADM_DEV void ms3_hs_fill(T* hs, const T* Hsep, int t
         const int dir = t / C::P, i = t % C::P;
         const int f = i / C::RB + C::RA * C::fB(i % C::RB);
         hs[t] = Hsep[dir * C::P + C::five_pass_pos(f)];
+    }
+}
+
+// The same tables for the free-space (near-field) transfer function, taken out of the prepared GENERAL table
+// Hf[px][py] = scale H[freq(py)][freq(px)] (adm_prepare_transfer_function; positions in the five-pass order, position 0
+// holds frequency 0) of an outer product H = hy (x) hx:  hy'(f) = Hf[0][pos(f)] = scale H(f, 0),
+// hx'(f) = Hf[pos(f)][0] / Hf[0][0] = H(0, f) / H(0, 0).
+template <class C, class T> ADM_DEV void ms3_hf_fill(T* hs, const T* Hf, int t) {
+    if (t < 2 * C::P) {
+        const int dir = t / C::P, i = t % C::P;
+        const int pos = C::five_pass_pos(i / C::RB + C::RA * C::fB(i % C::RB));
+        if (dir == 0) hs[t] = Hf[pos];
+        else {
+            const T a = Hf[pos * C::P], b = Hf[0];
+            const float n = 1.0f / (cx(b) * cx(b) + cy(b) * cy(b));
+            hs[t] = cscale(cmulc(a, b), n);
+        }
     }
 }
 
@@ -290,8 +308,9 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
             // back, the first reader (By) comes after the barrier that closes M
             if (!last && p.h_per_slice) ms3_hs_fill<C>(hs, (const T*)p.Hp + (size_t)z * 2 * P, t);
             // ---- M: [Ax^-1 Ay^-1] . checkpoint . modulation . [Ay Ax] ------------------------------------------
-            // (ONE code path for all slices: a second instantiation without the last-slice options measured 3.5 % slower --
-            // code size)
+            // (ONE code path for all slices with run-time checks of the last-slice options.  Measured alternatives: a second,
+            // branch-free instantiation for the other slices inside the loop 3.5 % slower; the last slice as a second
+            // instantiation BEHIND the loop 3 % slower; the detector transforms inside the loop 2 % slower.)
             if (mactive) {
                 mbar_wait(bar, ph);
                 T* ck = ckpt + (size_t)z * P * TP;
@@ -336,30 +355,57 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
             ph ^= 1;
             __syncthreads();
             if (t == 0 && z + 1 < sg.ze) issue_tile(z + 1);   // every thread has consumed tile(z): prefetch tile(z+1) behind the B passes
-            if (!go_on) break;
-            if (last) {
-                // far field: finish the forward 2-D transform and store fftshift-ed, natural order
-                if (active) ms3_B<C, true, 1>(psi, hs, q, l);
-                __syncthreads();
-                if (active) {
-                    T u[RB];
-#pragma unroll
-                    for (int r = 0; r < RB; ++r) u[r] = psi[l * S + RB * q + r];
-                    ms3_dftB<RB, false>(u);
-                    const int fy = (l / RB + RA * C::fB(l % RB) + P / 2) % P;
-#pragma unroll
-                    for (int s = 0; s < RB; ++s) {
-                        const int fx = (q + RA * C::fB(s) + P / 2) % P;
-                        T o = cscale(u[s], p.ff_scale);
-                        det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
-                    }
-                }
-                break;
-            }
+            if (last) break;      // exit wave: stored by the M pass; far / near field: detector transform behind the loop
             if (active) ms3_B<C, true, 0>(psi, hs, q, l);
             __syncthreads();
             if (active) ms3_B<C, false, 0>(psi, hs + P, q, l);
             __syncthreads();
+        }
+        // ---- detector transform of a chain that reached the last slice (kept out of the slice loop: code size) ----
+        if (sg.ze == p.Nz && p.free_prop == ADM_PROP_FAR) {
+            // far field: finish the forward 2-D transform and store fftshift-ed, natural order
+            if (active) ms3_B<C, true, 1>(psi, hs, q, l);
+            __syncthreads();
+            if (active) {
+                T u[RB];
+#pragma unroll
+                for (int r = 0; r < RB; ++r) u[r] = psi[l * S + RB * q + r];
+                ms3_dftB<RB, false>(u);
+                const int fy = (l / RB + RA * C::fB(l % RB) + P / 2) % P;
+#pragma unroll
+                for (int s = 0; s < RB; ++s) {
+                    const int fx = (q + RA * C::fB(s) + P / 2) % P;
+                    T o = cscale(u[s], p.ff_scale);
+                    det[fy * P + fx] = p.ff_conj ? cconj(o) : o;
+                }
+            }
+        } else if (sg.ze == p.Nz && p.free_prop == ADM_PROP_NEAR) {
+            // near field: the two B passes with the free-space tables, closing inverse stages, natural order store; then the
+            // in-object tables again (their next reader is behind the barriers of the next wavefield)
+            ms3_hf_fill<C>(hs, (const T*)p.Hf, t);
+            __syncthreads();
+            if (active) ms3_B<C, true, 0>(psi, hs, q, l);
+            __syncthreads();
+            if (active) ms3_B<C, false, 0>(psi, hs + P, q, l);
+            __syncthreads();
+            if (mactive) {
+#pragma unroll
+                for (int k = 0; k < C::MR; ++k) {
+                    if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
+                    const int ry = I.ry0 + C::RS * k;
+                    T w[RA][RA];
+#pragma unroll
+                    for (int jy = 0; jy < RA; ++jy)
+#pragma unroll
+                        for (int jx = 0; jx < RA; ++jx) w[jy][jx] = psi[(RB * jy + ry) * S + RB * jx + I.rx];
+                    ms3_A<true, RA>(w, I.wy[k], I.wx);
+#pragma unroll
+                    for (int jy = 0; jy < RA; ++jy)
+#pragma unroll
+                        for (int jx = 0; jx < RA; ++jx) det[(RB * jy + ry) * P + RB * jx + I.rx] = w[jy][jx];
+                }
+            }
+            if (!p.h_per_slice) ms3_hs_fill<C>(hs, (const T*)p.Hp, t);
         }
         if (sg.ze < p.Nz) {                 // early part of a cut chain: hand the wavefield to CTA c + 1
             float4* dst = p.handoff + (size_t)(c + 1) * p.slot_f4;
@@ -466,9 +512,12 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
             __syncthreads();
             if (active) ms3_B<C, true, 2>(psi, hs, q, l);
             __syncthreads();
-        } else if (p.free_prop == ADM_PROP_NONE && mactive) {
-            // exit-wave detection: dL/d(exit wave) enters the loop in the state every slice leaves behind (as the probe does
-            // in the forward kernel); every thread reads back exactly the positions it writes here: no barrier
+        } else if (mactive) {
+            // exit-wave / near-field detection: dL/d(detector wave) enters in the state every slice leaves behind (as the probe
+            // does in the forward kernel); every thread reads back exactly the positions it writes here: no barrier.  (The
+            // state carries 1 / RA^2, which the unnormalised inverse stages of M' return; the B passes of the near-field
+            // adjoint below bring that factor themselves.)
+            const float pre = p.free_prop == ADM_PROP_NEAR ? 1.0f : 1.0f / (float)(RA * RA);
 #pragma unroll
             for (int k = 0; k < C::MR; ++k) {
                 if (!C::full_round(k) && t + C::MT * k >= C::NB) break;
@@ -477,13 +526,24 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
 #pragma unroll
                 for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
-                    for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cscale(gdet[(RB * jy + ry) * P + RB * jx + I.rx], 1.0f / (float)(RA * RA));
+                    for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cscale(gdet[(RB * jy + ry) * P + RB * jx + I.rx], pre);
                 ms3_A<false, RA>(w, I.wy[k], I.wx);
 #pragma unroll
                 for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
                     for (int jx = 0; jx < RA; ++jx) psi[(RB * jy + ry) * S + RB * jx + I.rx] = w[jy][jx];
             }
+        }
+
+        if (sg.ze == p.Nz && p.free_prop == ADM_PROP_NEAR) {
+            // adjoint of the free-space propagation to the detector: the two B passes with the conjugate free-space tables
+            ms3_hf_fill<C>(hs, (const T*)p.Hf, t);
+            __syncthreads();
+            if (active) ms3_B<C, true, 0>(psi, hs, q, l);
+            __syncthreads();
+            if (active) ms3_B<C, false, 0>(psi, hs + P, q, l);
+            __syncthreads();
+            if (!p.h_per_slice) ms3_hs_fill<C>(hs, (const T*)p.Hp, t);      // next reader: behind the barrier that closes M'
         }
 
         for (int z = sg.ze - 1; z >= sg.zb; --z, phase ^= 1) {

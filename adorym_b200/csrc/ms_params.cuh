@@ -14,7 +14,7 @@ struct MsParams {
     cpx* g_probe;
     cpx* g_ckpt;        // adjoint only, optional: dL/d psi_z (gradient w.r.t. the wave entering slice z) [B][M][Nz][P][P]
     int Nz, Y, X, Xp, B, M;
-    int free_prop, probe_per_pattern, h_separable, h_per_slice;
+    int free_prop, probe_per_pattern, h_separable, h_per_slice, hfree_separable;
     float ff_scale;
     int ff_conj;
     // persistent balanced schedule (multislice.cu): the nwf * Nz slice steps of a launch are laid end to end and cut in

@@ -520,7 +520,7 @@ static int adm_variant(const char* name) {
 static bool ms3_wanted(const adm_multislice_cfg* cfg, const MsParams& p) {
     const char* e = getenv("ADM_MS3");
     if (e && atoi(e) == 0) return false;
-    return (cfg->P == 72 || cfg->P == 64) && p.h_separable && p.Nz > 1 && p.free_prop != ADM_PROP_NEAR;
+    return (cfg->P == 72 || cfg->P == 64) && p.h_separable && p.Nz > 1 && (p.free_prop != ADM_PROP_NEAR || p.hfree_separable);
 }
 
 // number of CTAs of `kern` that are co-resident on the device (SM count x occupancy); ADM_MS_GRID overrides it (tests)
@@ -584,6 +584,7 @@ static int fill_params(const adm_multislice_cfg* c, MsParams& p) {
     p.Nz = c->n_slices; p.Y = c->Y; p.X = c->X; p.Xp = ADM_TVOL_PITCH(c->X); p.B = c->B; p.M = c->M;
     p.free_prop = c->free_prop; p.probe_per_pattern = c->probe_per_pattern; p.h_separable = c->h_separable ? 1 : 0;
     p.h_per_slice = c->h_per_slice ? 1 : 0;
+    p.hfree_separable = c->hfree_separable ? 1 : 0;
     if (p.h_per_slice && !p.h_separable) return ADM_ERR_UNSUPPORTED;
     // far field: sign +1 -> fft2 (unnormalised or 1/P), sign -1 -> ifft2 (1/P^2 or 1/P)   (propagate.py:267-270)
     float Pf = (float)c->P;

@@ -95,6 +95,7 @@ class MultislicePlan(object):
         self.Hp = self.Hc = self.Hfp = self.Hfc = None
         self.h_separable = 0
         self.h_per_slice = 0
+        self.hfree_separable = 0
         if h_gaps is not None:
             if len(h_gaps) != self.n_slices - 1:
                 raise ValueError('h_gaps must hold n_slices - 1 transfer functions')
@@ -122,13 +123,16 @@ class MultislicePlan(object):
     def set_free_kernel(self, h_free):
         self.Hfp = prepare_transfer_function(h_free, self.device, conj=False)
         self.Hfc = prepare_transfer_function(h_free, self.device, conj=True)
+        # an outer product hy(ky) hx(kx) (the paraxial kernel always is): the three-pass kernels take the factors from the
+        # first row / column of the prepared table
+        self.hfree_separable = int(separate_transfer_function(h_free) is not None)
 
     def cfg(self, B, M, probe_per_pattern):
         return MultisliceCfg(P=self.P, n_slices=self.n_slices, B=int(B), M=int(M), Y=self.Y, X=self.X, k1=self.k1,
                              sign_convention=self.sign_convention, unknown_type=self.unknown_type,
                              free_prop=self.free_prop, normalize_fft=self.normalize_fft,
                              probe_per_pattern=int(bool(probe_per_pattern)), h_separable=self.h_separable,
-                             h_per_slice=self.h_per_slice)
+                             h_per_slice=self.h_per_slice, hfree_separable=self.hfree_separable)
 
 
 # ------------------------------------------------------------------------------------------------------

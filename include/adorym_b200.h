@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define ADM_ABI_VERSION 7
+#define ADM_ABI_VERSION 8
 
 /* unknown_type */
 #define ADM_DELTA_BETA 0
@@ -62,6 +62,10 @@ typedef struct adm_multislice_cfg {
     int h_per_slice;       /* 1 (needs h_separable): Hprep / HprepC are [n_slices-1][2][P][2], one separable transfer
                               function per gap between slices z and z+1 -- sparse multislice with unequal slice
                               spacings (propagate.py:479-534 sparse_multislice_propagate_batch)                 */
+    int hfree_separable;   /* 1: the free-space transfer function behind Hfree / HfreeC (ADM_PROP_NEAR) is an outer product
+                              hy(ky) hx(kx) -- the paraxial Fresnel kernel of propagate.py:72 always is.  The tables keep
+                              their general [P][P] form; the flag lets the three-pass kernels take the two factors out
+                              of their first row / column.  0: unknown (five-pass kernels).                          */
 } adm_multislice_cfg;
 
 /* ABI / build identification. */

@@ -86,15 +86,18 @@ def loss_and_grads_emu(obj, probe_real, probe_imag, pos, prj_abs, grid, H, k1, *
             ck(L.adm_prepare_transfer_function_separable(Pp, P(f(hy)), P(f(hx)), 0, 1.0 / (Pp * Pp), P(Hp[i]), None))
             ck(L.adm_prepare_transfer_function_separable(Pp, P(f(hy)), P(f(hx)), 1, 1.0 / (Pp * Pp), P(Hc[i]), None))
     Hfp = Hfc = None
+    hfsep = 0
     fp = {'none': 0, 'inf': 1, 'near': 2}[free_prop]
     if fp == 2:
+        hfsep = int(np.abs(np.outer(Hfree[:, 0], Hfree[0, :] / Hfree[0, 0]) - Hfree).max() < 1e-9)
         Hf = np.ascontiguousarray(np.stack([Hfree.real, Hfree.imag], -1), dtype='float32')
         Hfp, Hfc = np.zeros_like(Hf), np.zeros_like(Hf)
         ck(L.adm_prepare_transfer_function(Pp, P(Hf), 0, 1.0 / (Pp * Pp), P(Hfp), None))
         ck(L.adm_prepare_transfer_function(Pp, P(Hf), 1, 1.0 / (Pp * Pp), P(Hfc), None))
     cfg = MultisliceCfg(P=Pp, n_slices=Z, B=B, M=M, Y=Y, X=X, k1=float(np.float32(k1)), sign_convention=sign_convention,
                         unknown_type=0 if unknown_type == 'delta_beta' else 1, free_prop=fp,
-                        normalize_fft=int(normalize_fft), probe_per_pattern=ppp, h_separable=hsep, h_per_slice=hps)
+                        normalize_fft=int(normalize_fft), probe_per_pattern=ppp, h_separable=hsep, h_per_slice=hps,
+                        hfree_separable=hfsep)
     posi = np.ascontiguousarray(pos, dtype='int32')
     ckpt = np.full((B, M, Z, Pp, Pp + 2, 2), np.nan, 'float32')
     det = np.zeros((B, M, Pp, Pp, 2), 'float32')

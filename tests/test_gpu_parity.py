@@ -231,7 +231,7 @@ def test_multislice_propagate_batch_dropin():
     import adorym_b200 as ab
     dev = torch.device('cuda', 0)
     rs = np.random.RandomState(3)
-    for P, fp in ((64, 0), (72, 'inf'), (64, 'inf'), (64, 3e-4), (72, None), (128, 'inf'), (256, 3e-4)):
+    for P, fp in ((64, 0), (72, 'inf'), (64, 'inf'), (64, 3e-4), (72, 3e-4), (72, None), (128, 'inf'), (256, 3e-4)):
         B, Nz = 3, 5
         grid = np.stack([rs.uniform(0, 2e-3, (B, P, P, Nz)), rs.uniform(0, 2e-4, (B, P, P, Nz))], -1).astype('float32')
         pr = rs.normal(size=(P, P)).astype('float32')
@@ -272,11 +272,12 @@ def test_near_field_gradients_match_oracle():
     assert rel_err(gi.cpu().numpy(), gi64.numpy()) < TOL
 
 
-@pytest.mark.parametrize('P,fp', [(64, 'inf'), (64, 0), (72, 0)])
+@pytest.mark.parametrize('P,fp', [(64, 'inf'), (64, 0), (72, 0), (72, 2e-4), (64, 2e-4)])
 def test_three_pass_gradients_of_explicit_patch_stacks_match_oracle(P, fp):
     """Forward + adjoint of the three-pass kernels (ms3_kernels.cuh) through the propagate.py:131 drop-in for several
-    wavefields: 64-pixel probes (64 = 4 x 16) with far-field and exit-wave detection, 72-pixel probes with exit-wave
-    detection (the named cases cover 72 / far field and 64 / exit wave / one wavefield) vs fp64 autograd."""
+    wavefields: 64-pixel probes (64 = 4 x 16) with far-field, exit-wave and near-field detection, 72-pixel probes with
+    exit-wave and near-field detection (the named cases cover 72 / far field and 64 / exit wave / one wavefield) vs fp64
+    autograd."""
     import adorym_b200 as ab
     dev = torch.device('cuda', 0)
     rs = np.random.RandomState(7)

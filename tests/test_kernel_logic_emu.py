@@ -142,6 +142,34 @@ def test_emulated_three_pass_kernels_for_64_pixel_probes_with_handoff(monkeypatc
     assert abs(a['loss'] - b['loss']) <= 1e-5 * abs(b['loss'])
 
 
+@pytest.mark.parametrize('P', [72, 64])
+def test_emulated_three_pass_kernels_near_field_detection(P, monkeypatch):
+    """Near-field detection (finite free_prop_cm, propagate.py:271-280) on the three-pass kernels: the free-space transfer
+    function arrives as the general prepared table and, being an outer product (cfg.hfree_separable), is applied as two more
+    B passes with the factors taken from its first row / column; forward, object and probe gradients against the five-pass
+    kernels (which are pinned by the oracle in tests/test_gpu_parity.py::test_near_field_gradients_match_oracle)."""
+    rs = np.random.RandomState(13)
+    Y, X, Z, B = P + 21, P + 9, 4, 3
+    obj = np.zeros((Y, X, Z, 2), 'float32')
+    obj[..., 0] = 3e-3 * rs.uniform(size=(Y, X, Z))
+    obj[..., 1] = 3e-4 * rs.uniform(size=(Y, X, Z))
+    pr = rs.normal(size=(1, P, P)).astype('float32')
+    pi = rs.normal(size=(1, P, P)).astype('float32')
+    pos = np.array([[-7, 12], [15, -4], [9, 6]], 'int32')
+    prj = rs.uniform(0.5, 1.5, size=(B, P, P)).astype('float32')
+    voxel, lam = 1.0, 1240. / 5000
+    h = orc.get_kernel(voxel, lam, np.array([voxel] * 3), [P, P], fresnel_approx=True, sign_convention=1)
+    hf = orc.get_kernel(2e-4 * 1e7, lam, np.array([voxel] * 3), [P, P], fresnel_approx=True, sign_convention=1)
+    k1 = 2. * orc.PI * voxel / lam
+    kw = dict(unknown_type='delta_beta', free_prop='near', Hfree=hf, loss='lsq', raw_data_type='magnitude', separable=True)
+    a = emu_lib.loss_and_grads_emu(obj, pr, pi, pos, prj, None, h, k1, **kw)
+    monkeypatch.setenv('ADM_MS3', '0')
+    b = emu_lib.loss_and_grads_emu(obj, pr, pi, pos, prj, None, h, k1, **kw)
+    for k in ('det', 'pred', 'g_obj', 'g_probe_real', 'g_probe_imag'):
+        assert 0 < rel_err(a[k], b[k]) < 5e-5, k
+    assert abs(a['loss'] - b['loss']) <= 1e-5 * abs(b['loss'])
+
+
 @pytest.mark.parametrize('name', ['ptycho3d_p72_strongreg', 'fullfield64', 'ptycho2d_realimag_p64'])
 def test_emulated_fused_object_chain_matches_separate_kernels(name):
     """object_chain.cu (rotation + transmission in one pass, regulariser gradient as the initial value of the gradient
