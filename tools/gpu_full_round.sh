@@ -1,5 +1,5 @@
 #!/bin/bash
-TAG=${1:-r04i}
+TAG=${1:-r04}
 mkdir -p gpurun_out
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$TAG.log 2>&1
 echo "pytest rc=$?"; tail -6 gpurun_out/pytest_gpu_$TAG.log
