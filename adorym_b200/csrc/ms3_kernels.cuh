@@ -30,9 +30,10 @@
 // P = RA * RB per axis (72 = 3 x 24, 64 = 4 x 16).  NT threads per CTA; the B passes use the first P * RA of them (one
 // RB-point group each), the M pass MT of them with MR blocks each (thread t owns the blocks (t / RB + (MT / RB) k, t % RB),
 // k < MR, while t + MT k < RB^2).  MINB: CTAs per SM the registers are capped for.
-template <int P_, int RA_, int NT_, int MT_, int MR_, int MINB_> struct Ms3Cfg {
+template <int P_, int RA_, int NT_, int MT_, int MR_, int MINB_, bool COMB_ = false> struct Ms3Cfg {
     static constexpr int P = P_, RA = RA_, RB = P_ / RA_, S = P_ + 1, TP = P_ + 2, NACT = P_ * RA_, NTHREADS = NT_, MT = MT_, MR = MR_;
     static constexpr int RS = MT_ / RB, NB = RB * RB, MINB = MINB_;
+    static constexpr bool COMB = COMB_;      // products of the y and x twiddles as per-thread constants (one multiply instead of two)
     static constexpr size_t TILE = sizeof(cpx) * P * TP;                 // T' tile (forward) / checkpoint + dL/dT tile (adjoint)
     static constexpr size_t PSI = sizeof(cpx) * P * S;
     static constexpr size_t HS = sizeof(cpx) * 2 * P;
@@ -53,7 +54,7 @@ template <int P_, int RA_, int NT_, int MT_, int MR_, int MINB_> struct Ms3Cfg {
     }
 };
 typedef Ms3Cfg<72, 3, 224, 216, 3, 2> Ms3;      // adjoint: 7 warps, 128 registers (the T' values held across a barrier need them)
-typedef Ms3Cfg<72, 3, 288, 288, 2, 2> Ms3w;     // forward: 9 warps, M pass in two balanced rounds, 96 registers, no spills (2.70 vs 2.74 ms)
+typedef Ms3Cfg<72, 3, 288, 288, 2, 2, true> Ms3w;     // forward, many wavefields: 9 warps, M pass in two balanced rounds, combined twiddles (96 registers: 2.66 ms)
 typedef Ms3Cfg<64, 4, 256, 256, 1, 2> Ms3p64;   // 64-pixel probes: one 4 x 4 block and one 16-point group per thread
 
 // 24-point DFT in registers: Good-Thomas 3 x 8, n = (8 a + 3 b) mod 24, k = (16 ka + 9 kb) mod 24, slot (8 ka + 3 kb) mod 24.
@@ -158,37 +159,45 @@ template <bool INV, int RA, class T> ADM_DEV void ms3_dftA(T& a0, T& a1, T& a2, 
     if constexpr (RA == 3) dft3<INV>(a0, a1, a2);
     else dft4<INV>(a0, a1, a2, a3);
 }
-template <bool INV, int RA, class T> ADM_DEV void ms3_A(T (&w)[RA][RA], const T* wy, const T* wx) {
-    if constexpr (INV) {
+template <bool INV, int RA, bool COMB, class T> ADM_DEV void ms3_A(T (&w)[RA][RA], const T* wy, const T* wx, const T* wyx) {
+    // twiddle of element (k1y, k1x): wy[k1y-1] wx[k1x-1]; COMB: wyx holds the products, row-major (k1y-1, k1x-1), one multiply
+    // per element (needs (RA-1)^2 more constants per block; measured: forward 2.71 -> 2.66 ms, adjoint slower -- registers)
+    auto twiddle = [&](auto conj_tag) {
+        constexpr bool CJ = decltype(conj_tag)::value;
+        if constexpr (COMB) {
 #pragma unroll
-        for (int k = 1; k < RA; ++k)
+            for (int ky = 0; ky < RA; ++ky)
 #pragma unroll
-            for (int j = 0; j < RA; ++j) w[k][j] = cmulc(w[k][j], wy[k - 1]);
+                for (int kx = 0; kx < RA; ++kx) {
+                    if (ky == 0 && kx == 0) continue;
+                    const T f = (ky > 0 && kx > 0) ? wyx[(ky - 1) * (RA - 1) + kx - 1] : (ky > 0 ? wy[ky - 1] : wx[kx - 1]);
+                    w[ky][kx] = CJ ? cmulc(w[ky][kx], f) : cmul(w[ky][kx], f);
+                }
+        } else {
 #pragma unroll
-        for (int k = 1; k < RA; ++k)
+            for (int k = 1; k < RA; ++k)
 #pragma unroll
-            for (int j = 0; j < RA; ++j) w[j][k] = cmulc(w[j][k], wx[k - 1]);
-    }
+                for (int j = 0; j < RA; ++j) w[k][j] = CJ ? cmulc(w[k][j], wy[k - 1]) : cmul(w[k][j], wy[k - 1]);
+#pragma unroll
+            for (int k = 1; k < RA; ++k)
+#pragma unroll
+                for (int j = 0; j < RA; ++j) w[j][k] = CJ ? cmulc(w[j][k], wx[k - 1]) : cmul(w[j][k], wx[k - 1]);
+        }
+    };
+    if constexpr (INV) twiddle(std::true_type());
 #pragma unroll
     for (int j = 0; j < RA; ++j) ms3_dftA<INV, RA>(w[j][0], w[j][1], w[j][2], w[j][RA - 1]);
 #pragma unroll
     for (int j = 0; j < RA; ++j) ms3_dftA<INV, RA>(w[0][j], w[1][j], w[2][j], w[RA - 1][j]);
-    if constexpr (!INV) {
-#pragma unroll
-        for (int k = 1; k < RA; ++k)
-#pragma unroll
-            for (int j = 0; j < RA; ++j) w[k][j] = cmul(w[k][j], wy[k - 1]);
-#pragma unroll
-        for (int k = 1; k < RA; ++k)
-#pragma unroll
-            for (int j = 0; j < RA; ++j) w[j][k] = cmul(w[j][k], wx[k - 1]);
-    }
+    if constexpr (!INV) twiddle(std::false_type());
 }
 
 // per-thread constants of the M pass: thread t owns the blocks (ry0 + RS k, rx), k < MR
 template <class T, class C> struct Ms3Thread {
     int ry0, rx;
     T wy[C::MR][C::RA - 1], wx[C::RA - 1];
+    T wyx[C::COMB ? C::MR : 1][(C::RA - 1) * (C::RA - 1)];
+    ADM_HDM const T* comb(int k) const { return C::COMB ? wyx[k] : nullptr; }
 };
 template <class T, class C> ADM_DEV void ms3_thread_init(Ms3Thread<T, C>& I, int t) {
     I.ry0 = (t / C::RB) % C::RB; I.rx = t % C::RB;
@@ -198,6 +207,15 @@ template <class T, class C> ADM_DEV void ms3_thread_init(Ms3Thread<T, C>& I, int
         for (int e = 1; e < C::RA; ++e) I.wy[k][e - 1] = ms3_wP<T, C::P>(e * ((I.ry0 + C::RS * k) % C::RB));
 #pragma unroll
     for (int e = 1; e < C::RA; ++e) I.wx[e - 1] = ms3_wP<T, C::P>(e * I.rx);
+    if constexpr (C::COMB) {
+#pragma unroll
+        for (int k = 0; k < C::MR; ++k)
+#pragma unroll
+            for (int ey = 1; ey < C::RA; ++ey)
+#pragma unroll
+                for (int ex = 1; ex < C::RA; ++ex)
+                    I.wyx[k][(ey - 1) * (C::RA - 1) + ex - 1] = ms3_wP<T, C::P>((ey * ((I.ry0 + C::RS * k) % C::RB) + ex * I.rx) % C::P);
+    }
 }
 
 // B pass along y (YDIR, lanes along x: l = column) or along x (lanes along y: l = row) for group q = k1.
@@ -293,7 +311,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
                 for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
                     for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cscale(probe[(RB * jy + ry) * P + RB * jx + I.rx], 1.0f / (float)(RA * RA));
-                ms3_A<false, RA>(w, I.wy[k], I.wx);
+                ms3_A<false, RA, C::COMB>(w, I.wy[k], I.wx, I.comb(k));
 #pragma unroll
                 for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
@@ -323,7 +341,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
                     for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
                         for (int jx = 0; jx < RA; ++jx) w[jy][jx] = psi[(RB * jy + ry) * S + RB * jx + I.rx];
-                    ms3_A<true, RA>(w, I.wy[k], I.wx);
+                    ms3_A<true, RA, C::COMB>(w, I.wy[k], I.wx, I.comb(k));
 #pragma unroll
                     for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
@@ -345,7 +363,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
 #pragma unroll
                             for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cconj(w[jy][jx]);
                     }
-                    ms3_A<false, RA>(w, I.wy[k], I.wx);
+                    ms3_A<false, RA, C::COMB>(w, I.wy[k], I.wx, I.comb(k));
 #pragma unroll
                     for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
@@ -398,7 +416,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
                     for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
                         for (int jx = 0; jx < RA; ++jx) w[jy][jx] = psi[(RB * jy + ry) * S + RB * jx + I.rx];
-                    ms3_A<true, RA>(w, I.wy[k], I.wx);
+                    ms3_A<true, RA, C::COMB>(w, I.wy[k], I.wx, I.comb(k));
 #pragma unroll
                     for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
@@ -527,7 +545,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
                 for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
                     for (int jx = 0; jx < RA; ++jx) w[jy][jx] = cscale(gdet[(RB * jy + ry) * P + RB * jx + I.rx], pre);
-                ms3_A<false, RA>(w, I.wy[k], I.wx);
+                ms3_A<false, RA, C::COMB>(w, I.wy[k], I.wx, I.comb(k));
 #pragma unroll
                 for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
@@ -564,7 +582,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
                     for (int jy = 0; jy < RA; ++jy)
 #pragma unroll
                         for (int jx = 0; jx < RA; ++jx) w[jy][jx] = psi[(RB * jy + ry) * S + RB * jx + I.rx];
-                    ms3_A<true, RA>(w, I.wy[k], I.wx);
+                    ms3_A<true, RA, C::COMB>(w, I.wy[k], I.wx, I.comb(k));
                     if (KIND == 1 && p.ff_conj) {
 #pragma unroll
                         for (int jy = 0; jy < RA; ++jy)
@@ -586,7 +604,7 @@ template <class T, class C> __global__ void __launch_bounds__(C::NTHREADS, C::MI
                             w[jy][jx] = modulate_conj(w[jy][jx], tpa[k][jy][jx]);
                         }
                     if constexpr (KIND != 2) {
-                        ms3_A<false, RA>(w, I.wy[k], I.wx);
+                        ms3_A<false, RA, C::COMB>(w, I.wy[k], I.wx, I.comb(k));
 #pragma unroll
                         for (int jy = 0; jy < RA; ++jy)
 #pragma unroll

@@ -102,12 +102,13 @@ def test_emulated_five_pass_kernels_match_three_pass_kernels(name, monkeypatch):
     assert abs(a['loss'] - b['loss']) <= 1e-5 * abs(b['loss'])
     if name.startswith('ptycho3d_p72'):
         # the forward kernel has two thread configurations: 7 warps (few wavefields, as here) and 9 warps with the M pass in
-        # two rounds (more wavefields than SMs); ADM_MS3_FWD=2 forces the second one: same blocks, another thread mapping
+        # two rounds and the y / x twiddles combined into one factor per element (more wavefields than SMs); ADM_MS3_FWD=2
+        # forces the second one: same blocks, another thread mapping, another rounding of the twiddles
         monkeypatch.setenv('ADM_MS3', '1')
         monkeypatch.setenv('ADM_MS3_FWD', '2')
         _, c = run_emu_case(name, separable=True)
         for k in ('det', 'pred', 'g_obj'):
-            assert rel_err(c[k], a[k]) < 2e-6, k
+            assert 0 < rel_err(c[k], a[k]) < 5e-5, k
 
 
 def test_emulated_three_pass_kernels_for_64_pixel_probes_with_handoff(monkeypatch):
